@@ -1,0 +1,149 @@
+/* sdpb_b200 — C-ABI of the B200-native Schur-complement step of SDPB.
+ *
+ * SDPB has no plugin/FFI layer.  The seam this library replaces is the three
+ * free functions SDP_Solver::run / SDP_Solver::step call once per Newton
+ * iteration (paths relative to the reference checkout):
+ *
+ *   cholesky_decomposition              src/sdp_solve/SDP_Solver/run/run.cxx:14-17    (called :386-387)
+ *   compute_bilinear_pairings           src/sdp_solve/SDP_Solver/run/run.cxx:37-45    (called :390)
+ *   initialize_schur_complement_solver  src/sdp_solve/SDP_Solver/run/step/step.cxx:12-24 (called :123)
+ *
+ * plus the immutable SDP data they read (SDP::bases_blocks, SDP::free_var_matrix,
+ * src/sdp_solve/SDP.hxx:84-97) and the persistent syrk context created once in
+ * run.cxx:250-255.  INTEGRATION.md shows the shim a maintainer adds on the
+ * reference side.
+ *
+ * Scalars.  El::BigFloat is GMP's mpf_t.  Across this ABI every number is a
+ * "packed element" of sdpb_b200_elem_words(prec) 64-bit little-endian words:
+ *
+ *   word 0        low 32 bits: exponent in 64-bit limbs (int32, == _mp_exp)
+ *                 high 32 bits: sign (int32: -1, 0, +1)
+ *   word 1..NL    NL = (prec+63)/64 + 2 mantissa limbs, least significant
+ *                 first, TOP-ALIGNED: the mpf's |_mp_size| limbs occupy the
+ *                 highest positions, lower positions are zero
+ *   (one pad word when NL+1 is odd, so elements are 16-byte aligned)
+ *
+ * i.e. exactly the fields of __mpf_struct; sdpb_b200_pack_mpf below is the
+ * whole conversion.  Matrices are column-major arrays of packed elements with
+ * leading dimension = height.
+ *
+ * Threading: one caller thread per context; calls are synchronous.  The
+ * library owns all device memory and streams; host buffers are caller-owned
+ * and only touched during a call.  Every function returns 0 on success; on
+ * failure it returns non-zero and sdpb_b200_last_error(ctx) names the stage,
+ * block index and parity the way the reference's RUNTIME_ERROR texts do
+ * (cholesky_decomposition.cxx:20-25, compute_Q.cxx:33-38,
+ * initialize_schur_complement_solver.cxx:100-103).  There is no CPU fallback:
+ * without a CUDA device sdpb_b200_create fails.
+ */
+#ifndef SDPB_B200_H
+#define SDPB_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sdpb_b200_ctx sdpb_b200_ctx;
+
+/* error codes */
+#define SDPB_B200_OK 0
+#define SDPB_B200_ERR_ARG 1      /* bad argument / unsupported precision */
+#define SDPB_B200_ERR_CUDA 2     /* CUDA runtime failure (incl. no device) */
+#define SDPB_B200_ERR_NOT_HPD 3  /* non-positive pivot in a Cholesky */
+#define SDPB_B200_ERR_Q_DIAG 4   /* check_normalized_Q_diagonal failed */
+#define SDPB_B200_ERR_STATE 5    /* calls out of order */
+
+/* 64-bit words per packed element at this --precision; 0 if unsupported. */
+int sdpb_b200_elem_words(int prec_bits);
+/* mantissa limbs NL stored per element. */
+int sdpb_b200_stored_limbs(int prec_bits);
+
+/* Create the per-process solver context (replaces
+ * initialize_bigint_syrk_context, run.cxx:250-255, and the allocations of
+ * step.cxx:92-115).  dims[j], num_points[j] as in Block_Info
+ * (Block_Info.hxx:23-24) for the blocks owned by THIS process; N =
+ * dual_objective_b.Height().  `device` is the CUDA ordinal. */
+int sdpb_b200_create(sdpb_b200_ctx **ctx, int prec_bits, int device,
+                     int num_blocks, const int *dims, const int *num_points,
+                     int N, char *err, size_t errlen);
+void sdpb_b200_destroy(sdpb_b200_ctx *ctx);
+const char *sdpb_b200_last_error(const sdpb_b200_ctx *ctx);
+
+/* Upload the immutable SDP data of local block j (SDP.hxx:84-97):
+ *   B            free_var_matrix block, P_j x N, P_j = n*m*(m+1)/2
+ *   bases_even   bilinear_bases[2j],   (floor(d/2)+1) x n, d = n-1
+ *   bases_odd    bilinear_bases[2j+1], floor((d+1)/2) x n   (may be empty)
+ * The library forms bases_blocks = I_m (x) basis itself
+ * (SDP/set_bases_blocks.cxx:24-47). */
+int sdpb_b200_set_block(sdpb_b200_ctx *ctx, int j, const uint64_t *B,
+                        const uint64_t *bases_even, const uint64_t *bases_odd);
+
+/* cholesky_decomposition (run/cholesky_decomposition.cxx:5-28).
+ * which = 0: X -> X_cholesky (kept on the device for the pairings),
+ * which = 1: Y -> Y_cholesky.  A[b], L[b] for b = 2*j + parity are host
+ * pointers to s x s column-major matrices, s = psd_matrix_block_size
+ * (Block_Info.hxx:83-95); blocks with s == 0 may be NULL.  L may be NULL
+ * (results stay on the device). */
+int sdpb_b200_cholesky_decomposition(sdpb_b200_ctx *ctx, int which,
+                                     const uint64_t *const *A,
+                                     uint64_t *const *L);
+
+/* compute_bilinear_pairings (run/compute_bilinear_pairings/*.cxx).  Uses the
+ * device-resident X_cholesky of the preceding call and Y from the host.
+ * Outputs (optional, may be NULL): for b = 2*j + parity the full symmetric
+ * (m*n) x (m*n) matrices  V^T X^-1 V  and  V^T Y V ; the reference's tiles are
+ *   A_X_inv[parity][j][cb][rb](row,col) = AX[b][(cb*n+row) + (rb*n+col)*m*n]
+ *   A_Y    [parity][j][cb][rb](row,col) = AY[b][(cb*n+col) + (rb*n+row)*m*n]
+ * (compute_A_X_inv.cxx:45-55, compute_A_Y.cxx:51-63). */
+int sdpb_b200_compute_bilinear_pairings(sdpb_b200_ctx *ctx,
+                                        const uint64_t *const *Y,
+                                        uint64_t *const *A_X_inv,
+                                        uint64_t *const *A_Y);
+
+/* initialize_schur_complement_solver
+ * (run/step/initialize_schur_complement_solver/*.cxx): S assembly, per-block
+ * Cholesky + L^-1 B, column normalisation, exact integer syrk, restore,
+ * Cholesky(UPPER, Q).  Outputs (each may be NULL = keep on device only):
+ *   schur_complement_cholesky[j]  P_j x P_j lower factor L_j
+ *   schur_off_diagonal[j]         P_j x N  = L_j^-1 B_j (after the
+ *                                 normalise/restore round trip, compute_Q.cxx:117,130)
+ *   Q                             N x N, upper Cholesky factor, lower part 0
+ *   block_timings_ms[j]           += ms spent in cholesky_j + solve_j
+ *                                 (compute_Q.cxx:40,52) */
+int sdpb_b200_initialize_schur_complement_solver(
+  sdpb_b200_ctx *ctx, uint64_t *const *schur_complement_cholesky,
+  uint64_t *const *schur_off_diagonal, uint64_t *Q, int32_t *block_timings_ms);
+
+/* The whole hot path of one Newton iteration in one call:
+ * cholesky_decomposition(X), cholesky_decomposition(Y),
+ * compute_bilinear_pairings, initialize_schur_complement_solver, with a
+ * single host synchronisation at the end.  Pointer arguments as above. */
+int sdpb_b200_schur_step(sdpb_b200_ctx *ctx, const uint64_t *const *X,
+                         const uint64_t *const *Y, uint64_t *const *X_cholesky,
+                         uint64_t *const *Y_cholesky, uint64_t *const *A_X_inv,
+                         uint64_t *const *A_Y,
+                         uint64_t *const *schur_complement_cholesky,
+                         uint64_t *const *schur_off_diagonal, uint64_t *Q,
+                         int32_t *block_timings_ms);
+
+/* Device-side timing of the last step, milliseconds per stage (CUDA events):
+ * [0] cholesky X+Y  [1] bilinear pairings  [2] S assembly  [3] cholesky S_j +
+ * L^-1 B  [4] norms+normalise  [5] exact syrk  [6] restore  [7] Cholesky(Q)
+ * [8] whole step on device.  Fills min(n, 9) entries. */
+int sdpb_b200_last_timings_ms(const sdpb_b200_ctx *ctx, float *ms, int n);
+
+/* Convert between a GMP __mpf_struct's fields and a packed element.  Pure host
+ * helpers (no device work); this is all a reference-side shim needs. */
+void sdpb_b200_pack_mpf(int prec_bits, int mp_size, long mp_exp,
+                        const uint64_t *mp_d, uint64_t *out);
+/* Writes up to NL limbs to mp_d (caller-provided, >= NL limbs); returns the
+ * signed _mp_size and stores _mp_exp. */
+int sdpb_b200_unpack_mpf(int prec_bits, const uint64_t *in, uint64_t *mp_d,
+                         long *mp_exp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,323 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see hotpath_core.hpp).
+// The same call surface as include/sdpb_b200.h, implemented on the CPU with
+// libgmp, so tests drive both through identical inputs and compare bytes.
+// Build: make -C oracle   (-> oracle/liboracle.so)
+#include "hotpath_core.hpp"
+
+#include <chrono>
+#include <cstdio>
+#include <memory>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace oracle;
+using sdpb_host::elem_words;
+using sdpb_host::pack_matrix;
+using sdpb_host::unpack_matrix;
+
+struct oracle_ctx
+{
+  int prec, N, J;
+  std::vector<BlockShape> shapes;
+  std::vector<Matrix> B;               // J
+  std::vector<Matrix> V;               // 2J bases_blocks
+  std::vector<Matrix> X_cholesky;      // 2J
+  std::vector<Matrix> AX, AY;          // 2J
+  std::string error;
+  double stage_ms[9];
+};
+
+static void pack_out(const Matrix &m, uint64_t *out)
+{
+  if(out && m.a.size())
+    pack_matrix(m, out);
+}
+
+extern "C" {
+
+int oracle_elem_words(int prec_bits)
+{
+  return (((prec_bits + 63) / 64 + 2) + 2) & ~1;
+}
+
+int oracle_create(oracle_ctx **out, int prec_bits, int num_blocks,
+                  const int *dims, const int *num_points, int N)
+{
+  sdpb_host::set_precision(prec_bits);
+  auto *c = new oracle_ctx();
+  c->prec = prec_bits;
+  c->N = N;
+  c->J = num_blocks;
+  for(int j = 0; j < num_blocks; ++j)
+    c->shapes.push_back(BlockShape{dims[j], num_points[j]});
+  c->B.resize(num_blocks);
+  c->V.resize(2 * num_blocks);
+  c->X_cholesky.resize(2 * num_blocks);
+  c->AX.resize(2 * num_blocks);
+  c->AY.resize(2 * num_blocks);
+  for(double &x : c->stage_ms)
+    x = 0;
+  *out = c;
+  return 0;
+}
+void oracle_destroy(oracle_ctx *c) { delete c; }
+const char *oracle_last_error(const oracle_ctx *c) { return c->error.c_str(); }
+
+int oracle_set_block(oracle_ctx *c, int j, const uint64_t *B,
+                     const uint64_t *bases_even, const uint64_t *bases_odd)
+{
+  sdpb_host::set_precision(c->prec);
+  const BlockShape &sh = c->shapes[j];
+  unpack_matrix(c->B[j], sh.schur_size(), c->N, B);
+  for(int p = 0; p < 2; ++p)
+    {
+      Matrix basis;
+      const int h = sh.basis_height(p);
+      unpack_matrix(basis, h, sh.n, p == 0 ? bases_even : bases_odd);
+      if(h > 0)
+        make_bases_block(sh, p, basis, c->V[2 * j + p]);
+      else
+        c->V[2 * j + p].resize(0, sh.pairing_size());
+    }
+  return 0;
+}
+
+int oracle_cholesky_decomposition(oracle_ctx *c, int which,
+                                  const uint64_t *const *A, uint64_t *const *L)
+{
+  sdpb_host::set_precision(c->prec);
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = 0;
+  std::vector<Matrix> out(2 * c->J);
+#pragma omp parallel for schedule(dynamic)
+  for(int b = 0; b < 2 * c->J; ++b)
+    {
+      const int s = c->shapes[b / 2].psd_size(b % 2);
+      if(s == 0)
+        continue;
+      unpack_matrix(out[b], s, s, A[b]);
+      const int bad = cholesky_lower(out[b]);
+      if(bad >= 0)
+        {
+#pragma omp critical
+          if(rc == 0)
+            {
+              rc = 3;
+              c->error
+                = std::string("Error when computing Cholesky decomposition of "
+                              "Block_Diagonal_Matrix ")
+                  + (which == 0 ? "X" : "Y")
+                  + ", block index = " + std::to_string(b / 2)
+                  + ", parity = " + std::to_string(b % 2);
+            }
+        }
+    }
+  if(rc)
+    return rc;
+  for(int b = 0; b < 2 * c->J; ++b)
+    {
+      if(L && L[b])
+        pack_out(out[b], L[b]);
+      if(which == 0)
+        c->X_cholesky[b] = std::move(out[b]);
+    }
+  c->stage_ms[0] += std::chrono::duration<double, std::milli>(
+                      std::chrono::steady_clock::now() - t0)
+                      .count();
+  return 0;
+}
+
+int oracle_compute_bilinear_pairings(oracle_ctx *c, const uint64_t *const *Y,
+                                     uint64_t *const *A_X_inv,
+                                     uint64_t *const *A_Y)
+{
+  sdpb_host::set_precision(c->prec);
+  auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic)
+  for(int b = 0; b < 2 * c->J; ++b)
+    {
+      const BlockShape &sh = c->shapes[b / 2];
+      const int s = sh.psd_size(b % 2), mn = sh.pairing_size();
+      if(s == 0)
+        {
+          c->AX[b].resize(mn, mn);
+          c->AY[b].resize(mn, mn);
+        }
+      else
+        {
+          Matrix Yb;
+          unpack_matrix(Yb, s, s, Y[b]);
+          compute_A_X_inv(c->X_cholesky[b], c->V[b], c->AX[b]);
+          compute_A_Y(Yb, c->V[b], c->AY[b]);
+        }
+      if(A_X_inv && A_X_inv[b])
+        pack_out(c->AX[b], A_X_inv[b]);
+      if(A_Y && A_Y[b])
+        pack_out(c->AY[b], A_Y[b]);
+    }
+  c->stage_ms[1] = std::chrono::duration<double, std::milli>(
+                     std::chrono::steady_clock::now() - t0)
+                     .count();
+  return 0;
+}
+
+int oracle_initialize_schur_complement_solver(
+  oracle_ctx *c, uint64_t *const *schur_complement_cholesky,
+  uint64_t *const *schur_off_diagonal, uint64_t *Q, int32_t *block_timings_ms)
+{
+  (void)block_timings_ms;
+  sdpb_host::set_precision(c->prec);
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<Matrix> S(c->J);
+#pragma omp parallel for schedule(dynamic)
+  for(int j = 0; j < c->J; ++j)
+    {
+      std::array<Matrix, 2> AX{c->AX[2 * j], c->AX[2 * j + 1]};
+      std::array<Matrix, 2> AY{c->AY[2 * j], c->AY[2 * j + 1]};
+      compute_schur_block(c->shapes[j], AX, AY, S[j]);
+    }
+  c->stage_ms[2] = std::chrono::duration<double, std::milli>(
+                     std::chrono::steady_clock::now() - t0)
+                     .count();
+  SchurOutputs out;
+  compute_Q_and_factor(S, c->B, c->N, out);
+  if(!out.error.empty())
+    {
+      c->error = out.error;
+      return out.error.find("Normalized Q") != std::string::npos ? 4 : 3;
+    }
+  for(int j = 0; j < c->J; ++j)
+    {
+      if(schur_complement_cholesky && schur_complement_cholesky[j])
+        pack_out(out.schur_complement_cholesky[j],
+                 schur_complement_cholesky[j]);
+      if(schur_off_diagonal && schur_off_diagonal[j])
+        pack_out(out.schur_off_diagonal[j], schur_off_diagonal[j]);
+    }
+  if(Q)
+    pack_out(out.Q, Q);
+  c->stage_ms[8] = std::chrono::duration<double, std::milli>(
+                     std::chrono::steady_clock::now() - t0)
+                     .count();
+  return 0;
+}
+
+int oracle_schur_step(oracle_ctx *c, const uint64_t *const *X,
+                      const uint64_t *const *Y, uint64_t *const *X_cholesky,
+                      uint64_t *const *Y_cholesky, uint64_t *const *A_X_inv,
+                      uint64_t *const *A_Y,
+                      uint64_t *const *schur_complement_cholesky,
+                      uint64_t *const *schur_off_diagonal, uint64_t *Q,
+                      int32_t *block_timings_ms)
+{
+  int rc = oracle_cholesky_decomposition(c, 0, X, X_cholesky);
+  if(rc)
+    return rc;
+  rc = oracle_cholesky_decomposition(c, 1, Y, Y_cholesky);
+  if(rc)
+    return rc;
+  rc = oracle_compute_bilinear_pairings(c, Y, A_X_inv, A_Y);
+  if(rc)
+    return rc;
+  return oracle_initialize_schur_complement_solver(
+    c, schur_complement_cholesky, schur_off_diagonal, Q, block_timings_ms);
+}
+
+// ---- single-kernel entry points for unit parity tests -----------------
+int oracle_potrf(int prec, int s, int upper, const uint64_t *A, uint64_t *L)
+{
+  sdpb_host::set_precision(prec);
+  Matrix M;
+  unpack_matrix(M, s, s, A);
+  const int bad = upper ? cholesky_upper(M) : cholesky_lower(M);
+  pack_out(M, L);
+  return bad;
+}
+int oracle_trsm(int prec, int p, int ncols, const uint64_t *L,
+                const uint64_t *B, uint64_t *X)
+{
+  sdpb_host::set_precision(prec);
+  Matrix Lm, Bm;
+  unpack_matrix(Lm, p, p, L);
+  unpack_matrix(Bm, p, ncols, B);
+  trsm_lower(Lm, Bm);
+  pack_out(Bm, X);
+  return 0;
+}
+// scalar ops on packed elements, for device-vs-libgmp scalar parity
+// op: 0 mul 1 add 2 sub 3 div 4 sqrt(a) 5 a<<k 6 a>>k 7 a/4
+int oracle_scalar_op(int prec, int op, int k, long count, const uint64_t *a,
+                     const uint64_t *b, uint64_t *r)
+{
+  sdpb_host::set_precision(prec);
+  const int ew = elem_words();
+  BigFloat x, y, z, four(4);
+  for(long i = 0; i < count; ++i)
+    {
+      sdpb_host::unpack(x, a + i * ew);
+      sdpb_host::unpack(y, b + i * ew);
+      switch(op)
+        {
+        case 0: mpf_mul(z.v, x.v, y.v); break;
+        case 1: mpf_add(z.v, x.v, y.v); break;
+        case 2: mpf_sub(z.v, x.v, y.v); break;
+        case 3:
+          if(y.sgn() == 0)
+            z.zero();
+          else
+            mpf_div(z.v, x.v, y.v);
+          break;
+        case 4:
+          if(x.sgn() < 0)
+            z.zero();
+          else
+            mpf_sqrt(z.v, x.v);
+          break;
+        case 5: mpf_mul_2exp(z.v, x.v, (unsigned)k); break;
+        case 6: mpf_div_2exp(z.v, x.v, (unsigned)k); break;
+        case 7: mpf_div(z.v, x.v, four.v); break;
+        default: return 1;
+        }
+      sdpb_host::pack(z, r + i * ew);
+    }
+  return 0;
+}
+// decimal string -> packed element (mpf_set_str at `prec`), for fixtures
+int oracle_from_decimal(int prec, const char *dec, uint64_t *out)
+{
+  sdpb_host::set_precision(prec);
+  try
+    {
+      BigFloat x{std::string(dec)};
+      sdpb_host::pack(x, out);
+    }
+  catch(...)
+    {
+      return 1;
+    }
+  return 0;
+}
+double oracle_to_double(int prec, const uint64_t *in)
+{
+  sdpb_host::set_precision(prec);
+  BigFloat x;
+  sdpb_host::unpack(x, in);
+  return x.to_double();
+}
+int oracle_stage_ms(const oracle_ctx *c, double *ms, int n)
+{
+  for(int i = 0; i < n && i < 9; ++i)
+    ms[i] = c->stage_ms[i];
+  return 0;
+}
+int oracle_num_threads()
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+} // extern "C"
