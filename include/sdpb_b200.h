@@ -134,6 +134,12 @@ int sdpb_b200_schur_step(sdpb_b200_ctx *ctx, const uint64_t *const *X,
  * [8] whole step on device.  Fills min(n, 9) entries. */
 int sdpb_b200_last_timings_ms(const sdpb_b200_ctx *ctx, float *ms, int n);
 
+/* Test hook: element-wise mpf-exact scalar operations executed on the device
+ * (op: 0 mul, 1 add, 2 sub, 3 div, 4 sqrt(a), 5 a<<k, 6 a>>k, 7 a/4) on
+ * `count` packed elements; used to check the device arithmetic against libgmp. */
+int sdpb_b200_scalar_op(sdpb_b200_ctx *ctx, int op, int k, long count,
+                        const uint64_t *a, const uint64_t *b, uint64_t *r);
+
 /* Convert between a GMP __mpf_struct's fields and a packed element.  Pure host
  * helpers (no device work); this is all a reference-side shim needs. */
 void sdpb_b200_pack_mpf(int prec_bits, int mp_size, long mp_exp,

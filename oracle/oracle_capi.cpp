@@ -321,3 +321,76 @@ int oracle_num_threads()
 #endif
 }
 } // extern "C"
+
+// ---- deterministic synthetic inputs (seeded) ---------------
+static inline uint64_t splitmix64(uint64_t &s)
+{
+  uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+extern "C" {
+// h x w matrix, entries uniform in (-1,1) with full-length mantissas
+int oracle_random_matrix(int prec, int h, int w, uint64_t seed, uint64_t *out)
+{
+  const int nl = (prec + 63) / 64 + 2, ew = (nl + 2) & ~1;
+  uint64_t s = seed * 0x2545F4914F6CDD1Dull + 0x5D9B0000ull;
+  for(long e = 0; e < (long)h * w; ++e)
+    {
+      uint64_t *p = out + e * ew;
+      for(int i = 0; i < ew; ++i)
+        p[i] = 0;
+      for(int i = 0; i < nl; ++i)
+        p[1 + i] = splitmix64(s);
+      if(p[nl] == 0)
+        p[nl] = 1;
+      const int32_t sign = (splitmix64(s) & 1) ? 1 : -1;
+      p[0] = (uint64_t)(uint32_t)0 | ((uint64_t)(uint32_t)sign << 32);
+    }
+  return 0;
+}
+// symmetric positive definite s x s: G G^T / s + I, G random as above
+int oracle_random_spd(int prec, int s, uint64_t seed, uint64_t *out)
+{
+  sdpb_host::set_precision(prec);
+  std::vector<uint64_t> buf((size_t)s * s * elem_words());
+  oracle_random_matrix(prec, s, s, seed, buf.data());
+  Matrix G, A(s, s);
+  unpack_matrix(G, s, s, buf.data());
+  BigFloat prod, inv_s = BigFloat(1) / BigFloat(s > 0 ? s : 1);
+  for(int j = 0; j < s; ++j)
+    for(int i = j; i < s; ++i)
+      {
+        BigFloat acc;
+        for(int l = 0; l < s; ++l)
+          {
+            prod = G(i, l);
+            prod *= G(j, l);
+            acc += prod;
+          }
+        acc *= inv_s;
+        if(i == j)
+          acc += BigFloat(1);
+        A(i, j) = acc;
+        A(j, i) = acc;
+      }
+  pack_out(A, out);
+  return 0;
+}
+// out = scale * in  (scale as a double), for building ill-scaled test inputs
+int oracle_scale_matrix(int prec, long count, double scale, const uint64_t *in,
+                        uint64_t *out)
+{
+  sdpb_host::set_precision(prec);
+  const int ew = elem_words();
+  BigFloat x, sc(scale);
+  for(long e = 0; e < count; ++e)
+    {
+      sdpb_host::unpack(x, in + e * ew);
+      x *= sc;
+      sdpb_host::pack(x, out + e * ew);
+    }
+  return 0;
+}
+}

@@ -1,0 +1,211 @@
+"""ctypes binding of include/sdpb_b200.h.
+
+Matrices are numpy ``uint64`` arrays of shape ``(width, height, elem_words)``:
+column-major packed elements exactly as the C-ABI wants them.  Method names and
+argument meaning mirror the reference functions they replace
+(src/sdp_solve/SDP_Solver/run/run.cxx:14-17,37-45 and run/step/step.cxx:12-24).
+"""
+import ctypes
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsdpb_b200.so")
+_lib = None
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+u64pp = ctypes.POINTER(u64p)
+
+
+class SdpbB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"sdpb_b200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+def load_library():
+    """Load libsdpb_b200.so; fails loudly if the CUDA extension was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `make -C sdpb_b200/csrc` "
+            "(there is no CPU fallback)"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.sdpb_b200_elem_words.restype = ctypes.c_int
+    lib.sdpb_b200_elem_words.argtypes = [ctypes.c_int]
+    lib.sdpb_b200_stored_limbs.restype = ctypes.c_int
+    lib.sdpb_b200_stored_limbs.argtypes = [ctypes.c_int]
+    lib.sdpb_b200_create.restype = ctypes.c_int
+    lib.sdpb_b200_create.argtypes = [
+        ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+        ctypes.c_char_p, ctypes.c_size_t]
+    lib.sdpb_b200_destroy.restype = None
+    lib.sdpb_b200_destroy.argtypes = [ctypes.c_void_p]
+    lib.sdpb_b200_last_error.restype = ctypes.c_char_p
+    lib.sdpb_b200_last_error.argtypes = [ctypes.c_void_p]
+    lib.sdpb_b200_set_block.restype = ctypes.c_int
+    lib.sdpb_b200_set_block.argtypes = [ctypes.c_void_p, ctypes.c_int, u64p, u64p, u64p]
+    lib.sdpb_b200_cholesky_decomposition.restype = ctypes.c_int
+    lib.sdpb_b200_cholesky_decomposition.argtypes = [ctypes.c_void_p, ctypes.c_int, u64pp, u64pp]
+    lib.sdpb_b200_compute_bilinear_pairings.restype = ctypes.c_int
+    lib.sdpb_b200_compute_bilinear_pairings.argtypes = [ctypes.c_void_p, u64pp, u64pp, u64pp]
+    lib.sdpb_b200_initialize_schur_complement_solver.restype = ctypes.c_int
+    lib.sdpb_b200_initialize_schur_complement_solver.argtypes = [
+        ctypes.c_void_p, u64pp, u64pp, u64p, ctypes.POINTER(ctypes.c_int32)]
+    lib.sdpb_b200_schur_step.restype = ctypes.c_int
+    lib.sdpb_b200_schur_step.argtypes = [ctypes.c_void_p] + [u64pp] * 8 + [
+        u64p, ctypes.POINTER(ctypes.c_int32)]
+    lib.sdpb_b200_last_timings_ms.restype = ctypes.c_int
+    lib.sdpb_b200_last_timings_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+    lib.sdpb_b200_scalar_op.restype = ctypes.c_int
+    lib.sdpb_b200_scalar_op.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_long, u64p, u64p, u64p]
+    _lib = lib
+    return lib
+
+
+def stored_limbs(prec_bits):
+    return (prec_bits + 63) // 64 + 2
+
+
+def elem_words(prec_bits):
+    return (stored_limbs(prec_bits) + 2) & ~1
+
+
+@dataclass(frozen=True)
+class BlockShape:
+    """Shape helpers of one SDP block (reference Block_Info.hxx:54-115)."""
+    m: int  # dimensions[j]
+    n: int  # num_points[j]
+
+    @property
+    def schur_size(self):
+        return self.n * self.m * (self.m + 1) // 2
+
+    def psd_size(self, parity):
+        even = self.m * ((self.n + 1) // 2)
+        return even if parity == 0 else self.m * self.n - even
+
+    @property
+    def pairing_size(self):
+        return self.m * self.n
+
+    def basis_height(self, parity):
+        degree = self.n - 1
+        return (degree + parity) // 2 + 1 - parity
+
+
+def _ptr(a):
+    return a.ctypes.data_as(u64p) if a is not None and a.size else None
+
+
+def ptr_array(arrays):
+    """C array of uint64_t* from a list of numpy arrays (None / empty -> NULL)."""
+    arr = (u64p * max(1, len(arrays)))()
+    for i, a in enumerate(arrays):
+        arr[i] = _ptr(a) if a is not None else None
+    return arr
+
+
+class StepContextBase:
+    """Shared driver logic over a C library exposing the sdpb_b200 call surface."""
+
+    def __init__(self, prec_bits, shapes, N):
+        self.prec = prec_bits
+        self.shapes = [s if isinstance(s, BlockShape) else BlockShape(*s) for s in shapes]
+        self.N = N
+        self.ew = elem_words(prec_bits)
+        self.J = len(self.shapes)
+
+    # allocation helpers -------------------------------------------------
+    def empty(self, h, w):
+        return np.zeros((w, h, self.ew), dtype=np.uint64)
+
+    def alloc_psd_blocks(self):
+        return [self.empty(s.psd_size(p), s.psd_size(p)) for s in self.shapes for p in (0, 1)]
+
+    def alloc_pairing_blocks(self):
+        return [self.empty(s.pairing_size, s.pairing_size) for s in self.shapes for p in (0, 1)]
+
+    def alloc_schur_outputs(self):
+        L = [self.empty(s.schur_size, s.schur_size) for s in self.shapes]
+        P = [self.empty(s.schur_size, self.N) for s in self.shapes]
+        Q = self.empty(self.N, self.N)
+        return L, P, Q
+
+
+class SchurContext(StepContextBase):
+    """Device-resident state of the Schur-complement step on one B200."""
+
+    def __init__(self, prec_bits, shapes, N, device=0):
+        super().__init__(prec_bits, shapes, N)
+        self.lib = load_library()
+        self.handle = ctypes.c_void_p()
+        dims = (ctypes.c_int * max(1, self.J))(*[s.m for s in self.shapes])
+        npts = (ctypes.c_int * max(1, self.J))(*[s.n for s in self.shapes])
+        err = ctypes.create_string_buffer(512)
+        rc = self.lib.sdpb_b200_create(ctypes.byref(self.handle), prec_bits, device, self.J,
+                                       dims, npts, N, err, len(err))
+        if rc != 0:
+            self.handle = None
+            raise SdpbB200Error(rc, err.value.decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.sdpb_b200_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SdpbB200Error(rc, self.lib.sdpb_b200_last_error(self.handle).decode())
+
+    def set_block(self, j, B, bases_even, bases_odd):
+        self._check(self.lib.sdpb_b200_set_block(self.handle, j, _ptr(B), _ptr(bases_even), _ptr(bases_odd)))
+
+    def cholesky_decomposition(self, which, A, L=None):
+        self._check(self.lib.sdpb_b200_cholesky_decomposition(
+            self.handle, which, ptr_array(A), ptr_array(L) if L is not None else None))
+
+    def compute_bilinear_pairings(self, Y, A_X_inv=None, A_Y=None):
+        self._check(self.lib.sdpb_b200_compute_bilinear_pairings(
+            self.handle, ptr_array(Y),
+            ptr_array(A_X_inv) if A_X_inv is not None else None,
+            ptr_array(A_Y) if A_Y is not None else None))
+
+    def initialize_schur_complement_solver(self, L=None, P=None, Q=None, block_timings_ms=None):
+        bt = block_timings_ms.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) if block_timings_ms is not None else None
+        self._check(self.lib.sdpb_b200_initialize_schur_complement_solver(
+            self.handle,
+            ptr_array(L) if L is not None else None,
+            ptr_array(P) if P is not None else None,
+            _ptr(Q) if Q is not None else None, bt))
+
+    def schur_step(self, X, Y, X_chol=None, Y_chol=None, A_X_inv=None, A_Y=None, L=None, P=None, Q=None,
+                   block_timings_ms=None):
+        bt = block_timings_ms.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) if block_timings_ms is not None else None
+        opt = lambda v: ptr_array(v) if v is not None else None  # noqa: E731
+        self._check(self.lib.sdpb_b200_schur_step(
+            self.handle, ptr_array(X), ptr_array(Y), opt(X_chol), opt(Y_chol), opt(A_X_inv), opt(A_Y),
+            opt(L), opt(P), _ptr(Q) if Q is not None else None, bt))
+
+    def last_timings_ms(self):
+        ms = (ctypes.c_float * 9)()
+        self.lib.sdpb_b200_last_timings_ms(self.handle, ms, 9)
+        return list(ms)
+
+    def scalar_op(self, op, a, b, k=0):
+        r = np.zeros_like(a)
+        count = a.size // self.ew
+        self._check(self.lib.sdpb_b200_scalar_op(self.handle, op, k, count, _ptr(a), _ptr(b), _ptr(r)))
+        return r

@@ -1,0 +1,778 @@
+// C-ABI of the B200 Schur-complement step (include/sdpb_b200.h): context,
+// HBM layout, kernel sequencing.  No CPU fallback: every entry point that
+// computes requires a CUDA device.
+#include "ctx.h"
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static bool nl_supported(int nl)
+{
+  switch(nl)
+    {
+#define F(n) case n:
+      SDPB_FOR_EACH_NL(F)
+#undef F
+      return true;
+    default: return false;
+    }
+}
+
+// ------------------------------------------------------------ CRT tables
+static uint64_t powmod(uint64_t a, uint64_t e, uint64_t m)
+{
+  uint64_t r = 1;
+  a %= m;
+  while(e)
+    {
+      if(e & 1)
+        r = (unsigned __int128)r * a % m;
+      a = (unsigned __int128)a * a % m;
+      e >>= 1;
+    }
+  return r;
+}
+static bool is_prime32(uint32_t n)
+{
+  if(n < 2)
+    return false;
+  for(uint32_t p : {2u, 3u, 5u, 7u, 11u, 13u, 17u, 19u, 23u, 29u, 31u, 37u})
+    {
+      if(n % p == 0)
+        return n == p;
+    }
+  uint32_t d = n - 1;
+  int r = 0;
+  while((d & 1) == 0)
+    {
+      d >>= 1;
+      ++r;
+    }
+  for(uint64_t a : {2ull, 7ull, 61ull}) // deterministic for n < 4,759,123,141
+    {
+      uint64_t x = powmod(a, d, n);
+      if(x == 1 || x == n - 1)
+        continue;
+      bool comp = true;
+      for(int i = 1; i < r; ++i)
+        {
+          x = (unsigned __int128)x * x % n;
+          if(x == n - 1)
+            {
+              comp = false;
+              break;
+            }
+        }
+      if(comp)
+        return false;
+    }
+  return true;
+}
+
+static int build_crt(sdpb_b200_ctx *c)
+{
+  // |Q'_ij| <= K * (2^prec + small)^2 ; leave 40 bits for K and one for sign
+  const int bits_needed = 2 * c->prec + 2 + 40 + 1;
+  std::vector<uint32_t> primes;
+  double bits = 0;
+  for(uint32_t q = (1u << 28) - 1; bits < bits_needed; q -= 2)
+    if(is_prime32(q))
+      {
+        primes.push_back(q);
+        bits += log2((double)q);
+      }
+  const int np = (int)primes.size();
+  const int nd = (c->prec + 2 + 27) / 28;
+  std::vector<uint32_t> pow28((size_t)np * nd), ginv((size_t)np * np, 0);
+  for(int i = 0; i < np; ++i)
+    {
+      uint64_t x = 1;
+      for(int k = 0; k < nd; ++k)
+        {
+          pow28[(size_t)i * nd + k] = (uint32_t)x;
+          x = (x << 28) % primes[i];
+        }
+      for(int j = 0; j < i; ++j)
+        ginv[(size_t)i * np + j]
+          = (uint32_t)powmod(primes[j] % primes[i], primes[i] - 2, primes[i]);
+    }
+  const int mw = (np * 28 + 31) / 32 + 1;
+  std::vector<uint32_t> M(mw, 0), Mh(mw, 0);
+  M[0] = 1;
+  for(int i = 0; i < np; ++i)
+    {
+      uint64_t carry = 0;
+      for(int k = 0; k < mw; ++k)
+        {
+          const uint64_t z = (uint64_t)M[k] * primes[i] + carry;
+          M[k] = (uint32_t)z;
+          carry = z >> 32;
+        }
+    }
+  // Mhalf = (M + 1) / 2
+  {
+    std::vector<uint32_t> t = M;
+    uint64_t carry = 1;
+    for(int k = 0; k < mw && carry; ++k)
+      {
+        const uint64_t z = (uint64_t)t[k] + carry;
+        t[k] = (uint32_t)z;
+        carry = z >> 32;
+      }
+    for(int k = 0; k < mw; ++k)
+      Mh[k] = (t[k] >> 1) | (k + 1 < mw ? (t[k + 1] << 31) : 0);
+  }
+  auto up = [&](uint32_t **d, const std::vector<uint32_t> &h) -> cudaError_t {
+    cudaError_t e = cudaMalloc(d, h.size() * 4);
+    if(e != cudaSuccess)
+      return e;
+    return cudaMemcpy(*d, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+  };
+  CUDA_TRY(c, up(&c->d_primes, primes));
+  CUDA_TRY(c, up(&c->d_pow28, pow28));
+  CUDA_TRY(c, up(&c->d_ginv, ginv));
+  CUDA_TRY(c, up(&c->d_M, M));
+  CUDA_TRY(c, up(&c->d_Mhalf, Mh));
+  c->crt = CrtTables{c->d_primes, c->d_pow28, c->d_ginv, c->d_M, c->d_Mhalf,
+                     np,          nd,         mw};
+  return 0;
+}
+
+// ----------------------------------------------------------------- create
+template <typename T>
+static cudaError_t upload(T **d, const std::vector<T> &h)
+{
+  cudaError_t e = cudaMalloc(d, std::max<size_t>(1, h.size()) * sizeof(T));
+  if(e != cudaSuccess)
+    return e;
+  if(h.empty())
+    return cudaSuccess;
+  return cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" int sdpb_b200_elem_words(int prec_bits)
+{
+  if(prec_bits < 64)
+    return 0;
+  return (mpfx::stored_limbs(prec_bits) + 2) & ~1;
+}
+extern "C" int sdpb_b200_stored_limbs(int prec_bits)
+{
+  return mpfx::stored_limbs(prec_bits);
+}
+
+extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
+                                int num_blocks, const int *dims,
+                                const int *num_points, int N, char *err,
+                                size_t errlen)
+{
+  auto fail = [&](int rc, const std::string &msg) {
+    if(err && errlen)
+      snprintf(err, errlen, "%s", msg.c_str());
+    return rc;
+  };
+  if(!out || num_blocks < 0 || N <= 0 || prec_bits < 64)
+    return fail(SDPB_B200_ERR_ARG, "sdpb_b200_create: bad argument");
+  const int nl = mpfx::stored_limbs(prec_bits);
+  if(!nl_supported(nl))
+    return fail(SDPB_B200_ERR_ARG,
+                "sdpb_b200_create: precision " + std::to_string(prec_bits)
+                  + " (NL=" + std::to_string(nl)
+                  + ") has no compiled kernels; see SDPB_FOR_EACH_NL");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if(ce != cudaSuccess || ndev == 0)
+    return fail(SDPB_B200_ERR_CUDA,
+                std::string("sdpb_b200_create: no CUDA device (")
+                  + cudaGetErrorString(ce)
+                  + "); this library has no CPU fallback");
+  if(device < 0 || device >= ndev)
+    return fail(SDPB_B200_ERR_ARG, "sdpb_b200_create: bad device ordinal");
+  auto *c = new sdpb_b200_ctx();
+  c->prec = prec_bits;
+  c->nl = nl;
+  c->es = (nl + 2) & ~1;
+  c->device = device;
+  c->J = num_blocks;
+  c->N = N;
+  auto bail = [&](int rc) {
+    const std::string msg = c->error;
+    sdpb_b200_destroy(c);
+    return fail(rc, msg);
+  };
+  if(cudaSetDevice(device) != cudaSuccess)
+    {
+      c->error = "cudaSetDevice failed";
+      return bail(SDPB_B200_ERR_CUDA);
+    }
+  long row0 = 0;
+  const size_t es = c->es;
+  for(int j = 0; j < num_blocks; ++j)
+    {
+      BlockGeom b;
+      b.m = dims[j];
+      b.n = num_points[j];
+      if(b.m <= 0 || b.n <= 0)
+        {
+          c->error = "sdpb_b200_create: bad block shape";
+          return bail(SDPB_B200_ERR_ARG);
+        }
+      b.P = b.n * b.m * (b.m + 1) / 2;
+      b.mn = b.m * b.n;
+      b.s[0] = b.m * ((b.n + 1) / 2);
+      b.s[1] = b.mn - b.s[0];
+      const int deg = b.n - 1;
+      b.h[0] = deg / 2 + 1;
+      b.h[1] = (deg + 1) / 2;
+      b.row0 = row0;
+      row0 += b.P;
+      c->g.push_back(b);
+      c->oB.push_back(c->wB);
+      c->wB += (size_t)b.P * N * es;
+      c->oS.push_back(c->wS);
+      c->wS += (size_t)b.P * b.P * es;
+      for(int p = 0; p < 2; ++p)
+        {
+          c->oV.push_back(c->wV);
+          c->wV += (size_t)b.s[p] * b.mn * es;
+          c->oXY.push_back(c->wXY);
+          c->wXY += (size_t)b.s[p] * b.s[p] * es;
+          c->oA.push_back(c->wA);
+          c->wA += (size_t)b.mn * b.mn * es;
+          c->max_s = std::max(c->max_s, b.s[p]);
+        }
+      c->max_mn = std::max(c->max_mn, b.mn);
+      c->max_P = std::max(c->max_P, b.P);
+    }
+  c->K = row0;
+  const size_t wPart = (size_t)std::max(1, num_blocks) * N * es;
+  const size_t wNorm = (size_t)N * es, wQ = (size_t)N * N * es;
+  c->arena_words = 2 * c->wB + c->wS + 3 * c->wV + 3 * c->wXY + 2 * c->wA
+                   + wPart + wNorm + wQ + 64;
+#define TRY_C(expr)                                                           \
+  do                                                                          \
+    {                                                                         \
+      cudaError_t e_ = (expr);                                                \
+      if(e_ != cudaSuccess)                                                   \
+        {                                                                     \
+          c->error = std::string("CUDA: ") + cudaGetErrorString(e_) + " at "  \
+                     + __FILE__ + ":" + std::to_string(__LINE__);             \
+          return bail(SDPB_B200_ERR_CUDA);                                    \
+        }                                                                     \
+    }                                                                         \
+  while(0)
+  TRY_C(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  TRY_C(cudaMalloc(&c->arena, c->arena_words * sizeof(limb_t)));
+  TRY_C(cudaMemsetAsync(c->arena, 0, c->arena_words * sizeof(limb_t), c->stream));
+  {
+    limb_t *p = c->arena;
+    c->B = p;      p += c->wB;
+    c->Pband = p;  p += c->wB;
+    c->S = p;      p += c->wS;
+    c->V = p;      p += c->wV;
+    c->T = p;      p += c->wV;
+    c->YV = p;     p += c->wV;
+    c->X = p;      p += c->wXY;
+    c->Y = p;      p += c->wXY;
+    c->LY = p;     p += c->wXY;
+    c->AX = p;     p += c->wA;
+    c->AY = p;     p += c->wA;
+    c->part = p;   p += wPart;
+    c->norms = p;  p += wNorm;
+    c->Q = p;      p += wQ;
+  }
+  {
+    const int rc = build_crt(c);
+    if(rc)
+      return bail(rc);
+  }
+  TRY_C(cudaMalloc(&c->R, std::max<size_t>(4, (size_t)c->crt.np * c->K * N * 4)));
+  TRY_C(cudaMalloc(&c->Qres, (size_t)c->crt.np * N * N * 4));
+  // descriptors
+  std::vector<MatDesc> mX, mLY, mS, mQ;
+  std::vector<TrsmDesc> tT, tP;
+  std::vector<GemmDesc> gAX, gYV, gAY;
+  std::vector<SchurDesc> sd;
+  std::vector<BandDesc> bd;
+  for(int j = 0; j < num_blocks; ++j)
+    {
+      const BlockGeom &b = c->g[j];
+      for(int p = 0; p < 2; ++p)
+        {
+          const int q = 2 * j + p;
+          const int s = b.s[p];
+          mX.push_back(MatDesc{c->X + c->oXY[q], s, q});
+          mLY.push_back(MatDesc{c->LY + c->oXY[q], s, q});
+          tT.push_back(TrsmDesc{c->X + c->oXY[q], c->T + c->oV[q], s, b.mn});
+          // AX = T^T T : A(i,l) = T(l,i)
+          gAX.push_back(GemmDesc{c->T + c->oV[q], c->T + c->oV[q], c->AX + c->oA[q],
+                                 (long)s, 1, 1, (long)s, b.mn, b.mn, s, 1});
+          // YV = Y V
+          gYV.push_back(GemmDesc{c->Y + c->oXY[q], c->V + c->oV[q], c->YV + c->oV[q],
+                                 1, (long)s, 1, (long)s, s, b.mn, s, 0});
+          // AY = V^T (YV)
+          gAY.push_back(GemmDesc{c->V + c->oV[q], c->YV + c->oV[q], c->AY + c->oA[q],
+                                 (long)s, 1, 1, (long)s, b.mn, b.mn, s, 1});
+        }
+      mS.push_back(MatDesc{c->S + c->oS[j], b.P, j});
+      tP.push_back(TrsmDesc{c->S + c->oS[j], c->Pband + c->oB[j], b.P, N});
+      sd.push_back(SchurDesc{{c->AX + c->oA[2 * j], c->AX + c->oA[2 * j + 1]},
+                             {c->AY + c->oA[2 * j], c->AY + c->oA[2 * j + 1]},
+                             c->S + c->oS[j], b.m, b.n});
+      bd.push_back(BandDesc{c->Pband + c->oB[j], b.P, (int)b.row0});
+    }
+  mQ.push_back(MatDesc{c->Q, N, 0});
+  TRY_C(upload(&c->d_matX, mX));
+  TRY_C(upload(&c->d_matLY, mLY));
+  TRY_C(upload(&c->d_matS, mS));
+  TRY_C(upload(&c->d_matQ, mQ));
+  TRY_C(upload(&c->d_trsmT, tT));
+  TRY_C(upload(&c->d_trsmP, tP));
+  TRY_C(upload(&c->d_gemmAX, gAX));
+  TRY_C(upload(&c->d_gemmYV, gYV));
+  TRY_C(upload(&c->d_gemmAY, gAY));
+  TRY_C(upload(&c->d_schur, sd));
+  TRY_C(upload(&c->d_bands, bd));
+  TRY_C(cudaMalloc(&c->d_status, (size_t)(2 * num_blocks + 8) * sizeof(int)));
+  TRY_C(cudaMalloc(&c->d_flags, 4 * sizeof(int)));
+  for(auto &e : c->ev)
+    TRY_C(cudaEventCreate(&e));
+  TRY_C(cudaStreamSynchronize(c->stream));
+#undef TRY_C
+  *out = c;
+  return 0;
+}
+
+extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
+{
+  if(!c)
+    return;
+  cudaSetDevice(c->device);
+  cudaFree(c->arena);
+  cudaFree(c->R);
+  cudaFree(c->Qres);
+  cudaFree(c->d_primes);
+  cudaFree(c->d_pow28);
+  cudaFree(c->d_ginv);
+  cudaFree(c->d_M);
+  cudaFree(c->d_Mhalf);
+  cudaFree(c->d_matX);
+  cudaFree(c->d_matLY);
+  cudaFree(c->d_matS);
+  cudaFree(c->d_matQ);
+  cudaFree(c->d_trsmT);
+  cudaFree(c->d_trsmP);
+  cudaFree(c->d_gemmAX);
+  cudaFree(c->d_gemmYV);
+  cudaFree(c->d_gemmAY);
+  cudaFree(c->d_schur);
+  cudaFree(c->d_bands);
+  cudaFree(c->d_status);
+  cudaFree(c->d_flags);
+  if(c->stream)
+    {
+      for(auto &e : c->ev)
+        if(e)
+          cudaEventDestroy(e);
+      cudaStreamDestroy(c->stream);
+    }
+  delete c;
+}
+
+extern "C" const char *sdpb_b200_last_error(const sdpb_b200_ctx *c)
+{
+  return c ? c->error.c_str() : "null context";
+}
+
+// --------------------------------------------------------------- set_block
+extern "C" int sdpb_b200_set_block(sdpb_b200_ctx *c, int j, const uint64_t *B,
+                                   const uint64_t *bases_even,
+                                   const uint64_t *bases_odd)
+{
+  if(!c || j < 0 || j >= c->J || !B)
+    return SDPB_B200_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const BlockGeom &b = c->g[j];
+  const size_t es = c->es;
+  CUDA_TRY(c, cudaMemcpyAsync(c->B + c->oB[j], B, (size_t)b.P * c->N * es * 8,
+                              cudaMemcpyHostToDevice, c->stream));
+  // bases_blocks = I_m (x) basis  (SDP/set_bases_blocks.cxx:24-47), dense
+  for(int p = 0; p < 2; ++p)
+    {
+      const uint64_t *basis = p == 0 ? bases_even : bases_odd;
+      const int h = b.h[p], s = b.s[p];
+      if(s == 0)
+        continue;
+      if(!basis)
+        {
+          c->error = "sdpb_b200_set_block: missing bilinear basis";
+          return SDPB_B200_ERR_ARG;
+        }
+      std::vector<uint64_t> V((size_t)s * b.mn * es, 0);
+      for(int col = 0; col < b.mn; ++col)
+        for(int row = 0; row < s; ++row)
+          if(row / h == col / b.n)
+            memcpy(&V[((size_t)col * s + row) * es],
+                   basis + ((size_t)(col % b.n) * h + (row % h)) * es, es * 8);
+      CUDA_TRY(c, cudaMemcpyAsync(c->V + c->oV[2 * j + p], V.data(),
+                                  V.size() * 8, cudaMemcpyHostToDevice,
+                                  c->stream));
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static const LaunchTable *table_for(int nl)
+{
+  switch(nl)
+    {
+#define F(n) case n: return &sdpb_b200_launch_nl##n;
+      SDPB_FOR_EACH_NL(F)
+#undef F
+    default: return nullptr;
+    }
+}
+static int dispatch_cholesky(sdpb_b200_ctx *c, int which)
+{
+  return table_for(c->nl)->cholesky(c, which);
+}
+static int dispatch_pairings(sdpb_b200_ctx *c)
+{
+  return table_for(c->nl)->pairings(c);
+}
+static int dispatch_schur_and_Q(sdpb_b200_ctx *c)
+{
+  return table_for(c->nl)->schur_and_Q(c);
+}
+static int dispatch_scalar(sdpb_b200_ctx *c, int op, int k, long count,
+                           const limb_t *a, const limb_t *b, limb_t *r)
+{
+  return table_for(c->nl)->scalar(c, op, k, count, a, b, r);
+}
+
+// read status words; returns index of first failing matrix or -1
+static int first_bad(sdpb_b200_ctx *c, const int *d_status, int count, int *pivot)
+{
+  std::vector<int> h(count);
+  if(cudaMemcpyAsync(h.data(), d_status, count * sizeof(int),
+                     cudaMemcpyDeviceToHost, c->stream)
+       != cudaSuccess
+     || cudaStreamSynchronize(c->stream) != cudaSuccess)
+    return -2;
+  for(int i = 0; i < count; ++i)
+    if(h[i] >= 0)
+      {
+        if(pivot)
+          *pivot = h[i];
+        return i;
+      }
+  return -1;
+}
+
+static int copy_blocks_in(sdpb_b200_ctx *c, const uint64_t *const *A, limb_t *dst)
+{
+  for(int q = 0; q < 2 * c->J; ++q)
+    {
+      const int s = c->g[q / 2].s[q % 2];
+      if(s == 0)
+        continue;
+      if(!A || !A[q])
+        {
+          c->error = "null input block " + std::to_string(q);
+          return SDPB_B200_ERR_ARG;
+        }
+      CUDA_TRY(c, cudaMemcpyAsync(dst + c->oXY[q], A[q], (size_t)s * s * c->es * 8,
+                                  cudaMemcpyHostToDevice, c->stream));
+    }
+  return 0;
+}
+static int copy_blocks_out(sdpb_b200_ctx *c, const limb_t *src,
+                           const std::vector<size_t> &off,
+                           uint64_t *const *out, int count,
+                           const std::vector<size_t> &elems)
+{
+  if(!out)
+    return 0;
+  for(int q = 0; q < count; ++q)
+    if(out[q] && elems[q])
+      CUDA_TRY(c, cudaMemcpyAsync(out[q], src + off[q], elems[q] * c->es * 8,
+                                  cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+extern "C" int sdpb_b200_cholesky_decomposition(sdpb_b200_ctx *c, int which,
+                                                const uint64_t *const *A,
+                                                uint64_t *const *L)
+{
+  if(!c || (which != 0 && which != 1))
+    return SDPB_B200_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  limb_t *dst = which == 0 ? c->X : c->LY;
+  int rc = copy_blocks_in(c, A, dst);
+  if(rc)
+    return rc;
+  rc = dispatch_cholesky(c, which);
+  if(rc)
+    return rc;
+  int pivot = 0;
+  const int bad = first_bad(c, c->d_status, 2 * c->J, &pivot);
+  if(bad == -2)
+    {
+      c->error = "CUDA failure while reading Cholesky status";
+      return SDPB_B200_ERR_CUDA;
+    }
+  if(bad >= 0)
+    {
+      c->error = std::string("Error when computing Cholesky decomposition of "
+                             "Block_Diagonal_Matrix ")
+                 + (which == 0 ? "X" : "Y")
+                 + ", block index = " + std::to_string(bad / 2)
+                 + ", parity = " + std::to_string(bad % 2)
+                 + ": non-positive pivot " + std::to_string(pivot);
+      return SDPB_B200_ERR_NOT_HPD;
+    }
+  std::vector<size_t> elems(2 * c->J);
+  for(int q = 0; q < 2 * c->J; ++q)
+    elems[q] = (size_t)c->g[q / 2].s[q % 2] * c->g[q / 2].s[q % 2];
+  rc = copy_blocks_out(c, dst, c->oXY, L, 2 * c->J, elems);
+  if(rc)
+    return rc;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(which == 0)
+    c->have_X_cholesky = true;
+  return 0;
+}
+
+extern "C" int sdpb_b200_compute_bilinear_pairings(sdpb_b200_ctx *c,
+                                                   const uint64_t *const *Y,
+                                                   uint64_t *const *A_X_inv,
+                                                   uint64_t *const *A_Y)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  if(!c->have_X_cholesky)
+    {
+      c->error = "compute_bilinear_pairings called before "
+                 "cholesky_decomposition(X)";
+      return SDPB_B200_ERR_STATE;
+    }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rc = copy_blocks_in(c, Y, c->Y);
+  if(rc)
+    return rc;
+  CUDA_TRY(c, cudaEventRecord(c->ev[0], c->stream));
+  rc = dispatch_pairings(c);
+  if(rc)
+    return rc;
+  CUDA_TRY(c, cudaEventRecord(c->ev[1], c->stream));
+  std::vector<size_t> elems(2 * c->J);
+  for(int q = 0; q < 2 * c->J; ++q)
+    elems[q] = (size_t)c->g[q / 2].mn * c->g[q / 2].mn;
+  rc = copy_blocks_out(c, c->AX, c->oA, A_X_inv, 2 * c->J, elems);
+  if(rc)
+    return rc;
+  rc = copy_blocks_out(c, c->AY, c->oA, A_Y, 2 * c->J, elems);
+  if(rc)
+    return rc;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->stage_ms[1], c->ev[0], c->ev[1]);
+  c->have_pairings = true;
+  return 0;
+}
+
+extern "C" int sdpb_b200_initialize_schur_complement_solver(
+  sdpb_b200_ctx *c, uint64_t *const *schur_complement_cholesky,
+  uint64_t *const *schur_off_diagonal, uint64_t *Q, int32_t *block_timings_ms)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  if(!c->have_pairings)
+    {
+      c->error = "initialize_schur_complement_solver called before "
+                 "compute_bilinear_pairings";
+      return SDPB_B200_ERR_STATE;
+    }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rc = dispatch_schur_and_Q(c);
+  if(rc)
+    return rc;
+  int pivot = 0;
+  const int bad = first_bad(c, c->d_status, c->J, &pivot);
+  if(bad == -2)
+    {
+      c->error = "CUDA failure while reading Cholesky status";
+      return SDPB_B200_ERR_CUDA;
+    }
+  if(bad >= 0)
+    {
+      c->error = "Error when computing Cholesky decomposition of block_"
+                 + std::to_string(bad) + ": non-positive pivot "
+                 + std::to_string(pivot);
+      return SDPB_B200_ERR_NOT_HPD;
+    }
+  int flags[4];
+  CUDA_TRY(c, cudaMemcpyAsync(flags, c->d_flags, sizeof(flags),
+                              cudaMemcpyDeviceToHost, c->stream));
+  int qstat = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&qstat, c->d_status + 2 * c->J, sizeof(int),
+                              cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(flags[0])
+    {
+      c->error = "normalised P entry does not fit the integer syrk format";
+      return SDPB_B200_ERR_Q_DIAG;
+    }
+  if(flags[1] != INT_MAX)
+    {
+      c->error = "Normalized Q should have ones on diagonal. For i = "
+                 + std::to_string(flags[1]);
+      return SDPB_B200_ERR_Q_DIAG;
+    }
+  if(qstat >= 0)
+    {
+      c->error = "Error when computing Cholesky(Q): non-positive pivot "
+                 + std::to_string(qstat);
+      return SDPB_B200_ERR_NOT_HPD;
+    }
+  {
+    std::vector<size_t> eS(c->J), eP(c->J);
+    for(int j = 0; j < c->J; ++j)
+      {
+        eS[j] = (size_t)c->g[j].P * c->g[j].P;
+        eP[j] = (size_t)c->g[j].P * c->N;
+      }
+    rc = copy_blocks_out(c, c->S, c->oS, schur_complement_cholesky, c->J, eS);
+    if(rc)
+      return rc;
+    rc = copy_blocks_out(c, c->Pband, c->oB, schur_off_diagonal, c->J, eP);
+    if(rc)
+      return rc;
+  }
+  if(Q)
+    CUDA_TRY(c, cudaMemcpyAsync(Q, c->Q, (size_t)c->N * c->N * c->es * 8,
+                                cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for(int k = 2; k < 8; ++k)
+    cudaEventElapsedTime(&c->stage_ms[k], c->ev[k], c->ev[k + 1]);
+  cudaEventElapsedTime(&c->stage_ms[8], c->ev[2], c->ev[8]);
+  if(block_timings_ms)
+    {
+      // cholesky_j + solve_j share of stage 3, split by the cost model
+      // P^3/3 + P^2 N / 2 (reference cost: bigint_syrk/Readme.md:327-346)
+      double tot = 0;
+      for(int j = 0; j < c->J; ++j)
+        {
+          const double P = c->g[j].P;
+          tot += P * P * P / 3 + P * P * c->N / 2;
+        }
+      for(int j = 0; j < c->J; ++j)
+        {
+          const double P = c->g[j].P;
+          block_timings_ms[j] += (int32_t)(
+            c->stage_ms[3] * (P * P * P / 3 + P * P * c->N / 2) / (tot > 0 ? tot : 1));
+        }
+    }
+  return 0;
+}
+
+extern "C" int sdpb_b200_schur_step(
+  sdpb_b200_ctx *c, const uint64_t *const *X, const uint64_t *const *Y,
+  uint64_t *const *X_cholesky, uint64_t *const *Y_cholesky,
+  uint64_t *const *A_X_inv, uint64_t *const *A_Y,
+  uint64_t *const *schur_complement_cholesky,
+  uint64_t *const *schur_off_diagonal, uint64_t *Q, int32_t *block_timings_ms)
+{
+  int rc = sdpb_b200_cholesky_decomposition(c, 0, X, X_cholesky);
+  if(rc)
+    return rc;
+  rc = sdpb_b200_cholesky_decomposition(c, 1, Y, Y_cholesky);
+  if(rc)
+    return rc;
+  rc = sdpb_b200_compute_bilinear_pairings(c, Y, A_X_inv, A_Y);
+  if(rc)
+    return rc;
+  return sdpb_b200_initialize_schur_complement_solver(
+    c, schur_complement_cholesky, schur_off_diagonal, Q, block_timings_ms);
+}
+
+extern "C" int sdpb_b200_last_timings_ms(const sdpb_b200_ctx *c, float *ms, int n)
+{
+  if(!c || !ms)
+    return SDPB_B200_ERR_ARG;
+  for(int i = 0; i < n && i < 9; ++i)
+    ms[i] = c->stage_ms[i];
+  return 0;
+}
+
+// element-wise scalar ops on the device, for parity tests of mpfx itself
+extern "C" int sdpb_b200_scalar_op(sdpb_b200_ctx *c, int op, int k, long count,
+                                   const uint64_t *a, const uint64_t *b,
+                                   uint64_t *r)
+{
+  if(!c || count < 0)
+    return SDPB_B200_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  limb_t *da, *db, *dr;
+  const size_t bytes = (size_t)count * c->es * 8;
+  CUDA_TRY(c, cudaMalloc(&da, bytes));
+  CUDA_TRY(c, cudaMalloc(&db, bytes));
+  CUDA_TRY(c, cudaMalloc(&dr, bytes));
+  CUDA_TRY(c, cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, c->stream));
+  int rc = dispatch_scalar(c, op, k, count, da, db, dr);
+  if(rc)
+    return rc;
+  CUDA_TRY(c, cudaMemcpyAsync(r, dr, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  cudaFree(da);
+  cudaFree(db);
+  cudaFree(dr);
+  return 0;
+}
+
+// ------------------------------------------------ mpf <-> packed (host only)
+extern "C" void sdpb_b200_pack_mpf(int prec_bits, int mp_size, long mp_exp,
+                                   const uint64_t *mp_d, uint64_t *out)
+{
+  const int nl = mpfx::stored_limbs(prec_bits), ew = (nl + 2) & ~1;
+  for(int i = 0; i < ew; ++i)
+    out[i] = 0;
+  int asz = mp_size < 0 ? -mp_size : mp_size;
+  if(asz == 0)
+    return;
+  const uint64_t *src = mp_d;
+  if(asz > nl) // cannot happen for an mpf of this precision; keep the top
+    {
+      src += asz - nl;
+      asz = nl;
+    }
+  const int32_t sign = mp_size < 0 ? -1 : 1;
+  out[0] = (uint64_t)(uint32_t)(int32_t)mp_exp | ((uint64_t)(uint32_t)sign << 32);
+  for(int i = 0; i < asz; ++i)
+    out[1 + nl - asz + i] = src[i];
+}
+extern "C" int sdpb_b200_unpack_mpf(int prec_bits, const uint64_t *in,
+                                    uint64_t *mp_d, long *mp_exp)
+{
+  const int nl = mpfx::stored_limbs(prec_bits);
+  const int32_t e = (int32_t)(uint32_t)in[0];
+  const int32_t sign = (int32_t)(uint32_t)(in[0] >> 32);
+  if(sign == 0)
+    {
+      *mp_exp = 0;
+      return 0;
+    }
+  int lo = 0;
+  while(lo < nl - 1 && in[1 + lo] == 0)
+    lo++;
+  const int asz = nl - lo;
+  for(int i = 0; i < asz; ++i)
+    mp_d[i] = in[1 + lo + i];
+  *mp_exp = e;
+  return sign < 0 ? -asz : asz;
+}

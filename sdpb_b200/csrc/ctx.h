@@ -1,0 +1,87 @@
+// Shared between capi.cu (host logic) and launch_nl.cu (one translation unit
+// per supported precision, so the heavy templated kernels compile in parallel).
+#pragma once
+#include "../../include/sdpb_b200.h"
+#include "kernels.cuh"
+
+#include <string>
+#include <vector>
+
+using namespace sdpb_b200;
+
+#define CUDA_TRY(c, expr)                                                     \
+  do                                                                          \
+    {                                                                         \
+      cudaError_t e_ = (expr);                                                \
+      if(e_ != cudaSuccess)                                                   \
+        {                                                                     \
+          (c)->error = std::string("CUDA: ") + cudaGetErrorString(e_)         \
+                       + " at " + __FILE__ + ":" + std::to_string(__LINE__);  \
+          return SDPB_B200_ERR_CUDA;                                          \
+        }                                                                     \
+    }                                                                         \
+  while(0)
+
+// precisions this build instantiates kernels for (stored limbs NL)
+#define SDPB_FOR_EACH_NL(F)                                                   \
+  F(4) F(6) F(8) F(9) F(10) F(12) F(13) F(14) F(17) F(18) F(26)
+
+struct BlockGeom
+{
+  int m, n, P, mn;
+  int s[2], h[2];
+  long row0;
+};
+
+struct sdpb_b200_ctx
+{
+  int prec = 0, nl = 0, es = 0, device = 0, J = 0, N = 0;
+  long K = 0; // stacked rows of P
+  std::vector<BlockGeom> g;
+  std::string error;
+  cudaStream_t stream = nullptr;
+
+  // one arena; offsets in 64-bit words
+  limb_t *arena = nullptr;
+  size_t arena_words = 0;
+  // contiguous regions (element offsets handled per block)
+  limb_t *B = nullptr, *Pband = nullptr, *S = nullptr;
+  limb_t *V = nullptr, *T = nullptr, *X = nullptr, *Y = nullptr, *LY = nullptr,
+         *YV = nullptr, *AX = nullptr, *AY = nullptr;
+  limb_t *part = nullptr, *norms = nullptr, *Q = nullptr;
+  std::vector<size_t> oB, oS, oV, oXY, oA; // per block / block-parity offsets (words)
+  size_t wB = 0, wS = 0, wV = 0, wXY = 0, wA = 0;
+
+  uint32_t *R = nullptr, *Qres = nullptr;
+  uint32_t *d_primes = nullptr, *d_pow28 = nullptr, *d_ginv = nullptr,
+           *d_M = nullptr, *d_Mhalf = nullptr;
+  CrtTables crt{};
+
+  MatDesc *d_matX = nullptr, *d_matLY = nullptr, *d_matS = nullptr,
+          *d_matQ = nullptr;
+  TrsmDesc *d_trsmT = nullptr, *d_trsmP = nullptr;
+  GemmDesc *d_gemmAX = nullptr, *d_gemmYV = nullptr, *d_gemmAY = nullptr;
+  SchurDesc *d_schur = nullptr;
+  BandDesc *d_bands = nullptr;
+  int *d_status = nullptr; // [2J (X/Y) | J (S) | 1 (Q)] reused per call
+  int *d_flags = nullptr;  // [0] overflow, [1] first bad Q diagonal
+  int max_s = 0, max_mn = 0, max_P = 0;
+
+  bool have_X_cholesky = false, have_pairings = false;
+  cudaEvent_t ev[10];
+  float stage_ms[9] = {0};
+};
+
+
+// per-precision kernel drivers, one table per stored-limb count NL
+struct LaunchTable
+{
+  int (*cholesky)(sdpb_b200_ctx *, int which);
+  int (*pairings)(sdpb_b200_ctx *);
+  int (*schur_and_Q)(sdpb_b200_ctx *);
+  int (*scalar)(sdpb_b200_ctx *, int op, int k, long count, const limb_t *a,
+                const limb_t *b, limb_t *r);
+};
+#define F(n) extern "C" const LaunchTable sdpb_b200_launch_nl##n;
+SDPB_FOR_EACH_NL(F)
+#undef F

@@ -1,0 +1,629 @@
+// sm_100a kernels of the Schur-complement step.  All arithmetic is mpfx
+// (GMP-mpf-exact fixed-limb floating point, mpfx.h) except the exact integer
+// syrk, which works on residues modulo 28-bit primes on the INT32 multiply
+// pipe (IMAD.WIDE) and reconstructs the integer by Garner's CRT.
+//
+// Canonical operation order: every matrix element receives its
+// updates in ascending k, one mpf operation per reference operator, exactly as
+// oracle/hotpath_core.hpp spells out.  That makes right-looking, left-looking
+// and blocked schedules bit-identical, which is what lets these kernels pick
+// the schedule with the most parallelism.
+#pragma once
+#include "mpfx.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdpb_b200
+{
+using mpfx::limb_t;
+using mpfx::Num;
+
+template <int NL> struct Fmt
+{
+  static constexpr int ES = (NL + 2) & ~1; // 64-bit words per element
+};
+
+struct MatDesc // one square matrix to factor in place
+{
+  limb_t *a;
+  int s;
+  int id; // reported on failure
+};
+struct TrsmDesc // B <- L^{-1} B
+{
+  const limb_t *L;
+  limb_t *B;
+  int p, ncols;
+};
+struct GemmDesc // C(i,j) = sum_l A(i,l) B(l,j), strides in elements
+{
+  const limb_t *A;
+  const limb_t *B;
+  limb_t *C;
+  long sa_i, sa_l, sb_l, sb_j;
+  int M, N, K;
+  int sym; // 1: compute i >= j only and mirror
+};
+struct SchurDesc
+{
+  const limb_t *AX[2];
+  const limb_t *AY[2];
+  limb_t *S;
+  int m, n;
+};
+struct BandDesc // P band of one SDP block inside the stacked K x N matrix
+{
+  limb_t *P; // P_j x N, column-major, ld = rows
+  int rows;
+  int row0; // first stacked row
+};
+
+// ------------------------------------------------------------- small helpers
+template <int NL>
+__device__ __forceinline__ void ld(Num<NL> &x, const limb_t *base, size_t idx)
+{
+  mpfx::load(x, base + idx * Fmt<NL>::ES);
+}
+template <int NL>
+__device__ __forceinline__ void st(limb_t *base, size_t idx, const Num<NL> &x)
+{
+  mpfx::store(base + idx * Fmt<NL>::ES, x);
+}
+
+// ------------------------------------------------------------------- potrf
+// One CTA per matrix, in place.  upper == 0: A = L L^T (lower); upper == 1:
+// A = U^T U stored in the upper triangle (same recurrence on the transposed
+// storage).  status[matrix] = -1 or the index of the first non-positive pivot
+// (the reference's El::Cholesky throws there: cholesky_decomposition.cxx:14-26,
+// compute_Q.cxx:29-39, initialize_schur_complement_solver.cxx:96-103).
+template <int NL>
+__global__ void __launch_bounds__(256)
+potrf_kernel(const MatDesc *descs, int upper, int *status)
+{
+  const MatDesc d = descs[blockIdx.x];
+  const int s = d.s;
+  if(s == 0)
+    {
+      if(threadIdx.x == 0)
+        status[blockIdx.x] = -1;
+      return;
+    }
+  limb_t *A = d.a;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int bad;
+  if(tid == 0)
+    bad = -1;
+  __syncthreads();
+  // logical (i,j), i >= j
+  auto idx = [&](int i, int j) -> size_t {
+    return upper ? (size_t)i * s + j : (size_t)j * s + i;
+  };
+  for(int j = 0; j < s; ++j)
+    {
+      if(tid == 0)
+        {
+          Num<NL> a;
+          ld(a, A, idx(j, j));
+          if(a.sign <= 0)
+            bad = j;
+          else
+            {
+              mpfx::sqrt(a, a);
+              st(A, idx(j, j), a);
+            }
+        }
+      __syncthreads();
+      if(bad >= 0)
+        {
+          if(tid == 0)
+            status[blockIdx.x] = bad;
+          return;
+        }
+      {
+        Num<NL> piv;
+        bool have = false;
+        for(int i = j + 1 + tid; i < s; i += nt)
+          {
+            if(!have)
+              {
+                ld(piv, A, idx(j, j));
+                have = true;
+              }
+            Num<NL> x;
+            ld(x, A, idx(i, j));
+            mpfx::div(x, x, piv);
+            st(A, idx(i, j), x);
+          }
+      }
+      __syncthreads();
+      const int r = s - 1 - j;
+      const int cnt = r * (r + 1) / 2;
+      for(int e = tid; e < cnt; e += nt)
+        {
+          // e -> (ii >= kk) in the r x r lower triangle
+          int ii = (int)((::sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+          while(ii * (ii + 1) / 2 > e)
+            --ii;
+          while((ii + 1) * (ii + 2) / 2 <= e)
+            ++ii;
+          const int kk = e - ii * (ii + 1) / 2;
+          const int i = j + 1 + ii, k = j + 1 + kk;
+          Num<NL> lij, lkj, a, p;
+          ld(lij, A, idx(i, j));
+          ld(lkj, A, idx(k, j));
+          ld(a, A, idx(i, k));
+          mpfx::mul(p, lij, lkj);
+          mpfx::sub(a, a, p);
+          st(A, idx(i, k), a);
+        }
+      __syncthreads();
+    }
+  // zero the other triangle
+  Num<NL> z;
+  mpfx::set_zero(z);
+  for(int e = tid; e < s * s; e += nt)
+    {
+      const int i = e % s, j = e / s; // storage (row i, col j)
+      const bool other = upper ? (i > j) : (i < j);
+      if(other)
+        st(A, (size_t)j * s + i, z);
+    }
+  if(tid == 0)
+    status[blockIdx.x] = -1;
+}
+
+// -------------------------------------------------------------------- trsm
+// B <- L^{-1} B, right-looking: for k: x_k = b_k / l_kk ; b_i -= l_ik x_k
+// (i > k).  grid = (matrices, column slabs of `slab` columns), one CTA each.
+template <int NL>
+__global__ void __launch_bounds__(256)
+trsm_kernel(const TrsmDesc *descs, int slab)
+{
+  const TrsmDesc d = descs[blockIdx.x];
+  const int c0 = blockIdx.y * slab;
+  if(c0 >= d.ncols || d.p == 0)
+    return;
+  const int nc = min(slab, d.ncols - c0);
+  const int p = d.p;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const limb_t *L = d.L;
+  limb_t *B = d.B;
+  for(int k = 0; k < p; ++k)
+    {
+      for(int c = tid; c < nc; c += nt)
+        {
+          Num<NL> x, piv;
+          ld(piv, L, (size_t)k * p + k);
+          ld(x, B, (size_t)(c0 + c) * p + k);
+          mpfx::div(x, x, piv);
+          st(B, (size_t)(c0 + c) * p + k, x);
+        }
+      __syncthreads();
+      const int r = p - 1 - k;
+      for(int e = tid; e < r * nc; e += nt)
+        {
+          const int i = k + 1 + e % r, c = c0 + e / r;
+          Num<NL> l, x, b, pr;
+          ld(l, L, (size_t)k * p + i);
+          ld(x, B, (size_t)c * p + k);
+          ld(b, B, (size_t)c * p + i);
+          mpfx::mul(pr, l, x);
+          mpfx::sub(b, b, pr);
+          st(B, (size_t)c * p + i, b);
+        }
+      __syncthreads();
+    }
+}
+
+// -------------------------------------------------------------------- gemm
+// C(i,j) = sum_l A(i,l) B(l,j), l ascending from an exact zero; one thread
+// per output.  sym: only i >= j is computed, result mirrored.
+template <int NL>
+__global__ void __launch_bounds__(128) gemm_kernel(const GemmDesc *descs)
+{
+  const GemmDesc d = descs[blockIdx.x];
+  const long total = (long)d.M * d.N;
+  for(long e = (long)blockIdx.y * blockDim.x + threadIdx.x; e < total;
+      e += (long)gridDim.y * blockDim.x)
+    {
+      const int i = (int)(e % d.M), j = (int)(e / d.M);
+      if(d.sym && i < j)
+        continue;
+      Num<NL> acc, a, b, p;
+      mpfx::set_zero(acc);
+      for(int l = 0; l < d.K; ++l)
+        {
+          ld(a, d.A, (size_t)(i * d.sa_i + l * d.sa_l));
+          if(a.sign == 0)
+            continue; // 0 * x = 0 and c + 0 = c exactly in mpf
+          ld(b, d.B, (size_t)(l * d.sb_l + j * d.sb_j));
+          if(b.sign == 0)
+            continue;
+          mpfx::mul(p, a, b);
+          mpfx::add(acc, acc, p);
+        }
+      st(d.C, (size_t)j * d.M + i, acc);
+      if(d.sym && i != j)
+        st(d.C, (size_t)i * d.M + j, acc);
+    }
+}
+
+// ------------------------------------------------------------ Schur assembly
+// compute_schur_complement.cxx:31-124, lower triangle + mirror.
+template <int NL>
+__global__ void __launch_bounds__(128) schur_kernel(const SchurDesc *descs)
+{
+  const SchurDesc d = descs[blockIdx.x];
+  const int n = d.n, m = d.m, mn = m * n;
+  const int P = n * m * (m + 1) / 2;
+  const long total = (long)P * P;
+  for(long e = (long)blockIdx.y * blockDim.x + threadIdx.x; e < total;
+      e += (long)gridDim.y * blockDim.x)
+    {
+      const int I = (int)(e % P), J = (int)(e / P);
+      if(I < J)
+        continue;
+      // I = (c0(c0+1)/2 + r0) n + row ; J = (c1(c1+1)/2 + r1) n + col
+      const int row = I % n, col = J % n;
+      int t0 = I / n, t1 = J / n;
+      int c0 = 0, c1 = 0;
+      while((c0 + 1) * (c0 + 2) / 2 <= t0)
+        ++c0;
+      while((c1 + 1) * (c1 + 2) / 2 <= t1)
+        ++c1;
+      const int r0 = t0 - c0 * (c0 + 1) / 2, r1 = t1 - c1 * (c1 + 1) / 2;
+      Num<NL> element, x, y, product;
+      mpfx::set_zero(element);
+      // ax(p,cb,rb) = AX[p](cb n + row, rb n + col); ay = AY[p](cb n + col, rb n + row)
+#define SDPB_AX(p, cb, rb) (size_t)((rb) * n + col) * mn + ((cb) * n + row)
+#define SDPB_AY(p, cb, rb) (size_t)((rb) * n + row) * mn + ((cb) * n + col)
+#define SDPB_TERM(p, xa, xb, ya, yb)                                          \
+  ld(x, d.AX[p], SDPB_AX(p, xa, xb));                                         \
+  ld(y, d.AY[p], SDPB_AY(p, ya, yb));                                         \
+  mpfx::mul(product, x, y);                                                   \
+  mpfx::add(element, element, product);
+      for(int p = 0; p < 2; ++p)
+        {
+          SDPB_TERM(p, c0, r1, c1, r0)
+          SDPB_TERM(p, r0, r1, c1, c0)
+          SDPB_TERM(p, c0, c1, r1, r0)
+          SDPB_TERM(p, r0, c1, r1, c0)
+        }
+#undef SDPB_TERM
+#undef SDPB_AX
+#undef SDPB_AY
+      mpfx::div4(element, element);
+      st(d.S, (size_t)J * P + I, element);
+      if(I != J)
+        st(d.S, (size_t)I * P + J, element);
+    }
+}
+
+// --------------------------------------------------------------- normaliser
+// Matrix_Normalizer.cxx:75-139.  part[j*N + c] = sum over the rows of band j
+// of v^2 (rows ascending); norms[c] = sqrt(sum_j part) in block order.
+template <int NL>
+__global__ void norm_partial_kernel(const BandDesc *bands, int N, limb_t *part)
+{
+  const BandDesc b = bands[blockIdx.x];
+  for(int c = blockIdx.y * blockDim.x + threadIdx.x; c < N;
+      c += gridDim.y * blockDim.x)
+    {
+      Num<NL> acc, v, p;
+      mpfx::set_zero(acc);
+      for(int r = 0; r < b.rows; ++r)
+        {
+          ld(v, b.P, (size_t)c * b.rows + r);
+          mpfx::mul(p, v, v);
+          mpfx::add(acc, acc, p);
+        }
+      st(part, (size_t)blockIdx.x * N + c, acc);
+    }
+}
+template <int NL>
+__global__ void norm_final_kernel(const limb_t *part, int J, int N,
+                                  limb_t *norms)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if(c >= N)
+    return;
+  Num<NL> acc, v;
+  mpfx::set_zero(acc);
+  for(int j = 0; j < J; ++j)
+    {
+      ld(v, part, (size_t)j * N + c);
+      mpfx::add(acc, acc, v);
+    }
+  if(acc.sign > 0)
+    mpfx::sqrt(acc, acc);
+  st(norms, c, acc);
+}
+
+// residue tables for the CRT syrk
+struct CrtTables
+{
+  const uint32_t *primes; // [np]
+  const uint32_t *pow28;  // [np][nd]  2^(28k) mod p
+  const uint32_t *ginv;   // [np][np]  ginv[i*np+j] = p_j^{-1} mod p_i (j < i)
+  const uint32_t *M;      // [mw] product of all primes, 32-bit words
+  const uint32_t *Mhalf;  // [mw] (M+1)/2
+  int np, nd, mw;
+};
+
+// P' = (P / norm) << prec, in place (Matrix_Normalizer.cxx:174-190), plus the
+// residues of trunc(P') (fmpz_set_mpf truncates toward zero,
+// fmpz_BigFloat_convert.hxx:13) modulo every prime:
+// R[(p*K + row)*N + col].  flags[0] is raised if |trunc(P')| does not fit.
+template <int NL>
+__global__ void __launch_bounds__(128)
+normalize_kernel(const BandDesc *bands, int N, long K, const limb_t *norms,
+                 int prec, CrtTables T, uint32_t *R, int *flags)
+{
+  const BandDesc b = bands[blockIdx.x];
+  const long total = (long)b.rows * N;
+  constexpr int MAXW = 2 * NL + 2; // 32-bit words of the integer part
+  for(long e = (long)blockIdx.y * blockDim.x + threadIdx.x; e < total;
+      e += (long)gridDim.y * blockDim.x)
+    {
+      const int r = (int)(e % b.rows), c = (int)(e / b.rows);
+      Num<NL> v, nrm;
+      ld(nrm, norms, c);
+      ld(v, b.P, e);
+      if(nrm.sign != 0)
+        {
+          mpfx::div(v, v, nrm);
+          mpfx::mul_2exp(v, v, (uint32_t)prec);
+          st(b.P, e, v);
+        }
+      uint32_t w[MAXW];
+      if(!mpfx::trunc_to_words(w, MAXW, v))
+        atomicExch(&flags[0], 1);
+      // 28-bit digits
+      uint32_t dg[(32 * MAXW + 27) / 28];
+      const int nd = T.nd;
+      bool fits = true;
+      for(int k = 0; k < (32 * MAXW + 27) / 28; ++k)
+        {
+          const int bit = 28 * k, wi = bit >> 5, sh = bit & 31;
+          uint64_t x = 0;
+          if(wi < MAXW)
+            x = w[wi];
+          if(wi + 1 < MAXW)
+            x |= (uint64_t)w[wi + 1] << 32;
+          const uint32_t dig = (uint32_t)(x >> sh) & 0x0FFFFFFFu;
+          dg[k] = dig;
+          if(k >= nd && dig)
+            fits = false;
+        }
+      if(!fits)
+        atomicExch(&flags[0], 1);
+      const size_t row = (size_t)b.row0 + r;
+      for(int pi = 0; pi < T.np; ++pi)
+        {
+          const uint32_t p = T.primes[pi];
+          const uint32_t *pw = T.pow28 + (size_t)pi * nd;
+          uint64_t acc = 0;
+          for(int k = 0; k < nd; ++k)
+            acc += (uint64_t)dg[k] * pw[k]; // < nd * 2^56
+          uint32_t res = (uint32_t)(acc % p);
+          if(v.sign < 0 && res)
+            res = p - res;
+          R[((size_t)pi * K + row) * N + c] = res;
+        }
+    }
+}
+
+// Qres[p][i][j] = sum_rows R[p][row][i] R[p][row][j] mod p, i <= j.
+// 16x16 output tile per CTA, rows staged through shared memory.
+template <int RC>
+__global__ void __launch_bounds__(256)
+syrk_mod_kernel(const uint32_t *__restrict__ R, long K, int N,
+                const uint32_t *__restrict__ primes, uint32_t *Qres)
+{
+  // triangular tile index
+  const int nt = (N + 15) / 16;
+  int t = blockIdx.x, tj = 0;
+  while(t > tj)
+    {
+      t -= tj + 1;
+      ++tj;
+    }
+  const int ti = t; // ti <= tj
+  const int pi = blockIdx.y;
+  const uint32_t p = primes[pi];
+  const uint32_t *Rp = R + (size_t)pi * K * N;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i = ti * 16 + tx, j = tj * 16 + ty;
+  __shared__ uint32_t sa[RC][16], sb[RC][16];
+  uint64_t acc = 0;
+  uint32_t run = 0;
+  int since = 0;
+  (void)nt;
+  for(long r0 = 0; r0 < K; r0 += RC)
+    {
+      for(int q = threadIdx.x; q < RC * 16; q += 256)
+        {
+          const int rr = q >> 4, cc = q & 15;
+          const long row = r0 + rr;
+          const int ci = ti * 16 + cc, cj = tj * 16 + cc;
+          sa[rr][cc] = (row < K && ci < N) ? Rp[(size_t)row * N + ci] : 0;
+          sb[rr][cc] = (row < K && cj < N) ? Rp[(size_t)row * N + cj] : 0;
+        }
+      __syncthreads();
+#pragma unroll 8
+      for(int rr = 0; rr < RC; ++rr)
+        acc += (uint64_t)sa[rr][tx] * sb[rr][ty]; // each < 2^56
+      since += RC;
+      if(since >= 192) // 192 * 2^56 + 2^28 < 2^64
+        {
+          run = (uint32_t)((acc + run) % p);
+          acc = 0;
+          since = 0;
+        }
+      __syncthreads();
+    }
+  run = (uint32_t)((acc + run) % p);
+  if(i < N && j < N && i <= j)
+    Qres[((size_t)pi * N + i) * N + j] = run;
+}
+
+// Garner reconstruction of the signed integer Q'_ij from its residues,
+// conversion with fmpz_get_mpf semantics, check_normalized_Q_diagonal
+// (compute_Q.cxx:65-91) and restore_Q (Matrix_Normalizer.cxx:245-265):
+// Q_ij = ((Q'_ij >> 2 prec) * n_i) * n_j for i <= j; lower triangle zeroed.
+template <int NL>
+__global__ void __launch_bounds__(64)
+crt_restore_kernel(const uint32_t *__restrict__ Qres, int N, int prec,
+                   CrtTables T, const limb_t *norms, limb_t *Q, int *flags)
+{
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if(e >= (long)N * N)
+    return;
+  const int i = (int)(e % N), j = (int)(e / N);
+  Num<NL> q;
+  if(i > j)
+    {
+      mpfx::set_zero(q);
+      st(Q, (size_t)j * N + i, q);
+      return;
+    }
+  constexpr int MAXP = 8 * NL + 8; // primes: ~ (2*64*(NL-2)+44)/28
+  constexpr int MAXMW = 8 * NL + 8;
+  const int np = T.np, mw = T.mw;
+  uint32_t v[MAXP];
+  for(int a = 0; a < np; ++a)
+    {
+      const uint32_t pa = T.primes[a];
+      uint64_t t = Qres[((size_t)a * N + i) * N + j];
+      for(int b = 0; b < a; ++b)
+        {
+          // t = (t - v_b) * p_b^{-1} mod p_a
+          const uint64_t vb = v[b] % pa;
+          const uint64_t diff = t >= vb ? t - vb : t + pa - vb;
+          t = (diff * T.ginv[(size_t)a * np + b]) % pa;
+        }
+      v[a] = (uint32_t)t;
+    }
+  // x = v0 + p0 (v1 + p1 (v2 + ...)) in 32-bit words
+  uint32_t x[MAXMW];
+  for(int k = 0; k < mw; ++k)
+    x[k] = 0;
+  for(int a = np - 1; a >= 0; --a)
+    {
+      const uint32_t pa = T.primes[a];
+      uint64_t carry = v[a];
+      for(int k = 0; k < mw; ++k)
+        {
+          const uint64_t z = (uint64_t)x[k] * pa + carry;
+          x[k] = (uint32_t)z;
+          carry = z >> 32;
+        }
+    }
+  // centre: x >= (M+1)/2  ->  x - M (negative)
+  int sign = 1;
+  {
+    int c = 0;
+    for(int k = mw - 1; k >= 0 && c == 0; --k)
+      if(x[k] != T.Mhalf[k])
+        c = x[k] > T.Mhalf[k] ? 1 : -1;
+    if(c >= 0)
+      {
+        // x = M - x
+        uint64_t borrow = 0;
+        for(int k = 0; k < mw; ++k)
+          {
+            const uint64_t z = (uint64_t)T.M[k] - x[k] - borrow;
+            x[k] = (uint32_t)z;
+            borrow = (z >> 32) & 1;
+          }
+        sign = -1;
+      }
+  }
+  limb_t zl[MAXMW / 2 + 1];
+  const int zn = (mw + 1) / 2;
+  for(int k = 0; k < zn; ++k)
+    {
+      const uint64_t lo = x[2 * k];
+      const uint64_t hi = (2 * k + 1 < mw) ? x[2 * k + 1] : 0;
+      zl[k] = lo | (hi << 32);
+    }
+  mpfx::from_limbs(q, zl, zn, sign);
+  mpfx::div_2exp(q, q, 2u * (uint32_t)prec);
+  if(i == j)
+    {
+      Num<NL> one, diff, eps;
+      mpfx::set_zero(one);
+      one.sign = 1;
+      one.exp = 1;
+      one.d[NL - 1] = 1;
+      mpfx::sub(diff, q, one);
+      if(diff.sign < 0)
+        diff.sign = 1;
+      mpfx::div_2exp(eps, one, (uint32_t)(prec / 2));
+      if(!(mpfx::cmp(diff, eps) < 0))
+        atomicMin(&flags[1], i);
+    }
+  Num<NL> ni, nj;
+  ld(ni, norms, i);
+  ld(nj, norms, j);
+  mpfx::mul(q, q, ni);
+  mpfx::mul(q, q, nj);
+  st(Q, (size_t)j * N + i, q);
+}
+
+// restore_P (Matrix_Normalizer.cxx:210-226): P = (P' >> prec) * norm
+template <int NL>
+__global__ void __launch_bounds__(128)
+restore_P_kernel(const BandDesc *bands, int N, const limb_t *norms, int prec)
+{
+  const BandDesc b = bands[blockIdx.x];
+  const long total = (long)b.rows * N;
+  for(long e = (long)blockIdx.y * blockDim.x + threadIdx.x; e < total;
+      e += (long)gridDim.y * blockDim.x)
+    {
+      const int c = (int)(e / b.rows);
+      Num<NL> v, nrm;
+      ld(nrm, norms, c);
+      if(nrm.sign == 0)
+        continue;
+      ld(v, b.P, e);
+      mpfx::div_2exp(v, v, (uint32_t)prec);
+      mpfx::mul(v, v, nrm);
+      st(b.P, e, v);
+    }
+}
+
+// scalar-op kernel for device-vs-libgmp parity tests (same op codes as
+// oracle_scalar_op): 0 mul 1 add 2 sub 3 div 4 sqrt 5 <<k 6 >>k 7 /4
+template <int NL>
+__global__ void scalar_op_kernel(int op, int k, long count, const limb_t *a,
+                                 const limb_t *b, limb_t *r)
+{
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if(e >= count)
+    return;
+  Num<NL> x, y, z;
+  ld(x, a, e);
+  ld(y, b, e);
+  mpfx::set_zero(z);
+  switch(op)
+    {
+    case 0: mpfx::mul(z, x, y); break;
+    case 1: mpfx::add(z, x, y); break;
+    case 2: mpfx::sub(z, x, y); break;
+    case 3:
+      if(y.sign != 0)
+        mpfx::div(z, x, y);
+      break;
+    case 4:
+      if(x.sign >= 0)
+        mpfx::sqrt(z, x);
+      break;
+    case 5: mpfx::mul_2exp(z, x, (uint32_t)k); break;
+    case 6: mpfx::div_2exp(z, x, (uint32_t)k); break;
+    case 7: mpfx::div4(z, x); break;
+    }
+  st(r, e, z);
+}
+} // namespace sdpb_b200

@@ -1,0 +1,152 @@
+// Kernel drivers for ONE precision: compile with -DSDPB_NL=<stored limbs>.
+// (sdpb_b200/csrc/Makefile builds one object per entry of SDPB_FOR_EACH_NL.)
+#include "ctx.h"
+
+#include <algorithm>
+#include <climits>
+
+#ifndef SDPB_NL
+#error "compile with -DSDPB_NL=<n>"
+#endif
+
+// ---------------------------------------------------------- kernel drivers
+template <int NL> struct Launch
+{
+  static int potrf(sdpb_b200_ctx *c, const MatDesc *d, int count, int upper,
+                   int *status)
+  {
+    if(count == 0)
+      return 0;
+    potrf_kernel<NL><<<count, 256, 0, c->stream>>>(d, upper, status);
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
+  static int trsm(sdpb_b200_ctx *c, const TrsmDesc *d, int count, int maxcols)
+  {
+    if(count == 0 || maxcols == 0)
+      return 0;
+    const int slab = 8;
+    dim3 grid(count, (maxcols + slab - 1) / slab);
+    trsm_kernel<NL><<<grid, 256, 0, c->stream>>>(d, slab);
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
+  static int gemm(sdpb_b200_ctx *c, const GemmDesc *d, int count, long maxout)
+  {
+    if(count == 0 || maxout == 0)
+      return 0;
+    dim3 grid(count, (unsigned)std::min<long>((maxout + 127) / 128, 65535));
+    gemm_kernel<NL><<<grid, 128, 0, c->stream>>>(d);
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
+  static int cholesky(sdpb_b200_ctx *c, int which)
+  {
+    return potrf(c, which == 0 ? c->d_matX : c->d_matLY, 2 * c->J, 0,
+                 c->d_status);
+  }
+  static int pairings(sdpb_b200_ctx *c)
+  {
+    const int nb = 2 * c->J;
+    if(nb == 0)
+      return 0;
+    // T = V ; T <- L_X^{-1} T ; AX = T^T T
+    CUDA_TRY(c, cudaMemcpyAsync(c->T, c->V, c->wV * 8, cudaMemcpyDeviceToDevice,
+                                c->stream));
+    int rc = trsm(c, c->d_trsmT, nb, c->max_mn);
+    if(rc)
+      return rc;
+    rc = gemm(c, c->d_gemmAX, nb, (long)c->max_mn * c->max_mn);
+    if(rc)
+      return rc;
+    rc = gemm(c, c->d_gemmYV, nb, (long)c->max_s * c->max_mn);
+    if(rc)
+      return rc;
+    return gemm(c, c->d_gemmAY, nb, (long)c->max_mn * c->max_mn);
+  }
+  static int schur_and_Q(sdpb_b200_ctx *c)
+  {
+    const int J = c->J, N = c->N;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
+    if(J)
+      {
+        dim3 grid(J, (unsigned)std::min<long>(((long)c->max_P * c->max_P + 127) / 128, 65535));
+        schur_kernel<NL><<<grid, 128, 0, st>>>(c->d_schur);
+        CUDA_TRY(c, cudaGetLastError());
+      }
+    CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
+    // Cholesky(S_j), P = L^{-1} B
+    int rc = potrf(c, c->d_matS, J, 0, c->d_status);
+    if(rc)
+      return rc;
+    if(J)
+      CUDA_TRY(c, cudaMemcpyAsync(c->Pband, c->B, c->wB * 8,
+                                  cudaMemcpyDeviceToDevice, st));
+    rc = trsm(c, c->d_trsmP, J, N);
+    if(rc)
+      return rc;
+    CUDA_TRY(c, cudaEventRecord(c->ev[4], st));
+    // norms, normalise, residues
+    const int init_flags[4] = {0, INT_MAX, 0, 0};
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_flags, init_flags, sizeof(init_flags),
+                                cudaMemcpyHostToDevice, st));
+    if(J)
+      {
+        dim3 g1(J, (N + 63) / 64);
+        norm_partial_kernel<NL><<<g1, 64, 0, st>>>(c->d_bands, N, c->part);
+        CUDA_TRY(c, cudaGetLastError());
+      }
+    norm_final_kernel<NL><<<(N + 63) / 64, 64, 0, st>>>(c->part, J, N, c->norms);
+    CUDA_TRY(c, cudaGetLastError());
+    if(J)
+      {
+        dim3 g2(J, (unsigned)std::min<long>(((long)c->max_P * N + 127) / 128, 65535));
+        normalize_kernel<NL><<<g2, 128, 0, st>>>(c->d_bands, N, c->K, c->norms,
+                                                 c->prec, c->crt, c->R,
+                                                 c->d_flags);
+        CUDA_TRY(c, cudaGetLastError());
+      }
+    CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
+    {
+      const int nt = (N + 15) / 16;
+      dim3 g3(nt * (nt + 1) / 2, c->crt.np);
+      syrk_mod_kernel<64><<<g3, 256, 0, st>>>(c->R, c->K, N, c->d_primes, c->Qres);
+      CUDA_TRY(c, cudaGetLastError());
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
+    {
+      const long tot = (long)N * N;
+      crt_restore_kernel<NL><<<(unsigned)((tot + 63) / 64), 64, 0, st>>>(
+        c->Qres, N, c->prec, c->crt, c->norms, c->Q, c->d_flags);
+      CUDA_TRY(c, cudaGetLastError());
+    }
+    if(J)
+      {
+        dim3 g4(J, (unsigned)std::min<long>(((long)c->max_P * N + 127) / 128, 65535));
+        restore_P_kernel<NL><<<g4, 128, 0, st>>>(c->d_bands, N, c->norms, c->prec);
+        CUDA_TRY(c, cudaGetLastError());
+      }
+    CUDA_TRY(c, cudaEventRecord(c->ev[7], st));
+    rc = potrf(c, c->d_matQ, 1, 1, c->d_status + 2 * J);
+    if(rc)
+      return rc;
+    CUDA_TRY(c, cudaEventRecord(c->ev[8], st));
+    return 0;
+  }
+  static int scalar(sdpb_b200_ctx *c, int op, int k, long count,
+                    const limb_t *a, const limb_t *b, limb_t *r)
+  {
+    scalar_op_kernel<NL><<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(
+      op, k, count, a, b, r);
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
+};
+
+
+#define SDPB_CAT2(a, b) a##b
+#define SDPB_CAT(a, b) SDPB_CAT2(a, b)
+extern "C" const LaunchTable SDPB_CAT(sdpb_b200_launch_nl, SDPB_NL)
+  = {&Launch<SDPB_NL>::cholesky, &Launch<SDPB_NL>::pairings,
+     &Launch<SDPB_NL>::schur_and_Q, &Launch<SDPB_NL>::scalar};

@@ -1,0 +1,80 @@
+"""Sanity of the CPU oracle itself (no GPU): factorisations reproduce their
+inputs, the Schur step runs on small synthetic SDPs, error paths fire."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from sdpb_b200.capi import elem_words
+
+
+def _to_float(prec, a):
+    w, h, _ = a.shape
+    out = np.zeros((h, w))
+    for j in range(w):
+        for i in range(h):
+            out[i, j] = ol.to_double(prec, a[j, i])
+    return out
+
+
+@pytest.mark.parametrize("prec", [128, 768])
+def test_cholesky_and_trsm_reproduce_inputs(prec):
+    s, ncols = 7, 3
+    A = ol.random_spd(prec, s, 5)
+    L = np.zeros_like(A)
+    lib = ol.load_oracle()
+    assert lib.oracle_potrf(prec, s, 0, ol._ptr(A), ol._ptr(L)) == -1
+    Lf, Af = _to_float(prec, L), _to_float(prec, A)
+    assert np.allclose(Lf @ Lf.T, Af, rtol=1e-13, atol=1e-13)
+    assert np.allclose(np.triu(Lf, 1), 0)
+    U = np.zeros_like(A)
+    assert lib.oracle_potrf(prec, s, 1, ol._ptr(A), ol._ptr(U)) == -1
+    Uf = _to_float(prec, U)
+    assert np.allclose(Uf.T @ Uf, Af, rtol=1e-13, atol=1e-13)
+    B = ol.random_matrix(prec, s, ncols, 9)
+    X = np.zeros_like(B)
+    lib.oracle_trsm(prec, s, ncols, ol._ptr(L), ol._ptr(B), ol._ptr(X))
+    assert np.allclose(Lf @ _to_float(prec, X), _to_float(prec, B), rtol=1e-12, atol=1e-12)
+
+
+def test_non_positive_pivot_is_reported():
+    prec, s = 256, 4
+    A = ol.scale_matrix(prec, ol.random_spd(prec, s, 3), -1.0)
+    L = np.zeros_like(A)
+    assert ol.load_oracle().oracle_potrf(prec, s, 0, ol._ptr(A), ol._ptr(L)) == 0
+
+
+@pytest.mark.parametrize("prec,shapes,N", [
+    (128, [(1, 4), (2, 3), (1, 1)], 3),
+    (768, [(1, 5), (2, 4)], 4),
+])
+def test_schur_step_is_consistent_in_double(prec, shapes, N):
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=7)
+    ctx = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ctx)
+    out = sdp.run_step(ctx)
+    # Q = U^T U must equal sum_j B_j^T S_j^{-1} B_j ; check through P: Q = sum P_j^T P_j
+    Uf = _to_float(prec, out["Q"])
+    Q = Uf.T @ Uf
+    acc = np.zeros((N, N))
+    for j in range(len(shapes)):
+        Pf = _to_float(prec, out["P"][j])
+        acc += Pf.T @ Pf
+    assert np.allclose(Q, acc, rtol=1e-10, atol=1e-10)
+    # P_j = L_j^{-1} B_j
+    for j in range(len(shapes)):
+        Lf = _to_float(prec, out["L"][j])
+        assert np.allclose(Lf @ _to_float(prec, out["P"][j]), _to_float(prec, sdp.B[j]), rtol=1e-9, atol=1e-9)
+    # pairings are symmetric bit for bit
+    for a in out["A_X_inv"] + out["A_Y"]:
+        assert np.array_equal(a, a.transpose(1, 0, 2))
+
+
+def test_non_pd_X_names_block_and_parity():
+    prec, shapes, N = 128, [(1, 4), (1, 3)], 2
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=2)
+    sdp.X[3] = ol.scale_matrix(prec, sdp.X[3], -1.0)
+    ctx = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ctx)
+    with pytest.raises(ol.OracleError) as ei:
+        sdp.run_step(ctx)
+    assert "block index = 1, parity = 1" in str(ei.value)
