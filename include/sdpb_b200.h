@@ -128,11 +128,28 @@ int sdpb_b200_schur_step(sdpb_b200_ctx *ctx, const uint64_t *const *X,
                          uint64_t *const *schur_off_diagonal, uint64_t *Q,
                          int32_t *block_timings_ms);
 
+/* The same step split at the host<->device boundary, for callers that keep
+ * X and Y in HBM between iterations (and for measuring the kernels alone):
+ * upload_XY copies X and Y to the device; schur_step_resident runs the whole
+ * hot path on the resident copies (it does not modify them, so it can be
+ * repeated); download copies back whichever outputs are non-NULL. */
+int sdpb_b200_upload_XY(sdpb_b200_ctx *ctx, const uint64_t *const *X,
+                        const uint64_t *const *Y);
+int sdpb_b200_schur_step_resident(sdpb_b200_ctx *ctx);
+int sdpb_b200_download(sdpb_b200_ctx *ctx, uint64_t *const *X_cholesky,
+                       uint64_t *const *Y_cholesky, uint64_t *const *A_X_inv,
+                       uint64_t *const *A_Y,
+                       uint64_t *const *schur_complement_cholesky,
+                       uint64_t *const *schur_off_diagonal, uint64_t *Q);
+
 /* Device-side timing of the last step, milliseconds per stage (CUDA events):
  * [0] cholesky X+Y  [1] bilinear pairings  [2] S assembly  [3] cholesky S_j +
  * L^-1 B  [4] norms+normalise  [5] exact syrk  [6] restore  [7] Cholesky(Q)
  * [8] whole step on device.  Fills min(n, 9) entries. */
 int sdpb_b200_last_timings_ms(const sdpb_b200_ctx *ctx, float *ms, int n);
+
+/* Number of CUDA kernels this context has launched since creation. */
+long sdpb_b200_kernel_launches(const sdpb_b200_ctx *ctx);
 
 /* Test hook: element-wise mpf-exact scalar operations executed on the device
  * (op: 0 mul, 1 add, 2 sub, 3 div, 4 sqrt(a), 5 a<<k, 6 a>>k, 7 a/4) on

@@ -16,6 +16,7 @@
 #include "../sdpb_b200/csrc/host/bigfloat.hpp"
 
 #include <array>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -345,6 +346,7 @@ struct SchurOutputs
   Matrix Q;                                      // upper Cholesky factor of Q
   std::vector<BigFloat> norms;
   std::string error;                             // empty on success
+  double cholesky_Q_ms = 0, syrk_ms = 0, block_ms = 0; // wall clock of the three big parts
 };
 
 // compute_Q + Cholesky(Q)  (compute_Q.cxx:134-151,
@@ -355,6 +357,7 @@ inline void compute_Q_and_factor(const std::vector<Matrix> &S,
 {
   const int prec = sdpb_host::working_precision_bits();
   const size_t J = S.size();
+  const auto t_begin = std::chrono::steady_clock::now();
   out.schur_complement_cholesky.resize(J);
   out.schur_off_diagonal.resize(J);
   std::vector<int> failed(J, 0);
@@ -378,7 +381,11 @@ inline void compute_Q_and_factor(const std::vector<Matrix> &S,
                     + std::to_string(j);
         return;
       }
+  out.block_ms = std::chrono::duration<double, std::milli>(
+                   std::chrono::steady_clock::now() - t_begin)
+                   .count();
   // syrk_Q (compute_Q.cxx:94-132)
+  const auto ts = std::chrono::steady_clock::now();
   column_norms(out.schur_off_diagonal, N, out.norms);
 #pragma omp parallel for schedule(dynamic)
   for(size_t jb = 0; jb < J; ++jb) // Matrix_Normalizer.cxx:174-190
@@ -420,7 +427,12 @@ inline void compute_Q_and_factor(const std::vector<Matrix> &S,
     for(int i = 0; i <= j; ++i)
       out.Q(i, j) = (out.Q(i, j) >> (unsigned)(2 * prec)) * out.norms[i]
                     * out.norms[j];
+  const auto tq = std::chrono::steady_clock::now();
+  out.syrk_ms = std::chrono::duration<double, std::milli>(tq - ts).count();
   const int bad = cholesky_upper(out.Q);
+  out.cholesky_Q_ms = std::chrono::duration<double, std::milli>(
+                        std::chrono::steady_clock::now() - tq)
+                        .count();
   if(bad >= 0)
     out.error = "Error when computing Cholesky(Q)";
 }

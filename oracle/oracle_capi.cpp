@@ -183,6 +183,9 @@ int oracle_initialize_schur_complement_solver(
                      .count();
   SchurOutputs out;
   compute_Q_and_factor(S, c->B, c->N, out);
+  c->stage_ms[3] = out.block_ms;
+  c->stage_ms[5] = out.syrk_ms;
+  c->stage_ms[7] = out.cholesky_Q_ms;
   if(!out.error.empty())
     {
       c->error = out.error;

@@ -61,8 +61,16 @@ def load_library():
     lib.sdpb_b200_schur_step.restype = ctypes.c_int
     lib.sdpb_b200_schur_step.argtypes = [ctypes.c_void_p] + [u64pp] * 8 + [
         u64p, ctypes.POINTER(ctypes.c_int32)]
+    lib.sdpb_b200_upload_XY.restype = ctypes.c_int
+    lib.sdpb_b200_upload_XY.argtypes = [ctypes.c_void_p, u64pp, u64pp]
+    lib.sdpb_b200_schur_step_resident.restype = ctypes.c_int
+    lib.sdpb_b200_schur_step_resident.argtypes = [ctypes.c_void_p]
+    lib.sdpb_b200_download.restype = ctypes.c_int
+    lib.sdpb_b200_download.argtypes = [ctypes.c_void_p] + [u64pp] * 6 + [u64p]
     lib.sdpb_b200_last_timings_ms.restype = ctypes.c_int
     lib.sdpb_b200_last_timings_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+    lib.sdpb_b200_kernel_launches.restype = ctypes.c_long
+    lib.sdpb_b200_kernel_launches.argtypes = [ctypes.c_void_p]
     lib.sdpb_b200_scalar_op.restype = ctypes.c_int
     lib.sdpb_b200_scalar_op.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_long, u64p, u64p, u64p]
     _lib = lib
@@ -198,6 +206,21 @@ class SchurContext(StepContextBase):
         self._check(self.lib.sdpb_b200_schur_step(
             self.handle, ptr_array(X), ptr_array(Y), opt(X_chol), opt(Y_chol), opt(A_X_inv), opt(A_Y),
             opt(L), opt(P), _ptr(Q) if Q is not None else None, bt))
+
+    def upload_XY(self, X, Y):
+        self._check(self.lib.sdpb_b200_upload_XY(self.handle, ptr_array(X), ptr_array(Y)))
+
+    def schur_step_resident(self):
+        self._check(self.lib.sdpb_b200_schur_step_resident(self.handle))
+
+    def download(self, X_chol=None, Y_chol=None, A_X_inv=None, A_Y=None, L=None, P=None, Q=None):
+        opt = lambda v: ptr_array(v) if v is not None else None  # noqa: E731
+        self._check(self.lib.sdpb_b200_download(
+            self.handle, opt(X_chol), opt(Y_chol), opt(A_X_inv), opt(A_Y), opt(L), opt(P),
+            _ptr(Q) if Q is not None else None))
+
+    def kernel_launches(self):
+        return int(self.lib.sdpb_b200_kernel_launches(self.handle))
 
     def last_timings_ms(self):
         ms = (ctypes.c_float * 9)()

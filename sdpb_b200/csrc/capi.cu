@@ -10,17 +10,8 @@
 #include <string>
 #include <vector>
 
-static bool nl_supported(int nl)
-{
-  switch(nl)
-    {
-#define F(n) case n:
-      SDPB_FOR_EACH_NL(F)
-#undef F
-      return true;
-    default: return false;
-    }
-}
+static const LaunchTable *table_for(int nl);
+static bool nl_supported(int nl) { return table_for(nl) != nullptr; }
 
 // ------------------------------------------------------------ CRT tables
 static uint64_t powmod(uint64_t a, uint64_t e, uint64_t m)
@@ -251,7 +242,7 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
   c->K = row0;
   const size_t wPart = (size_t)std::max(1, num_blocks) * N * es;
   const size_t wNorm = (size_t)N * es, wQ = (size_t)N * N * es;
-  c->arena_words = 2 * c->wB + c->wS + 3 * c->wV + 3 * c->wXY + 2 * c->wA
+  c->arena_words = 2 * c->wB + c->wS + 3 * c->wV + 5 * c->wXY + 2 * c->wA
                    + wPart + wNorm + wQ + 64;
 #define TRY_C(expr)                                                           \
   do                                                                          \
@@ -279,6 +270,8 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
     c->X = p;      p += c->wXY;
     c->Y = p;      p += c->wXY;
     c->LY = p;     p += c->wXY;
+    c->Xin = p;    p += c->wXY;
+    c->Yin = p;    p += c->wXY;
     c->AX = p;     p += c->wA;
     c->AY = p;     p += c->wA;
     c->part = p;   p += wPart;
@@ -337,7 +330,7 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
   TRY_C(upload(&c->d_gemmAY, gAY));
   TRY_C(upload(&c->d_schur, sd));
   TRY_C(upload(&c->d_bands, bd));
-  TRY_C(cudaMalloc(&c->d_status, (size_t)(2 * num_blocks + 8) * sizeof(int)));
+  TRY_C(cudaMalloc(&c->d_status, (size_t)(5 * num_blocks + 8) * sizeof(int)));
   TRY_C(cudaMalloc(&c->d_flags, 4 * sizeof(int)));
   for(auto &e : c->ev)
     TRY_C(cudaEventCreate(&e));
@@ -373,6 +366,8 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
   cudaFree(c->d_bands);
   cudaFree(c->d_status);
   cudaFree(c->d_flags);
+  if(c->pinned)
+    cudaFreeHost(c->pinned);
   if(c->stream)
     {
       for(auto &e : c->ev)
@@ -520,7 +515,7 @@ extern "C" int sdpb_b200_cholesky_decomposition(sdpb_b200_ctx *c, int which,
   if(rc)
     return rc;
   int pivot = 0;
-  const int bad = first_bad(c, c->d_status, 2 * c->J, &pivot);
+  const int bad = first_bad(c, c->d_status + which * 2 * c->J, 2 * c->J, &pivot);
   if(bad == -2)
     {
       c->error = "CUDA failure while reading Cholesky status";
@@ -602,7 +597,7 @@ extern "C" int sdpb_b200_initialize_schur_complement_solver(
   if(rc)
     return rc;
   int pivot = 0;
-  const int bad = first_bad(c, c->d_status, c->J, &pivot);
+  const int bad = first_bad(c, c->d_status + 4 * c->J, c->J, &pivot);
   if(bad == -2)
     {
       c->error = "CUDA failure while reading Cholesky status";
@@ -619,7 +614,7 @@ extern "C" int sdpb_b200_initialize_schur_complement_solver(
   CUDA_TRY(c, cudaMemcpyAsync(flags, c->d_flags, sizeof(flags),
                               cudaMemcpyDeviceToHost, c->stream));
   int qstat = 0;
-  CUDA_TRY(c, cudaMemcpyAsync(&qstat, c->d_status + 2 * c->J, sizeof(int),
+  CUDA_TRY(c, cudaMemcpyAsync(&qstat, c->d_status + 5 * c->J, sizeof(int),
                               cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   if(flags[0])
@@ -680,6 +675,178 @@ extern "C" int sdpb_b200_initialize_schur_complement_solver(
   return 0;
 }
 
+// ----------------------------------------------------- resident step
+// H2D of X and Y through one pinned staging buffer (two large copies instead
+// of 4J small pageable ones).
+extern "C" int sdpb_b200_upload_XY(sdpb_b200_ctx *c, const uint64_t *const *X,
+                                   const uint64_t *const *Y)
+{
+  if(!c || !X || !Y)
+    return SDPB_B200_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if(c->pinned_words < 2 * c->wXY)
+    {
+      if(c->pinned)
+        cudaFreeHost(c->pinned);
+      c->pinned = nullptr;
+      c->pinned_words = 0;
+      CUDA_TRY(c, cudaMallocHost(&c->pinned, std::max<size_t>(8, 2 * c->wXY * 8)));
+      c->pinned_words = 2 * c->wXY;
+    }
+  for(int which = 0; which < 2; ++which)
+    {
+      const uint64_t *const *A = which == 0 ? X : Y;
+      uint64_t *dst = c->pinned + which * c->wXY;
+      for(int q = 0; q < 2 * c->J; ++q)
+        {
+          const int s = c->g[q / 2].s[q % 2];
+          if(s == 0)
+            continue;
+          if(!A[q])
+            {
+              c->error = "null input block " + std::to_string(q);
+              return SDPB_B200_ERR_ARG;
+            }
+          memcpy(dst + c->oXY[q], A[q], (size_t)s * s * c->es * 8);
+        }
+    }
+  if(c->wXY)
+    {
+      CUDA_TRY(c, cudaMemcpyAsync(c->Xin, c->pinned, c->wXY * 8,
+                                  cudaMemcpyHostToDevice, c->stream));
+      CUDA_TRY(c, cudaMemcpyAsync(c->Yin, c->pinned + c->wXY, c->wXY * 8,
+                                  cudaMemcpyHostToDevice, c->stream));
+    }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// The whole hot path from device-resident X, Y (sdpb_b200_upload_XY): every
+// kernel is enqueued back to back, one host synchronisation at the end.
+extern "C" int sdpb_b200_schur_step_resident(sdpb_b200_ctx *c)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int J = c->J;
+  CUDA_TRY(c, cudaEventRecord(c->ev[9], st));
+  if(c->wXY)
+    {
+      CUDA_TRY(c, cudaMemcpyAsync(c->X, c->Xin, c->wXY * 8, cudaMemcpyDeviceToDevice, st));
+      CUDA_TRY(c, cudaMemcpyAsync(c->Y, c->Yin, c->wXY * 8, cudaMemcpyDeviceToDevice, st));
+      CUDA_TRY(c, cudaMemcpyAsync(c->LY, c->Yin, c->wXY * 8, cudaMemcpyDeviceToDevice, st));
+    }
+  int rc = dispatch_cholesky(c, 0);
+  if(rc)
+    return rc;
+  rc = dispatch_cholesky(c, 1);
+  if(rc)
+    return rc;
+  CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
+  rc = dispatch_pairings(c);
+  if(rc)
+    return rc;
+  CUDA_TRY(c, cudaEventRecord(c->ev[1], st));
+  rc = dispatch_schur_and_Q(c);
+  if(rc)
+    return rc;
+  CUDA_TRY(c, cudaEventRecord(c->ev[10], st));
+  std::vector<int> status(5 * J + 1);
+  int flags[4];
+  CUDA_TRY(c, cudaMemcpyAsync(status.data(), c->d_status, status.size() * sizeof(int),
+                              cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaMemcpyAsync(flags, c->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&c->stage_ms[0], c->ev[9], c->ev[0]);
+  cudaEventElapsedTime(&c->stage_ms[1], c->ev[0], c->ev[1]);
+  for(int k = 2; k < 8; ++k)
+    cudaEventElapsedTime(&c->stage_ms[k], c->ev[k], c->ev[k + 1]);
+  cudaEventElapsedTime(&c->stage_ms[8], c->ev[9], c->ev[10]);
+  for(int which = 0; which < 2; ++which)
+    for(int q = 0; q < 2 * J; ++q)
+      if(status[which * 2 * J + q] >= 0)
+        {
+          c->error = std::string("Error when computing Cholesky decomposition of "
+                                 "Block_Diagonal_Matrix ")
+                     + (which == 0 ? "X" : "Y")
+                     + ", block index = " + std::to_string(q / 2)
+                     + ", parity = " + std::to_string(q % 2)
+                     + ": non-positive pivot "
+                     + std::to_string(status[which * 2 * J + q]);
+          return SDPB_B200_ERR_NOT_HPD;
+        }
+  for(int j = 0; j < J; ++j)
+    if(status[4 * J + j] >= 0)
+      {
+        c->error = "Error when computing Cholesky decomposition of block_"
+                   + std::to_string(j) + ": non-positive pivot "
+                   + std::to_string(status[4 * J + j]);
+        return SDPB_B200_ERR_NOT_HPD;
+      }
+  if(flags[0])
+    {
+      c->error = "normalised P entry does not fit the integer syrk format";
+      return SDPB_B200_ERR_Q_DIAG;
+    }
+  if(flags[1] != INT_MAX)
+    {
+      c->error = "Normalized Q should have ones on diagonal. For i = "
+                 + std::to_string(flags[1]);
+      return SDPB_B200_ERR_Q_DIAG;
+    }
+  if(status[5 * J] >= 0)
+    {
+      c->error = "Error when computing Cholesky(Q): non-positive pivot "
+                 + std::to_string(status[5 * J]);
+      return SDPB_B200_ERR_NOT_HPD;
+    }
+  c->have_X_cholesky = c->have_pairings = true;
+  return 0;
+}
+
+// D2H of whichever outputs of the last step the caller wants (NULL = skip).
+extern "C" int sdpb_b200_download(
+  sdpb_b200_ctx *c, uint64_t *const *X_cholesky, uint64_t *const *Y_cholesky,
+  uint64_t *const *A_X_inv, uint64_t *const *A_Y,
+  uint64_t *const *schur_complement_cholesky,
+  uint64_t *const *schur_off_diagonal, uint64_t *Q)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int J = c->J;
+  std::vector<size_t> eXY(2 * J), eA(2 * J), eS(J), eP(J);
+  for(int q = 0; q < 2 * J; ++q)
+    {
+      eXY[q] = (size_t)c->g[q / 2].s[q % 2] * c->g[q / 2].s[q % 2];
+      eA[q] = (size_t)c->g[q / 2].mn * c->g[q / 2].mn;
+    }
+  for(int j = 0; j < J; ++j)
+    {
+      eS[j] = (size_t)c->g[j].P * c->g[j].P;
+      eP[j] = (size_t)c->g[j].P * c->N;
+    }
+  int rc = copy_blocks_out(c, c->X, c->oXY, X_cholesky, 2 * J, eXY);
+  if(!rc)
+    rc = copy_blocks_out(c, c->LY, c->oXY, Y_cholesky, 2 * J, eXY);
+  if(!rc)
+    rc = copy_blocks_out(c, c->AX, c->oA, A_X_inv, 2 * J, eA);
+  if(!rc)
+    rc = copy_blocks_out(c, c->AY, c->oA, A_Y, 2 * J, eA);
+  if(!rc)
+    rc = copy_blocks_out(c, c->S, c->oS, schur_complement_cholesky, J, eS);
+  if(!rc)
+    rc = copy_blocks_out(c, c->Pband, c->oB, schur_off_diagonal, J, eP);
+  if(rc)
+    return rc;
+  if(Q)
+    CUDA_TRY(c, cudaMemcpyAsync(Q, c->Q, (size_t)c->N * c->N * c->es * 8,
+                                cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 extern "C" int sdpb_b200_schur_step(
   sdpb_b200_ctx *c, const uint64_t *const *X, const uint64_t *const *Y,
   uint64_t *const *X_cholesky, uint64_t *const *Y_cholesky,
@@ -687,17 +854,32 @@ extern "C" int sdpb_b200_schur_step(
   uint64_t *const *schur_complement_cholesky,
   uint64_t *const *schur_off_diagonal, uint64_t *Q, int32_t *block_timings_ms)
 {
-  int rc = sdpb_b200_cholesky_decomposition(c, 0, X, X_cholesky);
+  int rc = sdpb_b200_upload_XY(c, X, Y);
   if(rc)
     return rc;
-  rc = sdpb_b200_cholesky_decomposition(c, 1, Y, Y_cholesky);
+  rc = sdpb_b200_schur_step_resident(c);
   if(rc)
     return rc;
-  rc = sdpb_b200_compute_bilinear_pairings(c, Y, A_X_inv, A_Y);
+  rc = sdpb_b200_download(c, X_cholesky, Y_cholesky, A_X_inv, A_Y,
+                          schur_complement_cholesky, schur_off_diagonal, Q);
   if(rc)
     return rc;
-  return sdpb_b200_initialize_schur_complement_solver(
-    c, schur_complement_cholesky, schur_off_diagonal, Q, block_timings_ms);
+  if(block_timings_ms)
+    {
+      double tot = 0;
+      for(int j = 0; j < c->J; ++j)
+        {
+          const double P = c->g[j].P;
+          tot += P * P * P / 3 + P * P * c->N / 2;
+        }
+      for(int j = 0; j < c->J; ++j)
+        {
+          const double P = c->g[j].P;
+          block_timings_ms[j] += (int32_t)(
+            c->stage_ms[3] * (P * P * P / 3 + P * P * c->N / 2) / (tot > 0 ? tot : 1));
+        }
+    }
+  return 0;
 }
 
 extern "C" int sdpb_b200_last_timings_ms(const sdpb_b200_ctx *c, float *ms, int n)
@@ -775,4 +957,9 @@ extern "C" int sdpb_b200_unpack_mpf(int prec_bits, const uint64_t *in,
     mp_d[i] = in[1 + lo + i];
   *mp_exp = e;
   return sign < 0 ? -asz : asz;
+}
+
+extern "C" long sdpb_b200_kernel_launches(const sdpb_b200_ctx *c)
+{
+  return c ? c->launches : 0;
 }

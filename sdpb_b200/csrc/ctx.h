@@ -48,6 +48,9 @@ struct sdpb_b200_ctx
   limb_t *B = nullptr, *Pband = nullptr, *S = nullptr;
   limb_t *V = nullptr, *T = nullptr, *X = nullptr, *Y = nullptr, *LY = nullptr,
          *YV = nullptr, *AX = nullptr, *AY = nullptr;
+  limb_t *Xin = nullptr, *Yin = nullptr; // pristine inputs of the resident step
+  uint64_t *pinned = nullptr;            // host staging for X/Y uploads
+  size_t pinned_words = 0;
   limb_t *part = nullptr, *norms = nullptr, *Q = nullptr;
   std::vector<size_t> oB, oS, oV, oXY, oA; // per block / block-parity offsets (words)
   size_t wB = 0, wS = 0, wV = 0, wXY = 0, wA = 0;
@@ -63,12 +66,13 @@ struct sdpb_b200_ctx
   GemmDesc *d_gemmAX = nullptr, *d_gemmYV = nullptr, *d_gemmAY = nullptr;
   SchurDesc *d_schur = nullptr;
   BandDesc *d_bands = nullptr;
-  int *d_status = nullptr; // [2J (X/Y) | J (S) | 1 (Q)] reused per call
+  int *d_status = nullptr; // [2J X | 2J Y | J S | 1 Q]
   int *d_flags = nullptr;  // [0] overflow, [1] first bad Q diagonal
   int max_s = 0, max_mn = 0, max_P = 0;
 
   bool have_X_cholesky = false, have_pairings = false;
-  cudaEvent_t ev[10];
+  long launches = 0; // kernels launched since creation
+  cudaEvent_t ev[12]; // 0,1 pairings; 2..8 Schur stages; 9,10,11 resident step
   float stage_ms[9] = {0};
 };
 
@@ -82,6 +86,7 @@ struct LaunchTable
   int (*scalar)(sdpb_b200_ctx *, int op, int k, long count, const limb_t *a,
                 const limb_t *b, limb_t *r);
 };
-#define F(n) extern "C" const LaunchTable sdpb_b200_launch_nl##n;
+// weak: a development build may compile only some precisions (make NLS="14")
+#define F(n) extern "C" const LaunchTable sdpb_b200_launch_nl##n __attribute__((weak));
 SDPB_FOR_EACH_NL(F)
 #undef F

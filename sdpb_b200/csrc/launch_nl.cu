@@ -19,6 +19,7 @@ template <int NL> struct Launch
       return 0;
     potrf_kernel<NL><<<count, 256, 0, c->stream>>>(d, upper, status);
     CUDA_TRY(c, cudaGetLastError());
+    ++c->launches;
     return 0;
   }
   static int trsm(sdpb_b200_ctx *c, const TrsmDesc *d, int count, int maxcols)
@@ -29,6 +30,7 @@ template <int NL> struct Launch
     dim3 grid(count, (maxcols + slab - 1) / slab);
     trsm_kernel<NL><<<grid, 256, 0, c->stream>>>(d, slab);
     CUDA_TRY(c, cudaGetLastError());
+    ++c->launches;
     return 0;
   }
   static int gemm(sdpb_b200_ctx *c, const GemmDesc *d, int count, long maxout)
@@ -38,12 +40,13 @@ template <int NL> struct Launch
     dim3 grid(count, (unsigned)std::min<long>((maxout + 127) / 128, 65535));
     gemm_kernel<NL><<<grid, 128, 0, c->stream>>>(d);
     CUDA_TRY(c, cudaGetLastError());
+    ++c->launches;
     return 0;
   }
   static int cholesky(sdpb_b200_ctx *c, int which)
   {
     return potrf(c, which == 0 ? c->d_matX : c->d_matLY, 2 * c->J, 0,
-                 c->d_status);
+                 c->d_status + which * 2 * c->J);
   }
   static int pairings(sdpb_b200_ctx *c)
   {
@@ -74,10 +77,11 @@ template <int NL> struct Launch
         dim3 grid(J, (unsigned)std::min<long>(((long)c->max_P * c->max_P + 127) / 128, 65535));
         schur_kernel<NL><<<grid, 128, 0, st>>>(c->d_schur);
         CUDA_TRY(c, cudaGetLastError());
+    ++c->launches;
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
     // Cholesky(S_j), P = L^{-1} B
-    int rc = potrf(c, c->d_matS, J, 0, c->d_status);
+    int rc = potrf(c, c->d_matS, J, 0, c->d_status + 4 * J);
     if(rc)
       return rc;
     if(J)
@@ -96,9 +100,11 @@ template <int NL> struct Launch
         dim3 g1(J, (N + 63) / 64);
         norm_partial_kernel<NL><<<g1, 64, 0, st>>>(c->d_bands, N, c->part);
         CUDA_TRY(c, cudaGetLastError());
+    ++c->launches;
       }
     norm_final_kernel<NL><<<(N + 63) / 64, 64, 0, st>>>(c->part, J, N, c->norms);
     CUDA_TRY(c, cudaGetLastError());
+    ++c->launches;
     if(J)
       {
         dim3 g2(J, (unsigned)std::min<long>(((long)c->max_P * N + 127) / 128, 65535));
@@ -106,6 +112,7 @@ template <int NL> struct Launch
                                                  c->prec, c->crt, c->R,
                                                  c->d_flags);
         CUDA_TRY(c, cudaGetLastError());
+    ++c->launches;
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
     {
@@ -113,6 +120,7 @@ template <int NL> struct Launch
       dim3 g3(nt * (nt + 1) / 2, c->crt.np);
       syrk_mod_kernel<64><<<g3, 256, 0, st>>>(c->R, c->K, N, c->d_primes, c->Qres);
       CUDA_TRY(c, cudaGetLastError());
+    ++c->launches;
     }
     CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
     {
@@ -120,15 +128,17 @@ template <int NL> struct Launch
       crt_restore_kernel<NL><<<(unsigned)((tot + 63) / 64), 64, 0, st>>>(
         c->Qres, N, c->prec, c->crt, c->norms, c->Q, c->d_flags);
       CUDA_TRY(c, cudaGetLastError());
+    ++c->launches;
     }
     if(J)
       {
         dim3 g4(J, (unsigned)std::min<long>(((long)c->max_P * N + 127) / 128, 65535));
         restore_P_kernel<NL><<<g4, 128, 0, st>>>(c->d_bands, N, c->norms, c->prec);
         CUDA_TRY(c, cudaGetLastError());
+    ++c->launches;
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[7], st));
-    rc = potrf(c, c->d_matQ, 1, 1, c->d_status + 2 * J);
+    rc = potrf(c, c->d_matQ, 1, 1, c->d_status + 5 * J);
     if(rc)
       return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[8], st));
@@ -140,6 +150,7 @@ template <int NL> struct Launch
     scalar_op_kernel<NL><<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(
       op, k, count, a, b, r);
     CUDA_TRY(c, cudaGetLastError());
+    ++c->launches;
     return 0;
   }
 };
@@ -147,6 +158,6 @@ template <int NL> struct Launch
 
 #define SDPB_CAT2(a, b) a##b
 #define SDPB_CAT(a, b) SDPB_CAT2(a, b)
-extern "C" const LaunchTable SDPB_CAT(sdpb_b200_launch_nl, SDPB_NL)
-  = {&Launch<SDPB_NL>::cholesky, &Launch<SDPB_NL>::pairings,
+extern "C" __attribute__((visibility("default"))) const LaunchTable
+  SDPB_CAT(sdpb_b200_launch_nl, SDPB_NL) = {&Launch<SDPB_NL>::cholesky, &Launch<SDPB_NL>::pairings,
      &Launch<SDPB_NL>::schur_and_Q, &Launch<SDPB_NL>::scalar};
