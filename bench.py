@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the Schur-complement step (BASELINE.json: sec per Newton step at
+prec = 768 bits; multi-limb Schur kernels' GB/s vs the HBM peak).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl reference]
+
+One process per GPU (torchrun for N > 1).  A "step" is one pass of the hot path
+(cholesky_decomposition(X), (Y), compute_bilinear_pairings,
+initialize_schur_complement_solver) over one rank's blocks of a synthetic block
+SDP.  Weak scaling: every rank owns one copy of the workload's block list (the
+global SDP has N x as many blocks), N fixed columns; the cross-rank exchanges
+are the column-norm partials and the exact-syrk residues.
+
+`value`  = seconds per step with X and Y already resident in HBM, timed with
+           CUDA events on the library's stream, max over ranks.
+`e2e`    = the same step through the reference-facing call sdpb_b200_schur_step
+           with HOST buffers: X, Y uploaded from pinned memory and every output the
+           reference's downstream code consumes (X/Y Cholesky factors, L_j,
+           L_j^-1 B_j, Cholesky(Q)) copied back, inside the timed region.
+`--impl reference` times the CPU restatement of the reference algorithm
+(oracle/, libgmp mpf, OpenMP on all host cores) on a bounded sample of the same
+workload and extrapolates per stage; the reference binary itself cannot be
+built in this image.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.samples, self.stop = device, [], False
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ----------------------------------------------- algorithmic bytes
+def algorithmic_bytes(kernel, prec, shapes, N):
+    """Bytes one launch of `kernel` must move, from SURVEY.md §8(d):
+    E = 8(L+1)+8 bytes per stored element, L = prec/64+1 limbs."""
+    L = (prec + 63) // 64 + 1
+    E = 8 * (L + 1) + 8
+    tot = 0
+    K = sum(s.schur_size for s in shapes)
+    for s in shapes:
+        P, mn = s.schur_size, s.pairing_size
+        for p in (0, 1):
+            sp = s.psd_size(p)
+            if kernel in ("potrf_X", "potrf_Y"):
+                tot += sp * sp * E
+            elif kernel == "trsm_LXinv_V":
+                tot += (sp * sp // 2 + 2 * sp * mn) * E
+            elif kernel == "gemm_A_X_inv":
+                tot += (sp * mn + mn * mn) * E
+            elif kernel == "gemm_YV":
+                tot += (sp * sp + 2 * sp * mn) * E
+            elif kernel == "gemm_A_Y":
+                tot += (2 * sp * mn + mn * mn) * E
+        if kernel == "schur_kernel":
+            tot += (4 * mn * mn + P * P) * E
+        elif kernel == "potrf_S":
+            tot += P * P * E
+        elif kernel == "trsm_Linv_B":
+            tot += (P * P // 2 + 2 * P * N) * E
+        elif kernel in ("norm_partial_kernel",):
+            tot += P * N * E
+        elif kernel in ("normalize_kernel", "restore_P_kernel"):
+            tot += 2 * P * N * E
+    if kernel == "syrk_mod_kernel":  # exact integer syrk
+        tot = K * N * 8 * L + N * (N + 1) // 2 * 8 * (2 * L + 1)
+    elif kernel == "crt_restore_kernel":
+        tot = N * (N + 1) // 2 * (8 * (2 * L + 1) + E)
+    elif kernel == "potrf_Q":
+        tot = N * N * E
+    return tot
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------ CPU arm
+def cpu_sample(workload, steps, warmup):
+    """Time the CPU restatement (oracle/) on the bounded sample of `workload`
+    and extrapolate per stage to the full block list."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from sdpb_b200.synthetic import WORKLOADS, SyntheticSDP
+    prec, shapes, N = WORKLOADS[workload]
+    sname = workload + "-sample" if workload + "-sample" in WORKLOADS else workload
+    sprec, sshapes, sN = WORKLOADS[sname]
+    assert (sprec, sN) == (prec, N)
+    scale = len(shapes) / len(sshapes)
+    sdp = SyntheticSDP(sprec, sshapes, sN, seed=1)
+    ref = ol.OracleContext(sprec, sshapes, sN)
+    sdp.upload(ref)
+    L, P, Q = ref.alloc_schur_outputs()
+    per_step = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        ref.schur_step(sdp.X, sdp.Y, None, None, None, None, L, P, Q)
+        wall = time.perf_counter() - t0
+        ms = ref.stage_ms()
+        # stages 0-5 scale with the block count; Cholesky(Q) (7) does not
+        blocks_ms = ms[0] + ms[1] + ms[2] + ms[3] + ms[5]
+        full = (blocks_ms * scale + ms[7]) / 1e3
+        if it >= warmup:
+            per_step.append((wall, full))
+        log(f"[cpu] sample step {it}: wall {wall:.2f}s stages(ms) {[round(x) for x in ms]} -> full-size estimate {full:.1f}s")
+    cores = ol.load_oracle().oracle_num_threads()
+    full = float(np.mean([f for _, f in per_step]))
+    wall = float(np.mean([w for w, _ in per_step]))
+    sample = (f"{len(sshapes)} of {len(shapes)} blocks (same m,n mix), N={N}, prec={prec}; per-block stages scaled x{scale:g}, "
+              f"Cholesky(Q) counted once; {wall:.2f}s of CPU per sample step")
+    return {"value": full, "unit": "s/step", "cores": cores, "kind": "port", "sample": sample}, wall
+
+
+# --------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("SDPB_B200_WORKLOAD", "c3"))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--kernels", action="store_true", help="print the per-kernel timeline to stderr")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+
+    from sdpb_b200.synthetic import WORKLOADS, SyntheticSDP
+    prec, shapes_t, N = WORKLOADS[a.workload]
+    cfg = {"workload": f"{a.workload}: shape-synthetic block SDP, J={len(shapes_t)} blocks per GPU "
+                       f"({_mix(shapes_t)}), N={N}, prec={prec}",
+           "blocks_per_gpu": len(shapes_t), "N": N, "precision_bits": prec,
+           "parallelism": f"block-sharded x{world}", "l2": "working set >> 126 MB L2 (B, P, residues: GBs)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cb, wall = cpu_sample(a.workload, a.steps, a.warmup)
+        line = {"impl": "reference", "metric": "sec_per_newton_step_hot_path", "value": cb["value"], "unit": "s/step",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["value"] * 1e3,
+                "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "mpf%d" % prec,
+                "data": "synthetic", "config": cfg, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "s/step", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import sdpb_b200
+    from sdpb_b200.capi import PinnedPool
+
+    t0 = time.perf_counter()
+    sdp = SyntheticSDP(prec, shapes_t, N, seed=1 + rank)
+    ctx = sdpb_b200.SchurContext(prec, shapes_t, N, device=local)
+    if world > 1:
+        ctx.comm_init_from_torch(dist, rank, world)
+    sdp.upload(ctx)
+    sdp.B = None  # resident in HBM now
+    log(f"[rank {rank}] setup {time.perf_counter() - t0:.1f}s")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input timing (value) ---------------------------------
+    ctx.upload_XY(sdp.X, sdp.Y)
+    for _ in range(warmup):
+        ctx.schur_step_resident()
+    launches0 = ctx.kernel_launches()
+    dev_ms, ktimes = [], {}
+    barrier()
+    with ClockSampler(local) as clk:
+        w0 = time.perf_counter()
+        for _ in range(a.steps):
+            ctx.schur_step_resident()
+            dev_ms.append(ctx.last_timings_ms()[8])
+            for name, ms in ctx.kernel_timings():
+                ktimes.setdefault(name, []).append(ms)
+        barrier()
+        wall = time.perf_counter() - w0
+    launches = ctx.kernel_launches() - launches0
+    ms_step = float(np.mean(dev_ms))
+    stages = ctx.last_timings_ms()
+
+    # ---- end to end through the C-ABI with host buffers -----------------
+    pool = PinnedPool()
+    Xh, Yh = pool.like(sdp.X), pool.like(sdp.Y)
+    Xc = [pool.empty(x.shape) for x in sdp.X]
+    Yc = [pool.empty(x.shape) for x in sdp.X]
+    Lh = [pool.empty((s.schur_size, s.schur_size, ctx.ew)) for s in ctx.shapes]
+    Ph = [pool.empty((N, s.schur_size, ctx.ew)) for s in ctx.shapes]
+    Qh = pool.empty((N, N, ctx.ew))
+    h2d = sum(x.nbytes for x in Xh) + sum(x.nbytes for x in Yh)
+    d2h = sum(x.nbytes for x in Xc + Yc + Lh + Ph) + Qh.nbytes
+    ctx.schur_step(Xh, Yh, Xc, Yc, None, None, Lh, Ph, Qh)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(a.steps):
+        ctx.schur_step(Xh, Yh, Xc, Yc, None, None, Lh, Ph, Qh)
+    barrier()
+    e2e_s = (time.perf_counter() - e0) / a.steps
+
+    # ---- max over ranks -------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms_step, e2e_s, wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_s, wall = [float(x) for x in t.tolist()]
+    if rank != 0:
+        pool.close()
+        return
+
+    # ---- roofline of the dominant kernel -------------------------------
+    per_kernel = {k: (float(np.mean(v)) * len(v) / a.steps, len(v) // a.steps) for k, v in ktimes.items()}
+    dom = max(per_kernel, key=lambda k: per_kernel[k][0])
+    dom_ms, dom_launches = per_kernel[dom]
+    peak, which = peaks()
+    abytes = algorithmic_bytes(dom, prec, ctx.shapes, N) / max(1, dom_launches)
+    achieved = abytes / (dom_ms / max(1, dom_launches) * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": which,
+                "share_of_step": dom_ms / ms_step,
+                "note": "multi-limb contraction: the INT32 multiply pipe binds, not HBM (DESIGN.md §4)"}
+    if a.kernels:
+        for k, (ms, n) in sorted(per_kernel.items(), key=lambda kv: -kv[1][0]):
+            ab = algorithmic_bytes(k, prec, ctx.shapes, N)
+            log(f"  {k:24s} {ms:10.3f} ms/step  x{n}  {ab / 1e6:10.1f} MB  {ab / (ms * 1e-3) / 1e9 if ms else 0:8.1f} GB/s")
+        log(f"  stages(ms) {[round(x, 3) for x in stages]}")
+
+    cpu = None
+    if not a.no_cpu:
+        try:
+            cpu, _ = cpu_sample(a.workload, 1, 0)
+        except Exception as e:  # the product arm does not depend on the oracle
+            cpu = {"value": None, "unit": "s/step", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+
+    line = {"metric": "sec_per_newton_step_hot_path", "value": ms_step / 1e3, "unit": "s/step", "n_gpus": world,
+            "steps": a.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "dtype": "mpf%d" % prec, "data": "synthetic", "config": cfg,
+            "clocks": clk.summary(), "wall_ms_per_step": wall / a.steps * 1e3,
+            "e2e": {"value": e2e_s, "unit": "s/step", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "stages_ms": {n: round(float(v), 4) for n, v in zip(
+                ["chol_XY", "pairings", "schur_assembly", "chol_S+trsm", "normalize", "exact_syrk", "restore",
+                 "chol_Q", "step"], stages)}}
+    print(json.dumps(line), flush=True)
+    pool.close()
+    ctx.close()
+
+
+def _mix(shapes):
+    c = {}
+    for s in shapes:
+        c[s] = c.get(s, 0) + 1
+    return ", ".join(f"{n}x(m={m},n={nn})" for (m, nn), n in c.items())
+
+
+if __name__ == "__main__":
+    main()

@@ -148,6 +148,19 @@ int sdpb_b200_download(sdpb_b200_ctx *ctx, uint64_t *const *X_cholesky,
  * [8] whole step on device.  Fills min(n, 9) entries. */
 int sdpb_b200_last_timings_ms(const sdpb_b200_ctx *ctx, float *ms, int n);
 
+/* Per-launch timeline of the last sdpb_b200_schur_step_resident: every kernel
+ * launch is bracketed by two CUDA events on the launching stream.  Fills up to
+ * `max` (name, milliseconds) pairs in launch order; returns the count.  The
+ * names are static strings owned by the library. */
+int sdpb_b200_kernel_timings(const sdpb_b200_ctx *ctx, int max,
+                             const char **names, float *ms);
+
+/* Page-locked host memory for the caller's staging buffers (the reference-side
+ * shim packs El::BigFloat into such a buffer anyway; pinning it makes the
+ * H2D/D2H copies of a step asynchronous DMA). */
+int sdpb_b200_host_alloc(void **p, size_t bytes);
+void sdpb_b200_host_free(void *p);
+
 /* Number of CUDA kernels this context has launched since creation. */
 long sdpb_b200_kernel_launches(const sdpb_b200_ctx *ctx);
 

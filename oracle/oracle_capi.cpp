@@ -215,6 +215,8 @@ int oracle_schur_step(oracle_ctx *c, const uint64_t *const *X,
                       uint64_t *const *schur_off_diagonal, uint64_t *Q,
                       int32_t *block_timings_ms)
 {
+  for(double &x : c->stage_ms)
+    x = 0;
   int rc = oracle_cholesky_decomposition(c, 0, X, X_cholesky);
   if(rc)
     return rc;

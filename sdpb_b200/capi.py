@@ -71,6 +71,13 @@ def load_library():
     lib.sdpb_b200_last_timings_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
     lib.sdpb_b200_kernel_launches.restype = ctypes.c_long
     lib.sdpb_b200_kernel_launches.argtypes = [ctypes.c_void_p]
+    lib.sdpb_b200_kernel_timings.restype = ctypes.c_int
+    lib.sdpb_b200_kernel_timings.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
+                                             ctypes.POINTER(ctypes.c_float)]
+    lib.sdpb_b200_host_alloc.restype = ctypes.c_int
+    lib.sdpb_b200_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
+    lib.sdpb_b200_host_free.restype = None
+    lib.sdpb_b200_host_free.argtypes = [ctypes.c_void_p]
     lib.sdpb_b200_scalar_op.restype = ctypes.c_int
     lib.sdpb_b200_scalar_op.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_long, u64p, u64p, u64p]
     _lib = lib
@@ -118,6 +125,39 @@ def ptr_array(arrays):
     for i, a in enumerate(arrays):
         arr[i] = _ptr(a) if a is not None else None
     return arr
+
+
+class PinnedPool:
+    """Page-locked host arrays from sdpb_b200_host_alloc (freed on close)."""
+
+    def __init__(self):
+        self.lib = load_library()
+        self.ptrs = []
+
+    def empty(self, shape):
+        nbytes = int(np.prod(shape)) * 8
+        if nbytes == 0:
+            return np.zeros(shape, dtype=np.uint64)
+        p = ctypes.c_void_p()
+        rc = self.lib.sdpb_b200_host_alloc(ctypes.byref(p), nbytes)
+        if rc != 0:
+            raise SdpbB200Error(rc, "sdpb_b200_host_alloc failed")
+        self.ptrs.append(p)
+        buf = (ctypes.c_uint64 * (nbytes // 8)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint64).reshape(shape)
+
+    def like(self, arrays):
+        out = []
+        for a in arrays:
+            b = self.empty(a.shape)
+            b[...] = a
+            out.append(b)
+        return out
+
+    def close(self):
+        for p in self.ptrs:
+            self.lib.sdpb_b200_host_free(p)
+        self.ptrs = []
 
 
 class StepContextBase:
@@ -221,6 +261,14 @@ class SchurContext(StepContextBase):
 
     def kernel_launches(self):
         return int(self.lib.sdpb_b200_kernel_launches(self.handle))
+
+    def kernel_timings(self):
+        """[(kernel name, ms)] of the last resident step, in launch order."""
+        cap = 4096
+        names = (ctypes.c_char_p * cap)()
+        ms = (ctypes.c_float * cap)()
+        n = self.lib.sdpb_b200_kernel_timings(self.handle, cap, names, ms)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
 
     def last_timings_ms(self):
         ms = (ctypes.c_float * 9)()

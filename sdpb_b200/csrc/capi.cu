@@ -368,6 +368,11 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
   cudaFree(c->d_flags);
   if(c->pinned)
     cudaFreeHost(c->pinned);
+  for(auto &k : c->kt)
+    {
+      cudaEventDestroy(k.e0);
+      cudaEventDestroy(k.e1);
+    }
   if(c->stream)
     {
       for(auto &e : c->ev)
@@ -508,6 +513,8 @@ extern "C" int sdpb_b200_cholesky_decomposition(sdpb_b200_ctx *c, int which,
     return SDPB_B200_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->device));
   limb_t *dst = which == 0 ? c->X : c->LY;
+  if(which == 0)
+    c->kt_used = 0;
   int rc = copy_blocks_in(c, A, dst);
   if(rc)
     return rc;
@@ -730,6 +737,7 @@ extern "C" int sdpb_b200_schur_step_resident(sdpb_b200_ctx *c)
   CUDA_TRY(c, cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   const int J = c->J;
+  c->kt_used = 0;
   CUDA_TRY(c, cudaEventRecord(c->ev[9], st));
   if(c->wXY)
     {
@@ -899,6 +907,7 @@ extern "C" int sdpb_b200_scalar_op(sdpb_b200_ctx *c, int op, int k, long count,
   if(!c || count < 0)
     return SDPB_B200_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->device));
+  c->kt_used = 0;
   limb_t *da, *db, *dr;
   const size_t bytes = (size_t)count * c->es * 8;
   CUDA_TRY(c, cudaMalloc(&da, bytes));
@@ -957,6 +966,27 @@ extern "C" int sdpb_b200_unpack_mpf(int prec_bits, const uint64_t *in,
     mp_d[i] = in[1 + lo + i];
   *mp_exp = e;
   return sign < 0 ? -asz : asz;
+}
+
+extern "C" int sdpb_b200_host_alloc(void **p, size_t bytes)
+{
+  return cudaMallocHost(p, bytes) == cudaSuccess ? 0 : SDPB_B200_ERR_CUDA;
+}
+extern "C" void sdpb_b200_host_free(void *p) { cudaFreeHost(p); }
+
+extern "C" int sdpb_b200_kernel_timings(const sdpb_b200_ctx *c, int max,
+                                        const char **names, float *ms)
+{
+  if(!c)
+    return 0;
+  int n = 0;
+  for(int i = 0; i < c->kt_used && n < max; ++i, ++n)
+    {
+      names[n] = c->kt[i].name;
+      ms[n] = 0;
+      cudaEventElapsedTime(&ms[n], c->kt[i].e0, c->kt[i].e1);
+    }
+  return n;
 }
 
 extern "C" long sdpb_b200_kernel_launches(const sdpb_b200_ctx *c)

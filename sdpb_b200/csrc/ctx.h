@@ -74,6 +74,36 @@ struct sdpb_b200_ctx
   long launches = 0; // kernels launched since creation
   cudaEvent_t ev[12]; // 0,1 pairings; 2..8 Schur stages; 9,10,11 resident step
   float stage_ms[9] = {0};
+
+  // per-launch timeline of the last step: every kernel launch is bracketed by
+  // two events on the launching stream (kt_begin / kt_end)
+  struct KernelSpan
+  {
+    const char *name;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<KernelSpan> kt; // event pool, reused every step
+  int kt_used = 0;
+  int kt_begin(const char *name)
+  {
+    if(kt_used == (int)kt.size())
+      {
+        KernelSpan s{name, nullptr, nullptr};
+        if(cudaEventCreate(&s.e0) != cudaSuccess
+           || cudaEventCreate(&s.e1) != cudaSuccess)
+          return -1;
+        kt.push_back(s);
+      }
+    kt[kt_used].name = name;
+    cudaEventRecord(kt[kt_used].e0, stream);
+    return kt_used;
+  }
+  void kt_end()
+  {
+    cudaEventRecord(kt[kt_used].e1, stream);
+    ++kt_used;
+    ++launches;
+  }
 };
 
 

@@ -12,40 +12,45 @@
 // ---------------------------------------------------------- kernel drivers
 template <int NL> struct Launch
 {
-  static int potrf(sdpb_b200_ctx *c, const MatDesc *d, int count, int upper,
-                   int *status)
+  static int potrf(sdpb_b200_ctx *c, const char *label, const MatDesc *d,
+                   int count, int upper, int *status)
   {
     if(count == 0)
       return 0;
+    c->kt_begin(label);
     potrf_kernel<NL><<<count, 256, 0, c->stream>>>(d, upper, status);
+    c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
-    ++c->launches;
     return 0;
   }
-  static int trsm(sdpb_b200_ctx *c, const TrsmDesc *d, int count, int maxcols)
+  static int trsm(sdpb_b200_ctx *c, const char *label, const TrsmDesc *d,
+                  int count, int maxcols)
   {
     if(count == 0 || maxcols == 0)
       return 0;
     const int slab = 8;
     dim3 grid(count, (maxcols + slab - 1) / slab);
+    c->kt_begin(label);
     trsm_kernel<NL><<<grid, 256, 0, c->stream>>>(d, slab);
+    c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
-    ++c->launches;
     return 0;
   }
-  static int gemm(sdpb_b200_ctx *c, const GemmDesc *d, int count, long maxout)
+  static int gemm(sdpb_b200_ctx *c, const char *label, const GemmDesc *d,
+                  int count, long maxout)
   {
     if(count == 0 || maxout == 0)
       return 0;
     dim3 grid(count, (unsigned)std::min<long>((maxout + 127) / 128, 65535));
+    c->kt_begin(label);
     gemm_kernel<NL><<<grid, 128, 0, c->stream>>>(d);
+    c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
-    ++c->launches;
     return 0;
   }
   static int cholesky(sdpb_b200_ctx *c, int which)
   {
-    return potrf(c, which == 0 ? c->d_matX : c->d_matLY, 2 * c->J, 0,
+    return potrf(c, which == 0 ? "potrf_X" : "potrf_Y", which == 0 ? c->d_matX : c->d_matLY, 2 * c->J, 0,
                  c->d_status + which * 2 * c->J);
   }
   static int pairings(sdpb_b200_ctx *c)
@@ -56,16 +61,16 @@ template <int NL> struct Launch
     // T = V ; T <- L_X^{-1} T ; AX = T^T T
     CUDA_TRY(c, cudaMemcpyAsync(c->T, c->V, c->wV * 8, cudaMemcpyDeviceToDevice,
                                 c->stream));
-    int rc = trsm(c, c->d_trsmT, nb, c->max_mn);
+    int rc = trsm(c, "trsm_LXinv_V", c->d_trsmT, nb, c->max_mn);
     if(rc)
       return rc;
-    rc = gemm(c, c->d_gemmAX, nb, (long)c->max_mn * c->max_mn);
+    rc = gemm(c, "gemm_A_X_inv", c->d_gemmAX, nb, (long)c->max_mn * c->max_mn);
     if(rc)
       return rc;
-    rc = gemm(c, c->d_gemmYV, nb, (long)c->max_s * c->max_mn);
+    rc = gemm(c, "gemm_YV", c->d_gemmYV, nb, (long)c->max_s * c->max_mn);
     if(rc)
       return rc;
-    return gemm(c, c->d_gemmAY, nb, (long)c->max_mn * c->max_mn);
+    return gemm(c, "gemm_A_Y", c->d_gemmAY, nb, (long)c->max_mn * c->max_mn);
   }
   static int schur_and_Q(sdpb_b200_ctx *c)
   {
@@ -75,19 +80,20 @@ template <int NL> struct Launch
     if(J)
       {
         dim3 grid(J, (unsigned)std::min<long>(((long)c->max_P * c->max_P + 127) / 128, 65535));
+        c->kt_begin("schur_kernel");
         schur_kernel<NL><<<grid, 128, 0, st>>>(c->d_schur);
-        CUDA_TRY(c, cudaGetLastError());
-    ++c->launches;
+        c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
     // Cholesky(S_j), P = L^{-1} B
-    int rc = potrf(c, c->d_matS, J, 0, c->d_status + 4 * J);
+    int rc = potrf(c, "potrf_S", c->d_matS, J, 0, c->d_status + 4 * J);
     if(rc)
       return rc;
     if(J)
       CUDA_TRY(c, cudaMemcpyAsync(c->Pband, c->B, c->wB * 8,
                                   cudaMemcpyDeviceToDevice, st));
-    rc = trsm(c, c->d_trsmP, J, N);
+    rc = trsm(c, "trsm_Linv_B", c->d_trsmP, J, N);
     if(rc)
       return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[4], st));
@@ -98,47 +104,53 @@ template <int NL> struct Launch
     if(J)
       {
         dim3 g1(J, (N + 63) / 64);
+        c->kt_begin("norm_partial_kernel");
         norm_partial_kernel<NL><<<g1, 64, 0, st>>>(c->d_bands, N, c->part);
-        CUDA_TRY(c, cudaGetLastError());
-    ++c->launches;
-      }
-    norm_final_kernel<NL><<<(N + 63) / 64, 64, 0, st>>>(c->part, J, N, c->norms);
+        c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
-    ++c->launches;
+      }
+    c->kt_begin("norm_final_kernel");
+    norm_final_kernel<NL><<<(N + 63) / 64, 64, 0, st>>>(c->part, J, N, c->norms);
+    c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
     if(J)
       {
         dim3 g2(J, (unsigned)std::min<long>(((long)c->max_P * N + 127) / 128, 65535));
+        c->kt_begin("normalize_kernel");
         normalize_kernel<NL><<<g2, 128, 0, st>>>(c->d_bands, N, c->K, c->norms,
                                                  c->prec, c->crt, c->R,
                                                  c->d_flags);
-        CUDA_TRY(c, cudaGetLastError());
-    ++c->launches;
+        c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
     {
       const int nt = (N + 15) / 16;
       dim3 g3(nt * (nt + 1) / 2, c->crt.np);
+      c->kt_begin("syrk_mod_kernel");
       syrk_mod_kernel<64><<<g3, 256, 0, st>>>(c->R, c->K, N, c->d_primes, c->Qres);
-      CUDA_TRY(c, cudaGetLastError());
-    ++c->launches;
+      c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
     }
     CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
     {
       const long tot = (long)N * N;
+      c->kt_begin("crt_restore_kernel");
       crt_restore_kernel<NL><<<(unsigned)((tot + 63) / 64), 64, 0, st>>>(
         c->Qres, N, c->prec, c->crt, c->norms, c->Q, c->d_flags);
-      CUDA_TRY(c, cudaGetLastError());
-    ++c->launches;
+      c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
     }
     if(J)
       {
         dim3 g4(J, (unsigned)std::min<long>(((long)c->max_P * N + 127) / 128, 65535));
+        c->kt_begin("restore_P_kernel");
         restore_P_kernel<NL><<<g4, 128, 0, st>>>(c->d_bands, N, c->norms, c->prec);
-        CUDA_TRY(c, cudaGetLastError());
-    ++c->launches;
+        c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[7], st));
-    rc = potrf(c, c->d_matQ, 1, 1, c->d_status + 5 * J);
+    rc = potrf(c, "potrf_Q", c->d_matQ, 1, 1, c->d_status + 5 * J);
     if(rc)
       return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[8], st));
@@ -147,10 +159,11 @@ template <int NL> struct Launch
   static int scalar(sdpb_b200_ctx *c, int op, int k, long count,
                     const limb_t *a, const limb_t *b, limb_t *r)
   {
+    c->kt_begin("scalar_op_kernel");
     scalar_op_kernel<NL><<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(
       op, k, count, a, b, r);
+    c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
-    ++c->launches;
     return 0;
   }
 };
