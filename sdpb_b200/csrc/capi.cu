@@ -286,43 +286,94 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
   TRY_C(cudaMalloc(&c->R, std::max<size_t>(4, (size_t)c->crt.np * c->K * N * 4)));
   TRY_C(cudaMalloc(&c->Qres, (size_t)c->crt.np * N * N * 4));
   // descriptors
-  std::vector<MatDesc> mX, mLY, mS, mQ;
-  std::vector<TrsmDesc> tT, tP;
-  std::vector<GemmDesc> gAX, gYV, gAY;
+  const int rs = ((2 * nl + 4) + 3) & ~3; // TileGeom::RS
+  {
+    size_t nXY = 0;
+    for(const BlockGeom &b : c->g)
+      nXY += b.s[0] + b.s[1];
+    TRY_C(cudaMalloc(&c->recipX, std::max<size_t>(16, nXY * rs * 4)));
+    TRY_C(cudaMalloc(&c->recipY, std::max<size_t>(16, nXY * rs * 4)));
+    TRY_C(cudaMalloc(&c->recipS, std::max<size_t>(16, (size_t)c->K * rs * 4)));
+    TRY_C(cudaMalloc(&c->recipQ, (size_t)N * rs * 4));
+  }
+  std::vector<PotrfDesc> pX, pY, pS;
+  std::vector<TrsmTileDesc> tT, tP;
+  std::vector<GemmTileDesc> gAX, gYV, gAY;
   std::vector<SchurDesc> sd;
   std::vector<BandDesc> bd;
-  for(int j = 0; j < num_blocks; ++j)
-    {
-      const BlockGeom &b = c->g[j];
-      for(int p = 0; p < 2; ++p)
-        {
-          const int q = 2 * j + p;
-          const int s = b.s[p];
-          mX.push_back(MatDesc{c->X + c->oXY[q], s, q});
-          mLY.push_back(MatDesc{c->LY + c->oXY[q], s, q});
-          tT.push_back(TrsmDesc{c->X + c->oXY[q], c->T + c->oV[q], s, b.mn});
-          // AX = T^T T : A(i,l) = T(l,i)
-          gAX.push_back(GemmDesc{c->T + c->oV[q], c->T + c->oV[q], c->AX + c->oA[q],
-                                 (long)s, 1, 1, (long)s, b.mn, b.mn, s, 1});
-          // YV = Y V
-          gYV.push_back(GemmDesc{c->Y + c->oXY[q], c->V + c->oV[q], c->YV + c->oV[q],
-                                 1, (long)s, 1, (long)s, s, b.mn, s, 0});
-          // AY = V^T (YV)
-          gAY.push_back(GemmDesc{c->V + c->oV[q], c->YV + c->oV[q], c->AY + c->oA[q],
-                                 (long)s, 1, 1, (long)s, b.mn, b.mn, s, 1});
-        }
-      mS.push_back(MatDesc{c->S + c->oS[j], b.P, j});
-      tP.push_back(TrsmDesc{c->S + c->oS[j], c->Pband + c->oB[j], b.P, N});
-      sd.push_back(SchurDesc{{c->AX + c->oA[2 * j], c->AX + c->oA[2 * j + 1]},
-                             {c->AY + c->oA[2 * j], c->AY + c->oA[2 * j + 1]},
-                             c->S + c->oS[j], b.m, b.n});
-      bd.push_back(BandDesc{c->Pband + c->oB[j], b.P, (int)b.row0});
-    }
-  mQ.push_back(MatDesc{c->Q, N, 0});
-  TRY_C(upload(&c->d_matX, mX));
-  TRY_C(upload(&c->d_matLY, mLY));
-  TRY_C(upload(&c->d_matS, mS));
-  TRY_C(upload(&c->d_matQ, mQ));
+  {
+    size_t rXY = 0;
+    for(int j = 0; j < num_blocks; ++j)
+      {
+        const BlockGeom &b = c->g[j];
+        for(int p = 0; p < 2; ++p)
+          {
+            const int q = 2 * j + p;
+            const int s = b.s[p];
+            pX.push_back(PotrfDesc{c->X + c->oXY[q], c->recipX + rXY * rs, s, 1, (long)s, q});
+            pY.push_back(PotrfDesc{c->LY + c->oXY[q], c->recipY + rXY * rs, s, 1, (long)s, q});
+            tT.push_back(TrsmTileDesc{c->X + c->oXY[q], c->recipX + rXY * rs, c->T + c->oV[q],
+                                      s, b.mn, 0});
+            rXY += s;
+            // AX = T^T T : A(i,l) = T(l,i), B(l,j) = T(l,j)
+            gAX.push_back(GemmTileDesc{c->T + c->oV[q], c->T + c->oV[q], c->AX + c->oA[q],
+                                       (long)s, 1, 1, (long)s, b.mn, b.mn, s, 1, 0});
+            // YV = Y V
+            gYV.push_back(GemmTileDesc{c->Y + c->oXY[q], c->V + c->oV[q], c->YV + c->oV[q], 1,
+                                       (long)s, 1, (long)s, s, b.mn, s, 0, 0});
+            // AY = V^T (YV)
+            gAY.push_back(GemmTileDesc{c->V + c->oV[q], c->YV + c->oV[q], c->AY + c->oA[q],
+                                       (long)s, 1, 1, (long)s, b.mn, b.mn, s, 1, 0});
+          }
+        pS.push_back(PotrfDesc{c->S + c->oS[j], c->recipS + (size_t)b.row0 * rs, b.P, 1,
+                               (long)b.P, j});
+        tP.push_back(TrsmTileDesc{c->S + c->oS[j], c->recipS + (size_t)b.row0 * rs,
+                                  c->Pband + c->oB[j], b.P, N, 0});
+        sd.push_back(SchurDesc{{c->AX + c->oA[2 * j], c->AX + c->oA[2 * j + 1]},
+                               {c->AY + c->oA[2 * j], c->AY + c->oA[2 * j + 1]},
+                               c->S + c->oS[j], b.m, b.n});
+        bd.push_back(BandDesc{c->Pband + c->oB[j], b.P, (int)b.row0});
+      }
+  }
+  // largest matrices first: the long CTAs start early, the short ones fill in
+  auto by_size = [](const PotrfDesc &a, const PotrfDesc &b) { return a.s > b.s; };
+  std::stable_sort(pX.begin(), pX.end(), by_size);
+  std::stable_sort(pY.begin(), pY.end(), by_size);
+  std::stable_sort(pS.begin(), pS.end(), by_size);
+  auto sort_trsm = [](std::vector<TrsmTileDesc> &v) {
+    std::stable_sort(v.begin(), v.end(),
+                     [](const TrsmTileDesc &a, const TrsmTileDesc &b) { return a.p > b.p; });
+    int slabs = 0;
+    for(auto &d : v)
+      {
+        d.slab0 = slabs;
+        slabs += d.p > 0 ? (d.ncols + TS - 1) / TS : 0;
+      }
+    return slabs;
+  };
+  auto sort_gemm = [](std::vector<GemmTileDesc> &v) {
+    std::stable_sort(v.begin(), v.end(),
+                     [](const GemmTileDesc &a, const GemmTileDesc &b) { return a.K > b.K; });
+    int tiles = 0;
+    for(auto &d : v)
+      {
+        d.tile0 = tiles;
+        tiles += ((d.M + TS - 1) / TS) * ((d.N + TS - 1) / TS);
+      }
+    return tiles;
+  };
+  c->slabs_T = sort_trsm(tT);
+  c->slabs_P = sort_trsm(tP);
+  c->n_trsmT = (int)tT.size();
+  c->n_trsmP = (int)tP.size();
+  c->tiles_AX = sort_gemm(gAX);
+  c->tiles_YV = sort_gemm(gYV);
+  c->tiles_AY = sort_gemm(gAY);
+  c->n_gemm = (int)gAX.size();
+  c->potrfQ = PotrfDesc{c->Q, c->recipQ, N, (long)N, 1, 0}; // upper: A = U^T U
+  TRY_C(upload(&c->d_potrfX, pX));
+  TRY_C(upload(&c->d_potrfY, pY));
+  TRY_C(upload(&c->d_potrfS, pS));
   TRY_C(upload(&c->d_trsmT, tT));
   TRY_C(upload(&c->d_trsmP, tP));
   TRY_C(upload(&c->d_gemmAX, gAX));
@@ -353,10 +404,13 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
   cudaFree(c->d_ginv);
   cudaFree(c->d_M);
   cudaFree(c->d_Mhalf);
-  cudaFree(c->d_matX);
-  cudaFree(c->d_matLY);
-  cudaFree(c->d_matS);
-  cudaFree(c->d_matQ);
+  cudaFree(c->d_potrfX);
+  cudaFree(c->d_potrfY);
+  cudaFree(c->d_potrfS);
+  cudaFree(c->recipX);
+  cudaFree(c->recipY);
+  cudaFree(c->recipS);
+  cudaFree(c->recipQ);
   cudaFree(c->d_trsmT);
   cudaFree(c->d_trsmP);
   cudaFree(c->d_gemmAX);

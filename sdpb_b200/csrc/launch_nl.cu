@@ -12,46 +12,77 @@
 // ---------------------------------------------------------- kernel drivers
 template <int NL> struct Launch
 {
-  static int potrf(sdpb_b200_ctx *c, const char *label, const MatDesc *d,
-                   int count, int upper, int *status)
+  static constexpr size_t TILE_SMEM = sizeof(TileSmem<NL>);
+  // opt in to > 48 KB of dynamic shared memory, once per kernel and device
+  template <typename K> static int smem_opt_in(sdpb_b200_ctx *c, K kernel)
+  {
+    CUDA_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)TILE_SMEM));
+    return 0;
+  }
+  static int potrf(sdpb_b200_ctx *c, const char *label, const PotrfDesc *d,
+                   int count, int *status)
   {
     if(count == 0)
       return 0;
+    if(int rc = smem_opt_in(c, potrf_tile_kernel<NL>))
+      return rc;
     c->kt_begin(label);
-    potrf_kernel<NL><<<count, 256, 0, c->stream>>>(d, upper, status);
+    potrf_tile_kernel<NL><<<count, 256, TILE_SMEM, c->stream>>>(d, status);
     c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
     return 0;
   }
-  static int trsm(sdpb_b200_ctx *c, const char *label, const TrsmDesc *d,
-                  int count, int maxcols)
+  // Cholesky(UPPER, Q): one launch per block column and phase
+  static int potrf_big(sdpb_b200_ctx *c, const char *label, const PotrfDesc &d, int *status)
   {
-    if(count == 0 || maxcols == 0)
-      return 0;
-    const int slab = 8;
-    dim3 grid(count, (maxcols + slab - 1) / slab);
+    if(int rc = smem_opt_in(c, potrf_big_kernel<NL>))
+      return rc;
+    CUDA_TRY(c, cudaMemsetAsync(status, 0xFF, sizeof(int), c->stream));
+    const int T = (d.s + TS - 1) / TS;
     c->kt_begin(label);
-    trsm_kernel<NL><<<grid, 256, 0, c->stream>>>(d, slab);
+    for(int Jt = 0; Jt < T; ++Jt)
+      {
+        potrf_big_kernel<NL><<<1, 256, TILE_SMEM, c->stream>>>(d, Jt, 0, status);
+        if(T - Jt - 1 > 0)
+          potrf_big_kernel<NL><<<T - Jt - 1, 256, TILE_SMEM, c->stream>>>(d, Jt, 1, status);
+        c->launches += (T - Jt - 1 > 0) ? 2 : 1;
+      }
+    c->kt_end();
+    --c->launches; // kt_end counted one
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
+  static int trsm(sdpb_b200_ctx *c, const char *label, const TrsmTileDesc *d,
+                  int count, int slabs)
+  {
+    if(count == 0 || slabs == 0)
+      return 0;
+    if(int rc = smem_opt_in(c, trsm_tile_kernel<NL>))
+      return rc;
+    c->kt_begin(label);
+    trsm_tile_kernel<NL><<<slabs, 256, TILE_SMEM, c->stream>>>(d, count);
     c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
     return 0;
   }
-  static int gemm(sdpb_b200_ctx *c, const char *label, const GemmDesc *d,
-                  int count, long maxout)
+  static int gemm(sdpb_b200_ctx *c, const char *label, const GemmTileDesc *d,
+                  int count, int tiles)
   {
-    if(count == 0 || maxout == 0)
+    if(count == 0 || tiles == 0)
       return 0;
-    dim3 grid(count, (unsigned)std::min<long>((maxout + 127) / 128, 65535));
+    if(int rc = smem_opt_in(c, gemm_tile_kernel<NL>))
+      return rc;
     c->kt_begin(label);
-    gemm_kernel<NL><<<grid, 128, 0, c->stream>>>(d);
+    gemm_tile_kernel<NL><<<tiles, 256, TILE_SMEM, c->stream>>>(d, count);
     c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
     return 0;
   }
   static int cholesky(sdpb_b200_ctx *c, int which)
   {
-    return potrf(c, which == 0 ? "potrf_X" : "potrf_Y", which == 0 ? c->d_matX : c->d_matLY, 2 * c->J, 0,
-                 c->d_status + which * 2 * c->J);
+    return potrf(c, which == 0 ? "potrf_X" : "potrf_Y", which == 0 ? c->d_potrfX : c->d_potrfY,
+                 2 * c->J, c->d_status + which * 2 * c->J);
   }
   static int pairings(sdpb_b200_ctx *c)
   {
@@ -61,16 +92,16 @@ template <int NL> struct Launch
     // T = V ; T <- L_X^{-1} T ; AX = T^T T
     CUDA_TRY(c, cudaMemcpyAsync(c->T, c->V, c->wV * 8, cudaMemcpyDeviceToDevice,
                                 c->stream));
-    int rc = trsm(c, "trsm_LXinv_V", c->d_trsmT, nb, c->max_mn);
+    int rc = trsm(c, "trsm_LXinv_V", c->d_trsmT, c->n_trsmT, c->slabs_T);
     if(rc)
       return rc;
-    rc = gemm(c, "gemm_A_X_inv", c->d_gemmAX, nb, (long)c->max_mn * c->max_mn);
+    rc = gemm(c, "gemm_A_X_inv", c->d_gemmAX, c->n_gemm, c->tiles_AX);
     if(rc)
       return rc;
-    rc = gemm(c, "gemm_YV", c->d_gemmYV, nb, (long)c->max_s * c->max_mn);
+    rc = gemm(c, "gemm_YV", c->d_gemmYV, c->n_gemm, c->tiles_YV);
     if(rc)
       return rc;
-    return gemm(c, "gemm_A_Y", c->d_gemmAY, nb, (long)c->max_mn * c->max_mn);
+    return gemm(c, "gemm_A_Y", c->d_gemmAY, c->n_gemm, c->tiles_AY);
   }
   static int schur_and_Q(sdpb_b200_ctx *c)
   {
@@ -87,13 +118,13 @@ template <int NL> struct Launch
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
     // Cholesky(S_j), P = L^{-1} B
-    int rc = potrf(c, "potrf_S", c->d_matS, J, 0, c->d_status + 4 * J);
+    int rc = potrf(c, "potrf_S", c->d_potrfS, J, c->d_status + 4 * J);
     if(rc)
       return rc;
     if(J)
       CUDA_TRY(c, cudaMemcpyAsync(c->Pband, c->B, c->wB * 8,
                                   cudaMemcpyDeviceToDevice, st));
-    rc = trsm(c, "trsm_Linv_B", c->d_trsmP, J, N);
+    rc = trsm(c, "trsm_Linv_B", c->d_trsmP, c->n_trsmP, c->slabs_P);
     if(rc)
       return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[4], st));
@@ -150,7 +181,7 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaGetLastError());
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[7], st));
-    rc = potrf(c, "potrf_Q", c->d_matQ, 1, 1, c->d_status + 5 * J);
+    rc = potrf_big(c, "potrf_Q", c->potrfQ, c->d_status + 5 * J);
     if(rc)
       return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[8], st));

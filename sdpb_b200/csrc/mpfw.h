@@ -1,0 +1,1050 @@
+// mpfw — the hot-loop form of mpfx: the same GMP-mpf-exact arithmetic, but on
+// 32-bit words held entirely in registers, built around the operation every
+// GEMM-class kernel of the Schur step repeats ~10^9 times per Newton
+// iteration:    acc <- mpf_add/sub(acc, mpf_mul(a, b)).
+//
+// Multiply (GMP mpf/mul.c): the top P limbs of both operands, exact product,
+// top P+1 limbs kept.  Here: product scanning over 32-bit words with
+// IMAD.WIDE.U32 + carry (one instruction per partial product on sm_100a), and
+// only the columns that can reach the kept window are formed (a "short
+// product", ~31 % fewer partial products at 768 bits).  The dropped columns
+// can change the kept words only through a carry that has to cross a whole
+// guard word; when that guard word is within 2^-24 of overflowing the exact
+// full product is formed instead, so the result is always the truncated exact
+// product.
+//
+// Add/sub (GMP mpf/add.c, mpf/sub.c) on full-size operands reduce to: align the
+// operand with the smaller exponent by a whole-limb right shift (a barrel
+// shifter on registers, no dynamic indexing), add or subtract exactly over the
+// window GMP uses (P limbs for add, P+1 for sub), then strip leading zero
+// limbs.  mpf_sub's "operands extremely close" paths coincide with the exact
+// subtraction except when the exponents differ by one limb; that rare case
+// (and nothing else) is handed to the verified generic mpfx::sub.
+//
+// Every routine compiles for the host as well (portable carry primitives), and
+// tests/cpp/mpfw_fuzz.cpp checks them against mpfx (itself fuzzed against
+// libgmp) on random and adversarial operands.
+#pragma once
+#include "mpfx.h"
+
+namespace mpfw
+{
+#if defined(__CUDA_ARCH__)
+#define MPFW_D __device__ __forceinline__
+#define MPFW_NOINLINE __device__ __noinline__
+#elif defined(__CUDACC__)
+#define MPFW_D __host__ __device__ inline
+#define MPFW_NOINLINE __host__ __device__
+#else
+#define MPFW_D inline
+#define MPFW_NOINLINE
+#endif
+
+#ifdef MPFW_COUNT_RARE
+static long rare_mul_count = 0, rare_sub_count = 0, recip_fallbacks = 0, sqrt_fallbacks = 0; // host fuzz: rare paths exercised?
+#endif
+// ------------------------------------------------------------------ carries
+// (t2:t1:t0) += a * b
+MPFW_D void mac3(uint32_t &t0, uint32_t &t1, uint32_t &t2, uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32 %2, %2, 0;"
+      : "+r"(t0), "+r"(t1), "+r"(t2)
+      : "r"(a), "r"(b));
+#else
+  const uint64_t p = (uint64_t)a * b;
+  const uint64_t s0 = (uint64_t)t0 + (uint32_t)p;
+  const uint64_t s1 = (uint64_t)t1 + (uint32_t)(p >> 32) + (s0 >> 32);
+  t0 = (uint32_t)s0;
+  t1 = (uint32_t)s1;
+  t2 += (uint32_t)(s1 >> 32);
+#endif
+}
+
+// r = u + v (N words), returns the carry out
+template <int N>
+MPFW_D uint32_t add_n(uint32_t (&r)[N], const uint32_t (&u)[N], const uint32_t (&v)[N])
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r[0]) : "r"(u[0]), "r"(v[0]));
+#pragma unroll
+  for(int i = 1; i < N; ++i)
+    asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r[i]) : "r"(u[i]), "r"(v[i]));
+  uint32_t c;
+  asm volatile("addc.u32 %0, 0, 0;" : "=r"(c));
+  return c;
+#else
+  uint64_t c = 0;
+  for(int i = 0; i < N; ++i)
+    {
+      const uint64_t s = (uint64_t)u[i] + v[i] + c;
+      r[i] = (uint32_t)s;
+      c = s >> 32;
+    }
+  return (uint32_t)c;
+#endif
+}
+// r = u - v (N words), returns the borrow out (0 or 1)
+template <int N>
+MPFW_D uint32_t sub_n(uint32_t (&r)[N], const uint32_t (&u)[N], const uint32_t (&v)[N])
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r[0]) : "r"(u[0]), "r"(v[0]));
+#pragma unroll
+  for(int i = 1; i < N; ++i)
+    asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r[i]) : "r"(u[i]), "r"(v[i]));
+  uint32_t b;
+  asm volatile("subc.u32 %0, 0, 0;" : "=r"(b));
+  return b & 1u;
+#else
+  uint64_t b = 0;
+  for(int i = 0; i < N; ++i)
+    {
+      const uint64_t s = (uint64_t)u[i] - v[i] - b;
+      r[i] = (uint32_t)s;
+      b = (s >> 32) & 1;
+    }
+  return (uint32_t)b;
+#endif
+}
+// r = -r (two's complement over N words)
+template <int N> MPFW_D void neg_n(uint32_t (&r)[N])
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("sub.cc.u32 %0, 0, %0;" : "+r"(r[0]));
+#pragma unroll
+  for(int i = 1; i < N; ++i)
+    asm volatile("subc.cc.u32 %0, 0, %0;" : "+r"(r[i]));
+#else
+  uint64_t b = 0;
+  for(int i = 0; i < N; ++i)
+    {
+      const uint64_t s = (uint64_t)0 - r[i] - b;
+      r[i] = (uint32_t)s;
+      b = (s >> 32) & 1;
+    }
+#endif
+}
+
+// v >>= k limbs (k in [0, 2^ceil(log2 NL))), zeros shifted in; register barrel shifter
+template <int NL> MPFW_D void shr_limbs(uint32_t (&v)[2 * NL], int k)
+{
+#pragma unroll
+  for(int s = 1; s < NL; s <<= 1)
+    {
+      const bool on = (k & s) != 0;
+#pragma unroll
+      for(int i = 0; i < 2 * NL; ++i)
+        {
+          const uint32_t hi = (i + 2 * s < 2 * NL) ? v[i + 2 * s] : 0u;
+          v[i] = on ? hi : v[i];
+        }
+    }
+}
+// v <<= k limbs, zeros shifted in at the bottom
+template <int NL> MPFW_D void shl_limbs(uint32_t (&v)[2 * NL], int k)
+{
+#pragma unroll
+  for(int s = 1; s < NL; s <<= 1)
+    {
+      const bool on = (k & s) != 0;
+#pragma unroll
+      for(int i = 2 * NL - 1; i >= 0; --i)
+        {
+          const uint32_t lo = (i - 2 * s >= 0) ? v[i - 2 * s] : 0u;
+          v[i] = on ? lo : v[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------- number
+template <int NL> struct Reg
+{
+  int32_t sign; // -1, 0, +1
+  int32_t exp;  // in 64-bit limbs
+  uint32_t w[2 * NL]; // the NL limbs as 32-bit words, little-endian, top-aligned
+};
+
+template <int NL> MPFW_D void set_zero(Reg<NL> &r)
+{
+  r.sign = 0;
+  r.exp = 0;
+#pragma unroll
+  for(int i = 0; i < 2 * NL; ++i)
+    r.w[i] = 0;
+}
+// packed element (mpfx::load layout) viewed as 32-bit words:
+// [exp, sign, w0 .. w(2NL-1), pad]
+template <int NL> MPFW_D void load(Reg<NL> &r, const uint32_t *p)
+{
+  r.exp = (int32_t)p[0];
+  r.sign = (int32_t)p[1];
+#pragma unroll
+  for(int i = 0; i < 2 * NL; ++i)
+    r.w[i] = p[2 + i];
+}
+template <int NL> MPFW_D void store(uint32_t *p, const Reg<NL> &r)
+{
+  p[0] = (uint32_t)r.exp;
+  p[1] = (uint32_t)r.sign;
+#pragma unroll
+  for(int i = 0; i < 2 * NL; ++i)
+    p[2 + i] = r.w[i];
+  if((NL + 1) & 1)
+    {
+      p[2 + 2 * NL] = 0;
+      p[3 + 2 * NL] = 0;
+    }
+}
+template <int NL> MPFW_D void to_num(mpfx::Num<NL> &n, const Reg<NL> &r)
+{
+  n.sign = r.sign;
+  n.exp = r.exp;
+#pragma unroll
+  for(int i = 0; i < NL; ++i)
+    n.d[i] = (uint64_t)r.w[2 * i] | ((uint64_t)r.w[2 * i + 1] << 32);
+}
+template <int NL> MPFW_D void from_num(Reg<NL> &r, const mpfx::Num<NL> &n)
+{
+  r.sign = n.sign;
+  r.exp = n.exp;
+#pragma unroll
+  for(int i = 0; i < NL; ++i)
+    {
+      r.w[2 * i] = (uint32_t)n.d[i];
+      r.w[2 * i + 1] = (uint32_t)(n.d[i] >> 32);
+    }
+}
+
+// ----------------------------------------------------------------- multiply
+template <int NL> struct MulGeom
+{
+  static constexpr int W = 2 * (NL - 1);             // operand words used
+  static constexpr int C0 = (W - 6 > 0) ? W - 6 : 0; // first column formed
+  static constexpr int NO = 2 * W - C0;              // product words kept
+};
+
+// out[c - C0] = word c of the exact product of a[0..W) and b[0..W) for
+// c >= FROM, assuming nothing below column FROM carries in.
+template <int W, int FROM, int C0>
+MPFW_D void mul_columns(uint32_t (&out)[2 * W - C0], const uint32_t *a, const uint32_t *b)
+{
+  uint32_t t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+  for(int c = FROM; c < 2 * W - 1; ++c)
+    {
+#pragma unroll
+      for(int i = 0; i < W; ++i)
+        {
+          const int j = c - i;
+          if(j >= 0 && j < W)
+            mac3(t0, t1, t2, a[i], b[j]);
+        }
+      if(c >= C0)
+        out[c - C0] = t0;
+      t0 = t1;
+      t1 = t2;
+      t2 = 0;
+    }
+  out[2 * W - 1 - C0] = t0;
+}
+// the exact product, all columns (rare path; kept out of line, operands and
+// result by value so that the caller's arrays never have their address taken
+// and stay in registers)
+template <int NL> struct MulWords
+{
+  uint32_t w[2 * NL];
+};
+template <int NL> struct MulProd
+{
+  uint32_t p[MulGeom<NL>::NO];
+};
+template <int NL>
+MPFW_NOINLINE MulProd<NL> mul_full(MulWords<NL> a, MulWords<NL> b)
+{
+  MulProd<NL> r;
+  mul_columns<MulGeom<NL>::W, 0, MulGeom<NL>::C0>(r.p, a.w + 2, b.w + 2);
+  return r;
+}
+
+// r = mpf_mul(a, b); a and b are the mantissa words w[0..2NL) of non-zero
+// operands (their lowest limb is ignored, as GMP does).
+template <int NL>
+MPFW_D void mul(Reg<NL> &r, int32_t asign, int32_t aexp, const uint32_t (&aw)[2 * NL],
+                int32_t bsign, int32_t bexp, const uint32_t (&bw)[2 * NL])
+{
+  typedef MulGeom<NL> G;
+  constexpr int W = G::W, C0 = G::C0;
+  uint32_t p[G::NO];
+  mul_columns<W, C0, C0>(p, aw + 2, bw + 2);
+  if(C0 > 0 && p[1] >= 0xFFFFFF00u)
+    {
+#ifdef MPFW_COUNT_RARE
+      ++rare_mul_count;
+#endif
+      MulWords<NL> ca, cb;
+#pragma unroll
+      for(int i = 0; i < 2 * NL; ++i)
+        {
+          ca.w[i] = aw[i];
+          cb.w[i] = bw[i];
+        }
+      const MulProd<NL> full = mul_full<NL>(ca, cb);
+#pragma unroll
+      for(int i = 0; i < G::NO; ++i)
+        p[i] = full.p[i];
+    }
+  // top limb of the 2P-limb product zero?  -> one limb lower, exponent - 1
+  const bool adj = (p[2 * W - 1 - C0] | p[2 * W - 2 - C0]) == 0;
+  // kept words start at product word W-2 (adj: W-4)
+#pragma unroll
+  for(int i = 0; i < 2 * NL; ++i)
+    {
+      const uint32_t hi = p[W - 2 + i - C0];
+      const uint32_t lo = p[W - 4 + i - C0];
+      r.w[i] = adj ? lo : hi;
+    }
+  r.exp = aexp + bexp - (adj ? 1 : 0);
+  r.sign = asign * bsign;
+}
+
+// ------------------------------------------------------------------ add/sub
+template <int NL>
+MPFW_NOINLINE Reg<NL> addsub_generic(Reg<NL> acc, Reg<NL> v, int vsign)
+{
+  mpfx::Num<NL> a, b, r;
+  to_num(a, acc);
+  to_num(b, v);
+  b.sign = vsign;
+  mpfx::add(r, a, b);
+  Reg<NL> out;
+  from_num(out, r);
+  return out;
+}
+
+// acc <- mpf_add(acc, v) with v's sign replaced by vsign (so the same routine
+// serves mpf_sub).  Both operands non-zero is NOT required.
+template <int NL> MPFW_D void add_signed(Reg<NL> &acc, const Reg<NL> &v, int vsign)
+{
+  if(vsign == 0)
+    return; // x + 0 = x exactly
+  if(acc.sign == 0)
+    {
+      acc = v;
+      acc.sign = vsign;
+      return;
+    }
+  // u = operand with the larger exponent
+  const bool swap = acc.exp < v.exp;
+  const int32_t uexp = swap ? v.exp : acc.exp;
+  const int32_t usign = swap ? vsign : acc.sign;
+  const int64_t ediff64 = swap ? (int64_t)v.exp - acc.exp : (int64_t)acc.exp - v.exp;
+  const int ediff = ediff64 > NL ? NL : (int)ediff64;
+  uint32_t u[2 * NL], s[2 * NL];
+#pragma unroll
+  for(int i = 0; i < 2 * NL; ++i)
+    {
+      u[i] = swap ? v.w[i] : acc.w[i];
+      s[i] = swap ? acc.w[i] : v.w[i];
+    }
+  if(acc.sign == vsign)
+    {
+      // ---- magnitudes add: window = top P limbs of u (GMP mpf_add) ----
+      if(ediff >= NL - 1)
+        {
+#pragma unroll
+          for(int i = 0; i < 2 * NL; ++i)
+            s[i] = 0;
+        }
+      else
+        shr_limbs<NL>(s, ediff);
+      u[0] = u[1] = 0;
+      s[0] = s[1] = 0;
+      uint32_t r[2 * NL];
+      const uint32_t cy = add_n<2 * NL>(r, u, s);
+#pragma unroll
+      for(int i = 0; i < 2 * NL - 2; ++i)
+        acc.w[i] = cy ? r[i + 2] : r[i];
+      acc.w[2 * NL - 2] = cy ? 1u : r[2 * NL - 2];
+      acc.w[2 * NL - 1] = cy ? 0u : r[2 * NL - 1];
+      acc.exp = uexp + (int32_t)cy;
+      acc.sign = usign;
+      return;
+    }
+  // ---- magnitudes subtract (GMP mpf_sub) ----
+  if(ediff == 1)
+    {
+      // "extremely close" path of mpf_sub keeps v's lowest limb; rare
+      const bool close = u[2 * NL - 1] == 0 && u[2 * NL - 2] == 1
+                         && (NL < 2 || (u[2 * NL - 3] | u[2 * NL - 4]) == 0)
+                         && s[2 * NL - 1] == 0xFFFFFFFFu && s[2 * NL - 2] == 0xFFFFFFFFu;
+      if(close)
+        {
+#ifdef MPFW_COUNT_RARE
+          ++rare_sub_count;
+#endif
+          acc = addsub_generic<NL>(acc, v, vsign);
+          return;
+        }
+    }
+  if(ediff >= NL)
+    {
+      // v lies completely below the window: r = u
+#pragma unroll
+      for(int i = 0; i < 2 * NL; ++i)
+        acc.w[i] = u[i];
+      acc.exp = uexp;
+      acc.sign = usign;
+      return;
+    }
+  shr_limbs<NL>(s, ediff);
+  uint32_t r[2 * NL];
+  const uint32_t bw = sub_n<2 * NL>(r, u, s);
+  int32_t rsign = usign;
+  if(bw)
+    {
+      // only possible for ediff == 0: |v| > |u|
+      neg_n<2 * NL>(r);
+      rsign = -usign;
+    }
+  int32_t rexp = uexp;
+  if((r[2 * NL - 1] | r[2 * NL - 2]) == 0)
+    {
+      // strip leading zero limbs
+      int z = 0;
+      bool run = true;
+#pragma unroll
+      for(int l = NL - 1; l >= 0; --l)
+        {
+          run = run && (r[2 * l] | r[2 * l + 1]) == 0;
+          z += run ? 1 : 0;
+        }
+      if(z == NL)
+        {
+          set_zero(acc);
+          return;
+        }
+      shl_limbs<NL>(r, z);
+      rexp -= z;
+    }
+#pragma unroll
+  for(int i = 0; i < 2 * NL; ++i)
+    acc.w[i] = r[i];
+  acc.exp = rexp;
+  acc.sign = rsign;
+}
+
+// acc <- acc + a*b (negate == false) or acc - a*b (negate == true), one
+// mpf_mul followed by one mpf_add / mpf_sub.  a, b: packed elements as 32-bit
+// words (shared or global memory).
+template <int NL>
+MPFW_D void mac(Reg<NL> &acc, const uint32_t *a, const uint32_t *b, bool negate)
+{
+  const int32_t asign = (int32_t)a[1], bsign = (int32_t)b[1];
+  if(asign == 0 || bsign == 0)
+    return; // 0 * x = 0 and c + 0 = c exactly in mpf
+  uint32_t aw[2 * NL], bw[2 * NL];
+#pragma unroll
+  for(int i = 2; i < 2 * NL; ++i)
+    {
+      aw[i] = a[2 + i];
+      bw[i] = b[2 + i];
+    }
+  aw[0] = aw[1] = bw[0] = bw[1] = 0; // lowest limb: not used by mpf_mul
+  Reg<NL> p;
+  mul<NL>(p, asign, (int32_t)a[0], aw, bsign, (int32_t)b[0], bw);
+  add_signed<NL>(acc, p, negate ? -p.sign : p.sign);
+}
+template <int NL>
+MPFW_D void mac(Reg<NL> &acc, const Reg<NL> &a, const Reg<NL> &b, bool negate)
+{
+  if(a.sign == 0 || b.sign == 0)
+    return;
+  Reg<NL> p;
+  mul<NL>(p, a.sign, a.exp, a.w, b.sign, b.exp, b.w);
+  add_signed<NL>(acc, p, negate ? -p.sign : p.sign);
+}
+
+// ----------------------------------------------------------------- division
+// mpf_div(u, v) = floor(U * B^P / D) with U, D the NL-limb mantissas (GMP
+// mpf/div.c on full-size operands, restated in mpfx::div).  When many numbers
+// are divided by the same D (a Cholesky pivot, a column norm) the quotient is
+// formed from a precomputed reciprocal
+//     R = floor(beta^(4n+1) / D),   beta = 2^32, n = NL,   2n+4 words,
+// as  q~ = floor(U R / beta^(2n+3))  (a short product of the high columns),
+// which is q, q-1 or q-2; the exact remainder  U B^P - q~ D  (its low 2n+1
+// words, a short product of the low columns) then fixes q~ up.  The result is
+// the exact truncated quotient, i.e. bit-identical to mpf_div.
+template <int NL> struct DivGeom
+{
+  static constexpr int RW = 2 * NL + 4; // words of R
+};
+
+// R = floor(beta^(4n+1) / D) by Knuth long division (slow, once per divisor)
+template <int NL>
+MPFW_D void reciprocal(uint32_t (&R)[2 * NL + 4], const mpfx::Num<NL> &d)
+{
+  constexpr int NN = 2 * NL + 2; // limbs of the numerator beta^(4n+1) = 2^32 * B^(2n)
+  mpfx::limb_t np[NN], q[NN - NL + 1];
+  for(int i = 0; i < NN; ++i)
+    np[i] = 0;
+  np[2 * NL] = (mpfx::limb_t)1 << 32;
+  mpfx::n_div_q<2 * NN + 2>(q, np, 2 * NL + 1, d.d, NL);
+  // quotient has (2NL+1) - NL + 1 = NL + 2 limbs = 2NL + 4 words
+#pragma unroll
+  for(int i = 0; i < NL + 2; ++i)
+    {
+      R[2 * i] = (uint32_t)q[i];
+      R[2 * i + 1] = (uint32_t)(q[i] >> 32);
+    }
+}
+
+// ------------------------------------------------- fast reciprocal and sqrt
+// Newton iterations on fixed-point fractions with statically sized word
+// arrays, precision roughly doubling per level (w -> 2w-1 words, the lost word
+// absorbs the accumulated error), finished by an EXACT correction against the
+// remainder, so the results equal the Knuth / integer-Newton reference
+// routines of mpfx bit for bit.  They replace those on the critical path of
+// the Cholesky factorisations (one sqrt and one reciprocal per pivot).
+
+// out[0..NOUT) = low NOUT words of a*b (exact)
+template <int KA, int KB, int NOUT>
+MPFW_D void mul_low(uint32_t (&out)[NOUT], const uint32_t (&a)[KA], const uint32_t (&b)[KB])
+{
+  uint32_t t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+  for(int c = 0; c < NOUT; ++c)
+    {
+#pragma unroll
+      for(int i = 0; i < KA; ++i)
+        {
+          const int j = c - i;
+          if(j >= 0 && j < KB)
+            mac3(t0, t1, t2, a[i], b[j]);
+        }
+      out[c] = t0;
+      t0 = t1;
+      t1 = t2;
+      t2 = 0;
+    }
+}
+// out[c - FROM] = word c of a*b for c in [FROM, KA+KB), columns below FROM-2
+// are not formed (the result may be low by a few units of word FROM-1)
+template <int KA, int KB, int FROM>
+MPFW_D void mul_high(uint32_t (&out)[KA + KB - FROM], const uint32_t (&a)[KA],
+                     const uint32_t (&b)[KB])
+{
+  constexpr int C0 = FROM - 2 > 0 ? FROM - 2 : 0;
+  uint32_t t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+  for(int c = C0; c < KA + KB - 1; ++c)
+    {
+#pragma unroll
+      for(int i = 0; i < KA; ++i)
+        {
+          const int j = c - i;
+          if(j >= 0 && j < KB)
+            mac3(t0, t1, t2, a[i], b[j]);
+        }
+      if(c >= FROM)
+        out[c - FROM] = t0;
+      t0 = t1;
+      t1 = t2;
+      t2 = 0;
+    }
+  out[KA + KB - 1 - FROM] = t0;
+}
+// out[c - FROM] = word c of a*b for c in [FROM, TO); columns below FROM-2 are
+// not formed, the carry out of column TO-1 is dropped
+template <int KA, int KB, int FROM, int TO>
+MPFW_D void mul_mid(uint32_t (&out)[TO - FROM], const uint32_t (&a)[KA], const uint32_t (&b)[KB])
+{
+  constexpr int C0 = FROM - 2 > 0 ? FROM - 2 : 0;
+  uint32_t t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+  for(int c = C0; c < TO; ++c)
+    {
+#pragma unroll
+      for(int i = 0; i < KA; ++i)
+        {
+          const int j = c - i;
+          if(j >= 0 && j < KB)
+            mac3(t0, t1, t2, a[i], b[j]);
+        }
+      if(c >= FROM)
+        out[c - FROM] = t0;
+      t0 = t1;
+      t1 = t2;
+      t2 = 0;
+    }
+}
+// r -= small constant (borrow chain)
+template <int N> MPFW_D void sub_small(uint32_t (&r)[N], uint32_t k)
+{
+  uint32_t bw = k;
+#pragma unroll
+  for(int i = 0; i < N; ++i)
+    {
+      const uint32_t a = r[i];
+      r[i] = a - bw;
+      bw = a < bw ? 1u : 0u;
+    }
+}
+// v <<= sh bits, sh in [0, 32*N), zeros shifted in (static word stages + one bit stage)
+template <int N> MPFW_D void shl_bits(uint32_t (&v)[N], int sh)
+{
+  const int ws = sh >> 5, bs = sh & 31;
+#pragma unroll
+  for(int s = 1; s < N; s <<= 1)
+    {
+      const bool on = (ws & s) != 0;
+#pragma unroll
+      for(int i = N - 1; i >= 0; --i)
+        {
+          const uint32_t lo = (i - s >= 0) ? v[i - s] : 0u;
+          v[i] = on ? lo : v[i];
+        }
+    }
+  if(bs)
+    {
+#pragma unroll
+      for(int i = N - 1; i >= 0; --i)
+        {
+          const uint32_t lo = i > 0 ? v[i - 1] : 0u;
+          v[i] = (v[i] << bs) | (lo >> (32 - bs));
+        }
+    }
+}
+template <int N> MPFW_D void shr_bits(uint32_t (&v)[N], int sh)
+{
+  const int ws = sh >> 5, bs = sh & 31;
+#pragma unroll
+  for(int s = 1; s < N; s <<= 1)
+    {
+      const bool on = (ws & s) != 0;
+#pragma unroll
+      for(int i = 0; i < N; ++i)
+        {
+          const uint32_t hi = (i + s < N) ? v[i + s] : 0u;
+          v[i] = on ? hi : v[i];
+        }
+    }
+  if(bs)
+    {
+#pragma unroll
+      for(int i = 0; i < N; ++i)
+        {
+          const uint32_t hi = i + 1 < N ? v[i + 1] : 0u;
+          v[i] = (v[i] >> bs) | (hi << (32 - bs));
+        }
+    }
+}
+template <int N> MPFW_D int clz_words(const uint32_t (&v)[N])
+{
+  int z = 0;
+  bool run = true;
+#pragma unroll
+  for(int i = N - 1; i >= 0; --i)
+    {
+      const int c = mpfx::clz32(v[i]); // 32 for a zero word
+      z += run ? c : 0;
+      run = run && v[i] == 0;
+    }
+  return z;
+}
+
+// Y (W words) ~ beta^W / (2 d), d = Dn / beta^ND in [1/2, 1); 0 < Y/beta^W < 1/(2d),
+// short by at most a few dozen units.
+template <int ND, int W> struct RecipLevel
+{
+  static constexpr int WP = (W <= 2) ? 1 : (W + 2) / 2;
+  MPFW_D static void run(uint32_t (&Y)[W], const uint32_t (&Dn)[ND])
+  {
+    if constexpr(W == 1)
+      {
+        // floor(2^63 / (top word + 1)): below 2^31/d_top by < 2 units of 2^-32
+        const uint64_t dt = (uint64_t)Dn[ND - 1] + 1;
+        uint64_t q = ((uint64_t)1 << 63) / dt;
+        if(q > 0xFFFFFFFFull)
+          q = 0xFFFFFFFFull;
+        Y[0] = (uint32_t)q - 1u;
+      }
+    else
+      {
+        uint32_t Yp[WP];
+        RecipLevel<ND, WP>::run(Yp, Dn);
+        uint32_t Dt[W];
+#pragma unroll
+        for(int i = 0; i < W; ++i)
+          Dt[i] = (ND - W + i >= 0) ? Dn[ND - W + i] : 0u;
+        // G = beta^(W+WP) - 2 Dt Yp, low W+1 words (the rest is zero)
+        uint32_t G[W + 1];
+        mul_low<W, WP, W + 1>(G, Dt, Yp);
+#pragma unroll
+        for(int i = W; i >= 0; --i)
+          G[i] = (G[i] << 1) | (i > 0 ? (G[i - 1] >> 31) : 0u);
+        neg_n<W + 1>(G);
+        // Y = Yp beta^(W-WP) + floor(Yp G / beta^(2 WP))
+        uint32_t Q[WP + W + 1 - 2 * WP];
+        mul_high<WP, W + 1, 2 * WP>(Q, Yp, G);
+        uint32_t Ye[W + 1], Qe[W + 1];
+#pragma unroll
+        for(int i = 0; i <= W; ++i)
+          {
+            Ye[i] = (i >= W - WP && i < W) ? Yp[i - (W - WP)] : 0u;
+            Qe[i] = (i < W - WP + 1) ? Q[i] : 0u;
+          }
+        uint32_t S[W + 1];
+        add_n<W + 1>(S, Ye, Qe);
+#pragma unroll
+        for(int i = 0; i < W; ++i)
+          Y[i] = S[i];
+        if(S[W]) // cannot happen for a convergent iterate; saturate
+          {
+#pragma unroll
+            for(int i = 0; i < W; ++i)
+              Y[i] = 0xFFFFFFFFu;
+          }
+        sub_small<W>(Y, 4u);
+      }
+  }
+};
+
+// R = floor(beta^(4n+1) / D), same value as reciprocal() above
+template <int NL>
+MPFW_D void reciprocal_fast(uint32_t (&R)[2 * NL + 4], const Reg<NL> &d)
+{
+  constexpr int n2 = 2 * NL, WF = 2 * NL + 5;
+  uint32_t Dn[n2];
+#pragma unroll
+  for(int i = 0; i < n2; ++i)
+    Dn[i] = d.w[i];
+  const int s = clz_words<n2>(Dn); // < 64: the top limb is non-zero
+  shl_bits<n2>(Dn, s);
+  uint32_t Y[WF];
+  RecipLevel<n2, WF>::run(Y, Dn);
+  // R~ = floor(Y 2^(s+1) / beta^4) = Y >> (127 - s) bits
+  shr_bits<WF>(Y, 127 - s);
+  uint32_t Rt[n2 + 4];
+#pragma unroll
+  for(int i = 0; i < n2 + 4; ++i)
+    Rt[i] = Y[i];
+  // exact remainder beta^(4n+1) - R~ D, low 2n+2 words
+  uint32_t rem[n2 + 2];
+  {
+    uint32_t dw[n2];
+#pragma unroll
+    for(int i = 0; i < n2; ++i)
+      dw[i] = d.w[i];
+    mul_low<n2 + 4, n2, n2 + 2>(rem, Rt, dw);
+    neg_n<n2 + 2>(rem); // beta^(4n+1) = 0 mod beta^(2n+2)
+  }
+  uint32_t dext[n2 + 2];
+#pragma unroll
+  for(int i = 0; i < n2 + 2; ++i)
+    dext[i] = i < n2 ? d.w[i] : 0u;
+  bool ok = false;
+#pragma unroll
+  for(int round = 0; round < 4; ++round)
+    {
+      uint32_t tmp[n2 + 2];
+      const uint32_t bw = sub_n<n2 + 2>(tmp, rem, dext);
+      const bool ge = bw == 0 && !ok;
+      ok = ok || bw != 0;
+#pragma unroll
+      for(int c = 0; c < n2 + 2; ++c)
+        rem[c] = ge ? tmp[c] : rem[c];
+      uint32_t carry = ge ? 1u : 0u;
+#pragma unroll
+      for(int c = 0; c < n2 + 4; ++c)
+        {
+          const uint32_t t = Rt[c] + carry;
+          carry = (t < carry) ? 1u : 0u;
+          Rt[c] = t;
+        }
+    }
+  if(!ok)
+    {
+      // the iterate was further off than the analysis allows: exact slow path
+#ifdef MPFW_COUNT_RARE
+      ++recip_fallbacks;
+#endif
+      mpfx::Num<NL> dn;
+      to_num(dn, d);
+      reciprocal<NL>(R, dn);
+      return;
+    }
+#pragma unroll
+  for(int i = 0; i < n2 + 4; ++i)
+    R[i] = Rt[i];
+}
+
+// V (W words) ~ beta^W / (2 sqrt(t)), t = Tn / beta^NT in [1/4, 1), from below
+template <int NT, int W> struct RsqrtLevel
+{
+  static constexpr int WP = (W <= 2) ? 1 : (W + 2) / 2;
+  MPFW_D static void run(uint32_t (&V)[W], const uint32_t (&Tn)[NT])
+  {
+    if constexpr(W == 1)
+      {
+        // 32-bit estimate from the top 64 bits in double precision, then lowered
+        const double t = ((double)Tn[NT - 1] * 4294967296.0 + (double)Tn[NT - 2])
+                         / 18446744073709551616.0;
+        double v = 0.5 / ::sqrt(t);
+        v = v * 4294967296.0 - 8.0;
+        if(v > 4294967295.0)
+          v = 4294967295.0;
+        V[0] = (uint32_t)v;
+      }
+    else
+      {
+        uint32_t Vp[WP];
+        RsqrtLevel<NT, WP>::run(Vp, Tn);
+        uint32_t Tt[W];
+#pragma unroll
+        for(int i = 0; i < W; ++i)
+          Tt[i] = (NT - W + i >= 0) ? Tn[NT - W + i] : 0u;
+        // F = Tt Vp^2 ; G = beta^(2WP+W) - 4F < beta^(WP+W+1).  Only G's words
+        // from GL up matter for the quotient below, so only that slice of F is formed.
+        uint32_t V2[2 * WP];
+        mul_low<WP, WP, 2 * WP>(V2, Vp, Vp);
+        constexpr int GL = (2 * WP - 3 > 0) ? 2 * WP - 3 : 0;
+        constexpr int NG = WP + W + 1 - GL;
+        uint32_t G[NG];
+        mul_mid<2 * WP, W, GL, WP + W + 1>(G, V2, Tt);
+#pragma unroll
+        for(int i = NG - 1; i >= 0; --i)
+          G[i] = (G[i] << 2) | (i > 0 ? (G[i - 1] >> 30) : 0u);
+        neg_n<NG>(G);
+        // V = Vp beta^(W-WP) + floor(Vp G / (2 beta^(3 WP)))
+        constexpr int QF = 3 * WP - GL - 1; // keep one extra low word for the halving
+        constexpr int NQ = WP + NG - QF;
+        uint32_t Q[NQ];
+        mul_high<WP, NG, QF>(Q, Vp, G);
+        shr_bits<NQ>(Q, 1);
+        uint32_t Ve[W + 1], Qe[W + 1];
+#pragma unroll
+        for(int i = 0; i <= W; ++i)
+          {
+            Ve[i] = (i >= W - WP && i < W) ? Vp[i - (W - WP)] : 0u;
+            Qe[i] = (i + 1 < NQ) ? Q[i + 1] : 0u;
+          }
+        uint32_t S[W + 1];
+        add_n<W + 1>(S, Ve, Qe);
+#pragma unroll
+        for(int i = 0; i < W; ++i)
+          V[i] = S[i];
+        if(S[W])
+          {
+#pragma unroll
+            for(int i = 0; i < W; ++i)
+              V[i] = 0xFFFFFFFFu;
+          }
+        sub_small<W>(V, 4u);
+      }
+  }
+};
+
+// r = mpf_sqrt(u), u > 0: same value as mpfx::sqrt
+template <int NL> MPFW_D void sqrt_fast(Reg<NL> &r, const Reg<NL> &u)
+{
+  constexpr int P = NL - 1, NT = 4 * P, NR = 2 * P, WF = 2 * P + 3;
+  const int expodd = u.exp & 1;
+  // T: u's NL limbs top-aligned in 2P - expodd limbs, viewed in a 2P-limb frame
+  uint32_t T[NT];
+#pragma unroll
+  for(int i = 0; i < NT; ++i)
+    {
+      // expodd == 0: T word i = u.w[i - (NT - 2NL)]; expodd == 1: two words lower
+      const int a = i - (NT - 2 * NL), b = i - (NT - 2 * NL) + 2;
+      const uint32_t w0 = (a >= 0 && a < 2 * NL) ? u.w[a] : 0u;
+      const uint32_t w1 = (b >= 0 && b < 2 * NL) ? u.w[b] : 0u;
+      T[i] = expodd ? w1 : w0;
+    }
+  uint32_t Tn[NT];
+#pragma unroll
+  for(int i = 0; i < NT; ++i)
+    Tn[i] = T[i];
+  const int s = clz_words<NT>(Tn) & ~1; // even, < 128
+  shl_bits<NT>(Tn, s);
+  uint32_t V[WF];
+  RsqrtLevel<NT, WF>::run(V, Tn);
+  // sqrt(Tn) = 2 Tn V / (beta^(NT/2) beta^WF): top NR words of the product, then >> s/2
+  // use the top NR+3 words of Tn
+  uint32_t Tt[NR + 3];
+#pragma unroll
+  for(int i = 0; i < NR + 3; ++i)
+    Tt[i] = Tn[NT - (NR + 3) + i];
+  // Tn V / beta^(NT/2 + WF) = Tt V / beta^(NR + 3 - NT/2 ... ) : NT/2 = NR, so
+  // Tn ~ Tt beta^(NT-NR-3) and the quotient is Tt V / beta^(WF + 3 - (NT - 2 NR)) = Tt V / beta^(WF+3)
+  uint32_t Sx[NR + 3 + WF - (WF + 2)];
+  mul_high<NR + 3, WF, WF + 2>(Sx, Tt, V);
+  // Sx = floor(Tt V / beta^(WF+2)) = 2*beta * sqrt(Tn)/2 ... : sqrt(Tn) = 2 Tt V / beta^(WF+3)
+  // so sqrt(Tn) = Sx * 2 / beta; and sqrt(T) = sqrt(Tn) >> (s/2)
+  // S~ = (Sx >> (31 + s/2)) : Sx has NR+1 words
+  shr_bits<NR + 1>(Sx, 31 + (s >> 1));
+  uint32_t S[NR];
+#pragma unroll
+  for(int i = 0; i < NR; ++i)
+    S[i] = Sx[i];
+  // keep S~ <= floor(sqrt(T)): lower it by a few units, the correction walks up
+  sub_small<NR>(S, 2u);
+  // rem = T - S^2, low NR+2 words
+  uint32_t rem[NR + 2];
+  {
+    uint32_t sq[NR + 2];
+    mul_low<NR, NR, NR + 2>(sq, S, S);
+    uint32_t tl[NR + 2];
+#pragma unroll
+    for(int i = 0; i < NR + 2; ++i)
+      tl[i] = T[i];
+    sub_n<NR + 2>(rem, tl, sq);
+  }
+  bool ok = false;
+#pragma unroll
+  for(int round = 0; round < 8; ++round)
+    {
+      // (S+1)^2 <= T  <=>  rem >= 2S + 1
+      uint32_t step[NR + 2];
+#pragma unroll
+      for(int i = 0; i < NR + 2; ++i)
+        {
+          const uint32_t lo = (i < NR) ? S[i] : 0u;
+          const uint32_t below = (i > 0 && i - 1 < NR) ? S[i - 1] : 0u;
+          step[i] = (lo << 1) | (below >> 31);
+        }
+      step[0] |= 1u;
+      uint32_t tmp[NR + 2];
+      const uint32_t bw = sub_n<NR + 2>(tmp, rem, step);
+      const bool ge = bw == 0 && !ok;
+      ok = ok || bw != 0;
+#pragma unroll
+      for(int i = 0; i < NR + 2; ++i)
+        rem[i] = ge ? tmp[i] : rem[i];
+      uint32_t carry = ge ? 1u : 0u;
+#pragma unroll
+      for(int i = 0; i < NR; ++i)
+        {
+          const uint32_t t = S[i] + carry;
+          carry = (t < carry) ? 1u : 0u;
+          S[i] = t;
+        }
+    }
+  // rem must now be in [0, 2S]; a negative start (S~ too large) shows as a huge rem
+  if(!ok || rem[NR + 1] != 0)
+    {
+#ifdef MPFW_COUNT_RARE
+      ++sqrt_fallbacks;
+#endif
+      mpfx::Num<NL> a, b;
+      to_num(a, u);
+      mpfx::sqrt(b, a);
+      from_num(r, b);
+      return;
+    }
+  r.w[0] = r.w[1] = 0;
+#pragma unroll
+  for(int i = 0; i < NR; ++i)
+    r.w[i + 2] = S[i];
+  r.sign = 1;
+  r.exp = (u.exp + expodd) / 2;
+}
+
+// x <- mpf_div(x, d);  dw = mantissa words of d (2n), R = reciprocal(d).
+template <int NL>
+MPFW_D void div_recip(Reg<NL> &x, int32_t dsign, int32_t dexp, const uint32_t *dw,
+                      const uint32_t *R)
+{
+  if(x.sign == 0)
+    return;
+  constexpr int n2 = 2 * NL, RW = 2 * NL + 4;
+  // ---- q~ = words [2n+3, 4n+3) of U*R, columns >= 2n+1 only ----
+  uint32_t q[n2];
+  {
+    uint32_t t0 = 0, t1 = 0, t2 = 0;
+    constexpr int C0 = n2 + 1;
+#pragma unroll
+    for(int c = C0; c < n2 + RW - 1; ++c)
+      {
+#pragma unroll
+        for(int i = 0; i < n2; ++i)
+          {
+            const int j = c - i;
+            if(j >= 0 && j < RW)
+              mac3(t0, t1, t2, x.w[i], R[j]);
+          }
+        if(c >= n2 + 3 && c - (n2 + 3) < n2)
+          q[c - (n2 + 3)] = t0;
+        t0 = t1;
+        t1 = t2;
+        t2 = 0;
+      }
+    // column n2+RW-1 = 4n+3 is word 2n of q~: always zero (q < beta^(2n))
+  }
+  // ---- rem = (U beta^(2n-2) - q~ D) mod beta^(2n+1) ----
+  uint32_t rem[n2 + 1];
+  {
+    uint32_t t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+    for(int c = 0; c <= n2; ++c)
+      {
+#pragma unroll
+        for(int i = 0; i < n2; ++i)
+          {
+            const int j = c - i;
+            if(j >= 0 && j < n2)
+              mac3(t0, t1, t2, q[i], dw[j]);
+          }
+        rem[c] = t0;
+        t0 = t1;
+        t1 = t2;
+        t2 = 0;
+      }
+    uint32_t ulow[n2 + 1];
+#pragma unroll
+    for(int c = 0; c <= n2; ++c)
+      ulow[c] = (c >= n2 - 2) ? x.w[c - (n2 - 2)] : 0u;
+    uint32_t tmp[n2 + 1];
+    sub_n<n2 + 1>(tmp, ulow, rem);
+#pragma unroll
+    for(int c = 0; c <= n2; ++c)
+      rem[c] = tmp[c];
+  }
+  // ---- at most two corrections: while rem >= D: rem -= D, q~ += 1 ----
+  uint32_t dext[n2 + 1];
+#pragma unroll
+  for(int c = 0; c < n2; ++c)
+    dext[c] = dw[c];
+  dext[n2] = 0;
+#pragma unroll
+  for(int round = 0; round < 2; ++round)
+    {
+      uint32_t tmp[n2 + 1];
+      const uint32_t bw = sub_n<n2 + 1>(tmp, rem, dext);
+      const bool ge = bw == 0;
+#pragma unroll
+      for(int c = 0; c <= n2; ++c)
+        rem[c] = ge ? tmp[c] : rem[c];
+      // q += ge
+      uint32_t carry = ge ? 1u : 0u;
+#pragma unroll
+      for(int c = 0; c < n2; ++c)
+        {
+          const uint32_t s = q[c] + carry;
+          carry = (s < carry) ? 1u : 0u;
+          q[c] = s;
+        }
+    }
+  // ---- assemble (mpfx::div): strip one leading zero limb ----
+  const bool adj = (q[n2 - 1] | q[n2 - 2]) == 0;
+#pragma unroll
+  for(int i = n2 - 1; i >= 2; --i)
+    x.w[i] = adj ? q[i - 2] : q[i];
+  x.w[1] = adj ? 0u : q[1];
+  x.w[0] = adj ? 0u : q[0];
+  x.exp = x.exp - dexp + (adj ? 0 : 1);
+  x.sign = x.sign * dsign;
+}
+} // namespace mpfw

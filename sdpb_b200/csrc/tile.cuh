@@ -1,0 +1,518 @@
+// Tiled sm_100a kernels for the GEMM-class stages of the Schur step: batched
+// Cholesky, triangular solve and matrix product on mpf numbers.
+//
+// One scheme serves all three.  A CTA of 256 threads owns a 16x16 tile of
+// outputs, one mpf accumulator per thread, held in REGISTERS for the whole
+// k-loop (mpfw::Reg, 32-bit words).  Operand tiles (16 x 8 elements of A and
+// 8 x 16 of B per step) are staged into shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx, one 128-byte element per copy so that
+// any stride / transposition is free), double buffered, at a padded stride
+// that makes the 128-bit shared loads bank-conflict free.  Every output
+// element receives its updates in ascending k, one mpf_mul and one
+// mpf_add/sub per update: the canonical order of DESIGN.md §3, so the
+// left-looking schedule used here is bit-identical to the oracle's.
+//
+// Divisions by a Cholesky pivot use the exact reciprocal scheme of mpfw.h; the
+// reciprocals are produced once per pivot by the factorisation and kept in
+// HBM next to the factor (they are reused by the triangular solves).
+#pragma once
+#include "mpfw.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdpb_b200
+{
+using mpfw::Reg;
+
+constexpr int TS = 16; // tile side
+constexpr int KC = 4;  // k-chunk
+
+template <int NL> struct TileGeom
+{
+  static constexpr int ES = (NL + 2) & ~1;                  // 64-bit words / element
+  static constexpr int EW = 2 * ES;                         // 32-bit words / element
+  static constexpr int EB = 8 * ES;                         // bytes / element
+  static constexpr int SW = EW + ((ES % 4 == 0) ? 4 : 0);   // shared stride, 32-bit words
+  static constexpr int RW = 2 * NL + 4;                     // reciprocal words
+  static constexpr int RS = (RW + 3) & ~3;                  // reciprocal stride (16-byte multiple)
+};
+
+// ------------------------------------------------------------ TMA / mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(smem_u32(bar)), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                 smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// make this thread's earlier generic-proxy global writes visible to later TMA reads
+__device__ __forceinline__ void fence_async_proxy()
+{
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// One operand of the k-loop: element (x, k) lives at base + (x*sx + k*sk) elements.
+struct Operand
+{
+  const uint64_t *base;
+  long sx, sk;
+  int nx; // valid x in this tile (<= TS)
+};
+
+template <int NL> struct TileSmem
+{
+  typedef TileGeom<NL> G;
+  uint32_t a[2][KC * TS * G::SW];
+  uint32_t b[2][KC * TS * G::SW];
+  uint32_t diag[TS * TS * G::SW]; // a factored diagonal tile, [k][x]
+  uint32_t vec[2][TS * G::SW];    // a finished column / row of the current tile
+  uint32_t recip[TS * G::RS];     // reciprocals of the 16 pivots of `diag`
+  uint64_t bar[2];
+  int bad;
+};
+
+// acc -+= sum_k A(ti,k) B(k,tj), k ascending in [0, K); `it` counts the chunks
+// this CTA has staged so far (selects buffer and mbarrier phase).  All 256
+// threads must call this together.
+template <int NL>
+__device__ __forceinline__ void tile_k_loop(Reg<NL> &acc, bool negate, const Operand &A,
+                                            const Operand &B, int K, TileSmem<NL> &sm,
+                                            uint32_t &it, bool active)
+{
+  typedef TileGeom<NL> G;
+  const int t = threadIdx.x;
+  const int ti = t & (TS - 1), tj = t >> 4;
+  const int nchunks = (K + KC - 1) / KC;
+  if(nchunks == 0)
+    return;
+  // this thread's copy duty: t < KC*16 -> A element (x = t&15, kk = t>>4), the
+  // next KC*16 threads -> B element likewise; one TMA bulk copy each per chunk
+  const bool dutyA = t < KC * TS, duty = t < 2 * KC * TS;
+  const int dx = t & (TS - 1), dk = (t >> 4) & (KC - 1);
+  const Operand &O = dutyA ? A : B;
+  auto issue = [&](int c) {
+    const uint32_t s = (it + c) & 1;
+    const int k0 = c * KC;
+    const int kcnt = min(KC, K - k0);
+    if(t == 0)
+      mbar_expect_tx(&sm.bar[s], (uint32_t)(G::EB * kcnt * (A.nx + B.nx)));
+    if(duty && dx < O.nx && dk < kcnt)
+      {
+        uint32_t *dst = (dutyA ? sm.a[s] : sm.b[s]) + (dk * TS + dx) * G::SW;
+        bulk_g2s(dst, O.base + (dx * O.sx + (k0 + dk) * O.sk) * G::ES, G::EB, &sm.bar[s]);
+      }
+  };
+  issue(0);
+  for(int c = 0; c < nchunks; ++c)
+    {
+      if(c + 1 < nchunks)
+        issue(c + 1);
+      const uint32_t s = (it + c) & 1, parity = ((it + c) >> 1) & 1;
+      while(!mbar_try_wait(&sm.bar[s], parity))
+        {
+        }
+      const int kcnt = min(KC, K - c * KC);
+      if(active)
+        {
+          const uint32_t *pa = sm.a[s] + ti * G::SW, *pb = sm.b[s] + tj * G::SW;
+          for(int kk = 0; kk < kcnt; ++kk)
+            mpfw::mac<NL>(acc, pa + kk * TS * G::SW, pb + kk * TS * G::SW, negate);
+        }
+      __syncthreads();
+    }
+  it += nchunks;
+}
+
+template <int NL> __device__ __forceinline__ void tile_smem_init(TileSmem<NL> &sm)
+{
+  if(threadIdx.x == 0)
+    {
+      mbar_init(&sm.bar[0], 1);
+      mbar_init(&sm.bar[1], 1);
+      sm.bad = -1;
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  __syncthreads();
+}
+
+template <int NL> __device__ __forceinline__ void ldg_reg(Reg<NL> &r, const uint64_t *p)
+{
+  mpfw::load<NL>(r, reinterpret_cast<const uint32_t *>(p));
+}
+template <int NL> __device__ __forceinline__ void stg_reg(uint64_t *p, const Reg<NL> &r)
+{
+  mpfw::store<NL>(reinterpret_cast<uint32_t *>(p), r);
+}
+
+// ------------------------------------------------------------------- GEMM
+struct GemmTileDesc // C(i,j) = sum_l A(i,l) B(l,j); strides in elements
+{
+  const uint64_t *A, *B;
+  uint64_t *C;
+  long sa_i, sa_l, sb_l, sb_j;
+  int M, N, K;
+  int sym;   // 1: only tiles/elements with i >= j, result mirrored
+  int tile0; // first linear tile index of this matrix in the launch
+};
+
+// grid.x = total number of 16x16 tiles over all matrices (host prefix sums in
+// `tile0`); the matrix of a tile is found by binary search.
+template <int NL>
+__global__ void __launch_bounds__(256, 2)
+gemm_tile_kernel(const GemmTileDesc *descs, int count)
+{
+  typedef TileGeom<NL> G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
+  int lo = 0, hi = count - 1;
+  while(lo < hi)
+    {
+      const int mid = (lo + hi + 1) >> 1;
+      if(descs[mid].tile0 <= (int)blockIdx.x)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+  const GemmTileDesc d = descs[lo];
+  const int tiles_m = (d.M + TS - 1) / TS;
+  const int tile = blockIdx.x - d.tile0;
+  const int It = tile % tiles_m, Jt = tile / tiles_m;
+  if(Jt * TS >= d.N || (d.sym && It < Jt))
+    return;
+  tile_smem_init(sm);
+  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int i = It * TS + ti, j = Jt * TS + tj;
+  const bool active = i < d.M && j < d.N && (!d.sym || i >= j);
+  Reg<NL> acc;
+  mpfw::set_zero(acc);
+  uint32_t it = 0;
+  Operand A{d.A + (long)It * TS * d.sa_i * G::ES, d.sa_i, d.sa_l, min(TS, d.M - It * TS)};
+  Operand B{d.B + (long)Jt * TS * d.sb_j * G::ES, d.sb_j, d.sb_l, min(TS, d.N - Jt * TS)};
+  tile_k_loop<NL>(acc, false, A, B, d.K, sm, it, active);
+  if(active)
+    {
+      stg_reg<NL>(d.C + ((long)j * d.M + i) * G::ES, acc);
+      if(d.sym && i != j)
+        stg_reg<NL>(d.C + ((long)i * d.M + j) * G::ES, acc);
+    }
+}
+
+// ---------------------------------------------------------------- Cholesky
+struct PotrfDesc
+{
+  uint64_t *A;     // s x s, in place
+  uint32_t *recip; // s reciprocals of the pivots, stride TileGeom::RS words
+  int s;
+  long si, sj; // logical (i,j), i >= j, lives at A + (i*si + j*sj) elements:
+               // lower: si = 1, sj = s; upper (A = U^T U): si = s, sj = 1
+  int id;
+};
+
+// factor the diagonal tile Jt: acc(ti,tj) already holds a_ij - sum_{k<J0} l_ik l_jk.
+// Leaves the factored tile in sm.diag ([k][x] = L(J0+x, J0+k)) and the pivots'
+// reciprocals in sm.recip, and writes both to HBM.  Returns false (uniformly)
+// on a non-positive pivot, with its index in sm.bad.
+template <int NL>
+__device__ __forceinline__ bool potrf_diag_tile(Reg<NL> &acc, const PotrfDesc &d, int Jt,
+                                                TileSmem<NL> &sm)
+{
+  typedef TileGeom<NL> G;
+  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int J0 = Jt * TS;
+  const int nd = min(TS, d.s - J0);
+  for(int kk = 0; kk < nd; ++kk)
+    {
+      if(ti == kk && tj == kk)
+        {
+          if(acc.sign <= 0)
+            sm.bad = J0 + kk;
+          else
+            {
+              Reg<NL> root;
+              mpfw::sqrt_fast<NL>(root, acc);
+              acc = root;
+              uint32_t R[G::RW];
+              mpfw::reciprocal_fast<NL>(R, acc);
+              uint32_t *rs = sm.recip + kk * G::RS;
+              uint32_t *rg = d.recip + (long)(J0 + kk) * G::RS;
+#pragma unroll
+              for(int w = 0; w < G::RW; ++w)
+                {
+                  rs[w] = R[w];
+                  rg[w] = R[w];
+                }
+              mpfw::store<NL>(sm.diag + (kk * TS + kk) * G::SW, acc);
+            }
+        }
+      __syncthreads();
+      if(sm.bad >= 0)
+        return false;
+      if(tj == kk && ti > kk && ti < nd)
+        {
+          const uint32_t *piv = sm.diag + (kk * TS + kk) * G::SW;
+          mpfw::div_recip<NL>(acc, (int32_t)piv[1], (int32_t)piv[0], piv + 2, sm.recip + kk * G::RS);
+          mpfw::store<NL>(sm.diag + (kk * TS + ti) * G::SW, acc);
+        }
+      __syncthreads();
+      if(ti > kk && tj > kk && ti >= tj && ti < nd)
+        mpfw::mac<NL>(acc, sm.diag + (kk * TS + ti) * G::SW, sm.diag + (kk * TS + tj) * G::SW, true);
+    }
+  // write the tile: factor below/on the diagonal, exact zeros above
+  if(ti < nd && tj < nd)
+    {
+      if(ti >= tj)
+        stg_reg<NL>(d.A + ((long)(J0 + ti) * d.si + (long)(J0 + tj) * d.sj) * G::ES, acc);
+      else
+        {
+          Reg<NL> z;
+          mpfw::set_zero(z);
+          stg_reg<NL>(d.A + ((long)(J0 + ti) * d.si + (long)(J0 + tj) * d.sj) * G::ES, z);
+        }
+    }
+  return true;
+}
+
+// tile (It, Jt), It > Jt:  X = (A_tile - sum_k ...) L_JJ^{-T}; acc(ti,tj) holds
+// the updated a_ij; sm.diag / sm.recip hold the factored diagonal tile Jt.
+template <int NL>
+__device__ __forceinline__ void potrf_row_tile_solve(Reg<NL> &acc, const PotrfDesc &d, int It,
+                                                     int Jt, TileSmem<NL> &sm)
+{
+  typedef TileGeom<NL> G;
+  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int J0 = Jt * TS, I0 = It * TS;
+  const int nd = min(TS, d.s - J0), ni = min(TS, d.s - I0);
+  for(int kk = 0; kk < nd; ++kk)
+    {
+      uint32_t *xs = sm.vec[kk & 1];
+      if(tj == kk && ti < ni)
+        {
+          const uint32_t *piv = sm.diag + (kk * TS + kk) * G::SW;
+          mpfw::div_recip<NL>(acc, (int32_t)piv[1], (int32_t)piv[0], piv + 2, sm.recip + kk * G::RS);
+          mpfw::store<NL>(xs + ti * G::SW, acc);
+        }
+      __syncthreads();
+      if(tj > kk && tj < nd && ti < ni)
+        mpfw::mac<NL>(acc, xs + ti * G::SW, sm.diag + (kk * TS + tj) * G::SW, true);
+    }
+  if(ti < ni && tj < nd)
+    {
+      stg_reg<NL>(d.A + ((long)(I0 + ti) * d.si + (long)(J0 + tj) * d.sj) * G::ES, acc);
+      Reg<NL> z;
+      mpfw::set_zero(z);
+      stg_reg<NL>(d.A + ((long)(J0 + tj) * d.si + (long)(I0 + ti) * d.sj) * G::ES, z);
+    }
+}
+
+// load the factored diagonal tile Jt and its reciprocals from HBM into shared
+template <int NL>
+__device__ __forceinline__ void load_diag_tile(const uint64_t *A, long si, long sj,
+                                               const uint32_t *recip, int s, int Jt,
+                                               TileSmem<NL> &sm)
+{
+  typedef TileGeom<NL> G;
+  const int J0 = Jt * TS, nd = min(TS, s - J0);
+  const int x = threadIdx.x & (TS - 1), k = threadIdx.x >> 4;
+  if(x < nd && k < nd && x >= k)
+    {
+      const uint4 *src
+        = reinterpret_cast<const uint4 *>(A + ((long)(J0 + x) * si + (long)(J0 + k) * sj) * G::ES);
+      uint4 *dst = reinterpret_cast<uint4 *>(sm.diag + (k * TS + x) * G::SW);
+#pragma unroll
+      for(int w = 0; w < G::EB / 16; ++w)
+        dst[w] = src[w];
+    }
+  for(int w = threadIdx.x; w < nd * G::RS; w += blockDim.x)
+    sm.recip[w] = recip[(long)J0 * G::RS + w];
+  __syncthreads();
+}
+
+// acc(ti,tj) = A(I0+ti, J0+tj) - sum_{k < J0} L(I0+ti,k) L(J0+tj,k)
+template <int NL>
+__device__ __forceinline__ void potrf_tile_update(Reg<NL> &acc, const PotrfDesc &d, int It, int Jt,
+                                                  TileSmem<NL> &sm, uint32_t &it)
+{
+  typedef TileGeom<NL> G;
+  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int I0 = It * TS, J0 = Jt * TS;
+  const int ni = min(TS, d.s - I0), nj = min(TS, d.s - J0);
+  const bool active = ti < ni && tj < nj && (It > Jt || ti >= tj);
+  if(active)
+    ldg_reg<NL>(acc, d.A + ((long)(I0 + ti) * d.si + (long)(J0 + tj) * d.sj) * G::ES);
+  else
+    mpfw::set_zero(acc);
+  Operand A{d.A + (long)I0 * d.si * G::ES, d.si, d.sj, ni};
+  Operand B{d.A + (long)J0 * d.si * G::ES, d.si, d.sj, nj};
+  tile_k_loop<NL>(acc, true, A, B, J0, sm, it, active);
+}
+
+// One CTA factors one matrix (left-looking by block column).
+template <int NL>
+__global__ void __launch_bounds__(256, 2) potrf_tile_kernel(const PotrfDesc *descs, int *status)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
+  const PotrfDesc d = descs[blockIdx.x];
+  if(d.s == 0)
+    {
+      if(threadIdx.x == 0)
+        status[d.id] = -1;
+      return;
+    }
+  tile_smem_init(sm);
+  const int T = (d.s + TS - 1) / TS;
+  uint32_t it = 0;
+  Reg<NL> acc;
+  for(int Jt = 0; Jt < T; ++Jt)
+    {
+      potrf_tile_update<NL>(acc, d, Jt, Jt, sm, it);
+      if(!potrf_diag_tile<NL>(acc, d, Jt, sm))
+        {
+          if(threadIdx.x == 0)
+            status[d.id] = sm.bad;
+          return;
+        }
+      __syncthreads();
+      for(int It = Jt + 1; It < T; ++It)
+        {
+          potrf_tile_update<NL>(acc, d, It, Jt, sm, it);
+          potrf_row_tile_solve<NL>(acc, d, It, Jt, sm);
+          __syncthreads();
+        }
+      // the finished block column is read back through TMA by later columns
+      fence_async_proxy();
+      __syncthreads();
+    }
+  if(threadIdx.x == 0)
+    status[d.id] = -1;
+}
+
+// Large matrix (Q): one launch per block column and phase.
+// phase 0: the diagonal tile (1 CTA); phase 1: the row tiles below (T-Jt-1 CTAs).
+template <int NL>
+__global__ void __launch_bounds__(256, 2)
+potrf_big_kernel(PotrfDesc d, int Jt, int phase, int *status)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
+  if(*status >= 0)
+    return; // an earlier pivot already failed
+  tile_smem_init(sm);
+  uint32_t it = 0;
+  Reg<NL> acc;
+  if(phase == 0)
+    {
+      potrf_tile_update<NL>(acc, d, Jt, Jt, sm, it);
+      if(!potrf_diag_tile<NL>(acc, d, Jt, sm))
+        {
+          if(threadIdx.x == 0)
+            *status = sm.bad;
+        }
+      return;
+    }
+  const int It = Jt + 1 + blockIdx.x;
+  potrf_tile_update<NL>(acc, d, It, Jt, sm, it);
+  load_diag_tile<NL>(d.A, d.si, d.sj, d.recip, d.s, Jt, sm);
+  potrf_row_tile_solve<NL>(acc, d, It, Jt, sm);
+}
+
+// -------------------------------------------------------- triangular solve
+struct TrsmTileDesc // X <- L^{-1} B in place, L lower p x p (column-major)
+{
+  const uint64_t *L;
+  const uint32_t *recip; // reciprocals of diag(L)
+  uint64_t *B;           // p x ncols, column-major, ld = p
+  int p, ncols;
+  int slab0; // first linear slab index of this matrix in the launch
+};
+
+// grid.x = total number of 16-column slabs; each CTA sweeps the row tiles of
+// its slab top to bottom.
+template <int NL>
+__global__ void __launch_bounds__(256, 2)
+trsm_tile_kernel(const TrsmTileDesc *descs, int count)
+{
+  typedef TileGeom<NL> G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
+  int lo = 0, hi = count - 1;
+  while(lo < hi)
+    {
+      const int mid = (lo + hi + 1) >> 1;
+      if(descs[mid].slab0 <= (int)blockIdx.x)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+  const TrsmTileDesc d = descs[lo];
+  const int c0 = (blockIdx.x - d.slab0) * TS;
+  if(c0 >= d.ncols || d.p == 0)
+    return;
+  tile_smem_init(sm);
+  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int nc = min(TS, d.ncols - c0);
+  const int T = (d.p + TS - 1) / TS;
+  uint32_t it = 0;
+  for(int It = 0; It < T; ++It)
+    {
+      const int I0 = It * TS, ni = min(TS, d.p - I0);
+      const bool active = ti < ni && tj < nc;
+      Reg<NL> acc;
+      uint64_t *mine = d.B + ((long)(c0 + tj) * d.p + I0 + ti) * G::ES;
+      if(active)
+        ldg_reg<NL>(acc, mine);
+      else
+        mpfw::set_zero(acc);
+      // b_i -= sum_{k < I0} l_ik x_k
+      Operand A{d.L + (long)I0 * G::ES, 1, d.p, ni};
+      Operand B{d.B + (long)c0 * d.p * G::ES, d.p, 1, nc};
+      tile_k_loop<NL>(acc, true, A, B, I0, sm, it, active);
+      // the 16 rows of this tile, top to bottom
+      load_diag_tile<NL>(d.L, 1, d.p, d.recip, d.p, It, sm);
+      for(int kk = 0; kk < ni; ++kk)
+        {
+          uint32_t *xs = sm.vec[kk & 1];
+          if(ti == kk && tj < nc)
+            {
+              const uint32_t *piv = sm.diag + (kk * TS + kk) * G::SW;
+              mpfw::div_recip<NL>(acc, (int32_t)piv[1], (int32_t)piv[0], piv + 2,
+                                  sm.recip + kk * G::RS);
+              mpfw::store<NL>(xs + tj * G::SW, acc);
+            }
+          __syncthreads();
+          if(ti > kk && active)
+            mpfw::mac<NL>(acc, sm.diag + (kk * TS + ti) * G::SW, xs + tj * G::SW, true);
+        }
+      if(active)
+        stg_reg<NL>(mine, acc);
+      fence_async_proxy();
+      __syncthreads();
+    }
+}
+} // namespace sdpb_b200
