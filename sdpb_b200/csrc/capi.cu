@@ -295,6 +295,7 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
     TRY_C(cudaMalloc(&c->recipY, std::max<size_t>(16, nXY * rs * 4)));
     TRY_C(cudaMalloc(&c->recipS, std::max<size_t>(16, (size_t)c->K * rs * 4)));
     TRY_C(cudaMalloc(&c->recipQ, (size_t)N * rs * 4));
+    TRY_C(cudaMalloc(&c->recipN, (size_t)N * rs * 4));
   }
   std::vector<PotrfDesc> pX, pY, pS;
   std::vector<TrsmTileDesc> tT, tP;
@@ -313,7 +314,7 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
             pX.push_back(PotrfDesc{c->X + c->oXY[q], c->recipX + rXY * rs, s, 1, (long)s, q});
             pY.push_back(PotrfDesc{c->LY + c->oXY[q], c->recipY + rXY * rs, s, 1, (long)s, q});
             tT.push_back(TrsmTileDesc{c->X + c->oXY[q], c->recipX + rXY * rs, c->T + c->oV[q],
-                                      s, b.mn, 0});
+                                      s, b.mn});
             rXY += s;
             // AX = T^T T : A(i,l) = T(l,i), B(l,j) = T(l,j)
             gAX.push_back(GemmTileDesc{c->T + c->oV[q], c->T + c->oV[q], c->AX + c->oA[q],
@@ -328,7 +329,7 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
         pS.push_back(PotrfDesc{c->S + c->oS[j], c->recipS + (size_t)b.row0 * rs, b.P, 1,
                                (long)b.P, j});
         tP.push_back(TrsmTileDesc{c->S + c->oS[j], c->recipS + (size_t)b.row0 * rs,
-                                  c->Pband + c->oB[j], b.P, N, 0});
+                                  c->Pband + c->oB[j], b.P, N});
         sd.push_back(SchurDesc{{c->AX + c->oA[2 * j], c->AX + c->oA[2 * j + 1]},
                                {c->AY + c->oA[2 * j], c->AY + c->oA[2 * j + 1]},
                                c->S + c->oS[j], b.m, b.n});
@@ -340,16 +341,12 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
   std::stable_sort(pX.begin(), pX.end(), by_size);
   std::stable_sort(pY.begin(), pY.end(), by_size);
   std::stable_sort(pS.begin(), pS.end(), by_size);
-  auto sort_trsm = [](std::vector<TrsmTileDesc> &v) {
+  auto sort_trsm = [](std::vector<TrsmTileDesc> &v, std::vector<int> &sizes) {
     std::stable_sort(v.begin(), v.end(),
                      [](const TrsmTileDesc &a, const TrsmTileDesc &b) { return a.p > b.p; });
-    int slabs = 0;
+    sizes.clear();
     for(auto &d : v)
-      {
-        d.slab0 = slabs;
-        slabs += d.p > 0 ? (d.ncols + TS - 1) / TS : 0;
-      }
-    return slabs;
+      sizes.push_back(d.p);
   };
   auto sort_gemm = [](std::vector<GemmTileDesc> &v) {
     std::stable_sort(v.begin(), v.end(),
@@ -362,15 +359,19 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
       }
     return tiles;
   };
-  c->slabs_T = sort_trsm(tT);
-  c->slabs_P = sort_trsm(tP);
-  c->n_trsmT = (int)tT.size();
-  c->n_trsmP = (int)tP.size();
+  sort_trsm(tT, c->szT);
+  sort_trsm(tP, c->szP);
+  for(auto &d : pX)
+    c->szXY.push_back(d.s);
+  for(auto &d : pS)
+    c->szS.push_back(d.s);
   c->tiles_AX = sort_gemm(gAX);
   c->tiles_YV = sort_gemm(gYV);
   c->tiles_AY = sort_gemm(gAY);
   c->n_gemm = (int)gAX.size();
-  c->potrfQ = PotrfDesc{c->Q, c->recipQ, N, (long)N, 1, 0}; // upper: A = U^T U
+  std::vector<PotrfDesc> pQ{PotrfDesc{c->Q, c->recipQ, N, (long)N, 1, 0}}; // upper: A = U^T U
+  c->szQ.assign(1, N);
+  TRY_C(upload(&c->d_potrfQ, pQ));
   TRY_C(upload(&c->d_potrfX, pX));
   TRY_C(upload(&c->d_potrfY, pY));
   TRY_C(upload(&c->d_potrfS, pS));
@@ -407,10 +408,12 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
   cudaFree(c->d_potrfX);
   cudaFree(c->d_potrfY);
   cudaFree(c->d_potrfS);
+  cudaFree(c->d_potrfQ);
   cudaFree(c->recipX);
   cudaFree(c->recipY);
   cudaFree(c->recipS);
   cudaFree(c->recipQ);
+  cudaFree(c->recipN);
   cudaFree(c->d_trsmT);
   cudaFree(c->d_trsmP);
   cudaFree(c->d_gemmAX);

@@ -3,7 +3,6 @@
 #pragma once
 #include "../../include/sdpb_b200.h"
 #include "kernels.cuh"
-#include "tile.cuh"
 
 #include <string>
 #include <vector>
@@ -63,13 +62,15 @@ struct sdpb_b200_ctx
 
   // tile-kernel descriptors (tile.cuh); matrices sorted by cost, largest first
   PotrfDesc *d_potrfX = nullptr, *d_potrfY = nullptr, *d_potrfS = nullptr;
-  PotrfDesc potrfQ{};
+  PotrfDesc *d_potrfQ = nullptr;
   TrsmTileDesc *d_trsmT = nullptr, *d_trsmP = nullptr;
   GemmTileDesc *d_gemmAX = nullptr, *d_gemmYV = nullptr, *d_gemmAY = nullptr;
-  int n_trsmT = 0, n_trsmP = 0, slabs_T = 0, slabs_P = 0;
+  // sizes of the sorted batches (host copies, for the per-level grids)
+  std::vector<int> szXY, szS, szT, szP, szQ;
   int n_gemm = 0, tiles_AX = 0, tiles_YV = 0, tiles_AY = 0;
   // pivot reciprocals (TileGeom::RS 32-bit words each)
-  uint32_t *recipX = nullptr, *recipY = nullptr, *recipS = nullptr, *recipQ = nullptr;
+  uint32_t *recipX = nullptr, *recipY = nullptr, *recipS = nullptr, *recipQ = nullptr,
+           *recipN = nullptr;
   SchurDesc *d_schur = nullptr;
   BandDesc *d_bands = nullptr;
   int *d_status = nullptr; // [2J X | 2J Y | J S | 1 Q]

@@ -10,6 +10,7 @@
 // the schedule with the most parallelism.
 #pragma once
 #include "mpfx.h"
+#include "tile.cuh"
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -250,7 +251,8 @@ __global__ void __launch_bounds__(128) gemm_kernel(const GemmDesc *descs)
 }
 
 // ------------------------------------------------------------ Schur assembly
-// compute_schur_complement.cxx:31-124, lower triangle + mirror.
+// compute_schur_complement.cxx:31-124, lower triangle + mirror; one thread per
+// element, the eight products in the order the reference spells out.
 template <int NL>
 __global__ void __launch_bounds__(128) schur_kernel(const SchurDesc *descs)
 {
@@ -258,6 +260,7 @@ __global__ void __launch_bounds__(128) schur_kernel(const SchurDesc *descs)
   const int n = d.n, m = d.m, mn = m * n;
   const int P = n * m * (m + 1) / 2;
   const long total = (long)P * P;
+  constexpr int EW = 2 * Fmt<NL>::ES;
   for(long e = (long)blockIdx.y * blockDim.x + threadIdx.x; e < total;
       e += (long)gridDim.y * blockDim.x)
     {
@@ -273,16 +276,15 @@ __global__ void __launch_bounds__(128) schur_kernel(const SchurDesc *descs)
       while((c1 + 1) * (c1 + 2) / 2 <= t1)
         ++c1;
       const int r0 = t0 - c0 * (c0 + 1) / 2, r1 = t1 - c1 * (c1 + 1) / 2;
-      Num<NL> element, x, y, product;
-      mpfx::set_zero(element);
+      Reg<NL> element;
+      mpfw::set_zero(element);
       // ax(p,cb,rb) = AX[p](cb n + row, rb n + col); ay = AY[p](cb n + col, rb n + row)
-#define SDPB_AX(p, cb, rb) (size_t)((rb) * n + col) * mn + ((cb) * n + row)
-#define SDPB_AY(p, cb, rb) (size_t)((rb) * n + row) * mn + ((cb) * n + col)
+#define SDPB_AX(cb, rb) ((size_t)((rb) * n + col) * mn + ((cb) * n + row))
+#define SDPB_AY(cb, rb) ((size_t)((rb) * n + row) * mn + ((cb) * n + col))
 #define SDPB_TERM(p, xa, xb, ya, yb)                                          \
-  ld(x, d.AX[p], SDPB_AX(p, xa, xb));                                         \
-  ld(y, d.AY[p], SDPB_AY(p, ya, yb));                                         \
-  mpfx::mul(product, x, y);                                                   \
-  mpfx::add(element, element, product);
+  element = mac_nl<NL>(                                                       \
+    element, reinterpret_cast<const uint32_t *>(d.AX[p]) + SDPB_AX(xa, xb) * EW, \
+    reinterpret_cast<const uint32_t *>(d.AY[p]) + SDPB_AY(ya, yb) * EW, false);
       for(int p = 0; p < 2; ++p)
         {
           SDPB_TERM(p, c0, r1, c1, r0)
@@ -293,10 +295,10 @@ __global__ void __launch_bounds__(128) schur_kernel(const SchurDesc *descs)
 #undef SDPB_TERM
 #undef SDPB_AX
 #undef SDPB_AY
-      mpfx::div4(element, element);
-      st(d.S, (size_t)J * P + I, element);
+      mpfw::div4<NL>(element);
+      stg_reg<NL>(d.S + ((size_t)J * P + I) * Fmt<NL>::ES, element);
       if(I != J)
-        st(d.S, (size_t)I * P + J, element);
+        stg_reg<NL>(d.S + ((size_t)I * P + J) * Fmt<NL>::ES, element);
     }
 }
 
@@ -323,7 +325,7 @@ __global__ void norm_partial_kernel(const BandDesc *bands, int N, limb_t *part)
 }
 template <int NL>
 __global__ void norm_final_kernel(const limb_t *part, int J, int N,
-                                  limb_t *norms)
+                                  limb_t *norms, uint32_t *recip)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if(c >= N)
@@ -336,7 +338,15 @@ __global__ void norm_final_kernel(const limb_t *part, int J, int N,
       mpfx::add(acc, acc, v);
     }
   if(acc.sign > 0)
-    mpfx::sqrt(acc, acc);
+    {
+      Reg<NL> r;
+      mpfw::from_num(r, acc);
+      r = sqrt_nl<NL>(r);
+      const RecipWords<NL> rw = recip_nl<NL>(r);
+      for(int w = 0; w < TileGeom<NL>::RW; ++w)
+        recip[(size_t)c * TileGeom<NL>::RS + w] = rw.w[w];
+      mpfw::to_num(acc, r);
+    }
   st(norms, c, acc);
 }
 
@@ -358,7 +368,7 @@ struct CrtTables
 template <int NL>
 __global__ void __launch_bounds__(128)
 normalize_kernel(const BandDesc *bands, int N, long K, const limb_t *norms,
-                 int prec, CrtTables T, uint32_t *R, int *flags)
+                 const uint32_t *recip, int prec, CrtTables T, uint32_t *R, int *flags)
 {
   const BandDesc b = bands[blockIdx.x];
   const long total = (long)b.rows * N;
@@ -372,7 +382,11 @@ normalize_kernel(const BandDesc *bands, int N, long K, const limb_t *norms,
       ld(v, b.P, e);
       if(nrm.sign != 0)
         {
-          mpfx::div(v, v, nrm);
+          Reg<NL> rv;
+          mpfw::from_num(rv, v);
+          rv = div_nl<NL>(rv, reinterpret_cast<const uint32_t *>(norms + (size_t)c * Fmt<NL>::ES),
+                          recip + (size_t)c * TileGeom<NL>::RS);
+          mpfw::to_num(v, rv);
           mpfx::mul_2exp(v, v, (uint32_t)prec);
           st(b.P, e, v);
         }

@@ -20,49 +20,80 @@ template <int NL> struct Launch
                                      (int)TILE_SMEM));
     return 0;
   }
-  static int potrf(sdpb_b200_ctx *c, const char *label, const PotrfDesc *d,
-                   int count, int *status)
+  static constexpr size_t DIAG_SMEM = sizeof(DiagSmem<NL>);
+  // matrices of a batch (sorted, largest first) that still have tile index `t`
+  static int alive(const std::vector<int> &sizes, int t)
   {
-    if(count == 0)
-      return 0;
-    if(int rc = smem_opt_in(c, potrf_tile_kernel<NL>))
-      return rc;
-    c->kt_begin(label);
-    potrf_tile_kernel<NL><<<count, 256, TILE_SMEM, c->stream>>>(d, status);
-    c->kt_end();
-    CUDA_TRY(c, cudaGetLastError());
-    return 0;
+    int n = 0;
+    while(n < (int)sizes.size() && sizes[n] > t * TS)
+      ++n;
+    return n;
   }
-  // Cholesky(UPPER, Q): one launch per block column and phase
-  static int potrf_big(sdpb_b200_ctx *c, const char *label, const PotrfDesc &d, int *status)
+  // batched Cholesky, level-synchronous (tile.cuh); sizes sorted descending
+  static int potrf(sdpb_b200_ctx *c, const char *label, const PotrfDesc *d,
+                   const std::vector<int> &sizes, int *status, int nstatus)
   {
-    if(int rc = smem_opt_in(c, potrf_big_kernel<NL>))
+    if(sizes.empty() || nstatus == 0)
+      return 0;
+    if(int rc = smem_opt_in(c, potrf_diag_level<NL>))
       return rc;
-    CUDA_TRY(c, cudaMemsetAsync(status, 0xFF, sizeof(int), c->stream));
-    const int T = (d.s + TS - 1) / TS;
+    if(int rc = smem_opt_in(c, potrf_gemm_level<NL>))
+      return rc;
+    CUDA_TRY(c, cudaFuncSetAttribute(potrf_solve_level<NL>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+    CUDA_TRY(c, cudaMemsetAsync(status, 0xFF, (size_t)nstatus * sizeof(int), c->stream));
+    const int T = (sizes[0] + TS - 1) / TS;
     c->kt_begin(label);
     for(int Jt = 0; Jt < T; ++Jt)
       {
-        potrf_big_kernel<NL><<<1, 256, TILE_SMEM, c->stream>>>(d, Jt, 0, status);
-        if(T - Jt - 1 > 0)
-          potrf_big_kernel<NL><<<T - Jt - 1, 256, TILE_SMEM, c->stream>>>(d, Jt, 1, status);
-        c->launches += (T - Jt - 1 > 0) ? 2 : 1;
+        const int n = alive(sizes, Jt), nbelow = alive(sizes, Jt + 1);
+        potrf_diag_level<NL><<<n, 256, TILE_SMEM, c->stream>>>(d, Jt, status);
+        ++c->launches;
+        if(nbelow == 0)
+          continue;
+        const int rows_below = sizes[0] - (Jt + 1) * TS;
+        if(Jt > 0)
+          {
+            dim3 g(nbelow, (rows_below + TS - 1) / TS);
+            potrf_gemm_level<NL><<<g, 256, TILE_SMEM, c->stream>>>(d, Jt, status);
+            ++c->launches;
+          }
+        dim3 g2(nbelow, (rows_below + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
+        potrf_solve_level<NL><<<g2, ROWS_PER_CTA, DIAG_SMEM, c->stream>>>(d, Jt, status);
+        ++c->launches;
       }
     c->kt_end();
     --c->launches; // kt_end counted one
     CUDA_TRY(c, cudaGetLastError());
     return 0;
   }
+  // batched X <- L^{-1} B, level-synchronous; sizes sorted descending
   static int trsm(sdpb_b200_ctx *c, const char *label, const TrsmTileDesc *d,
-                  int count, int slabs)
+                  const std::vector<int> &sizes, int maxcols)
   {
-    if(count == 0 || slabs == 0)
+    if(sizes.empty() || sizes[0] == 0 || maxcols == 0)
       return 0;
-    if(int rc = smem_opt_in(c, trsm_tile_kernel<NL>))
+    if(int rc = smem_opt_in(c, trsm_gemm_level<NL>))
       return rc;
+    CUDA_TRY(c, cudaFuncSetAttribute(trsm_diag_level<NL>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+    const int T = (sizes[0] + TS - 1) / TS;
     c->kt_begin(label);
-    trsm_tile_kernel<NL><<<slabs, 256, TILE_SMEM, c->stream>>>(d, count);
+    for(int It = 0; It < T; ++It)
+      {
+        const int n = alive(sizes, It);
+        if(It > 0)
+          {
+            dim3 g(n, (maxcols + TS - 1) / TS);
+            trsm_gemm_level<NL><<<g, 256, TILE_SMEM, c->stream>>>(d, It);
+            ++c->launches;
+          }
+        dim3 g2(n, (maxcols + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
+        trsm_diag_level<NL><<<g2, ROWS_PER_CTA, DIAG_SMEM, c->stream>>>(d, It);
+        ++c->launches;
+      }
     c->kt_end();
+    --c->launches;
     CUDA_TRY(c, cudaGetLastError());
     return 0;
   }
@@ -82,7 +113,7 @@ template <int NL> struct Launch
   static int cholesky(sdpb_b200_ctx *c, int which)
   {
     return potrf(c, which == 0 ? "potrf_X" : "potrf_Y", which == 0 ? c->d_potrfX : c->d_potrfY,
-                 2 * c->J, c->d_status + which * 2 * c->J);
+                 c->szXY, c->d_status + which * 2 * c->J, 2 * c->J);
   }
   static int pairings(sdpb_b200_ctx *c)
   {
@@ -92,7 +123,7 @@ template <int NL> struct Launch
     // T = V ; T <- L_X^{-1} T ; AX = T^T T
     CUDA_TRY(c, cudaMemcpyAsync(c->T, c->V, c->wV * 8, cudaMemcpyDeviceToDevice,
                                 c->stream));
-    int rc = trsm(c, "trsm_LXinv_V", c->d_trsmT, c->n_trsmT, c->slabs_T);
+    int rc = trsm(c, "trsm_LXinv_V", c->d_trsmT, c->szT, c->max_mn);
     if(rc)
       return rc;
     rc = gemm(c, "gemm_A_X_inv", c->d_gemmAX, c->n_gemm, c->tiles_AX);
@@ -118,13 +149,13 @@ template <int NL> struct Launch
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
     // Cholesky(S_j), P = L^{-1} B
-    int rc = potrf(c, "potrf_S", c->d_potrfS, J, c->d_status + 4 * J);
+    int rc = potrf(c, "potrf_S", c->d_potrfS, c->szS, c->d_status + 4 * J, J);
     if(rc)
       return rc;
     if(J)
       CUDA_TRY(c, cudaMemcpyAsync(c->Pband, c->B, c->wB * 8,
                                   cudaMemcpyDeviceToDevice, st));
-    rc = trsm(c, "trsm_Linv_B", c->d_trsmP, c->n_trsmP, c->slabs_P);
+    rc = trsm(c, "trsm_Linv_B", c->d_trsmP, c->szP, N);
     if(rc)
       return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[4], st));
@@ -141,14 +172,14 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaGetLastError());
       }
     c->kt_begin("norm_final_kernel");
-    norm_final_kernel<NL><<<(N + 63) / 64, 64, 0, st>>>(c->part, J, N, c->norms);
+    norm_final_kernel<NL><<<(N + 63) / 64, 64, 0, st>>>(c->part, J, N, c->norms, c->recipN);
     c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
     if(J)
       {
         dim3 g2(J, (unsigned)std::min<long>(((long)c->max_P * N + 127) / 128, 65535));
         c->kt_begin("normalize_kernel");
-        normalize_kernel<NL><<<g2, 128, 0, st>>>(c->d_bands, N, c->K, c->norms,
+        normalize_kernel<NL><<<g2, 128, 0, st>>>(c->d_bands, N, c->K, c->norms, c->recipN,
                                                  c->prec, c->crt, c->R,
                                                  c->d_flags);
         c->kt_end();
@@ -181,7 +212,7 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaGetLastError());
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[7], st));
-    rc = potrf_big(c, "potrf_Q", c->potrfQ, c->d_status + 5 * J);
+    rc = potrf(c, "potrf_Q", c->d_potrfQ, c->szQ, c->d_status + 5 * J, 1);
     if(rc)
       return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[8], st));

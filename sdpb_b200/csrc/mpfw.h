@@ -177,13 +177,11 @@ template <int NL> MPFW_D void set_zero(Reg<NL> &r)
 }
 // packed element (mpfx::load layout) viewed as 32-bit words:
 // [exp, sign, w0 .. w(2NL-1), pad]
+template <int NL>
+MPFW_D void load_packed(int32_t &exp, int32_t &sign, uint32_t (&w)[2 * NL], const uint32_t *p);
 template <int NL> MPFW_D void load(Reg<NL> &r, const uint32_t *p)
 {
-  r.exp = (int32_t)p[0];
-  r.sign = (int32_t)p[1];
-#pragma unroll
-  for(int i = 0; i < 2 * NL; ++i)
-    r.w[i] = p[2 + i];
+  load_packed<NL>(r.exp, r.sign, r.w, p);
 }
 template <int NL> MPFW_D void store(uint32_t *p, const Reg<NL> &r)
 {
@@ -324,8 +322,37 @@ MPFW_NOINLINE Reg<NL> addsub_generic(Reg<NL> acc, Reg<NL> v, int vsign)
   return out;
 }
 
+// r = u + (s ^ mask) + cin over N words (mask = 0 / ~0 and cin = 0 / 1 give
+// u + s and u - s); returns the carry out
+template <int N>
+MPFW_D uint32_t addx_n(uint32_t (&r)[N], const uint32_t (&u)[N], const uint32_t (&s)[N],
+                       uint32_t mask)
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t dummy;
+  asm volatile("add.cc.u32 %0, %1, 1;" : "=r"(dummy) : "r"(mask)); // CC = (mask == ~0)
+#pragma unroll
+  for(int i = 0; i < N; ++i)
+    asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r[i]) : "r"(u[i]), "r"(s[i] ^ mask));
+  uint32_t c;
+  asm volatile("addc.u32 %0, 0, 0;" : "=r"(c));
+  return c;
+#else
+  uint64_t c = mask & 1u;
+  for(int i = 0; i < N; ++i)
+    {
+      const uint64_t t = (uint64_t)u[i] + (s[i] ^ mask) + c;
+      r[i] = (uint32_t)t;
+      c = t >> 32;
+    }
+  return (uint32_t)c;
+#endif
+}
+
 // acc <- mpf_add(acc, v) with v's sign replaced by vsign (so the same routine
-// serves mpf_sub).  Both operands non-zero is NOT required.
+// serves mpf_sub).  One code path for both magnitude-add and magnitude-subtract
+// (the lanes of a warp disagree on the sign all the time); only the rare
+// post-processing steps branch.
 template <int NL> MPFW_D void add_signed(Reg<NL> &acc, const Reg<NL> &v, int vsign)
 {
   if(vsign == 0)
@@ -336,11 +363,14 @@ template <int NL> MPFW_D void add_signed(Reg<NL> &acc, const Reg<NL> &v, int vsi
       acc.sign = vsign;
       return;
     }
-  // u = operand with the larger exponent
+  // u = operand with the larger exponent, s = the other one
   const bool swap = acc.exp < v.exp;
+  const bool sub = acc.sign != vsign;
   const int32_t uexp = swap ? v.exp : acc.exp;
   const int32_t usign = swap ? vsign : acc.sign;
   const int64_t ediff64 = swap ? (int64_t)v.exp - acc.exp : (int64_t)acc.exp - v.exp;
+  // add: s is ignored from ediff = NL-1 on; sub: from ediff = NL on (r = u):
+  // s is cleared explicitly for ediff >= NL, smaller shifts go through the shifter
   const int ediff = ediff64 > NL ? NL : (int)ediff64;
   uint32_t u[2 * NL], s[2 * NL];
 #pragma unroll
@@ -349,32 +379,7 @@ template <int NL> MPFW_D void add_signed(Reg<NL> &acc, const Reg<NL> &v, int vsi
       u[i] = swap ? v.w[i] : acc.w[i];
       s[i] = swap ? acc.w[i] : v.w[i];
     }
-  if(acc.sign == vsign)
-    {
-      // ---- magnitudes add: window = top P limbs of u (GMP mpf_add) ----
-      if(ediff >= NL - 1)
-        {
-#pragma unroll
-          for(int i = 0; i < 2 * NL; ++i)
-            s[i] = 0;
-        }
-      else
-        shr_limbs<NL>(s, ediff);
-      u[0] = u[1] = 0;
-      s[0] = s[1] = 0;
-      uint32_t r[2 * NL];
-      const uint32_t cy = add_n<2 * NL>(r, u, s);
-#pragma unroll
-      for(int i = 0; i < 2 * NL - 2; ++i)
-        acc.w[i] = cy ? r[i + 2] : r[i];
-      acc.w[2 * NL - 2] = cy ? 1u : r[2 * NL - 2];
-      acc.w[2 * NL - 1] = cy ? 0u : r[2 * NL - 1];
-      acc.exp = uexp + (int32_t)cy;
-      acc.sign = usign;
-      return;
-    }
-  // ---- magnitudes subtract (GMP mpf_sub) ----
-  if(ediff == 1)
+  if(sub && ediff == 1)
     {
       // "extremely close" path of mpf_sub keeps v's lowest limb; rare
       const bool close = u[2 * NL - 1] == 0 && u[2 * NL - 2] == 1
@@ -389,45 +394,84 @@ template <int NL> MPFW_D void add_signed(Reg<NL> &acc, const Reg<NL> &v, int vsi
           return;
         }
     }
-  if(ediff >= NL)
+  // align: s >>= ediff limbs (the two low stages inline, the high ones only when needed)
+#pragma unroll
+  for(int st = 1; st < NL && st <= 2; st <<= 1)
     {
-      // v lies completely below the window: r = u
+      const bool on = (ediff & st) != 0;
 #pragma unroll
       for(int i = 0; i < 2 * NL; ++i)
-        acc.w[i] = u[i];
-      acc.exp = uexp;
-      acc.sign = usign;
-      return;
+        {
+          const uint32_t hi = (i + 2 * st < 2 * NL) ? s[i + 2 * st] : 0u;
+          s[i] = on ? hi : s[i];
+        }
     }
-  shr_limbs<NL>(s, ediff);
-  uint32_t r[2 * NL];
-  const uint32_t bw = sub_n<2 * NL>(r, u, s);
-  int32_t rsign = usign;
-  if(bw)
+  if(ediff >= 4)
     {
-      // only possible for ediff == 0: |v| > |u|
-      neg_n<2 * NL>(r);
-      rsign = -usign;
-    }
-  int32_t rexp = uexp;
-  if((r[2 * NL - 1] | r[2 * NL - 2]) == 0)
-    {
-      // strip leading zero limbs
-      int z = 0;
-      bool run = true;
+      if(ediff64 >= NL)
+        {
 #pragma unroll
-      for(int l = NL - 1; l >= 0; --l)
-        {
-          run = run && (r[2 * l] | r[2 * l + 1]) == 0;
-          z += run ? 1 : 0;
+          for(int i = 0; i < 2 * NL; ++i)
+            s[i] = 0;
         }
-      if(z == NL)
+#pragma unroll
+      for(int st = 4; st < NL; st <<= 1)
         {
-          set_zero(acc);
-          return;
+          const bool on = (ediff & st) != 0;
+#pragma unroll
+          for(int i = 0; i < 2 * NL; ++i)
+            {
+              const uint32_t hi = (i + 2 * st < 2 * NL) ? s[i + 2 * st] : 0u;
+              s[i] = on ? hi : s[i];
+            }
         }
-      shl_limbs<NL>(r, z);
-      rexp -= z;
+    }
+  // mpf_add works on the top P limbs only: drop the lowest limb of both
+  if(!sub)
+    u[0] = u[1] = s[0] = s[1] = 0;
+  uint32_t r[2 * NL];
+  const uint32_t cy = addx_n<2 * NL>(r, u, s, sub ? 0xFFFFFFFFu : 0u);
+  int32_t rexp = uexp, rsign = usign;
+  if(!sub)
+    {
+      if(cy)
+        {
+          // a new top limb "1": everything moves down one limb
+#pragma unroll
+          for(int i = 0; i < 2 * NL - 2; ++i)
+            r[i] = r[i + 2];
+          r[2 * NL - 2] = 1u;
+          r[2 * NL - 1] = 0u;
+          rexp += 1;
+        }
+    }
+  else
+    {
+      if(!cy)
+        {
+          // borrow: only possible for ediff == 0 with |s| > |u|
+          neg_n<2 * NL>(r);
+          rsign = -usign;
+        }
+      if((r[2 * NL - 1] | r[2 * NL - 2]) == 0)
+        {
+          // strip leading zero limbs
+          int z = 0;
+          bool run = true;
+#pragma unroll
+          for(int l = NL - 1; l >= 0; --l)
+            {
+              run = run && (r[2 * l] | r[2 * l + 1]) == 0;
+              z += run ? 1 : 0;
+            }
+          if(z == NL)
+            {
+              set_zero(acc);
+              return;
+            }
+          shl_limbs<NL>(r, z);
+          rexp -= z;
+        }
     }
 #pragma unroll
   for(int i = 0; i < 2 * NL; ++i)
@@ -439,22 +483,46 @@ template <int NL> MPFW_D void add_signed(Reg<NL> &acc, const Reg<NL> &v, int vsi
 // acc <- acc + a*b (negate == false) or acc - a*b (negate == true), one
 // mpf_mul followed by one mpf_add / mpf_sub.  a, b: packed elements as 32-bit
 // words (shared or global memory).
+// header and mantissa words of a packed element (16-byte aligned): 128-bit loads
+template <int NL>
+MPFW_D void load_packed(int32_t &exp, int32_t &sign, uint32_t (&w)[2 * NL], const uint32_t *p)
+{
+#if defined(__CUDA_ARCH__)
+  constexpr int EW = 2 * ((NL + 2) & ~1);
+  uint32_t t[EW];
+  const uint4 *p4 = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+  for(int q = 0; q < EW / 4; ++q)
+    {
+      const uint4 x = p4[q];
+      t[4 * q] = x.x;
+      t[4 * q + 1] = x.y;
+      t[4 * q + 2] = x.z;
+      t[4 * q + 3] = x.w;
+    }
+  exp = (int32_t)t[0];
+  sign = (int32_t)t[1];
+#pragma unroll
+  for(int i = 0; i < 2 * NL; ++i)
+    w[i] = t[2 + i];
+#else
+  exp = (int32_t)p[0];
+  sign = (int32_t)p[1];
+  for(int i = 0; i < 2 * NL; ++i)
+    w[i] = p[2 + i];
+#endif
+}
 template <int NL>
 MPFW_D void mac(Reg<NL> &acc, const uint32_t *a, const uint32_t *b, bool negate)
 {
-  const int32_t asign = (int32_t)a[1], bsign = (int32_t)b[1];
+  int32_t aexp, asign, bexp, bsign;
+  uint32_t aw[2 * NL], bw[2 * NL];
+  load_packed<NL>(aexp, asign, aw, a);
+  load_packed<NL>(bexp, bsign, bw, b);
   if(asign == 0 || bsign == 0)
     return; // 0 * x = 0 and c + 0 = c exactly in mpf
-  uint32_t aw[2 * NL], bw[2 * NL];
-#pragma unroll
-  for(int i = 2; i < 2 * NL; ++i)
-    {
-      aw[i] = a[2 + i];
-      bw[i] = b[2 + i];
-    }
-  aw[0] = aw[1] = bw[0] = bw[1] = 0; // lowest limb: not used by mpf_mul
   Reg<NL> p;
-  mul<NL>(p, asign, (int32_t)a[0], aw, bsign, (int32_t)b[0], bw);
+  mul<NL>(p, asign, aexp, aw, bsign, bexp, bw);
   add_signed<NL>(acc, p, negate ? -p.sign : p.sign);
 }
 template <int NL>
@@ -499,6 +567,25 @@ MPFW_D void reciprocal(uint32_t (&R)[2 * NL + 4], const mpfx::Num<NL> &d)
       R[2 * i] = (uint32_t)q[i];
       R[2 * i + 1] = (uint32_t)(q[i] >> 32);
     }
+}
+
+// `x /= 4` of compute_schur_complement.cxx:102 (mpfx::div4): mantissa shifted
+// right by two bits, a vanished top limb stripped
+template <int NL> MPFW_D void div4(Reg<NL> &x)
+{
+  if(x.sign == 0)
+    return;
+  uint32_t q[2 * NL];
+#pragma unroll
+  for(int i = 0; i < 2 * NL; ++i)
+    q[i] = (x.w[i] >> 2) | (i + 1 < 2 * NL ? (x.w[i + 1] << 30) : 0u);
+  const bool adj = (q[2 * NL - 1] | q[2 * NL - 2]) == 0;
+#pragma unroll
+  for(int i = 2 * NL - 1; i >= 2; --i)
+    x.w[i] = adj ? q[i - 2] : q[i];
+  x.w[1] = adj ? 0u : q[1];
+  x.w[0] = adj ? 0u : q[0];
+  x.exp -= adj ? 1 : 0;
 }
 
 // ------------------------------------------------- fast reciprocal and sqrt

@@ -38,6 +38,41 @@ template <int NL> struct TileGeom
   static constexpr int RS = (RW + 3) & ~3;                  // reciprocal stride (16-byte multiple)
 };
 
+// The big arithmetic bodies are kept out of line (one copy per precision): the
+// accumulator travels in registers through the call, the ~70 register moves
+// are a few percent of a multiply-accumulate, and compile time and code size
+// stay bounded at 1536 bits.
+template <int NL>
+__device__ __noinline__ Reg<NL> mac_nl(Reg<NL> acc, const uint32_t *a, const uint32_t *b,
+                                       bool negate)
+{
+  mpfw::mac<NL>(acc, a, b, negate);
+  return acc;
+}
+// x / pivot, pivot given as a packed element, R its reciprocal
+template <int NL>
+__device__ __noinline__ Reg<NL> div_nl(Reg<NL> x, const uint32_t *piv, const uint32_t *R)
+{
+  mpfw::div_recip<NL>(x, (int32_t)piv[1], (int32_t)piv[0], piv + 2, R);
+  return x;
+}
+template <int NL> __device__ __noinline__ Reg<NL> sqrt_nl(Reg<NL> a)
+{
+  Reg<NL> r;
+  mpfw::sqrt_fast<NL>(r, a);
+  return r;
+}
+template <int NL> struct RecipWords
+{
+  uint32_t w[2 * NL + 4];
+};
+template <int NL> __device__ __noinline__ RecipWords<NL> recip_nl(Reg<NL> a)
+{
+  RecipWords<NL> r;
+  mpfw::reciprocal_fast<NL>(r.w, a);
+  return r;
+}
+
 // ------------------------------------------------------------ TMA / mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -142,7 +177,7 @@ __device__ __forceinline__ void tile_k_loop(Reg<NL> &acc, bool negate, const Ope
         {
           const uint32_t *pa = sm.a[s] + ti * G::SW, *pb = sm.b[s] + tj * G::SW;
           for(int kk = 0; kk < kcnt; ++kk)
-            mpfw::mac<NL>(acc, pa + kk * TS * G::SW, pb + kk * TS * G::SW, negate);
+            acc = mac_nl<NL>(acc, pa + kk * TS * G::SW, pb + kk * TS * G::SW, negate);
         }
       __syncthreads();
     }
@@ -254,11 +289,9 @@ __device__ __forceinline__ bool potrf_diag_tile(Reg<NL> &acc, const PotrfDesc &d
             sm.bad = J0 + kk;
           else
             {
-              Reg<NL> root;
-              mpfw::sqrt_fast<NL>(root, acc);
-              acc = root;
-              uint32_t R[G::RW];
-              mpfw::reciprocal_fast<NL>(R, acc);
+              acc = sqrt_nl<NL>(acc);
+              const RecipWords<NL> rw = recip_nl<NL>(acc);
+              const uint32_t(&R)[G::RW] = rw.w;
               uint32_t *rs = sm.recip + kk * G::RS;
               uint32_t *rg = d.recip + (long)(J0 + kk) * G::RS;
 #pragma unroll
@@ -276,12 +309,12 @@ __device__ __forceinline__ bool potrf_diag_tile(Reg<NL> &acc, const PotrfDesc &d
       if(tj == kk && ti > kk && ti < nd)
         {
           const uint32_t *piv = sm.diag + (kk * TS + kk) * G::SW;
-          mpfw::div_recip<NL>(acc, (int32_t)piv[1], (int32_t)piv[0], piv + 2, sm.recip + kk * G::RS);
+          acc = div_nl<NL>(acc, piv, sm.recip + kk * G::RS);
           mpfw::store<NL>(sm.diag + (kk * TS + ti) * G::SW, acc);
         }
       __syncthreads();
       if(ti > kk && tj > kk && ti >= tj && ti < nd)
-        mpfw::mac<NL>(acc, sm.diag + (kk * TS + ti) * G::SW, sm.diag + (kk * TS + tj) * G::SW, true);
+        acc = mac_nl<NL>(acc, sm.diag + (kk * TS + ti) * G::SW, sm.diag + (kk * TS + tj) * G::SW, true);
     }
   // write the tile: factor below/on the diagonal, exact zeros above
   if(ti < nd && tj < nd)
@@ -314,12 +347,12 @@ __device__ __forceinline__ void potrf_row_tile_solve(Reg<NL> &acc, const PotrfDe
       if(tj == kk && ti < ni)
         {
           const uint32_t *piv = sm.diag + (kk * TS + kk) * G::SW;
-          mpfw::div_recip<NL>(acc, (int32_t)piv[1], (int32_t)piv[0], piv + 2, sm.recip + kk * G::RS);
+          acc = div_nl<NL>(acc, piv, sm.recip + kk * G::RS);
           mpfw::store<NL>(xs + ti * G::SW, acc);
         }
       __syncthreads();
       if(tj > kk && tj < nd && ti < ni)
-        mpfw::mac<NL>(acc, xs + ti * G::SW, sm.diag + (kk * TS + tj) * G::SW, true);
+        acc = mac_nl<NL>(acc, xs + ti * G::SW, sm.diag + (kk * TS + tj) * G::SW, true);
     }
   if(ti < ni && tj < nd)
     {
@@ -372,74 +405,119 @@ __device__ __forceinline__ void potrf_tile_update(Reg<NL> &acc, const PotrfDesc 
   tile_k_loop<NL>(acc, true, A, B, J0, sm, it, active);
 }
 
-// One CTA factors one matrix (left-looking by block column).
+// ---- level-synchronous batched Cholesky --------------------------------
+// Block column Jt of every matrix of the batch is finished by three launches:
+//   potrf_diag_level   one CTA per matrix: update + factor the diagonal tile
+//   potrf_gemm_level   one CTA per tile below it: a_ij -= sum_{k<J0} l_ik l_jk
+//   potrf_solve_level  one THREAD per row below it: the 16 unknowns of that row
+//                      against the factored diagonal tile (16 divisions and 120
+//                      multiply-accumulates, sequential by nature, so rows are
+//                      the parallel dimension)
+// `descs` is sorted by size (largest first); grid.x covers the prefix of
+// matrices that still have a block column Jt.
 template <int NL>
-__global__ void __launch_bounds__(256, 2) potrf_tile_kernel(const PotrfDesc *descs, int *status)
+__global__ void __launch_bounds__(256, 2)
+potrf_diag_level(const PotrfDesc *descs, int Jt, int *status)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
   const PotrfDesc d = descs[blockIdx.x];
-  if(d.s == 0)
+  if(Jt * TS >= d.s || status[d.id] >= 0)
+    return;
+  tile_smem_init(sm);
+  uint32_t it = 0;
+  Reg<NL> acc;
+  potrf_tile_update<NL>(acc, d, Jt, Jt, sm, it);
+  if(!potrf_diag_tile<NL>(acc, d, Jt, sm))
     {
       if(threadIdx.x == 0)
-        status[d.id] = -1;
-      return;
+        status[d.id] = sm.bad;
     }
-  tile_smem_init(sm);
-  const int T = (d.s + TS - 1) / TS;
-  uint32_t it = 0;
-  Reg<NL> acc;
-  for(int Jt = 0; Jt < T; ++Jt)
-    {
-      potrf_tile_update<NL>(acc, d, Jt, Jt, sm, it);
-      if(!potrf_diag_tile<NL>(acc, d, Jt, sm))
-        {
-          if(threadIdx.x == 0)
-            status[d.id] = sm.bad;
-          return;
-        }
-      __syncthreads();
-      for(int It = Jt + 1; It < T; ++It)
-        {
-          potrf_tile_update<NL>(acc, d, It, Jt, sm, it);
-          potrf_row_tile_solve<NL>(acc, d, It, Jt, sm);
-          __syncthreads();
-        }
-      // the finished block column is read back through TMA by later columns
-      fence_async_proxy();
-      __syncthreads();
-    }
-  if(threadIdx.x == 0)
-    status[d.id] = -1;
 }
-
-// Large matrix (Q): one launch per block column and phase.
-// phase 0: the diagonal tile (1 CTA); phase 1: the row tiles below (T-Jt-1 CTAs).
 template <int NL>
 __global__ void __launch_bounds__(256, 2)
-potrf_big_kernel(PotrfDesc d, int Jt, int phase, int *status)
+potrf_gemm_level(const PotrfDesc *descs, int Jt, const int *status)
 {
+  typedef TileGeom<NL> G;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
-  if(*status >= 0)
-    return; // an earlier pivot already failed
+  const PotrfDesc d = descs[blockIdx.x];
+  const int It = Jt + 1 + blockIdx.y;
+  if(It * TS >= d.s || status[d.id] >= 0)
+    return;
   tile_smem_init(sm);
   uint32_t it = 0;
   Reg<NL> acc;
-  if(phase == 0)
-    {
-      potrf_tile_update<NL>(acc, d, Jt, Jt, sm, it);
-      if(!potrf_diag_tile<NL>(acc, d, Jt, sm))
-        {
-          if(threadIdx.x == 0)
-            *status = sm.bad;
-        }
-      return;
-    }
-  const int It = Jt + 1 + blockIdx.x;
   potrf_tile_update<NL>(acc, d, It, Jt, sm, it);
-  load_diag_tile<NL>(d.A, d.si, d.sj, d.recip, d.s, Jt, sm);
-  potrf_row_tile_solve<NL>(acc, d, It, Jt, sm);
+  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  if(It * TS + ti < d.s && Jt * TS + tj < d.s)
+    stg_reg<NL>(d.A + ((long)(It * TS + ti) * d.si + (long)(Jt * TS + tj) * d.sj) * G::ES, acc);
+}
+
+template <int NL> struct DiagSmem
+{
+  typedef TileGeom<NL> G;
+  uint32_t diag[TS * TS * G::SW]; // [k][x] = L(J0+x, J0+k)
+  uint32_t recip[TS * G::RS];
+};
+// cooperative load of a factored diagonal tile and its reciprocals
+template <int NL>
+__device__ __forceinline__ void load_diag(DiagSmem<NL> &sm, const uint64_t *A, long si, long sj,
+                                          const uint32_t *recip, int s, int Jt)
+{
+  typedef TileGeom<NL> G;
+  const int J0 = Jt * TS, nd = min(TS, s - J0);
+  for(int e = threadIdx.x; e < TS * TS; e += blockDim.x)
+    {
+      const int x = e & (TS - 1), k = e >> 4;
+      if(x < nd && k < nd && x >= k)
+        {
+          const uint4 *src = reinterpret_cast<const uint4 *>(
+            A + ((long)(J0 + x) * si + (long)(J0 + k) * sj) * G::ES);
+          uint4 *dst = reinterpret_cast<uint4 *>(sm.diag + (k * TS + x) * G::SW);
+#pragma unroll
+          for(int w = 0; w < G::EB / 16; ++w)
+            dst[w] = src[w];
+        }
+    }
+  for(int w = threadIdx.x; w < nd * G::RS; w += blockDim.x)
+    sm.recip[w] = recip[(long)J0 * G::RS + w];
+  __syncthreads();
+}
+
+constexpr int ROWS_PER_CTA = 128;
+template <int NL>
+__global__ void __launch_bounds__(ROWS_PER_CTA, 4)
+potrf_solve_level(const PotrfDesc *descs, int Jt, const int *status)
+{
+  typedef TileGeom<NL> G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  DiagSmem<NL> &sm = *reinterpret_cast<DiagSmem<NL> *>(smem_raw);
+  const PotrfDesc d = descs[blockIdx.x];
+  const int J0 = Jt * TS;
+  const int row0 = J0 + TS + blockIdx.y * ROWS_PER_CTA;
+  if(row0 >= d.s || status[d.id] >= 0)
+    return;
+  load_diag<NL>(sm, d.A, d.si, d.sj, d.recip, d.s, Jt);
+  const int row = row0 + threadIdx.x;
+  if(row >= d.s)
+    return;
+  Reg<NL> z;
+  mpfw::set_zero(z);
+  for(int kk = 0; kk < TS; ++kk) // the diagonal tile is full here (rows exist below it)
+    {
+      uint64_t *mine = d.A + ((long)row * d.si + (long)(J0 + kk) * d.sj) * G::ES;
+      Reg<NL> acc;
+      ldg_reg<NL>(acc, mine);
+      for(int k = 0; k < kk; ++k)
+        acc = mac_nl<NL>(acc,
+                         reinterpret_cast<const uint32_t *>(
+                           d.A + ((long)row * d.si + (long)(J0 + k) * d.sj) * G::ES),
+                         sm.diag + (k * TS + kk) * G::SW, true);
+      acc = div_nl<NL>(acc, sm.diag + (kk * TS + kk) * G::SW, sm.recip + kk * G::RS);
+      stg_reg<NL>(mine, acc);
+      stg_reg<NL>(d.A + ((long)(J0 + kk) * d.si + (long)row * d.sj) * G::ES, z);
+    }
 }
 
 // -------------------------------------------------------- triangular solve
@@ -449,70 +527,64 @@ struct TrsmTileDesc // X <- L^{-1} B in place, L lower p x p (column-major)
   const uint32_t *recip; // reciprocals of diag(L)
   uint64_t *B;           // p x ncols, column-major, ld = p
   int p, ncols;
-  int slab0; // first linear slab index of this matrix in the launch
 };
 
-// grid.x = total number of 16-column slabs; each CTA sweeps the row tiles of
-// its slab top to bottom.
+// Row tile It of every solve of the batch (sorted by p, largest first):
+//   trsm_gemm_level  16x16 tiles: b_ic -= sum_{k<I0} l_ik x_kc
+//   trsm_diag_level  one THREAD per column: the 16 rows of the tile top to bottom
 template <int NL>
-__global__ void __launch_bounds__(256, 2)
-trsm_tile_kernel(const TrsmTileDesc *descs, int count)
+__global__ void __launch_bounds__(256, 2) trsm_gemm_level(const TrsmTileDesc *descs, int It)
 {
   typedef TileGeom<NL> G;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
-  int lo = 0, hi = count - 1;
-  while(lo < hi)
-    {
-      const int mid = (lo + hi + 1) >> 1;
-      if(descs[mid].slab0 <= (int)blockIdx.x)
-        lo = mid;
-      else
-        hi = mid - 1;
-    }
-  const TrsmTileDesc d = descs[lo];
-  const int c0 = (blockIdx.x - d.slab0) * TS;
-  if(c0 >= d.ncols || d.p == 0)
+  const TrsmTileDesc d = descs[blockIdx.x];
+  const int c0 = blockIdx.y * TS, I0 = It * TS;
+  if(I0 >= d.p || c0 >= d.ncols)
     return;
   tile_smem_init(sm);
   const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
-  const int nc = min(TS, d.ncols - c0);
-  const int T = (d.p + TS - 1) / TS;
+  const int nc = min(TS, d.ncols - c0), ni = min(TS, d.p - I0);
+  const bool active = ti < ni && tj < nc;
+  Reg<NL> acc;
+  uint64_t *mine = d.B + ((long)(c0 + tj) * d.p + I0 + ti) * G::ES;
+  if(active)
+    ldg_reg<NL>(acc, mine);
+  else
+    mpfw::set_zero(acc);
   uint32_t it = 0;
-  for(int It = 0; It < T; ++It)
+  Operand A{d.L + (long)I0 * G::ES, 1, d.p, ni};
+  Operand B{d.B + (long)c0 * d.p * G::ES, d.p, 1, nc};
+  tile_k_loop<NL>(acc, true, A, B, I0, sm, it, active);
+  if(active)
+    stg_reg<NL>(mine, acc);
+}
+template <int NL>
+__global__ void __launch_bounds__(ROWS_PER_CTA, 4)
+trsm_diag_level(const TrsmTileDesc *descs, int It)
+{
+  typedef TileGeom<NL> G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  DiagSmem<NL> &sm = *reinterpret_cast<DiagSmem<NL> *>(smem_raw);
+  const TrsmTileDesc d = descs[blockIdx.x];
+  const int I0 = It * TS, col0 = blockIdx.y * ROWS_PER_CTA;
+  if(I0 >= d.p || col0 >= d.ncols)
+    return;
+  load_diag<NL>(sm, d.L, 1, d.p, d.recip, d.p, It);
+  const int col = col0 + threadIdx.x;
+  if(col >= d.ncols)
+    return;
+  const int ni = min(TS, d.p - I0);
+  uint64_t *colp = d.B + ((long)col * d.p + I0) * G::ES;
+  for(int ii = 0; ii < ni; ++ii)
     {
-      const int I0 = It * TS, ni = min(TS, d.p - I0);
-      const bool active = ti < ni && tj < nc;
       Reg<NL> acc;
-      uint64_t *mine = d.B + ((long)(c0 + tj) * d.p + I0 + ti) * G::ES;
-      if(active)
-        ldg_reg<NL>(acc, mine);
-      else
-        mpfw::set_zero(acc);
-      // b_i -= sum_{k < I0} l_ik x_k
-      Operand A{d.L + (long)I0 * G::ES, 1, d.p, ni};
-      Operand B{d.B + (long)c0 * d.p * G::ES, d.p, 1, nc};
-      tile_k_loop<NL>(acc, true, A, B, I0, sm, it, active);
-      // the 16 rows of this tile, top to bottom
-      load_diag_tile<NL>(d.L, 1, d.p, d.recip, d.p, It, sm);
-      for(int kk = 0; kk < ni; ++kk)
-        {
-          uint32_t *xs = sm.vec[kk & 1];
-          if(ti == kk && tj < nc)
-            {
-              const uint32_t *piv = sm.diag + (kk * TS + kk) * G::SW;
-              mpfw::div_recip<NL>(acc, (int32_t)piv[1], (int32_t)piv[0], piv + 2,
-                                  sm.recip + kk * G::RS);
-              mpfw::store<NL>(xs + tj * G::SW, acc);
-            }
-          __syncthreads();
-          if(ti > kk && active)
-            mpfw::mac<NL>(acc, sm.diag + (kk * TS + ti) * G::SW, xs + tj * G::SW, true);
-        }
-      if(active)
-        stg_reg<NL>(mine, acc);
-      fence_async_proxy();
-      __syncthreads();
+      ldg_reg<NL>(acc, colp + (long)ii * G::ES);
+      for(int kk = 0; kk < ii; ++kk)
+        acc = mac_nl<NL>(acc, sm.diag + (kk * TS + ii) * G::SW,
+                         reinterpret_cast<const uint32_t *>(colp + (long)kk * G::ES), true);
+      acc = div_nl<NL>(acc, sm.diag + (ii * TS + ii) * G::SW, sm.recip + ii * G::RS);
+      stg_reg<NL>(colp + (long)ii * G::ES, acc);
     }
 }
 } // namespace sdpb_b200

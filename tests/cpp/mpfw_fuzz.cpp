@@ -53,7 +53,7 @@ template <int NL> static void random_num(mpfx::Num<NL> &x, int mode)
   if(x.d[NL - 1] == 0)
     x.d[NL - 1] = 1;
   x.sign = (rnd() & 1) ? 1 : -1;
-  x.exp = (int32_t)(rnd() % 7) - 3;
+  x.exp = (rnd() & 3) ? (int32_t)(rnd() % 7) - 3 : (int32_t)(rnd() % (4 * NL)) - 2 * NL;
   if(rnd() % 37 == 0)
     mpfx::set_zero(x);
 }
@@ -168,6 +168,20 @@ template <int NL> static long run(long iters)
                 u.d[0] ^= 1;
             }
         }
+      {
+        mpfx::Num<NL> w4, g4;
+        mpfx::div4(w4, u);
+        mpfw::Reg<NL> r4;
+        mpfw::from_num(r4, u);
+        mpfw::div4<NL>(r4);
+        mpfw::to_num(g4, r4);
+        if(!same(g4, w4))
+          {
+            if(dbad < 5)
+              printf("DIV4 MISMATCH NL=%d\n", NL);
+            ++dbad;
+          }
+      }
       mpfx::div(want, u, d);
       uint32_t R[2 * NL + 4];
       mpfw::reciprocal<NL>(R, d);
