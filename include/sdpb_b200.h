@@ -90,7 +90,7 @@ int sdpb_b200_cholesky_decomposition(sdpb_b200_ctx *ctx, int which,
                                      const uint64_t *const *A,
                                      uint64_t *const *L);
 
-/* compute_bilinear_pairings (run/compute_bilinear_pairings/*.cxx).  Uses the
+/* compute_bilinear_pairings (run/compute_bilinear_pairings/).  Uses the
  * device-resident X_cholesky of the preceding call and Y from the host.
  * Outputs (optional, may be NULL): for b = 2*j + parity the full symmetric
  * (m*n) x (m*n) matrices  V^T X^-1 V  and  V^T Y V ; the reference's tiles are
@@ -103,7 +103,7 @@ int sdpb_b200_compute_bilinear_pairings(sdpb_b200_ctx *ctx,
                                         uint64_t *const *A_Y);
 
 /* initialize_schur_complement_solver
- * (run/step/initialize_schur_complement_solver/*.cxx): S assembly, per-block
+ * (run/step/initialize_schur_complement_solver/): S assembly, per-block
  * Cholesky + L^-1 B, column normalisation, exact integer syrk, restore,
  * Cholesky(UPPER, Q).  Outputs (each may be NULL = keep on device only):
  *   schur_complement_cholesky[j]  P_j x P_j lower factor L_j

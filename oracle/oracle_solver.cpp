@@ -1,0 +1,88 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  The host solver of
+// sdpb_b200/csrc/host/solver.hpp (SDP_Solver::run/step, reference
+// src/sdp_solve/SDP_Solver/run/run.cxx:184-470) bound to the CPU oracle's hot
+// path (oracle_capi.cpp), so that the oracle can be replayed against the
+// reference's own end-to-end goldens (test/data/end-to-end_tests/*/output) on
+// a machine without a GPU.  tests/test_golden_trajectory.py is the caller.
+#include "../sdpb_b200/csrc/host/cli.hpp"
+#include "../sdpb_b200/csrc/host/hot_path_c.hpp"
+
+#include <cstring>
+
+struct oracle_ctx;
+extern "C" {
+int oracle_create(oracle_ctx **out, int prec_bits, int num_blocks, const int *dims, const int *num_points,
+                  int N);
+void oracle_destroy(oracle_ctx *c);
+const char *oracle_last_error(const oracle_ctx *c);
+int oracle_set_block(oracle_ctx *c, int j, const uint64_t *B, const uint64_t *bases_even,
+                     const uint64_t *bases_odd);
+int oracle_cholesky_decomposition(oracle_ctx *c, int which, const uint64_t *const *A, uint64_t *const *L);
+int oracle_compute_bilinear_pairings(oracle_ctx *c, const uint64_t *const *Y, uint64_t *const *A_X_inv,
+                                     uint64_t *const *A_Y);
+int oracle_initialize_schur_complement_solver(oracle_ctx *c, uint64_t *const *schur_complement_cholesky,
+                                              uint64_t *const *schur_off_diagonal, uint64_t *Q,
+                                              int32_t *block_timings_ms);
+}
+
+using namespace sdpb_host;
+
+static Hot_Path_Table oracle_table(const Block_Info &bi, const SDP &sdp, int prec)
+{
+  oracle_ctx *c = nullptr;
+  if(oracle_create(&c, prec, bi.num_blocks(), bi.dimensions.data(), bi.num_points.data(), sdp.N()))
+    throw std::runtime_error("oracle_create failed");
+  Hot_Path_Table t;
+  t.ctx = c;
+  t.set_block = [](void *x, int j, const uint64_t *B, const uint64_t *e, const uint64_t *o) {
+    return oracle_set_block((oracle_ctx *)x, j, B, e, o);
+  };
+  t.cholesky_decomposition = [](void *x, int which, const uint64_t *const *A, uint64_t *const *L) {
+    return oracle_cholesky_decomposition((oracle_ctx *)x, which, A, L);
+  };
+  t.compute_bilinear_pairings
+    = [](void *x, const uint64_t *const *Y, uint64_t *const *AX, uint64_t *const *AY) {
+        return oracle_compute_bilinear_pairings((oracle_ctx *)x, Y, AX, AY);
+      };
+  t.initialize_schur_complement_solver
+    = [](void *x, uint64_t *const *L, uint64_t *const *P, uint64_t *Q, int32_t *ms) {
+        return oracle_initialize_schur_complement_solver((oracle_ctx *)x, L, P, Q, ms);
+      };
+  t.last_error = [](const void *x) { return oracle_last_error((const oracle_ctx *)x); };
+  t.destroy = [](void *x) { oracle_destroy((oracle_ctx *)x); };
+  t.name = "cpu-oracle(libgmp)";
+  return t;
+}
+
+// argv: the reference's sdpb options (--sdpDir, --outDir, --precision, ...).
+// Returns 0 and writes a one-line JSON summary, or 1 with the error text.
+extern "C" int oracle_solve(int argc, const char *const *argv, char *summary, size_t summary_len)
+{
+  try
+    {
+      const Solve_Options o = parse_options(argc, argv);
+      std::string s;
+      solve(
+        o.sdp_dir, o.out_dir, o.parameters,
+        [&](const Block_Info &bi, const SDP &sdp) {
+          return std::unique_ptr<Hot_Path>(
+            new Hot_Path_C(oracle_table(bi, sdp, o.parameters.precision), bi, sdp));
+        },
+        o.verbose, &s);
+      if(summary && summary_len)
+        {
+          strncpy(summary, s.c_str(), summary_len - 1);
+          summary[summary_len - 1] = 0;
+        }
+      return 0;
+    }
+  catch(std::exception &e)
+    {
+      if(summary && summary_len)
+        {
+          strncpy(summary, e.what(), summary_len - 1);
+          summary[summary_len - 1] = 0;
+        }
+      return 1;
+    }
+}

@@ -1,0 +1,71 @@
+// The product hot path: Hot_Path bound to the sm_100a kernels through the
+// C-ABI of include/sdpb_b200.h (libsdpb_b200.so), and the sdpb_b200_solve entry
+// point of include/sdpb_b200_solver.h.  No CPU implementation of the hot path
+// is linked here; sdpb_b200_create fails loudly without a CUDA device.
+#include "../../../include/sdpb_b200.h"
+#include "../../../include/sdpb_b200_solver.h"
+#include "cli.hpp"
+#include "hot_path_c.hpp"
+
+#include <cstring>
+
+using namespace sdpb_host;
+
+static Hot_Path_Table b200_table(const Block_Info &bi, const SDP &sdp, int prec, int device)
+{
+  sdpb_b200_ctx *c = nullptr;
+  char err[512] = {0};
+  if(sdpb_b200_create(&c, prec, device, bi.num_blocks(), bi.dimensions.data(), bi.num_points.data(),
+                      sdp.N(), err, sizeof err))
+    throw std::runtime_error(std::string("sdpb_b200_create: ") + err);
+  Hot_Path_Table t;
+  t.ctx = c;
+  t.set_block = [](void *x, int j, const uint64_t *B, const uint64_t *e, const uint64_t *o) {
+    return sdpb_b200_set_block((sdpb_b200_ctx *)x, j, B, e, o);
+  };
+  t.cholesky_decomposition = [](void *x, int which, const uint64_t *const *A, uint64_t *const *L) {
+    return sdpb_b200_cholesky_decomposition((sdpb_b200_ctx *)x, which, A, L);
+  };
+  t.compute_bilinear_pairings
+    = [](void *x, const uint64_t *const *Y, uint64_t *const *AX, uint64_t *const *AY) {
+        return sdpb_b200_compute_bilinear_pairings((sdpb_b200_ctx *)x, Y, AX, AY);
+      };
+  t.initialize_schur_complement_solver
+    = [](void *x, uint64_t *const *L, uint64_t *const *P, uint64_t *Q, int32_t *ms) {
+        return sdpb_b200_initialize_schur_complement_solver((sdpb_b200_ctx *)x, L, P, Q, ms);
+      };
+  t.last_error = [](const void *x) { return sdpb_b200_last_error((const sdpb_b200_ctx *)x); };
+  t.destroy = [](void *x) { sdpb_b200_destroy((sdpb_b200_ctx *)x); };
+  t.name = "sm_100a(libsdpb_b200.so)";
+  return t;
+}
+
+extern "C" int sdpb_b200_solve(int argc, const char *const *argv, char *summary, size_t summary_len)
+{
+  auto put = [&](const std::string &s) {
+    if(summary && summary_len)
+      {
+        strncpy(summary, s.c_str(), summary_len - 1);
+        summary[summary_len - 1] = 0;
+      }
+  };
+  try
+    {
+      const Solve_Options o = parse_options(argc, argv);
+      std::string s;
+      solve(
+        o.sdp_dir, o.out_dir, o.parameters,
+        [&](const Block_Info &bi, const SDP &sdp) {
+          return std::unique_ptr<Hot_Path>(
+            new Hot_Path_C(b200_table(bi, sdp, o.parameters.precision, o.device), bi, sdp));
+        },
+        o.verbose, &s);
+      put(s);
+      return 0;
+    }
+  catch(std::exception &e)
+    {
+      put(e.what());
+      return 1;
+    }
+}

@@ -1,0 +1,171 @@
+// Hot_Path over a table of C entry points with the signatures of
+// include/sdpb_b200.h.  The product binds the table to the sdpb_b200_* symbols
+// of libsdpb_b200.so (hot_path_b200.cpp); the tests bind the same adaptor to the
+// CPU oracle's oracle_* symbols, so both run through identical host code.
+// This is the shim INTEGRATION.md describes for the reference side: pack
+// El::BigFloat -> packed elements, call, unpack, turn rc != 0 into RUNTIME_ERROR.
+#pragma once
+#include "solver.hpp"
+
+namespace sdpb_host
+{
+struct Hot_Path_Table
+{
+  void *ctx = nullptr;
+  int (*set_block)(void *, int, const uint64_t *, const uint64_t *, const uint64_t *) = nullptr;
+  int (*cholesky_decomposition)(void *, int, const uint64_t *const *, uint64_t *const *) = nullptr;
+  int (*compute_bilinear_pairings)(void *, const uint64_t *const *, uint64_t *const *, uint64_t *const *)
+    = nullptr;
+  int (*initialize_schur_complement_solver)(void *, uint64_t *const *, uint64_t *const *, uint64_t *, int32_t *)
+    = nullptr;
+  const char *(*last_error)(const void *) = nullptr;
+  void (*destroy)(void *) = nullptr;
+  std::string name;
+};
+
+class Hot_Path_C : public Hot_Path
+{
+  Hot_Path_Table t;
+  const Block_Info &bi;
+  int N;
+  typedef std::vector<uint64_t> Buf;
+  std::vector<Buf> in2J, out2J, outJ_L, outJ_P;
+  Buf outQ;
+  std::vector<int32_t> block_timings_ms;
+
+  static std::vector<const uint64_t *> cptrs(const std::vector<Buf> &v)
+  {
+    std::vector<const uint64_t *> p(v.size());
+    for(size_t i = 0; i < v.size(); ++i)
+      p[i] = v[i].empty() ? nullptr : v[i].data();
+    return p;
+  }
+  static std::vector<uint64_t *> ptrs(std::vector<Buf> &v)
+  {
+    std::vector<uint64_t *> p(v.size());
+    for(size_t i = 0; i < v.size(); ++i)
+      p[i] = v[i].empty() ? nullptr : v[i].data();
+    return p;
+  }
+  void check(int rc) const
+  {
+    if(rc)
+      throw std::runtime_error(t.last_error(t.ctx));
+  }
+  void pack_psd(const std::vector<Matrix> &A)
+  {
+    const size_t ew = (size_t)elem_words();
+#pragma omp parallel for schedule(dynamic)
+    for(size_t b = 0; b < A.size(); ++b)
+      {
+        in2J[b].resize(A[b].a.size() * ew);
+        if(!A[b].a.empty())
+          pack_matrix(A[b], in2J[b].data());
+      }
+  }
+
+public:
+  Hot_Path_C(const Hot_Path_Table &table, const Block_Info &block_info, const SDP &sdp)
+      : t(table), bi(block_info), N(sdp.N())
+  {
+    const int J = bi.num_blocks();
+    const size_t ew = (size_t)elem_words();
+    in2J.resize(2 * J);
+    out2J.resize(2 * J);
+    outJ_L.resize(J);
+    outJ_P.resize(J);
+    block_timings_ms.assign(J, 0);
+    for(int j = 0; j < J; ++j)
+      {
+        Buf B(sdp.free_var_matrix[j].a.size() * ew), e(sdp.bilinear_bases[2 * j].a.size() * ew),
+          o(sdp.bilinear_bases[2 * j + 1].a.size() * ew);
+        if(!B.empty())
+          pack_matrix(sdp.free_var_matrix[j], B.data());
+        if(!e.empty())
+          pack_matrix(sdp.bilinear_bases[2 * j], e.data());
+        if(!o.empty())
+          pack_matrix(sdp.bilinear_bases[2 * j + 1], o.data());
+        // never hand out NULL for an empty matrix: the callee may form base + 0
+        B.resize(B.size() + 1);
+        e.resize(e.size() + 1);
+        o.resize(o.size() + 1);
+        check(t.set_block(t.ctx, j, B.data(), e.data(), o.data()));
+      }
+    outQ.resize((size_t)N * N * ew);
+  }
+  ~Hot_Path_C() override
+  {
+    if(t.destroy && t.ctx)
+      t.destroy(t.ctx);
+  }
+  std::string name() const override { return t.name; }
+
+  void cholesky_decomposition(int which, const std::vector<Matrix> &A, std::vector<Matrix> &L) override
+  {
+    const size_t ew = (size_t)elem_words();
+    pack_psd(A);
+    for(size_t b = 0; b < A.size(); ++b)
+      out2J[b].resize(A[b].a.size() * ew);
+    const auto in = cptrs(in2J);
+    const auto out = ptrs(out2J);
+    check(t.cholesky_decomposition(t.ctx, which, in.data(), out.data()));
+    L.resize(A.size());
+#pragma omp parallel for schedule(dynamic)
+    for(size_t b = 0; b < A.size(); ++b)
+      {
+        if(A[b].h)
+          unpack_matrix(L[b], A[b].h, A[b].w, out2J[b].data());
+        else
+          L[b].resize(0, 0);
+      }
+  }
+
+  void compute_bilinear_pairings(const std::vector<Matrix> &Y, std::vector<Matrix> &A_Y) override
+  {
+    const size_t ew = (size_t)elem_words();
+    pack_psd(Y);
+    const int J = bi.num_blocks();
+    for(int b = 0; b < 2 * J; ++b)
+      {
+        const size_t mn = (size_t)bi.bilinear_pairing_block_size(b / 2);
+        out2J[b].resize(mn * mn * ew);
+      }
+    const auto in = cptrs(in2J);
+    const auto out = ptrs(out2J);
+    check(t.compute_bilinear_pairings(t.ctx, in.data(), nullptr, out.data()));
+    A_Y.resize(2 * J);
+#pragma omp parallel for schedule(dynamic)
+    for(int b = 0; b < 2 * J; ++b)
+      {
+        const int mn = bi.bilinear_pairing_block_size(b / 2);
+        unpack_matrix(A_Y[b], mn, mn, out2J[b].data());
+      }
+  }
+
+  void initialize_schur_complement_solver(std::vector<Matrix> &L, std::vector<Matrix> &P, Matrix &Q) override
+  {
+    const size_t ew = (size_t)elem_words();
+    const int J = bi.num_blocks();
+    for(int j = 0; j < J; ++j)
+      {
+        const size_t Pj = (size_t)bi.schur_block_size(j);
+        outJ_L[j].resize(Pj * Pj * ew);
+        outJ_P[j].resize(Pj * (size_t)N * ew);
+      }
+    const auto pl = ptrs(outJ_L);
+    const auto pp = ptrs(outJ_P);
+    check(t.initialize_schur_complement_solver(t.ctx, pl.data(), pp.data(), outQ.data(),
+                                               block_timings_ms.data()));
+    L.resize(J);
+    P.resize(J);
+#pragma omp parallel for schedule(dynamic)
+    for(int j = 0; j < J; ++j)
+      {
+        const int Pj = bi.schur_block_size(j);
+        unpack_matrix(L[j], Pj, Pj, outJ_L[j].data());
+        unpack_matrix(P[j], Pj, N, outJ_P[j].data());
+      }
+    unpack_matrix(Q, N, N, outQ.data());
+  }
+};
+} // namespace sdpb_host

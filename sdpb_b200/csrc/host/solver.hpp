@@ -1,0 +1,1094 @@
+// Host side of the solver: SDP_Solver::run / SDP_Solver::step with the
+// reference's structure (reference src/sdp_solve/SDP_Solver/run/run.cxx:184-470,
+// run/step/step.cxx:51-229), single process, GMP mpf scalars.  The hot path —
+// cholesky_decomposition, compute_bilinear_pairings,
+// initialize_schur_complement_solver — is NOT implemented here: it is reached
+// through the Hot_Path interface below, whose product implementation
+// (hot_path_b200.cpp) calls the sm_100a kernels through the C-ABI of
+// include/sdpb_b200.h.  Everything else in an iteration (objectives, residues,
+// search direction, step length, termination, iterations.json / out.txt) is
+// cheap O(sum s_p^3 + P N) host work and stays on the CPU as in the reference.
+#pragma once
+#include "eig.hpp"
+#include "sdp.hpp"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <functional>
+#include <sys/stat.h>
+
+namespace sdpb_host
+{
+// The three free functions SDP_Solver::run/step call (run.cxx:14-17,37-45;
+// step.cxx:12-24) plus the upload of the immutable SDP data.  Errors are
+// std::runtime_error with the reference's texts.
+struct Hot_Path
+{
+  virtual ~Hot_Path() {}
+  // cholesky_decomposition.cxx:5-28; which = 0: X, 1: Y.  L[b] = lower factor.
+  virtual void cholesky_decomposition(int which, const std::vector<Matrix> &A, std::vector<Matrix> &L) = 0;
+  // compute_bilinear_pairings.cxx:17-31.  A_X_inv stays with the implementation
+  // (only the Schur assembly reads it); A_Y[b] = V^T Y V, (m n) x (m n).
+  virtual void compute_bilinear_pairings(const std::vector<Matrix> &Y, std::vector<Matrix> &A_Y) = 0;
+  // initialize_schur_complement_solver.cxx:62-104
+  virtual void initialize_schur_complement_solver(std::vector<Matrix> &schur_complement_cholesky,
+                                                  std::vector<Matrix> &schur_off_diagonal, Matrix &Q)
+    = 0;
+  virtual std::string name() const = 0;
+};
+
+// Solver_Parameters (reference src/sdp_solve/Solver_Parameters/Solver_Parameters.cxx:20-157);
+// defaults are parsed from the same decimal strings at working precision (:13-18).
+struct Solver_Parameters
+{
+  int precision = 400;
+  long max_iterations = 500;
+  long max_runtime = 1L << 60;
+  bool find_primal_feasible = false, find_dual_feasible = false;
+  bool detect_primal_feasible_jump = false, detect_dual_feasible_jump = false;
+  std::string duality_gap_threshold = "1e-30", primal_error_threshold = "1e-30",
+              dual_error_threshold = "1e-30", initial_matrix_scale_primal = "1e20",
+              initial_matrix_scale_dual = "1e20", feasible_centering_parameter = "0.1",
+              infeasible_centering_parameter = "0.3", step_length_reduction = "0.7",
+              max_complementarity = "1e100", min_primal_step = "0", min_dual_step = "0";
+  std::string write_solution = "x,y"; // Write_Solution.cxx
+  bool set(const std::string &key, const std::string &value)
+  {
+    auto flag = [&](bool &b) { b = value.empty() || value == "1" || value == "true"; };
+    if(key == "precision") precision = std::stoi(value);
+    else if(key == "maxIterations") max_iterations = std::stol(value);
+    else if(key == "maxRuntime") max_runtime = std::stol(value);
+    else if(key == "findPrimalFeasible") flag(find_primal_feasible);
+    else if(key == "findDualFeasible") flag(find_dual_feasible);
+    else if(key == "detectPrimalFeasibleJump") flag(detect_primal_feasible_jump);
+    else if(key == "detectDualFeasibleJump") flag(detect_dual_feasible_jump);
+    else if(key == "dualityGapThreshold") duality_gap_threshold = value;
+    else if(key == "primalErrorThreshold") primal_error_threshold = value;
+    else if(key == "dualErrorThreshold") dual_error_threshold = value;
+    else if(key == "initialMatrixScalePrimal") initial_matrix_scale_primal = value;
+    else if(key == "initialMatrixScaleDual") initial_matrix_scale_dual = value;
+    else if(key == "feasibleCenteringParameter") feasible_centering_parameter = value;
+    else if(key == "infeasibleCenteringParameter") infeasible_centering_parameter = value;
+    else if(key == "stepLengthReduction") step_length_reduction = value;
+    else if(key == "maxComplementarity") max_complementarity = value;
+    else if(key == "minPrimalStep") min_primal_step = value;
+    else if(key == "minDualStep") min_dual_step = value;
+    else if(key == "writeSolution") write_solution = value;
+    else if(key == "checkpointInterval" || key == "verbosity" || key == "procGranularity"
+            || key == "maxSharedMemory" || key == "checkpointDir" || key == "noFinalCheckpoint")
+      ; // accepted for command-line compatibility; no effect in this host
+    else
+      return false;
+    return true;
+  }
+};
+
+enum class Terminate_Reason
+{
+  PrimalDualOptimal,
+  PrimalFeasible,
+  DualFeasible,
+  PrimalFeasibleJumpDetected,
+  DualFeasibleJumpDetected,
+  MaxComplementarityExceeded,
+  MaxIterationsExceeded,
+  MaxRuntimeExceeded,
+  PrimalStepTooSmall,
+  DualStepTooSmall
+};
+// SDP_Solver_Terminate_Reason.cxx:5-45
+inline const char *to_string(Terminate_Reason r)
+{
+  switch(r)
+    {
+    case Terminate_Reason::PrimalDualOptimal: return "found primal-dual optimal solution";
+    case Terminate_Reason::PrimalFeasible: return "found primal feasible solution";
+    case Terminate_Reason::DualFeasible: return "found dual feasible solution";
+    case Terminate_Reason::PrimalFeasibleJumpDetected: return "primal feasible jump detected";
+    case Terminate_Reason::DualFeasibleJumpDetected: return "dual feasible jump detected";
+    case Terminate_Reason::MaxIterationsExceeded: return "maxIterations exceeded";
+    case Terminate_Reason::MaxRuntimeExceeded: return "maxRuntime exceeded";
+    case Terminate_Reason::MaxComplementarityExceeded: return "maxComplementarity exceeded";
+    case Terminate_Reason::PrimalStepTooSmall: return "primal step too small";
+    case Terminate_Reason::DualStepTooSmall: return "dual step too small";
+    }
+  return "?";
+}
+
+// operator<< of a BigFloat in the reference's streams: default float format
+// with ceil(prec log10 2) + 1 significant digits (sdpb_util/ostream/set_stream_precision.hxx:7-11),
+// i.e. printf's %g: exponent form when exp10 < -4 or >= digits, trailing zeros dropped.
+inline std::string format_bigfloat(const BigFloat &x)
+{
+  const int digits = (int)std::ceil(working_precision_bits() * std::log10(2.0)) + 1;
+  if(x.sgn() == 0)
+    return "0";
+  mp_exp_t e;
+  char *s = mpf_get_str(nullptr, &e, 10, (size_t)digits, x.v);
+  std::string m(s);
+  free(s);
+  std::string out;
+  if(m[0] == '-')
+    {
+      out = "-";
+      m = m.substr(1);
+    }
+  const long x10 = (long)e - 1; // value = 0.m * 10^e = m[0].m[1..] * 10^(e-1)
+  if(x10 < -4 || x10 >= digits)
+    {
+      out += m.substr(0, 1);
+      if(m.size() > 1)
+        out += "." + m.substr(1);
+      out += (x10 < 0 ? "e-" : "e+");
+      const long a = x10 < 0 ? -x10 : x10;
+      if(a < 10)
+        out += "0";
+      out += std::to_string(a);
+    }
+  else if(x10 < 0)
+    out += "0." + std::string((size_t)(-x10 - 1), '0') + m;
+  else
+    {
+      if((long)m.size() <= x10 + 1)
+        out += m + std::string((size_t)(x10 + 1 - (long)m.size()), '0');
+      else
+        out += m.substr(0, (size_t)x10 + 1) + "." + m.substr((size_t)x10 + 1);
+    }
+  return out;
+}
+
+// ---- small dense helpers (the reference calls El::Gemm / Trsm / Dotu here;
+// Elemental's operation order is not observable, results are pinned to 2^-99) ----
+// C = alpha A B + beta C
+inline void gemm_nn(const BigFloat &alpha, const Matrix &A, const Matrix &B, const BigFloat &beta, Matrix &C)
+{
+  BigFloat acc, t;
+  const bool beta_zero = beta.sgn() == 0;
+  for(int j = 0; j < B.w; ++j)
+    for(int i = 0; i < A.h; ++i)
+      {
+        acc.zero();
+        for(int l = 0; l < A.w; ++l)
+          {
+            t = A(i, l);
+            t *= B(l, j);
+            acc += t;
+          }
+        acc *= alpha;
+        if(beta_zero)
+          C(i, j) = acc;
+        else
+          {
+            C(i, j) *= beta;
+            C(i, j) += acc;
+          }
+      }
+}
+// B <- L^{-1} B (forward substitution)
+inline void trsm_lower_left(const Matrix &L, Matrix &B)
+{
+  BigFloat t;
+  for(int c = 0; c < B.w; ++c)
+    for(int i = 0; i < B.h; ++i)
+      {
+        for(int k = 0; k < i; ++k)
+          {
+            t = L(i, k);
+            t *= B(k, c);
+            B(i, c) -= t;
+          }
+        B(i, c) /= L(i, i);
+      }
+}
+// B <- L^{-T} B (back substitution)
+inline void trsm_lower_transpose_left(const Matrix &L, Matrix &B)
+{
+  BigFloat t;
+  for(int c = 0; c < B.w; ++c)
+    for(int i = B.h - 1; i >= 0; --i)
+      {
+        for(int k = i + 1; k < B.h; ++k)
+          {
+            t = L(k, i);
+            t *= B(k, c);
+            B(i, c) -= t;
+          }
+        B(i, c) /= L(i, i);
+      }
+}
+// B <- B L^{-T}
+inline void trsm_lower_transpose_right(const Matrix &L, Matrix &B)
+{
+  BigFloat t;
+  for(int r = 0; r < B.h; ++r)
+    for(int j = 0; j < B.w; ++j)
+      {
+        for(int k = 0; k < j; ++k)
+          {
+            t = B(r, k);
+            t *= L(j, k);
+            B(r, j) -= t;
+          }
+        B(r, j) /= L(j, j);
+      }
+}
+// cholesky::SolveAfter(UPPER) with Q = U^T U: x <- U^{-1} U^{-T} x
+inline void cholesky_upper_solve(const Matrix &U, Matrix &x)
+{
+  BigFloat t;
+  const int n = U.h;
+  for(int c = 0; c < x.w; ++c)
+    {
+      for(int i = 0; i < n; ++i)
+        {
+          for(int k = 0; k < i; ++k)
+            {
+              t = U(k, i);
+              t *= x(k, c);
+              x(i, c) -= t;
+            }
+          x(i, c) /= U(i, i);
+        }
+      for(int i = n - 1; i >= 0; --i)
+        {
+          for(int k = i + 1; k < n; ++k)
+            {
+              t = U(i, k);
+              t *= x(k, c);
+              x(i, c) -= t;
+            }
+          x(i, c) /= U(i, i);
+        }
+    }
+}
+inline BigFloat max_abs(const Matrix &A)
+{
+  BigFloat m;
+  for(const auto &x : A.a)
+    {
+      const BigFloat a = Abs(x);
+      if(a > m)
+        m = a;
+    }
+  return m;
+}
+inline BigFloat dotu(const Matrix &A, const Matrix &B)
+{
+  BigFloat acc, t;
+  for(size_t i = 0; i < A.a.size(); ++i)
+    {
+      t = A.a[i];
+      t *= B.a[i];
+      acc += t;
+    }
+  return acc;
+}
+inline void axpy(const BigFloat &alpha, const Matrix &X, Matrix &Y)
+{
+  BigFloat t;
+  for(size_t i = 0; i < X.a.size(); ++i)
+    {
+      t = X.a[i];
+      t *= alpha;
+      Y.a[i] += t;
+    }
+}
+// Block_Diagonal_Matrix::symmetrize (Block_Diagonal_Matrix.hxx:95-109)
+inline void symmetrize(Matrix &A)
+{
+  const BigFloat half(0.5);
+  for(auto &x : A.a)
+    x *= half;
+  for(int j = 0; j < A.w; ++j)
+    for(int i = 0; i < j; ++i)
+      {
+        const BigFloat s = A(i, j) + A(j, i);
+        A(i, j) = s;
+        A(j, i) = s;
+      }
+  for(int i = 0; i < A.h; ++i)
+    A(i, i) += A(i, i);
+}
+// cholesky_condition_number (sdpb_util/cholesky_condition_number.hxx:8-36)
+inline BigFloat cholesky_condition_number(const Matrix &L)
+{
+  if(L.h == 0)
+    return BigFloat(0);
+  BigFloat mx = L(0, 0), mn = L(0, 0);
+  for(int i = 1; i < L.h; ++i)
+    {
+      if(L(i, i) > mx)
+        mx = L(i, i);
+      if(L(i, i) < mn)
+        mn = L(i, i);
+    }
+  const BigFloat ratio = mx / mn;
+  return ratio * ratio;
+}
+
+struct Iteration_Record
+{
+  long iteration;
+  double total_time, iter_time;
+  BigFloat mu, primal_objective, dual_objective, duality_gap, primal_error_P, primal_error_p,
+    dual_error, R_error, primal_step_length, dual_step_length, beta_corrector, Q_cond_number,
+    max_block_cond_number;
+  std::string block_name;
+};
+
+class SDP_Solver
+{
+public:
+  const Block_Info &block_info;
+  const SDP &sdp;
+  Hot_Path &hot;
+  // SDP_Solver.hxx:27-60
+  std::vector<Matrix> x;        // J, P_j x 1
+  std::vector<Matrix> X, Y;     // 2J
+  Matrix y;                     // N x 1 (the reference keeps one copy per block)
+  std::vector<Matrix> primal_residues; // 2J
+  std::vector<Matrix> dual_residues;   // J
+  BigFloat primal_objective, dual_objective, duality_gap, primal_error_P, primal_error_p, dual_error,
+    R_error;
+  std::vector<Iteration_Record> iterations;
+  double hot_path_seconds = 0, host_seconds = 0;
+  std::function<void(const Iteration_Record &)> on_iteration;
+
+  BigFloat primal_error() const { return Max(primal_error_P, primal_error_p); }
+
+  // SDP_Solver::SDP_Solver (SDP_Solver/SDP_Solver.cxx:3-38): X = Omega_p I, Y = Omega_d I, x = y = 0
+  SDP_Solver(const Solver_Parameters &parameters, const Block_Info &bi, const SDP &s, Hot_Path &h)
+      : block_info(bi), sdp(s), hot(h)
+  {
+    const int J = bi.num_blocks();
+    x.resize(J);
+    dual_residues.resize(J);
+    X.resize(2 * J);
+    Y.resize(2 * J);
+    primal_residues.resize(2 * J);
+    const BigFloat op(parameters.initial_matrix_scale_primal), od(parameters.initial_matrix_scale_dual);
+    for(int j = 0; j < J; ++j)
+      {
+        x[j].resize(bi.schur_block_size(j), 1);
+        dual_residues[j].resize(bi.schur_block_size(j), 1);
+        for(int p = 0; p < 2; ++p)
+          {
+            const int s_p = bi.psd_matrix_block_size(j, p);
+            X[2 * j + p].resize(s_p, s_p);
+            Y[2 * j + p].resize(s_p, s_p);
+            primal_residues[2 * j + p].resize(s_p, s_p);
+            for(int i = 0; i < s_p; ++i)
+              {
+                X[2 * j + p](i, i) = op;
+                Y[2 * j + p](i, i) = od;
+              }
+          }
+      }
+    y.resize(s.N(), 1);
+  }
+
+  // constraint_matrix_weighted_sum.cxx:14-66
+  void constraint_matrix_weighted_sum(const std::vector<Matrix> &a, std::vector<Matrix> &result) const
+  {
+    const int J = block_info.num_blocks();
+#pragma omp parallel for schedule(dynamic)
+    for(int j = 0; j < J; ++j)
+      {
+        const int n = block_info.num_points[j], m = block_info.dimensions[j];
+        BigFloat acc, t;
+        const BigFloat half(0.5);
+        for(int parity = 0; parity < 2; ++parity)
+          {
+            Matrix &R = result[2 * j + parity];
+            const Matrix &bases = sdp.bilinear_bases[2 * j + parity];
+            const int h = bases.h;
+            R.zero();
+            for(int cb = 0; cb < m; ++cb)
+              for(int rb = 0; rb <= cb; ++rb)
+                {
+                  const int voff = (cb * (cb + 1) / 2 + rb) * n;
+                  for(int c = 0; c < h; ++c)
+                    for(int r = 0; r < h; ++r)
+                      {
+                        acc.zero();
+                        for(int k = 0; k < n; ++k)
+                          {
+                            t = bases(c, k);
+                            t *= a[j](voff + k, 0);
+                            t *= bases(r, k);
+                            acc += t;
+                          }
+                        if(cb != rb)
+                          acc *= half;
+                        R(rb * h + r, cb * h + c) = acc;
+                      }
+                }
+            if(m > 1)
+              for(int c = 0; c < R.w; ++c)
+                for(int r = c + 1; r < R.h; ++r)
+                  R(r, c) = R(c, r); // MakeSymmetric(UPPER)
+          }
+      }
+  }
+
+  // compute_objectives.cxx
+  void compute_objectives()
+  {
+    BigFloat s;
+    for(size_t j = 0; j < x.size(); ++j)
+      s += dotu(sdp.primal_objective_c[j], x[j]);
+    primal_objective = sdp.objective_const + s;
+    dual_objective = sdp.objective_const + dotu(sdp.dual_objective_b, y);
+    duality_gap = Abs(primal_objective - dual_objective)
+                  / Max(Abs(primal_objective) + Abs(dual_objective), BigFloat(1));
+  }
+
+  // compute_dual_residues_and_error.cxx:9-70.  A_Y[b] is the full (m n) x (m n)
+  // matrix; the reference's tile [cb][rb](row,col) = A_Y[b](cb n + col, rb n + row).
+  void compute_dual_residues_and_error(const std::vector<Matrix> &A_Y)
+  {
+    const int J = block_info.num_blocks();
+    std::vector<BigFloat> local_max(J);
+#pragma omp parallel for schedule(dynamic)
+    for(int j = 0; j < J; ++j)
+      {
+        const int n = block_info.num_points[j], m = block_info.dimensions[j];
+        Matrix &res = dual_residues[j];
+        res.zero();
+        for(int parity = 0; parity < 2; ++parity)
+          {
+            const Matrix &A = A_Y[2 * j + parity];
+            if(A.h == 0)
+              continue;
+            for(int cb = 0; cb < m; ++cb)
+              for(int rb = 0; rb <= cb; ++rb)
+                {
+                  const int off = (cb * (cb + 1) / 2 + rb) * n;
+                  for(int k = 0; k < n; ++k)
+                    res(off + k, 0) -= A(cb * n + k, rb * n + k);
+                }
+          }
+        // dualResidues -= B y ; += c
+        gemm_nn(BigFloat(-1), sdp.free_var_matrix[j], y, BigFloat(1), res);
+        axpy(BigFloat(1), sdp.primal_objective_c[j], res);
+        local_max[j] = max_abs(res);
+      }
+    dual_error.zero();
+    for(int j = 0; j < J; ++j)
+      dual_error = Max(dual_error, local_max[j]);
+  }
+
+  // compute_primal_residues_and_error_P_Ax_X.cxx
+  void compute_primal_residues_and_error_P_Ax_X()
+  {
+    constraint_matrix_weighted_sum(x, primal_residues);
+    primal_error_P.zero();
+    for(size_t b = 0; b < X.size(); ++b)
+      {
+        for(size_t i = 0; i < X[b].a.size(); ++i)
+          primal_residues[b].a[i] -= X[b].a[i];
+        primal_error_P = Max(primal_error_P, max_abs(primal_residues[b]));
+      }
+  }
+  // compute_primal_residues_and_error_p_b_Bx.cxx: p = b - B^T x (summed over blocks)
+  void compute_primal_residues_and_error_p_b_Bx(Matrix &primal_residue_p)
+  {
+    const int N = sdp.N(), J = block_info.num_blocks();
+    primal_residue_p.resize(N, 1);
+    std::vector<Matrix> part(J);
+#pragma omp parallel for schedule(dynamic)
+    for(int j = 0; j < J; ++j)
+      {
+        part[j].resize(N, 1);
+        BigFloat acc, t;
+        const Matrix &B = sdp.free_var_matrix[j];
+        for(int c = 0; c < N; ++c)
+          {
+            acc.zero();
+            for(int r = 0; r < B.h; ++r)
+              {
+                t = B(r, c);
+                t *= x[j](r, 0);
+                acc += t;
+              }
+            part[j](c, 0) = -acc;
+          }
+      }
+    for(int c = 0; c < N; ++c)
+      primal_residue_p(c, 0) = sdp.dual_objective_b(c, 0);
+    for(int j = 0; j < J; ++j)
+      for(int c = 0; c < N; ++c)
+        primal_residue_p(c, 0) += part[j](c, 0);
+    primal_error_p = max_abs(primal_residue_p);
+  }
+
+  // compute_feasible_and_termination.cxx:5-75
+  void compute_feasible_and_termination(const Solver_Parameters &parameters, const BigFloat &primal_step_length,
+                                        const BigFloat &dual_step_length, long iteration,
+                                        const std::chrono::steady_clock::time_point &start,
+                                        bool &is_primal_and_dual_feasible, Terminate_Reason &reason,
+                                        bool &terminate_now) const
+  {
+    const bool is_dual_feasible = dual_error < BigFloat(parameters.dual_error_threshold),
+               is_primal_feasible = primal_error() < BigFloat(parameters.primal_error_threshold);
+    is_primal_and_dual_feasible = is_primal_feasible && is_dual_feasible;
+    const bool is_optimal = duality_gap < BigFloat(parameters.duality_gap_threshold);
+    terminate_now = true;
+    if(is_primal_and_dual_feasible && is_optimal)
+      reason = Terminate_Reason::PrimalDualOptimal;
+    else if(is_dual_feasible && parameters.find_dual_feasible)
+      reason = Terminate_Reason::DualFeasible;
+    else if(is_primal_feasible && parameters.find_primal_feasible)
+      reason = Terminate_Reason::PrimalFeasible;
+    else if(dual_step_length == BigFloat(1) && parameters.detect_dual_feasible_jump)
+      reason = Terminate_Reason::DualFeasibleJumpDetected;
+    else if(primal_step_length == BigFloat(1) && parameters.detect_primal_feasible_jump)
+      reason = Terminate_Reason::PrimalFeasibleJumpDetected;
+    else if(iteration > parameters.max_iterations)
+      reason = Terminate_Reason::MaxIterationsExceeded;
+    else if(std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - start).count()
+            >= parameters.max_runtime)
+      reason = Terminate_Reason::MaxRuntimeExceeded;
+    else if(iteration > 1 && primal_step_length < BigFloat(parameters.min_primal_step))
+      reason = Terminate_Reason::PrimalStepTooSmall;
+    else if(iteration > 1 && dual_step_length < BigFloat(parameters.min_dual_step))
+      reason = Terminate_Reason::DualStepTooSmall;
+    else
+      terminate_now = false;
+  }
+
+  // cholesky_solve.cxx: Z <- L^{-T} L^{-1} Z per block
+  static void cholesky_solve(const std::vector<Matrix> &L, std::vector<Matrix> &Z)
+  {
+#pragma omp parallel for schedule(dynamic)
+    for(size_t b = 0; b < Z.size(); ++b)
+      {
+        trsm_lower_left(L[b], Z[b]);
+        trsm_lower_transpose_left(L[b], Z[b]);
+      }
+  }
+  // C = alpha A B + beta C per block (scale_multiply_add.cxx)
+  static void scale_multiply_add(const BigFloat &alpha, const std::vector<Matrix> &A,
+                                 const std::vector<Matrix> &B, const BigFloat &beta, std::vector<Matrix> &C)
+  {
+#pragma omp parallel for schedule(dynamic)
+    for(size_t b = 0; b < A.size(); ++b)
+      gemm_nn(alpha, A[b], B[b], beta, C[b]);
+  }
+
+  // compute_schur_RHS.cxx:21-86: dx = -dual_residues - Tr(A_p Z)
+  void compute_schur_RHS(const std::vector<Matrix> &Z, std::vector<Matrix> &dx) const
+  {
+    const int J = block_info.num_blocks();
+#pragma omp parallel for schedule(dynamic)
+    for(int j = 0; j < J; ++j)
+      {
+        const int n = block_info.num_points[j], m = block_info.dimensions[j];
+        dx[j] = dual_residues[j];
+        for(auto &e : dx[j].a)
+          e = -e;
+        BigFloat acc, t, zq;
+        for(int parity = 0; parity < 2; ++parity)
+          {
+            const Matrix &bases = sdp.bilinear_bases[2 * j + parity];
+            const Matrix &Zb = Z[2 * j + parity];
+            const int h = bases.h;
+            for(int cb = 0; cb < m; ++cb)
+              for(int rb = 0; rb <= cb; ++rb)
+                {
+                  const int off = (cb * (cb + 1) / 2 + rb) * n;
+                  for(int k = 0; k < n; ++k)
+                    {
+                      // sum_a bases(a,k) * (Z_sub bases)(a,k), Z_sub = Z[rb h .., cb h ..]
+                      acc.zero();
+                      for(int a = 0; a < h; ++a)
+                        {
+                          zq.zero();
+                          for(int b = 0; b < h; ++b)
+                            {
+                              t = Zb(rb * h + a, cb * h + b);
+                              t *= bases(b, k);
+                              zq += t;
+                            }
+                          zq *= bases(a, k);
+                          acc += zq;
+                        }
+                      dx[j](off + k, 0) -= acc;
+                    }
+                }
+          }
+      }
+  }
+
+  // solve_schur_complement_equation.cxx:16-79
+  void solve_schur_complement_equation(const std::vector<Matrix> &L, const std::vector<Matrix> &P,
+                                       const Matrix &Q, std::vector<Matrix> &dx, Matrix &dy) const
+  {
+    const int J = block_info.num_blocks(), N = sdp.N();
+    std::vector<Matrix> part(J);
+#pragma omp parallel for schedule(dynamic)
+    for(int j = 0; j < J; ++j)
+      {
+        trsm_lower_left(L[j], dx[j]); // dx = L^{-1} dx
+        part[j].resize(N, 1);
+        BigFloat acc, t;
+        for(int c = 0; c < N; ++c) // - P^T dx
+          {
+            acc.zero();
+            for(int r = 0; r < P[j].h; ++r)
+              {
+                t = P[j](r, c);
+                t *= dx[j](r, 0);
+                acc += t;
+              }
+            part[j](c, 0) = -acc;
+          }
+      }
+    for(int j = 0; j < J; ++j)
+      for(int c = 0; c < N; ++c)
+        dy(c, 0) += part[j](c, 0);
+    cholesky_upper_solve(Q, dy); // dy = Q^{-1} dy
+#pragma omp parallel for schedule(dynamic)
+    for(int j = 0; j < J; ++j)
+      {
+        BigFloat acc, t;
+        for(int r = 0; r < P[j].h; ++r) // dx += P dy
+          {
+            acc.zero();
+            for(int c = 0; c < N; ++c)
+              {
+                t = P[j](r, c);
+                t *= dy(c, 0);
+                acc += t;
+              }
+            dx[j](r, 0) += acc;
+          }
+        trsm_lower_transpose_left(L[j], dx[j]); // dx = L^{-T} dx
+      }
+  }
+
+  // compute_search_direction.cxx:44-90
+  void compute_search_direction(const std::vector<Matrix> &minus_XY, const std::vector<Matrix> &L,
+                                const std::vector<Matrix> &P, const Matrix &Q,
+                                const std::vector<Matrix> &X_cholesky, const BigFloat &beta, const BigFloat &mu,
+                                const Matrix &primal_residue_p, bool is_corrector_phase,
+                                std::vector<Matrix> &dx, std::vector<Matrix> &dX, Matrix &dy,
+                                std::vector<Matrix> &dY) const
+  {
+    std::vector<Matrix> R(minus_XY);
+    if(is_corrector_phase)
+      scale_multiply_add(BigFloat(-1), dX, dY, BigFloat(1), R);
+    const BigFloat bm = beta * mu;
+    for(auto &blk : R)
+      for(int i = 0; i < blk.h; ++i)
+        blk(i, i) += bm;
+    // Z = Symmetrize(X^{-1} (PrimalResidues Y - R))
+    std::vector<Matrix> Z(X);
+    scale_multiply_add(BigFloat(1), primal_residues, Y, BigFloat(0), Z);
+    for(size_t b = 0; b < Z.size(); ++b)
+      for(size_t i = 0; i < Z[b].a.size(); ++i)
+        Z[b].a[i] -= R[b].a[i];
+    cholesky_solve(X_cholesky, Z);
+    for(auto &blk : Z)
+      symmetrize(blk);
+    compute_schur_RHS(Z, dx);
+    dy = primal_residue_p;
+    solve_schur_complement_equation(L, P, Q, dx, dy);
+    // dX = PrimalResidues + sum_p A_p dx[p]
+    constraint_matrix_weighted_sum(dx, dX);
+    for(size_t b = 0; b < dX.size(); ++b)
+      for(size_t i = 0; i < dX[b].a.size(); ++i)
+        dX[b].a[i] += primal_residues[b].a[i];
+    // dY = Symmetrize(X^{-1} (R - dX Y))
+    scale_multiply_add(BigFloat(1), dX, Y, BigFloat(0), dY);
+    for(size_t b = 0; b < dY.size(); ++b)
+      for(size_t i = 0; i < dY[b].a.size(); ++i)
+        dY[b].a[i] -= R[b].a[i];
+    cholesky_solve(X_cholesky, dY);
+    for(auto &blk : dY)
+      {
+        symmetrize(blk);
+        for(auto &e : blk.a)
+          e = -e;
+      }
+  }
+
+  // step_length.cxx:27-46 (+ lower_triangular_inverse_congruence.cxx, min_eigenvalue.cxx)
+  static BigFloat step_length(const std::vector<Matrix> &MCholesky, const std::vector<Matrix> &dM,
+                              const BigFloat &gamma)
+  {
+    std::vector<BigFloat> mins(dM.size());
+    std::vector<int> have(dM.size(), 0);
+    std::string error;
+#pragma omp parallel for schedule(dynamic)
+    for(size_t b = 0; b < dM.size(); ++b)
+      {
+        if(dM[b].h == 0)
+          continue;
+        Matrix A(dM[b]);
+        trsm_lower_transpose_right(MCholesky[b], A); // A L^{-T}
+        trsm_lower_left(MCholesky[b], A);            // L^{-1} A
+        try
+          {
+            mins[b] = min_eigenvalue_symmetric(A);
+            have[b] = 1;
+          }
+        catch(std::exception &e)
+          {
+#pragma omp critical
+            error = e.what();
+          }
+      }
+    if(!error.empty())
+      throw std::runtime_error(error);
+    bool first = true;
+    BigFloat lambda;
+    for(size_t b = 0; b < dM.size(); ++b)
+      if(have[b] && (first || mins[b] < lambda))
+        {
+          lambda = mins[b];
+          first = false;
+        }
+    if(first || lambda > -gamma)
+      return BigFloat(1);
+    return -gamma / lambda;
+  }
+
+  // SDP_Solver::step (step/step.cxx:51-229)
+  void step(const Solver_Parameters &parameters, size_t total_psd_rows, bool is_primal_and_dual_feasible,
+            const std::vector<Matrix> &X_cholesky, const std::vector<Matrix> &Y_cholesky,
+            const Matrix &primal_residue_p, BigFloat &mu, BigFloat &beta_corrector,
+            BigFloat &primal_step_length, BigFloat &dual_step_length, bool &terminate_now,
+            BigFloat &Q_cond_number, BigFloat &max_block_cond_number, std::string &max_block_cond_number_name)
+  {
+    const int J = block_info.num_blocks();
+    std::vector<Matrix> dx(x), dX(X), dY(Y);
+    Matrix dy(y);
+    {
+      std::vector<Matrix> schur_complement_cholesky, schur_off_diagonal;
+      Matrix Q;
+      const auto t0 = std::chrono::steady_clock::now();
+      hot.initialize_schur_complement_solver(schur_complement_cholesky, schur_off_diagonal, Q);
+      hot_path_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+      std::vector<Matrix> minus_XY(X);
+      scale_multiply_add(BigFloat(-1), X, Y, BigFloat(0), minus_XY);
+      {
+        BigFloat tr;
+        for(const auto &blk : minus_XY)
+          for(int i = 0; i < blk.h; ++i)
+            tr += blk(i, i);
+        mu = -tr / BigFloat((long)total_psd_rows);
+      }
+      if(mu > BigFloat(parameters.max_complementarity))
+        {
+          terminate_now = true;
+          return;
+        }
+      // compute_R_error.hxx
+      R_error.zero();
+      for(const auto &blk : minus_XY)
+        for(int j = 0; j < blk.w; ++j)
+          for(int i = 0; i < blk.h; ++i)
+            {
+              BigFloat v = blk(i, j);
+              if(i == j)
+                v += mu;
+              R_error = Max(R_error, Abs(v));
+            }
+      // predictor_centering_parameter.cxx
+      const BigFloat beta_predictor
+        = is_primal_and_dual_feasible ? BigFloat(0) : BigFloat(parameters.infeasible_centering_parameter);
+      compute_search_direction(minus_XY, schur_complement_cholesky, schur_off_diagonal, Q, X_cholesky,
+                               beta_predictor, mu, primal_residue_p, false, dx, dX, dy, dY);
+      // corrector_centering_parameter.cxx (+ frobenius_product_of_sums.cxx)
+      {
+        BigFloat fp;
+        for(size_t b = 0; b < X.size(); ++b)
+          {
+            BigFloat t, u;
+            for(size_t i = 0; i < X[b].a.size(); ++i)
+              {
+                t = X[b].a[i] + dX[b].a[i];
+                u = Y[b].a[i] + dY[b].a[i];
+                t *= u;
+                fp += t;
+              }
+          }
+        const BigFloat r = fp / (mu * BigFloat((long)total_psd_rows));
+        const BigFloat beta = r < BigFloat(1) ? r * r : r;
+        if(is_primal_and_dual_feasible)
+          beta_corrector = Min(Max(BigFloat(parameters.feasible_centering_parameter), beta), BigFloat(1));
+        else
+          beta_corrector = Max(BigFloat(parameters.infeasible_centering_parameter), beta);
+      }
+      compute_search_direction(minus_XY, schur_complement_cholesky, schur_off_diagonal, Q, X_cholesky,
+                               beta_corrector, mu, primal_residue_p, true, dx, dX, dy, dY);
+      // update_cond_numbers.hxx
+      Q_cond_number = cholesky_condition_number(Q);
+      max_block_cond_number.zero();
+      max_block_cond_number_name = "";
+      for(int j = 0; j < J; ++j)
+        {
+          const BigFloat cs = cholesky_condition_number(schur_complement_cholesky[j]);
+          if(max_block_cond_number < cs)
+            {
+              max_block_cond_number = cs;
+              max_block_cond_number_name = "schur_complement_cholesky.block_" + std::to_string(j);
+            }
+          for(int parity = 0; parity < 2; ++parity)
+            {
+              const BigFloat cx = cholesky_condition_number(X_cholesky[2 * j + parity]);
+              if(max_block_cond_number < cx)
+                {
+                  max_block_cond_number = cx;
+                  max_block_cond_number_name
+                    = "X_cholesky.block_" + std::to_string(j) + "_" + std::to_string(parity);
+                }
+              const BigFloat cy = cholesky_condition_number(Y_cholesky[2 * j + parity]);
+              if(max_block_cond_number < cy)
+                {
+                  max_block_cond_number = cy;
+                  max_block_cond_number_name
+                    = "Y_cholesky.block_" + std::to_string(j) + "_" + std::to_string(parity);
+                }
+            }
+        }
+    }
+    const BigFloat gamma(parameters.step_length_reduction);
+    primal_step_length = step_length(X_cholesky, dX, gamma);
+    dual_step_length = step_length(Y_cholesky, dY, gamma);
+    if(is_primal_and_dual_feasible)
+      {
+        primal_step_length = Min(primal_step_length, dual_step_length);
+        dual_step_length = primal_step_length;
+      }
+    for(size_t j = 0; j < x.size(); ++j)
+      axpy(primal_step_length, dx[j], x[j]);
+    for(size_t b = 0; b < X.size(); ++b)
+      axpy(primal_step_length, dX[b], X[b]);
+    axpy(dual_step_length, dy, y);
+    for(size_t b = 0; b < Y.size(); ++b)
+      axpy(dual_step_length, dY[b], Y[b]);
+  }
+
+  // SDP_Solver::run (run/run.cxx:184-470), without checkpoints and signals
+  Terminate_Reason run(const Solver_Parameters &parameters)
+  {
+    Terminate_Reason reason = Terminate_Reason::MaxIterationsExceeded;
+    const auto start = std::chrono::steady_clock::now();
+    BigFloat primal_step_length(0), dual_step_length(0);
+    std::vector<Matrix> X_cholesky, Y_cholesky, A_Y;
+    const size_t total_psd_rows = block_info.total_psd_rows();
+    for(long iteration = 1;; ++iteration)
+      {
+        const auto iter_start = std::chrono::steady_clock::now();
+        compute_objectives();
+        {
+          const auto t0 = std::chrono::steady_clock::now();
+          hot.cholesky_decomposition(0, X, X_cholesky);
+          hot.cholesky_decomposition(1, Y, Y_cholesky);
+          hot.compute_bilinear_pairings(Y, A_Y);
+          hot_path_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        }
+        compute_dual_residues_and_error(A_Y);
+        compute_primal_residues_and_error_P_Ax_X();
+        Matrix primal_residue_p;
+        compute_primal_residues_and_error_p_b_Bx(primal_residue_p);
+        bool terminate_now, is_primal_and_dual_feasible;
+        compute_feasible_and_termination(parameters, primal_step_length, dual_step_length, iteration, start,
+                                         is_primal_and_dual_feasible, reason, terminate_now);
+        if(terminate_now)
+          break;
+        Iteration_Record rec;
+        terminate_now = false;
+        step(parameters, total_psd_rows, is_primal_and_dual_feasible, X_cholesky, Y_cholesky, primal_residue_p,
+             rec.mu, rec.beta_corrector, primal_step_length, dual_step_length, terminate_now, rec.Q_cond_number,
+             rec.max_block_cond_number, rec.block_name);
+        if(terminate_now)
+          {
+            reason = Terminate_Reason::MaxComplementarityExceeded;
+            break;
+          }
+        // print_iteration.cxx:77-108
+        const auto now = std::chrono::steady_clock::now();
+        rec.iteration = iteration;
+        rec.total_time = std::chrono::duration<double>(now - start).count();
+        rec.iter_time = std::chrono::duration<double>(now - iter_start).count();
+        rec.primal_objective = primal_objective;
+        rec.dual_objective = dual_objective;
+        rec.duality_gap = duality_gap;
+        rec.primal_error_P = primal_error_P;
+        rec.primal_error_p = primal_error_p;
+        rec.dual_error = dual_error;
+        rec.R_error = R_error;
+        rec.primal_step_length = primal_step_length;
+        rec.dual_step_length = dual_step_length;
+        if(on_iteration)
+          on_iteration(rec);
+        iterations.push_back(std::move(rec));
+      }
+    host_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count()
+                   - hot_path_seconds;
+    return reason;
+  }
+};
+
+// ---- output files (src/sdpb/save_solution.cxx:21-165, print_iteration.cxx:77-108,
+// save_c_minus_By.hxx, sdpb_util/write_distmatrix.hxx:5-18) ----
+inline void write_vector_file(const std::string &path, const Matrix &v)
+{
+  std::ofstream f(path);
+  f << v.h << " " << v.w << "\n";
+  for(int j = 0; j < v.w; ++j)
+    for(int i = 0; i < v.h; ++i)
+      f << format_bigfloat(v(i, j)) << "\n";
+  if(!f.good())
+    throw std::runtime_error("Error when writing to: " + path);
+}
+inline void write_iterations_json(const std::string &path, const std::vector<Iteration_Record> &its)
+{
+  std::ofstream f(path);
+  f << "[";
+  for(size_t k = 0; k < its.size(); ++k)
+    {
+      const Iteration_Record &r = its[k];
+      char tm[96];
+      snprintf(tm, sizeof tm, ", \"total_time\": %.3f, \"iter_time\": %.3f", r.total_time, r.iter_time);
+      f << (k ? "," : "") << "\n{ \"iteration\":" << r.iteration << tm << ", \"mu\": \""
+        << format_bigfloat(r.mu) << "\", \"P-obj\": \"" << format_bigfloat(r.primal_objective)
+        << "\", \"D-obj\": \"" << format_bigfloat(r.dual_objective) << "\", \"gap\": \""
+        << format_bigfloat(r.duality_gap) << "\", \"P-err\": \"" << format_bigfloat(r.primal_error_P)
+        << "\", \"p-err\": \"" << format_bigfloat(r.primal_error_p) << "\", \"D-err\": \""
+        << format_bigfloat(r.dual_error) << "\", \"R-err\": \"" << format_bigfloat(r.R_error)
+        << "\", \"P-step\": \"" << format_bigfloat(r.primal_step_length) << "\", \"D-step\": \""
+        << format_bigfloat(r.dual_step_length) << "\", \"beta\": \"" << format_bigfloat(r.beta_corrector)
+        << "\", \"Q_cond_number\": \"" << format_bigfloat(r.Q_cond_number)
+        << "\", \"max_block_cond_number\": \"" << format_bigfloat(r.max_block_cond_number)
+        << "\", \"block_name\": \"" << r.block_name << "\" }";
+    }
+  f << "\n]";
+  if(!f.good())
+    throw std::runtime_error("Error when writing to: " + path);
+}
+inline void save_solution(const SDP_Solver &solver, Terminate_Reason reason, long runtime_seconds,
+                          const std::string &out_dir, const std::string &write_solution)
+{
+  mkdir(out_dir.c_str(), 0777);
+  {
+    std::ofstream f(out_dir + "/out.txt");
+    f << "terminateReason = \"" << to_string(reason) << "\";\n"
+      << "primalObjective = " << format_bigfloat(solver.primal_objective) << ";\n"
+      << "dualObjective   = " << format_bigfloat(solver.dual_objective) << ";\n"
+      << "dualityGap      = " << format_bigfloat(solver.duality_gap) << ";\n"
+      << "primalError     = " << format_bigfloat(solver.primal_error()) << ";\n"
+      << "dualError       = " << format_bigfloat(solver.dual_error) << ";\n"
+      << "Solver runtime  = " << runtime_seconds << ";\n";
+    if(!f.good())
+      throw std::runtime_error("Error when writing to: " + out_dir + "/out.txt");
+  }
+  auto wants = [&](const std::string &what) {
+    std::stringstream ss(write_solution);
+    std::string item;
+    while(std::getline(ss, item, ','))
+      if(item == what)
+        return true;
+    return false;
+  };
+  if(wants("y"))
+    write_vector_file(out_dir + "/y.txt", solver.y);
+  if(wants("z") && !solver.sdp.normalization.empty())
+    {
+      // save_solution.cxx:75-118: insert z[max_index] so that n.z == 1
+      const auto &nrm = solver.sdp.normalization;
+      size_t max_index = 0;
+      for(size_t i = 1; i < nrm.size(); ++i)
+        if(Abs(nrm[i]) > Abs(nrm[max_index]))
+          max_index = i;
+      const int Ny = solver.y.h;
+      Matrix z(Ny + 1, 1);
+      for(int i = 0; i < (int)max_index; ++i)
+        z(i, 0) = solver.y(i, 0);
+      for(int i = (int)max_index; i < Ny; ++i)
+        z(i + 1, 0) = solver.y(i, 0);
+      BigFloat nz;
+      for(int i = 0; i <= Ny; ++i)
+        nz += nrm[i] * z(i, 0);
+      z((int)max_index, 0) = (BigFloat(1) - nz) / nrm[max_index];
+      write_vector_file(out_dir + "/z.txt", z);
+    }
+  for(size_t j = 0; j < solver.x.size(); ++j)
+    {
+      if(wants("x"))
+        write_vector_file(out_dir + "/x_" + std::to_string(j) + ".txt", solver.x[j]);
+      for(int parity = 0; parity < 2; ++parity)
+        {
+          const std::string suffix = std::to_string(2 * j + parity) + ".txt";
+          if(wants("X") && solver.X[2 * j + parity].h)
+            write_vector_file(out_dir + "/X_matrix_" + suffix, solver.X[2 * j + parity]);
+          if(wants("Y") && solver.Y[2 * j + parity].h)
+            write_vector_file(out_dir + "/Y_matrix_" + suffix, solver.Y[2 * j + parity]);
+        }
+    }
+  // c - B y (save_c_minus_By.hxx)
+  {
+    mkdir((out_dir + "/c_minus_By").c_str(), 0777);
+    std::ofstream f(out_dir + "/c_minus_By/c_minus_By.json");
+    f << "{\"c_minus_By\":[";
+    for(size_t j = 0; j < solver.x.size(); ++j)
+      {
+        Matrix v(solver.sdp.primal_objective_c[j]);
+        gemm_nn(BigFloat(-1), solver.sdp.free_var_matrix[j], solver.y, BigFloat(1), v);
+        f << (j ? "," : "") << "[";
+        for(int i = 0; i < v.h; ++i)
+          f << (i ? "," : "") << "\"" << format_bigfloat(v(i, 0)) << "\"";
+        f << "]";
+      }
+    f << "]}";
+  }
+}
+
+// Reads the SDP, runs the solver on `hot`, writes out_dir/{out.txt, iterations.json, x_j, y, z, c_minus_By}.
+// `make_hot_path` is called after the SDP is read (it needs the shapes).
+inline Terminate_Reason
+solve(const std::string &sdp_dir, const std::string &out_dir, const Solver_Parameters &parameters,
+      const std::function<std::unique_ptr<Hot_Path>(const Block_Info &, const SDP &)> &make_hot_path,
+      bool verbose, std::string *summary = nullptr)
+{
+  set_precision(parameters.precision);
+  Block_Info block_info;
+  SDP sdp;
+  read_sdp(sdp_dir, block_info, sdp);
+  std::unique_ptr<Hot_Path> hot = make_hot_path(block_info, sdp);
+  SDP_Solver solver(parameters, block_info, sdp, *hot);
+  if(verbose)
+    solver.on_iteration = [](const Iteration_Record &r) {
+      printf("%4ld %8.2f  mu %.3e  P-obj %.10e  D-obj %.10e  gap %.2e  P-err %.2e  D-err %.2e  steps %.3g %.3g\n",
+             r.iteration, r.total_time, r.mu.to_double(), r.primal_objective.to_double(),
+             r.dual_objective.to_double(), r.duality_gap.to_double(),
+             Max(r.primal_error_P, r.primal_error_p).to_double(), r.dual_error.to_double(),
+             r.primal_step_length.to_double(), r.dual_step_length.to_double());
+      fflush(stdout);
+    };
+  const auto t0 = std::chrono::steady_clock::now();
+  const Terminate_Reason reason = solver.run(parameters);
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if(!out_dir.empty())
+    {
+      save_solution(solver, reason, (long)secs, out_dir, parameters.write_solution);
+      write_iterations_json(out_dir + "/iterations.json", solver.iterations);
+    }
+  if(summary)
+    {
+      char buf[512];
+      snprintf(buf, sizeof buf,
+               "{\"terminateReason\": \"%s\", \"iterations\": %zu, \"seconds\": %.3f, \"hot_path_seconds\": %.3f, "
+               "\"host_seconds\": %.3f, \"hot_path\": \"%s\"}",
+               to_string(reason), solver.iterations.size(), secs, solver.hot_path_seconds, solver.host_seconds,
+               hot->name().c_str());
+      *summary = buf;
+    }
+  return reason;
+}
+} // namespace sdpb_host
