@@ -214,7 +214,10 @@ def main():
     sdp = SyntheticSDP(prec, shapes_t, N, seed=1 + rank)
     ctx = sdpb_b200.SchurContext(prec, shapes_t, N, device=local)
     if world > 1:
-        ctx.comm_init_from_torch(dist, rank, world)
+        # weak scaling: every rank owns its own J blocks of a J*world-block SDP (global index
+        # rank*J + j); the column-norm partials and the exact Q' residues cross NVLink (NCCL)
+        J = len(shapes_t)
+        ctx.comm_init_from_torch(dist, rank, world, J * world, [rank * J + j for j in range(J)])
     sdp.upload(ctx)
     sdp.B = None  # resident in HBM now
     log(f"[rank {rank}] setup {time.perf_counter() - t0:.1f}s")

@@ -142,6 +142,25 @@ int sdpb_b200_download(sdpb_b200_ctx *ctx, uint64_t *const *X_cholesky,
                        uint64_t *const *schur_complement_cholesky,
                        uint64_t *const *schur_off_diagonal, uint64_t *Q);
 
+/* Multi-GPU: the J SDP blocks are sharded over `world` processes, one GPU each
+ * (the reference's block parallelism: Block_Info::block_indices,
+ * sdpb_util/block_mapping/compute_block_grid_mapping.hxx:58-183).  Each process
+ * creates its context with ITS blocks only and then joins the communicator:
+ * rank 0 calls sdpb_b200_comm_get_unique_id (128 bytes) and the host distributes
+ * them (MPI_Bcast in the reference's environment, torch.distributed in bench.py);
+ * every rank calls sdpb_b200_comm_init with the global block count and the
+ * global index of each of its local blocks.  From then on
+ * initialize_schur_complement_solver / schur_step are collective: the per-block
+ * column-norm partials (Matrix_Normalizer.cxx:116-139) and the exact integer
+ * Q' partial sums (bigint_syrk/restore_and_reduce.cxx:137-212) are combined
+ * with NCCL over NVLink; every rank ends up with the same Q factor, and with
+ * L_j, L_j^-1 B_j for its own blocks.  The column norms are summed in GLOBAL
+ * block order, so results are bit-identical for every sharding. */
+#define SDPB_B200_COMM_ID_BYTES 128
+int sdpb_b200_comm_get_unique_id(void *id);
+int sdpb_b200_comm_init(sdpb_b200_ctx *ctx, int rank, int world, const void *id,
+                        int num_blocks_global, const int *global_block_index);
+
 /* Device-side timing of the last step, milliseconds per stage (CUDA events):
  * [0] cholesky X+Y  [1] bilinear pairings  [2] S assembly  [3] cholesky S_j +
  * L^-1 B  [4] norms+normalise  [5] exact syrk  [6] restore  [7] Cholesky(Q)

@@ -262,14 +262,12 @@ inline void compute_schur_block(const BlockShape &sh,
 }
 
 // Matrix_Normalizer (bigint_syrk/Matrix_Normalizer.cxx:75-139): per-block
-// partial sums of squares (rows ascending), partials added in block order
-// (the reference's AllReduce leaves the cross-rank order open), sqrt.
-inline void column_norms(const std::vector<Matrix> &P_blocks, int N,
-                         std::vector<BigFloat> &norms)
+// partial sums of squares (rows ascending) ...
+inline void column_norm_partials(const std::vector<Matrix> &P_blocks, int N,
+                                 std::vector<std::vector<BigFloat>> &part)
 {
-  std::vector<BigFloat> total(N);
   const int J = (int)P_blocks.size();
-  std::vector<std::vector<BigFloat>> part(J);
+  part.assign(J, std::vector<BigFloat>());
 #pragma omp parallel
   {
     BigFloat prod;
@@ -287,7 +285,14 @@ inline void column_norms(const std::vector<Matrix> &P_blocks, int N,
             }
       }
   }
-  for(int j = 0; j < J; ++j)
+}
+// ... partials added in (global) block order (the reference's AllReduce leaves
+// the cross-rank order open, Matrix_Normalizer.cxx:131), then sqrt (:136).
+inline void norms_from_partials(const std::vector<std::vector<BigFloat>> &part, int N,
+                                std::vector<BigFloat> &norms)
+{
+  std::vector<BigFloat> total(N);
+  for(size_t j = 0; j < part.size(); ++j)
     for(int c = 0; c < N; ++c)
       total[c] += part[j][c];
   norms.assign(N, BigFloat());
@@ -295,14 +300,20 @@ inline void column_norms(const std::vector<Matrix> &P_blocks, int N,
     if(total[c].sgn() > 0)
       norms[c] = Sqrt(total[c]);
 }
+inline void column_norms(const std::vector<Matrix> &P_blocks, int N,
+                         std::vector<BigFloat> &norms)
+{
+  std::vector<std::vector<BigFloat>> part;
+  column_norm_partials(P_blocks, N, part);
+  norms_from_partials(part, N, norms);
+}
 
 // Exact Q' = P'^T P' on truncated integers (bigint_syrk_blas; the CRT/BLAS
-// machinery computes exactly this integer, Readme.md:27-55), upper triangle,
-// converted back with fmpz_get_mpf semantics (fmpz_BigFloat_convert.hxx:9).
-inline void exact_syrk_upper(const std::vector<Matrix> &Pn_blocks, int N,
-                             Matrix &Q)
+// machinery computes exactly this integer, Readme.md:27-55), upper triangle
+// Qz[j*N + i], i <= j (caller owns the mpz's: N*N initialised entries).
+inline void exact_syrk_upper_integer(const std::vector<Matrix> &Pn_blocks, int N,
+                                     std::vector<__mpz_struct> &Qz)
 {
-  Q.resize(N, N);
   size_t rows = 0;
   for(const auto &b : Pn_blocks)
     rows += b.h;
@@ -320,23 +331,32 @@ inline void exact_syrk_upper(const std::vector<Matrix> &Pn_blocks, int N,
           }
       r0 += b.h;
     }
-#pragma omp parallel
-  {
-    mpz_t acc;
-    mpz_init(acc);
-#pragma omp for schedule(dynamic, 1)
-    for(int j = 0; j < N; ++j)
-      for(int i = 0; i <= j; ++i)
-        {
-          mpz_set_ui(acc, 0);
-          for(size_t r = 0; r < rows; ++r)
-            mpz_addmul(acc, &z[r * N + i], &z[r * N + j]);
-          mpf_set_z(Q(i, j).v, acc);
-        }
-    mpz_clear(acc);
-  }
+#pragma omp parallel for schedule(dynamic, 1)
+  for(int j = 0; j < N; ++j)
+    for(int i = 0; i <= j; ++i)
+      {
+        __mpz_struct *acc = &Qz[(size_t)j * N + i];
+        mpz_set_ui(acc, 0);
+        for(size_t r = 0; r < rows; ++r)
+          mpz_addmul(acc, &z[r * N + i], &z[r * N + j]);
+      }
   for(auto &p : z)
     mpz_clear(&p);
+}
+// ... converted back with fmpz_get_mpf semantics (fmpz_BigFloat_convert.hxx:9).
+inline void exact_syrk_upper(const std::vector<Matrix> &Pn_blocks, int N,
+                             Matrix &Q)
+{
+  Q.resize(N, N);
+  std::vector<__mpz_struct> Qz((size_t)N * N);
+  for(auto &q : Qz)
+    mpz_init(&q);
+  exact_syrk_upper_integer(Pn_blocks, N, Qz);
+  for(int j = 0; j < N; ++j)
+    for(int i = 0; i <= j; ++i)
+      mpf_set_z(Q(i, j).v, &Qz[(size_t)j * N + i]);
+  for(auto &q : Qz)
+    mpz_clear(&q);
 }
 
 struct SchurOutputs
@@ -349,13 +369,15 @@ struct SchurOutputs
   double cholesky_Q_ms = 0, syrk_ms = 0, block_ms = 0; // wall clock of the three big parts
 };
 
-// compute_Q + Cholesky(Q)  (compute_Q.cxx:134-151,
-// initialize_schur_complement_solver.cxx:89-103)
-inline void compute_Q_and_factor(const std::vector<Matrix> &S,
-                                 const std::vector<Matrix> &B, int N,
-                                 SchurOutputs &out)
+// ---- compute_Q + Cholesky(Q) in stages (compute_Q.cxx:134-151,
+// initialize_schur_complement_solver.cxx:89-103).  The single-process driver
+// compute_Q_and_factor below runs them back to back; the sharded model used by
+// the world_size-2 tests runs stage 1 and 2 per rank and exchanges in between.
+
+// stage 1 (compute_Q.cxx:20-54): per local block Cholesky(S_j), P_j = L_j^{-1} B_j
+inline void factor_and_solve_blocks(const std::vector<Matrix> &S, const std::vector<Matrix> &B,
+                                    SchurOutputs &out)
 {
-  const int prec = sdpb_host::working_precision_bits();
   const size_t J = S.size();
   const auto t_begin = std::chrono::steady_clock::now();
   out.schur_complement_cholesky.resize(J);
@@ -384,22 +406,29 @@ inline void compute_Q_and_factor(const std::vector<Matrix> &S,
   out.block_ms = std::chrono::duration<double, std::milli>(
                    std::chrono::steady_clock::now() - t_begin)
                    .count();
-  // syrk_Q (compute_Q.cxx:94-132)
-  const auto ts = std::chrono::steady_clock::now();
-  column_norms(out.schur_off_diagonal, N, out.norms);
+}
+// stage 2 (Matrix_Normalizer.cxx:174-190): P' = (P / norm) << prec in place
+inline void normalize_and_shift(std::vector<Matrix> &P, const std::vector<BigFloat> &norms, int N)
+{
+  const int prec = sdpb_host::working_precision_bits();
 #pragma omp parallel for schedule(dynamic)
-  for(size_t jb = 0; jb < J; ++jb) // Matrix_Normalizer.cxx:174-190
+  for(size_t jb = 0; jb < P.size(); ++jb)
     for(int c = 0; c < N; ++c)
       {
-        Matrix &blk = out.schur_off_diagonal[jb];
-        if(out.norms[c].sgn() == 0)
+        Matrix &blk = P[jb];
+        if(norms[c].sgn() == 0)
           continue;
         for(int r = 0; r < blk.h; ++r)
-          blk(r, c) = (blk(r, c) / out.norms[c]) << (unsigned)prec;
+          blk(r, c) = (blk(r, c) / norms[c]) << (unsigned)prec;
       }
-  exact_syrk_upper(out.schur_off_diagonal, N, out.Q);
+}
+// stage 3: check_normalized_Q_diagonal (compute_Q.cxx:65-91), restore_P
+// (Matrix_Normalizer.cxx:210-226), restore_Q upper (:245-265), Cholesky(UPPER, Q);
+// out.Q holds Q' (as BigFloat) on entry.
+inline void restore_and_factor_Q(SchurOutputs &out, int N)
+{
+  const int prec = sdpb_host::working_precision_bits();
   {
-    // check_normalized_Q_diagonal (compute_Q.cxx:65-91)
     const BigFloat one(1), eps = BigFloat(1) >> (unsigned)(prec / 2);
     for(int i = 0; i < N; ++i)
       {
@@ -414,7 +443,7 @@ inline void compute_Q_and_factor(const std::vector<Matrix> &S,
       }
   }
 #pragma omp parallel for schedule(dynamic)
-  for(size_t jb = 0; jb < J; ++jb) // restore_P, Matrix_Normalizer.cxx:210-226
+  for(size_t jb = 0; jb < out.schur_off_diagonal.size(); ++jb)
     for(int c = 0; c < N; ++c)
       {
         Matrix &blk = out.schur_off_diagonal[jb];
@@ -423,17 +452,35 @@ inline void compute_Q_and_factor(const std::vector<Matrix> &S,
         for(int r = 0; r < blk.h; ++r)
           blk(r, c) = (blk(r, c) >> (unsigned)prec) * out.norms[c];
       }
-  for(int j = 0; j < N; ++j) // restore_Q upper, Matrix_Normalizer.cxx:245-265
+  for(int j = 0; j < N; ++j)
     for(int i = 0; i <= j; ++i)
       out.Q(i, j) = (out.Q(i, j) >> (unsigned)(2 * prec)) * out.norms[i]
                     * out.norms[j];
   const auto tq = std::chrono::steady_clock::now();
-  out.syrk_ms = std::chrono::duration<double, std::milli>(tq - ts).count();
   const int bad = cholesky_upper(out.Q);
   out.cholesky_Q_ms = std::chrono::duration<double, std::milli>(
                         std::chrono::steady_clock::now() - tq)
                         .count();
   if(bad >= 0)
     out.error = "Error when computing Cholesky(Q)";
+}
+
+inline void compute_Q_and_factor(const std::vector<Matrix> &S,
+                                 const std::vector<Matrix> &B, int N,
+                                 SchurOutputs &out)
+{
+  factor_and_solve_blocks(S, B, out);
+  if(!out.error.empty())
+    return;
+  // syrk_Q (compute_Q.cxx:94-132)
+  const auto ts = std::chrono::steady_clock::now();
+  column_norms(out.schur_off_diagonal, N, out.norms);
+  normalize_and_shift(out.schur_off_diagonal, out.norms, N);
+  exact_syrk_upper(out.schur_off_diagonal, N, out.Q);
+  restore_and_factor_Q(out, N);
+  out.syrk_ms = std::chrono::duration<double, std::milli>(
+                  std::chrono::steady_clock::now() - ts)
+                  .count()
+                - out.cholesky_Q_ms;
 }
 } // namespace oracle

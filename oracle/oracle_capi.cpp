@@ -27,6 +27,7 @@ struct oracle_ctx
   std::vector<Matrix> AX, AY;          // 2J
   std::string error;
   double stage_ms[9];
+  SchurOutputs shard; // state between the stages of the sharded model
 };
 
 static void pack_out(const Matrix &m, uint64_t *out)
@@ -228,6 +229,135 @@ int oracle_schur_step(oracle_ctx *c, const uint64_t *const *X,
     return rc;
   return oracle_initialize_schur_complement_solver(
     c, schur_complement_cholesky, schur_off_diagonal, Q, block_timings_ms);
+}
+
+// ---- sharded model (multi-GPU semantics on the CPU) ---------------------
+// The blocks of one SDP are split over several oracle contexts ("ranks"); the
+// two exchanges of DESIGN.md §7 happen in the caller (tests: torch.distributed
+// gloo, world_size 2) between these stages.  Q' partials travel as exact
+// integers: per entry  [sign (0, 1, ~0), magnitude limbs...]  oracle_qprime_words(prec) words.
+int oracle_qprime_words(int prec_bits) { return 2 * ((prec_bits + 63) / 64 + 2) + 4; }
+
+// stage 1: Cholesky X, Y, pairings, S, Cholesky(S_j), L_j^{-1} B_j for the local
+// blocks; part[j*N + c] = sum over the rows of local block j of P(r,c)^2
+int oracle_shard_stage1(oracle_ctx *c, const uint64_t *const *X, const uint64_t *const *Y,
+                        uint64_t *part)
+{
+  int rc = oracle_cholesky_decomposition(c, 0, X, nullptr);
+  if(rc)
+    return rc;
+  rc = oracle_cholesky_decomposition(c, 1, Y, nullptr);
+  if(rc)
+    return rc;
+  rc = oracle_compute_bilinear_pairings(c, Y, nullptr, nullptr);
+  if(rc)
+    return rc;
+  std::vector<Matrix> S(c->J);
+#pragma omp parallel for schedule(dynamic)
+  for(int j = 0; j < c->J; ++j)
+    {
+      std::array<Matrix, 2> AX{c->AX[2 * j], c->AX[2 * j + 1]};
+      std::array<Matrix, 2> AY{c->AY[2 * j], c->AY[2 * j + 1]};
+      compute_schur_block(c->shapes[j], AX, AY, S[j]);
+    }
+  c->shard = SchurOutputs();
+  factor_and_solve_blocks(S, c->B, c->shard);
+  if(!c->shard.error.empty())
+    {
+      c->error = c->shard.error;
+      return 3;
+    }
+  std::vector<std::vector<BigFloat>> partials;
+  column_norm_partials(c->shard.schur_off_diagonal, c->N, partials);
+  const int ew = elem_words();
+  for(int j = 0; j < c->J; ++j)
+    for(int col = 0; col < c->N; ++col)
+      sdpb_host::pack(partials[j][col], part + ((size_t)j * c->N + col) * ew);
+  return 0;
+}
+// stage 2: norms from ALL blocks' partials in global block order; normalise the
+// local P; exact integer Q' of the local rows
+int oracle_shard_stage2(oracle_ctx *c, const uint64_t *part_global, int J_global, uint64_t *qprime)
+{
+  sdpb_host::set_precision(c->prec);
+  const int ew = elem_words(), N = c->N;
+  std::vector<std::vector<BigFloat>> partials(J_global, std::vector<BigFloat>(N));
+  for(int j = 0; j < J_global; ++j)
+    for(int col = 0; col < N; ++col)
+      sdpb_host::unpack(partials[j][col], part_global + ((size_t)j * N + col) * ew);
+  norms_from_partials(partials, N, c->shard.norms);
+  normalize_and_shift(c->shard.schur_off_diagonal, c->shard.norms, N);
+  std::vector<__mpz_struct> Qz((size_t)N * N);
+  for(auto &q : Qz)
+    mpz_init(&q);
+  exact_syrk_upper_integer(c->shard.schur_off_diagonal, N, Qz);
+  const int W = oracle_qprime_words(c->prec);
+  for(size_t e = 0; e < (size_t)N * N; ++e)
+    {
+      uint64_t *o = qprime + e * W;
+      for(int k = 0; k < W; ++k)
+        o[k] = 0;
+      const int sz = Qz[e]._mp_size, asz = sz < 0 ? -sz : sz;
+      if(asz > W - 1)
+        {
+          c->error = "Q' entry too large for the exchange record";
+          return 1;
+        }
+      o[0] = sz == 0 ? 0 : (sz > 0 ? 1 : ~(uint64_t)0);
+      for(int k = 0; k < asz; ++k)
+        o[1 + k] = Qz[e]._mp_d[k];
+    }
+  for(auto &q : Qz)
+    mpz_clear(&q);
+  return 0;
+}
+// stage 3: Q' = sum of every rank's partial (exact, order-free), back to mpf,
+// diagonal check, restore the local P and Q, Cholesky(UPPER, Q)
+int oracle_shard_stage3(oracle_ctx *c, int nparts, const uint64_t *const *qprimes,
+                        uint64_t *const *schur_complement_cholesky, uint64_t *const *schur_off_diagonal,
+                        uint64_t *Q)
+{
+  sdpb_host::set_precision(c->prec);
+  const int N = c->N, W = oracle_qprime_words(c->prec);
+  c->shard.Q.resize(N, N);
+  mpz_t acc, term;
+  mpz_init(acc);
+  mpz_init(term);
+  for(int j = 0; j < N; ++j)
+    for(int i = 0; i <= j; ++i)
+      {
+        const size_t e = (size_t)j * N + i;
+        mpz_set_ui(acc, 0);
+        for(int p = 0; p < nparts; ++p)
+          {
+            const uint64_t *o = qprimes[p] + e * W;
+            if(o[0] == 0)
+              continue;
+            mpz_import(term, W - 1, -1, 8, 0, 0, o + 1);
+            if(o[0] != 1)
+              term[0]._mp_size = -term[0]._mp_size;
+            mpz_add(acc, acc, term);
+          }
+        mpf_set_z(c->shard.Q(i, j).v, acc);
+      }
+  mpz_clear(acc);
+  mpz_clear(term);
+  restore_and_factor_Q(c->shard, N);
+  if(!c->shard.error.empty())
+    {
+      c->error = c->shard.error;
+      return c->error.find("Normalized Q") != std::string::npos ? 4 : 3;
+    }
+  for(int j = 0; j < c->J; ++j)
+    {
+      if(schur_complement_cholesky && schur_complement_cholesky[j])
+        pack_out(c->shard.schur_complement_cholesky[j], schur_complement_cholesky[j]);
+      if(schur_off_diagonal && schur_off_diagonal[j])
+        pack_out(c->shard.schur_off_diagonal[j], schur_off_diagonal[j]);
+    }
+  if(Q)
+    pack_out(c->shard.Q, Q);
+  return 0;
 }
 
 // ---- single-kernel entry points for unit parity tests -----------------

@@ -78,6 +78,11 @@ def load_library():
     lib.sdpb_b200_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
     lib.sdpb_b200_host_free.restype = None
     lib.sdpb_b200_host_free.argtypes = [ctypes.c_void_p]
+    lib.sdpb_b200_comm_get_unique_id.restype = ctypes.c_int
+    lib.sdpb_b200_comm_get_unique_id.argtypes = [ctypes.c_void_p]
+    lib.sdpb_b200_comm_init.restype = ctypes.c_int
+    lib.sdpb_b200_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                        ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     lib.sdpb_b200_scalar_op.restype = ctypes.c_int
     lib.sdpb_b200_scalar_op.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_long, u64p, u64p, u64p]
     _lib = lib
@@ -258,6 +263,34 @@ class SchurContext(StepContextBase):
         self._check(self.lib.sdpb_b200_download(
             self.handle, opt(X_chol), opt(Y_chol), opt(A_X_inv), opt(A_Y), opt(L), opt(P),
             _ptr(Q) if Q is not None else None))
+
+    # multi-GPU ----------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id (call on rank 0, then broadcast it to the other ranks)."""
+        lib = load_library()
+        buf = ctypes.create_string_buffer(128)
+        rc = lib.sdpb_b200_comm_get_unique_id(buf)
+        if rc != 0:
+            raise SdpbB200Error(rc, "sdpb_b200_comm_get_unique_id failed (is libnccl.so.2 loadable?)")
+        return buf.raw
+
+    def comm_init(self, rank, world, unique_id, num_blocks_global, global_block_index):
+        """Join the communicator; this context holds the blocks `global_block_index` of
+        `num_blocks_global` (Block_Info::block_indices in the reference)."""
+        assert len(global_block_index) == self.J and len(unique_id) == 128
+        idx = (ctypes.c_int * max(1, self.J))(*global_block_index)
+        self._check(self.lib.sdpb_b200_comm_init(self.handle, rank, world, unique_id, num_blocks_global, idx))
+
+    def comm_init_from_torch(self, dist, rank, world, num_blocks_global, global_block_index):
+        """Rendezvous through an initialised torch.distributed group (any backend)."""
+        import torch
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(self.comm_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, 0)
+        self.comm_init(rank, world, bytes(t.cpu().numpy().tobytes()), num_blocks_global, global_block_index)
 
     def kernel_launches(self):
         return int(self.lib.sdpb_b200_kernel_launches(self.handle))

@@ -2,6 +2,7 @@
 // HBM layout, kernel sequencing.  No CPU fallback: every entry point that
 // computes requires a CUDA device.
 #include "ctx.h"
+#include "nccl_dyn.h"
 
 #include <algorithm>
 #include <climits>
@@ -285,6 +286,7 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
   }
   TRY_C(cudaMalloc(&c->R, std::max<size_t>(4, (size_t)c->crt.np * c->K * N * 4)));
   TRY_C(cudaMalloc(&c->Qres, (size_t)c->crt.np * N * N * 4));
+  TRY_C(cudaMemset(c->Qres, 0, (size_t)c->crt.np * N * N * 4));
   // descriptors
   const int rs = ((2 * nl + 4) + 3) & ~3; // TileGeom::RS
   {
@@ -333,7 +335,7 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
         sd.push_back(SchurDesc{{c->AX + c->oA[2 * j], c->AX + c->oA[2 * j + 1]},
                                {c->AY + c->oA[2 * j], c->AY + c->oA[2 * j + 1]},
                                c->S + c->oS[j], b.m, b.n});
-        bd.push_back(BandDesc{c->Pband + c->oB[j], b.P, (int)b.row0});
+        bd.push_back(BandDesc{c->Pband + c->oB[j], b.P, (int)b.row0, j});
       }
   }
   // largest matrices first: the long CTAs start early, the short ones fill in
@@ -381,6 +383,7 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
   TRY_C(upload(&c->d_gemmYV, gYV));
   TRY_C(upload(&c->d_gemmAY, gAY));
   TRY_C(upload(&c->d_schur, sd));
+  c->h_bands = bd;
   TRY_C(upload(&c->d_bands, bd));
   TRY_C(cudaMalloc(&c->d_status, (size_t)(5 * num_blocks + 8) * sizeof(int)));
   TRY_C(cudaMalloc(&c->d_flags, 4 * sizeof(int)));
@@ -392,11 +395,105 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
   return 0;
 }
 
+// ------------------------------------------------------------- multi-GPU
+// The SDP blocks are sharded over `world` processes, one GPU each (the
+// reference's block parallelism, block_mapping/compute_block_grid_mapping.hxx:58-183).
+// Two exchanges remain inside initialize_schur_complement_solver: the per-block
+// column-norm partials (Matrix_Normalizer.cxx:131 is an MPI AllReduce) and the
+// exact integer Q' partial sums (restore_and_reduce.cxx:137-212 is a ring of
+// SendRecv); both are one ncclAllReduce here.  Cholesky(Q) is replicated.
+static int nccl_allreduce(sdpb_b200_ctx *c, void *buf, size_t count, int is_u64, const char *label)
+{
+  NcclApi &api = nccl_api();
+  c->kt_begin(label);
+  const ncclResult_t r = api.AllReduce(buf, buf, count, is_u64 ? ncclUint64 : ncclUint32, ncclSum,
+                                       (ncclComm_t)c->comm, c->stream);
+  c->kt_end();
+  --c->launches; // NCCL's kernel, not one of ours
+  if(r != ncclSuccess)
+    {
+      c->error = std::string("NCCL: ") + api.GetErrorString(r) + " in " + label;
+      return SDPB_B200_ERR_CUDA;
+    }
+  return 0;
+}
+
+extern "C" int sdpb_b200_comm_get_unique_id(void *id)
+{
+  NcclApi &api = nccl_api();
+  if(!id || !api.load())
+    return SDPB_B200_ERR_CUDA;
+  ncclUniqueId u;
+  if(api.GetUniqueId(&u) != ncclSuccess)
+    return SDPB_B200_ERR_CUDA;
+  memcpy(id, u.internal, NCCL_UNIQUE_ID_BYTES);
+  return 0;
+}
+
+extern "C" int sdpb_b200_comm_init(sdpb_b200_ctx *c, int rank, int world, const void *id,
+                                   int num_blocks_global, const int *global_block_index)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  if(world < 1 || world > 16 || rank < 0 || rank >= world || !id || num_blocks_global < c->J
+     || (c->J && !global_block_index))
+    {
+      c->error = "sdpb_b200_comm_init: bad argument (1 <= world <= 16: u32 residue sums must not overflow)";
+      return SDPB_B200_ERR_ARG;
+    }
+  if(c->comm)
+    {
+      c->error = "sdpb_b200_comm_init: communicator already initialised";
+      return SDPB_B200_ERR_STATE;
+    }
+  for(int j = 0; j < c->J; ++j)
+    {
+      if(global_block_index[j] < 0 || global_block_index[j] >= num_blocks_global)
+        {
+          c->error = "sdpb_b200_comm_init: global block index out of range";
+          return SDPB_B200_ERR_ARG;
+        }
+      c->h_bands[j].gidx = global_block_index[j];
+    }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if(c->J)
+    CUDA_TRY(c, cudaMemcpy(c->d_bands, c->h_bands.data(), c->h_bands.size() * sizeof(BandDesc),
+                           cudaMemcpyHostToDevice));
+  CUDA_TRY(c, cudaMalloc(&c->part_global, (size_t)std::max(1, num_blocks_global) * c->N * c->es * 8));
+  NcclApi &api = nccl_api();
+  if(!api.load())
+    {
+      c->error = api.error;
+      return SDPB_B200_ERR_CUDA;
+    }
+  ncclUniqueId u;
+  memcpy(u.internal, id, NCCL_UNIQUE_ID_BYTES);
+  ncclComm_t comm;
+  const ncclResult_t r = api.CommInitRank(&comm, world, u, rank);
+  if(r != ncclSuccess)
+    {
+      c->error = std::string("NCCL: ncclCommInitRank: ") + api.GetErrorString(r);
+      return SDPB_B200_ERR_CUDA;
+    }
+  c->comm = comm;
+  c->rank = rank;
+  c->world = world;
+  c->J_global = num_blocks_global;
+  c->allreduce = &nccl_allreduce;
+  return 0;
+}
+
 extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
 {
   if(!c)
     return;
   cudaSetDevice(c->device);
+  if(c->comm)
+    {
+      cudaStreamSynchronize(c->stream);
+      nccl_api().CommDestroy((ncclComm_t)c->comm);
+    }
+  cudaFree(c->part_global);
   cudaFree(c->arena);
   cudaFree(c->R);
   cudaFree(c->Qres);

@@ -73,9 +73,17 @@ struct sdpb_b200_ctx
            *recipN = nullptr;
   SchurDesc *d_schur = nullptr;
   BandDesc *d_bands = nullptr;
+  std::vector<BandDesc> h_bands;
   int *d_status = nullptr; // [2J X | 2J Y | J S | 1 Q]
   int *d_flags = nullptr;  // [0] overflow, [1] first bad Q diagonal
   int max_s = 0, max_mn = 0, max_P = 0;
+
+  // multi-GPU (sdpb_b200_comm_init): blocks sharded over `world` ranks; `part`
+  // then holds one row of column-norm partials per GLOBAL block
+  void *comm = nullptr; // ncclComm_t
+  int rank = 0, world = 1, J_global = 0;
+  limb_t *part_global = nullptr;
+  int (*allreduce)(sdpb_b200_ctx *, void *buf, size_t count, int is_u64, const char *label) = nullptr;
 
   bool have_X_cholesky = false, have_pairings = false;
   long launches = 0; // kernels launched since creation

@@ -58,6 +58,7 @@ struct BandDesc // P band of one SDP block inside the stacked K x N matrix
   limb_t *P; // P_j x N, column-major, ld = rows
   int rows;
   int row0; // first stacked row
+  int gidx; // global block index (row of the norm partials; == local index on one GPU)
 };
 
 // ------------------------------------------------------------- small helpers
@@ -320,7 +321,7 @@ __global__ void norm_partial_kernel(const BandDesc *bands, int N, limb_t *part)
           mpfx::mul(p, v, v);
           mpfx::add(acc, acc, p);
         }
-      st(part, (size_t)blockIdx.x * N + c, acc);
+      st(part, (size_t)b.gidx * N + c, acc);
     }
 }
 template <int NL>
@@ -509,7 +510,8 @@ crt_restore_kernel(const uint32_t *__restrict__ Qres, int N, int prec,
   for(int a = 0; a < np; ++a)
     {
       const uint32_t pa = T.primes[a];
-      uint64_t t = Qres[((size_t)a * N + i) * N + j];
+      // a sum of per-rank residues when the blocks are sharded over GPUs
+      uint64_t t = Qres[((size_t)a * N + i) * N + j] % pa;
       for(int b = 0; b < a; ++b)
         {
           // t = (t - v_b) * p_b^{-1} mod p_a

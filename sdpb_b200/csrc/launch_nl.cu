@@ -163,16 +163,26 @@ template <int NL> struct Launch
     const int init_flags[4] = {0, INT_MAX, 0, 0};
     CUDA_TRY(c, cudaMemcpyAsync(c->d_flags, init_flags, sizeof(init_flags),
                                 cudaMemcpyHostToDevice, st));
+    const bool sharded = c->world > 1;
+    limb_t *part = sharded ? c->part_global : c->part;
+    const int Jsum = sharded ? c->J_global : J;
+    if(sharded) // rows of blocks owned elsewhere: exact zeros, so the sum below is a gather
+      CUDA_TRY(c, cudaMemsetAsync(part, 0, (size_t)Jsum * N * Fmt<NL>::ES * 8, st));
     if(J)
       {
         dim3 g1(J, (N + 63) / 64);
         c->kt_begin("norm_partial_kernel");
-        norm_partial_kernel<NL><<<g1, 64, 0, st>>>(c->d_bands, N, c->part);
+        norm_partial_kernel<NL><<<g1, 64, 0, st>>>(c->d_bands, N, part);
         c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
       }
+    if(sharded)
+      if(int rc2 = c->allreduce(c, part, (size_t)Jsum * N * Fmt<NL>::ES, 1, "nccl_allreduce_norm_partials"))
+        return rc2;
+    // every rank adds the per-block partials in GLOBAL block order: the norms do
+    // not depend on how the blocks are sharded
     c->kt_begin("norm_final_kernel");
-    norm_final_kernel<NL><<<(N + 63) / 64, 64, 0, st>>>(c->part, J, N, c->norms, c->recipN);
+    norm_final_kernel<NL><<<(N + 63) / 64, 64, 0, st>>>(part, Jsum, N, c->norms, c->recipN);
     c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
     if(J)
@@ -194,6 +204,11 @@ template <int NL> struct Launch
       c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
     }
+    // exact integers: the cross-GPU sum is order-free.  Residues are < 2^28, so a
+    // plain u32 sum over <= 16 ranks cannot overflow; the CRT kernel reduces mod p.
+    if(sharded)
+      if(int rc2 = c->allreduce(c, c->Qres, (size_t)c->crt.np * N * N, 0, "nccl_allreduce_Q_residues"))
+        return rc2;
     CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
     {
       const long tot = (long)N * N;

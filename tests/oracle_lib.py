@@ -34,6 +34,14 @@ def load_oracle():
     lib.oracle_destroy.argtypes = [ctypes.c_void_p]
     lib.oracle_destroy.restype = None
     lib.oracle_last_error.restype = ctypes.c_char_p
+    lib.oracle_qprime_words.restype = ctypes.c_int
+    lib.oracle_qprime_words.argtypes = [ctypes.c_int]
+    lib.oracle_shard_stage1.restype = ctypes.c_int
+    lib.oracle_shard_stage1.argtypes = [ctypes.c_void_p, u64pp, u64pp, u64p]
+    lib.oracle_shard_stage2.restype = ctypes.c_int
+    lib.oracle_shard_stage2.argtypes = [ctypes.c_void_p, u64p, ctypes.c_int, u64p]
+    lib.oracle_shard_stage3.restype = ctypes.c_int
+    lib.oracle_shard_stage3.argtypes = [ctypes.c_void_p, ctypes.c_int, u64pp, u64pp, u64pp, u64p]
     lib.oracle_last_error.argtypes = [ctypes.c_void_p]
     lib.oracle_set_block.argtypes = [ctypes.c_void_p, ctypes.c_int, u64p, u64p, u64p]
     lib.oracle_cholesky_decomposition.argtypes = [ctypes.c_void_p, ctypes.c_int, u64pp, u64pp]
@@ -114,6 +122,26 @@ class OracleContext(StepContextBase):
             self.handle, ptr_array(X), ptr_array(Y), opt(X_chol), opt(Y_chol), opt(A_X_inv), opt(A_Y),
             opt(L), opt(P), _ptr(Q) if Q is not None else None, None))
 
+    # sharded model (oracle_shard_stage1..3): the caller does the two exchanges
+    def shard_stage1(self, X, Y):
+        part = np.zeros((self.J, self.N, self.ew), dtype=np.uint64)
+        self._check(self.lib.oracle_shard_stage1(self.handle, ptr_array(X), ptr_array(Y), _ptr(part)))
+        return part
+
+    def shard_stage2(self, part_global):
+        part_global = np.ascontiguousarray(part_global, dtype=np.uint64)
+        W = self.lib.oracle_qprime_words(self.prec)
+        q = np.zeros((self.N, self.N, W), dtype=np.uint64)
+        self._check(self.lib.oracle_shard_stage2(self.handle, _ptr(part_global), part_global.shape[0], _ptr(q)))
+        return q
+
+    def shard_stage3(self, qparts):
+        L, P, Q = self.alloc_schur_outputs()
+        qparts = [np.ascontiguousarray(q, dtype=np.uint64) for q in qparts]
+        self._check(self.lib.oracle_shard_stage3(self.handle, len(qparts), ptr_array(qparts), ptr_array(L),
+                                                 ptr_array(P), _ptr(Q)))
+        return L, P, Q
+
     def stage_ms(self):
         ms = (ctypes.c_double * 9)()
         self.lib.oracle_stage_ms(self.handle, ms, 9)
@@ -166,14 +194,17 @@ class SyntheticSDP:
     bases and B with entries U(-1,1), full-length mantissas; X, Y symmetric
     positive definite.  The same object feeds the oracle and the CUDA library."""
 
-    def __init__(self, prec, shapes, N, seed=1):
+    def __init__(self, prec, shapes, N, seed=1, block_ids=None):
+        """block_ids: global indices of `shapes` when this object holds one rank's share of a
+        sharded SDP (the data of a block depends only on its global index)."""
         from sdpb_b200.capi import BlockShape
         self.prec = prec
         self.shapes = [s if isinstance(s, BlockShape) else BlockShape(*s) for s in shapes]
         self.N = N
         self.B, self.bases = [], []
         self.X, self.Y = [], []
-        for j, s in enumerate(self.shapes):
+        ids = list(block_ids) if block_ids is not None else list(range(len(self.shapes)))
+        for j, s in zip(ids, self.shapes):
             base = seed * 1000003 + j * 101
             self.B.append(random_matrix(prec, s.schur_size, N, base + 1))
             self.bases.append((random_matrix(prec, s.basis_height(0), s.n, base + 2),
