@@ -124,13 +124,27 @@ static int build_crt(sdpb_b200_ctx *c)
       return e;
     return cudaMemcpy(*d, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
   };
+  // the same powers with rows zero-padded to a multiple of 4 digits (normalize_kernel's
+  // shared-memory table, NormGeom<NL>::NDP) and the Barrett constants floor((2^64-1)/p)
+  const int ndp = ((64 * (c->nl - 2) + 2 + 27) / 28 + 3) & ~3;
+  std::vector<uint32_t> pow28p((size_t)np * ndp, 0);
+  std::vector<uint64_t> inv64(np);
+  for(int i = 0; i < np; ++i)
+    {
+      for(int k = 0; k < nd && k < ndp; ++k)
+        pow28p[(size_t)i * ndp + k] = pow28[(size_t)i * nd + k];
+      inv64[i] = ~0ull / primes[i];
+    }
+  CUDA_TRY(c, up(&c->d_pow28p, pow28p));
+  CUDA_TRY(c, cudaMalloc(&c->d_inv64, inv64.size() * 8));
+  CUDA_TRY(c, cudaMemcpy(c->d_inv64, inv64.data(), inv64.size() * 8, cudaMemcpyHostToDevice));
   CUDA_TRY(c, up(&c->d_primes, primes));
   CUDA_TRY(c, up(&c->d_pow28, pow28));
   CUDA_TRY(c, up(&c->d_ginv, ginv));
   CUDA_TRY(c, up(&c->d_M, M));
   CUDA_TRY(c, up(&c->d_Mhalf, Mh));
   c->crt = CrtTables{c->d_primes, c->d_pow28, c->d_ginv, c->d_M, c->d_Mhalf,
-                     np,          nd,         mw};
+                     np,          nd,         mw,        c->d_pow28p, c->d_inv64, ndp};
   return 0;
 }
 
@@ -284,7 +298,9 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
     if(rc)
       return bail(rc);
   }
-  TRY_C(cudaMalloc(&c->R, std::max<size_t>(4, (size_t)c->crt.np * c->K * N * 4)));
+  c->NS = (N + 15) & ~15; // residue row stride: whole 16-column tiles, pad columns stay zero
+  TRY_C(cudaMalloc(&c->R, std::max<size_t>(4, (size_t)c->crt.np * c->K * c->NS * 4)));
+  TRY_C(cudaMemset(c->R, 0, std::max<size_t>(4, (size_t)c->crt.np * c->K * c->NS * 4)));
   TRY_C(cudaMalloc(&c->Qres, (size_t)c->crt.np * N * N * 4));
   TRY_C(cudaMemset(c->Qres, 0, (size_t)c->crt.np * N * N * 4));
   // descriptors
@@ -499,6 +515,8 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
   cudaFree(c->Qres);
   cudaFree(c->d_primes);
   cudaFree(c->d_pow28);
+  cudaFree(c->d_pow28p);
+  cudaFree(c->d_inv64);
   cudaFree(c->d_ginv);
   cudaFree(c->d_M);
   cudaFree(c->d_Mhalf);

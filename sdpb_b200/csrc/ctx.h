@@ -57,7 +57,9 @@ struct sdpb_b200_ctx
 
   uint32_t *R = nullptr, *Qres = nullptr;
   uint32_t *d_primes = nullptr, *d_pow28 = nullptr, *d_ginv = nullptr,
-           *d_M = nullptr, *d_Mhalf = nullptr;
+           *d_M = nullptr, *d_Mhalf = nullptr, *d_pow28p = nullptr;
+  uint64_t *d_inv64 = nullptr;
+  int NS = 0; // row stride of the residue planes R (N rounded up to 16)
   CrtTables crt{};
 
   // tile-kernel descriptors (tile.cuh); matrices sorted by cost, largest first

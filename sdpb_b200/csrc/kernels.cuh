@@ -307,21 +307,18 @@ __global__ void __launch_bounds__(128) schur_kernel(const SchurDesc *descs)
 // Matrix_Normalizer.cxx:75-139.  part[j*N + c] = sum over the rows of band j
 // of v^2 (rows ascending); norms[c] = sqrt(sum_j part) in block order.
 template <int NL>
-__global__ void norm_partial_kernel(const BandDesc *bands, int N, limb_t *part)
+__global__ void __launch_bounds__(64) norm_partial_kernel(const BandDesc *bands, int N, limb_t *part)
 {
   const BandDesc b = bands[blockIdx.x];
   for(int c = blockIdx.y * blockDim.x + threadIdx.x; c < N;
       c += gridDim.y * blockDim.x)
     {
-      Num<NL> acc, v, p;
-      mpfx::set_zero(acc);
-      for(int r = 0; r < b.rows; ++r)
-        {
-          ld(v, b.P, (size_t)c * b.rows + r);
-          mpfx::mul(p, v, v);
-          mpfx::add(acc, acc, p);
-        }
-      st(part, (size_t)b.gidx * N + c, acc);
+      Reg<NL> acc;
+      mpfw::set_zero(acc);
+      const uint32_t *col = reinterpret_cast<const uint32_t *>(b.P + (size_t)c * b.rows * Fmt<NL>::ES);
+      for(int r = 0; r < b.rows; ++r) // acc += v * v: one mpf_mul, one mpf_add (Matrix_Normalizer.cxx:82-88)
+        acc = mac_nl<NL>(acc, col + (size_t)r * 2 * Fmt<NL>::ES, col + (size_t)r * 2 * Fmt<NL>::ES, false);
+      stg_reg<NL>(part + ((size_t)b.gidx * N + c) * Fmt<NL>::ES, acc);
     }
 }
 template <int NL>
@@ -360,84 +357,169 @@ struct CrtTables
   const uint32_t *M;      // [mw] product of all primes, 32-bit words
   const uint32_t *Mhalf;  // [mw] (M+1)/2
   int np, nd, mw;
+  const uint32_t *pow28p; // [np][ndp] the same powers, rows zero-padded to ndp (a multiple of 4)
+  const uint64_t *inv64;  // [np] floor((2^64 - 1) / p): Barrett constant
+  int ndp;
 };
+
+// x mod p for x < 2^63, p < 2^28, inv = floor((2^64 - 1) / p)
+__device__ __forceinline__ uint32_t barrett_mod(uint64_t x, uint32_t p, uint64_t inv)
+{
+  const uint64_t q = __umul64hi(x, inv); // floor(x / p) - 2 <= q <= floor(x / p)
+  uint32_t r = (uint32_t)x - (uint32_t)q * p;
+  if(r >= p)
+    r -= p;
+  if(r >= p)
+    r -= p;
+  return r;
+}
 
 // P' = (P / norm) << prec, in place (Matrix_Normalizer.cxx:174-190), plus the
 // residues of trunc(P') (fmpz_set_mpf truncates toward zero,
 // fmpz_BigFloat_convert.hxx:13) modulo every prime:
-// R[(p*K + row)*N + col].  flags[0] is raised if |trunc(P')| does not fit.
+// R[(p*K + row)*NS + col], NS = row stride (N rounded up to 16; the pad
+// columns stay zero).  flags[0] is raised if |trunc(P')| does not fit.
+//
+// One thread per element, consecutive threads on consecutive COLUMNS of one
+// row, so the residue stores coalesce (an element is a whole 128-byte line
+// either way).  The integer part is cut into 28-bit digits held in registers;
+// a residue is sum_k digit_k * (2^(28k) mod p) -- IMAD.WIDE against a table in
+// shared memory -- followed by one Barrett reduction.
+template <int NL> struct NormGeom
+{
+  static constexpr int ND = (64 * (NL - 2) + 2 + 27) / 28; // digits of an integer below 2^(prec+2), prec <= 64 (NL-2)
+  static constexpr int NDP = (ND + 3) & ~3;
+};
 template <int NL>
 __global__ void __launch_bounds__(128)
-normalize_kernel(const BandDesc *bands, int N, long K, const limb_t *norms,
+normalize_kernel(const BandDesc *bands, int N, int NS, long K, const limb_t *norms,
                  const uint32_t *recip, int prec, CrtTables T, uint32_t *R, int *flags)
 {
+  typedef NormGeom<NL> G;
+  extern __shared__ __align__(16) uint32_t nsm[]; // [np][NDP] powers, then [np] primes, then [np] inv64
+  uint32_t *s_pow = nsm;
+  uint32_t *s_p = nsm + (size_t)T.np * G::NDP;
+  uint64_t *s_inv = reinterpret_cast<uint64_t *>(s_p + ((T.np + 1) & ~1));
+  for(int q = threadIdx.x; q < T.np * G::NDP; q += blockDim.x)
+    {
+      const int pi = q / G::NDP, k = q % G::NDP;
+      s_pow[q] = k < T.ndp ? T.pow28p[(size_t)pi * T.ndp + k] : 0u;
+    }
+  for(int q = threadIdx.x; q < T.np; q += blockDim.x)
+    {
+      s_p[q] = T.primes[q];
+      s_inv[q] = T.inv64[q];
+    }
+  __syncthreads();
   const BandDesc b = bands[blockIdx.x];
   const long total = (long)b.rows * N;
-  constexpr int MAXW = 2 * NL + 2; // 32-bit words of the integer part
+  const int nd = T.nd;
   for(long e = (long)blockIdx.y * blockDim.x + threadIdx.x; e < total;
       e += (long)gridDim.y * blockDim.x)
     {
-      const int r = (int)(e % b.rows), c = (int)(e / b.rows);
-      Num<NL> v, nrm;
-      ld(nrm, norms, c);
-      ld(v, b.P, e);
-      if(nrm.sign != 0)
+      const int c = (int)(e % N), r = (int)(e / N);
+      limb_t *elem = b.P + ((size_t)c * b.rows + r) * Fmt<NL>::ES;
+      const uint32_t *nrm = reinterpret_cast<const uint32_t *>(norms + (size_t)c * Fmt<NL>::ES);
+      Reg<NL> v;
+      ldg_reg<NL>(v, elem);
+      if((int32_t)nrm[1] != 0)
         {
-          Reg<NL> rv;
-          mpfw::from_num(rv, v);
-          rv = div_nl<NL>(rv, reinterpret_cast<const uint32_t *>(norms + (size_t)c * Fmt<NL>::ES),
-                          recip + (size_t)c * TileGeom<NL>::RS);
-          mpfw::to_num(v, rv);
-          mpfx::mul_2exp(v, v, (uint32_t)prec);
-          st(b.P, e, v);
+          v = div_nl<NL>(v, nrm, recip + (size_t)c * TileGeom<NL>::RS);
+          if((prec & 63) == 0)
+            {
+              if(v.sign != 0)
+                v.exp += prec >> 6; // mpf_mul_2exp by whole limbs: exponent only
+            }
+          else
+            {
+              Num<NL> t;
+              mpfw::to_num(t, v);
+              mpfx::mul_2exp(t, t, (uint32_t)prec);
+              mpfw::from_num(v, t);
+            }
+          stg_reg<NL>(elem, v);
         }
-      uint32_t w[MAXW];
-      if(!mpfx::trunc_to_words(w, MAXW, v))
-        atomicExch(&flags[0], 1);
-      // 28-bit digits
-      uint32_t dg[(32 * MAXW + 27) / 28];
-      const int nd = T.nd;
+      // integer part: the mantissa shifted right by NL - exp limbs
+      uint32_t iw[2 * NL];
+#pragma unroll
+      for(int i = 0; i < 2 * NL; ++i)
+        iw[i] = v.w[i];
       bool fits = true;
-      for(int k = 0; k < (32 * MAXW + 27) / 28; ++k)
+      if(v.sign == 0 || v.exp <= 0)
+        {
+#pragma unroll
+          for(int i = 0; i < 2 * NL; ++i)
+            iw[i] = 0;
+        }
+      else if(v.exp > NL)
+        fits = false;
+      else
+        mpfw::shr_limbs<NL>(iw, NL - v.exp);
+      // 28-bit digits
+      uint32_t dg[G::NDP];
+#pragma unroll
+      for(int k = 0; k < G::NDP; ++k)
         {
           const int bit = 28 * k, wi = bit >> 5, sh = bit & 31;
-          uint64_t x = 0;
-          if(wi < MAXW)
-            x = w[wi];
-          if(wi + 1 < MAXW)
-            x |= (uint64_t)w[wi + 1] << 32;
-          const uint32_t dig = (uint32_t)(x >> sh) & 0x0FFFFFFFu;
-          dg[k] = dig;
-          if(k >= nd && dig)
+          uint32_t x = 0;
+          if(k < G::ND && wi < 2 * NL)
+            {
+              x = iw[wi] >> sh;
+              if(sh > 4 && wi + 1 < 2 * NL)
+                x |= iw[wi + 1] << (32 - sh);
+              x &= 0x0FFFFFFFu;
+            }
+          dg[k] = x;
+          if(k >= nd && x)
             fits = false;
+        }
+#pragma unroll
+      for(int i = 0; i < 2 * NL; ++i) // bits beyond the last digit
+        {
+          const int lo = 32 * i, cut = 28 * G::ND;
+          if(lo >= cut)
+            fits = fits && iw[i] == 0;
+          else if(lo + 32 > cut)
+            fits = fits && (iw[i] >> (cut - lo)) == 0;
         }
       if(!fits)
         atomicExch(&flags[0], 1);
-      const size_t row = (size_t)b.row0 + r;
+      uint32_t *out = R + ((size_t)b.row0 + r) * NS + c;
+      const bool neg = v.sign < 0;
       for(int pi = 0; pi < T.np; ++pi)
         {
-          const uint32_t p = T.primes[pi];
-          const uint32_t *pw = T.pow28 + (size_t)pi * nd;
-          uint64_t acc = 0;
-          for(int k = 0; k < nd; ++k)
-            acc += (uint64_t)dg[k] * pw[k]; // < nd * 2^56
-          uint32_t res = (uint32_t)(acc % p);
-          if(v.sign < 0 && res)
+          const uint4 *pw = reinterpret_cast<const uint4 *>(s_pow + (size_t)pi * G::NDP);
+          uint64_t acc = 0; // < ND * 2^56
+#pragma unroll
+          for(int k4 = 0; k4 < G::NDP / 4; ++k4)
+            {
+              const uint4 t = pw[k4];
+              acc += (uint64_t)dg[4 * k4] * t.x;
+              acc += (uint64_t)dg[4 * k4 + 1] * t.y;
+              acc += (uint64_t)dg[4 * k4 + 2] * t.z;
+              acc += (uint64_t)dg[4 * k4 + 3] * t.w;
+            }
+          const uint32_t p = s_p[pi];
+          uint32_t res = barrett_mod(acc, p, s_inv[pi]);
+          if(neg && res)
             res = p - res;
-          R[((size_t)pi * K + row) * N + c] = res;
+          out[(size_t)pi * K * NS] = res;
         }
     }
 }
 
 // Qres[p][i][j] = sum_rows R[p][row][i] R[p][row][j] mod p, i <= j.
-// 16x16 output tile per CTA, rows staged through shared memory.
-template <int RC>
-__global__ void __launch_bounds__(256)
-syrk_mod_kernel(const uint32_t *__restrict__ R, long K, int N,
+// A CTA owns one 16x16 output tile of one prime.  Its 256 threads form 16
+// groups of 16; group g takes the rows congruent to g modulo 16 and each of
+// its threads a 4x4 patch of the tile in registers, fed by two 128-bit loads
+// per row (16 IMAD.WIDE per 2 loads).  Products are below 2^56; every 128 rows
+// the 64-bit sums are folded with 2^32 mod p, which keeps them below 2^61.
+// The 16 partial tiles meet in shared memory at the end.
+template <int UNROLL>
+__global__ void __launch_bounds__(256, 2)
+syrk_mod_kernel(const uint32_t *__restrict__ R, long K, int N, int NS,
                 const uint32_t *__restrict__ primes, uint32_t *Qres)
 {
-  // triangular tile index
-  const int nt = (N + 15) / 16;
   int t = blockIdx.x, tj = 0;
   while(t > tj)
     {
@@ -447,40 +529,74 @@ syrk_mod_kernel(const uint32_t *__restrict__ R, long K, int N,
   const int ti = t; // ti <= tj
   const int pi = blockIdx.y;
   const uint32_t p = primes[pi];
-  const uint32_t *Rp = R + (size_t)pi * K * N;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int i = ti * 16 + tx, j = tj * 16 + ty;
-  __shared__ uint32_t sa[RC][16], sb[RC][16];
-  uint64_t acc = 0;
-  uint32_t run = 0;
+  const uint32_t c32 = (uint32_t)((1ull << 32) % p);
+  const int g = threadIdx.x >> 4, l = threadIdx.x & 15;
+  const int tx = l & 3, ty = l >> 2;
+  const uint32_t *Ra = R + (size_t)pi * K * NS + ti * 16 + 4 * tx;
+  const uint32_t *Rb = R + (size_t)pi * K * NS + tj * 16 + 4 * ty;
+  uint64_t acc[4][4];
+#pragma unroll
+  for(int a = 0; a < 4; ++a)
+#pragma unroll
+    for(int b = 0; b < 4; ++b)
+      acc[a][b] = 0;
   int since = 0;
-  (void)nt;
-  for(long r0 = 0; r0 < K; r0 += RC)
+  long row = g;
+  auto step = [&](const uint4 &va, const uint4 &vb) {
+    const uint32_t xa[4] = {va.x, va.y, va.z, va.w}, xb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for(int a = 0; a < 4; ++a)
+#pragma unroll
+      for(int b = 0; b < 4; ++b)
+        acc[a][b] += (uint64_t)xa[a] * xb[b];
+  };
+  auto fold = [&]() {
+#pragma unroll
+    for(int a = 0; a < 4; ++a)
+#pragma unroll
+      for(int b = 0; b < 4; ++b)
+        acc[a][b] = (acc[a][b] & 0xFFFFFFFFull) + (acc[a][b] >> 32) * c32;
+  };
+  for(; row + 16 * (UNROLL - 1) < K; row += 16 * UNROLL)
     {
-      for(int q = threadIdx.x; q < RC * 16; q += 256)
+      uint4 va[UNROLL], vb[UNROLL];
+#pragma unroll
+      for(int u = 0; u < UNROLL; ++u)
         {
-          const int rr = q >> 4, cc = q & 15;
-          const long row = r0 + rr;
-          const int ci = ti * 16 + cc, cj = tj * 16 + cc;
-          sa[rr][cc] = (row < K && ci < N) ? Rp[(size_t)row * N + ci] : 0;
-          sb[rr][cc] = (row < K && cj < N) ? Rp[(size_t)row * N + cj] : 0;
+          va[u] = __ldg(reinterpret_cast<const uint4 *>(Ra + (size_t)(row + 16 * u) * NS));
+          vb[u] = __ldg(reinterpret_cast<const uint4 *>(Rb + (size_t)(row + 16 * u) * NS));
         }
-      __syncthreads();
-#pragma unroll 8
-      for(int rr = 0; rr < RC; ++rr)
-        acc += (uint64_t)sa[rr][tx] * sb[rr][ty]; // each < 2^56
-      since += RC;
-      if(since >= 192) // 192 * 2^56 + 2^28 < 2^64
+#pragma unroll
+      for(int u = 0; u < UNROLL; ++u)
+        step(va[u], vb[u]);
+      since += UNROLL;
+      if(since >= 128)
         {
-          run = (uint32_t)((acc + run) % p);
-          acc = 0;
+          fold();
           since = 0;
         }
-      __syncthreads();
     }
-  run = (uint32_t)((acc + run) % p);
+  for(; row < K; row += 16)
+    {
+      const uint4 va = __ldg(reinterpret_cast<const uint4 *>(Ra + (size_t)row * NS));
+      const uint4 vb = __ldg(reinterpret_cast<const uint4 *>(Rb + (size_t)row * NS));
+      step(va, vb);
+    }
+  // <= 2^61 + 3 * 2^56 each: reduce, then add the 16 groups' partial tiles
+  __shared__ uint32_t part[16][256];
+#pragma unroll
+  for(int a = 0; a < 4; ++a)
+#pragma unroll
+    for(int b = 0; b < 4; ++b)
+      part[g][(4 * ty + b) * 16 + 4 * tx + a] = (uint32_t)(acc[a][b] % p);
+  __syncthreads();
+  uint32_t sum = 0; // 16 * (p - 1) < 2^32
+#pragma unroll
+  for(int q = 0; q < 16; ++q)
+    sum += part[q][threadIdx.x];
+  const int i = ti * 16 + (threadIdx.x & 15), j = tj * 16 + (threadIdx.x >> 4);
   if(i < N && j < N && i <= j)
-    Qres[((size_t)pi * N + i) * N + j] = run;
+    Qres[((size_t)pi * N + i) * N + j] = sum % p;
 }
 
 // Garner reconstruction of the signed integer Q'_ij from its residues,
@@ -590,6 +706,22 @@ crt_restore_kernel(const uint32_t *__restrict__ Qres, int N, int prec,
 
 // restore_P (Matrix_Normalizer.cxx:210-226): P = (P' >> prec) * norm
 template <int NL>
+__device__ __noinline__ Reg<NL> mul_nl(Reg<NL> a, const uint32_t *b)
+{
+  Reg<NL> r;
+  if(a.sign == 0 || (int32_t)b[1] == 0)
+    {
+      mpfw::set_zero(r);
+      return r;
+    }
+  int32_t bexp, bsign;
+  uint32_t bw[2 * NL];
+  mpfw::load_packed<NL>(bexp, bsign, bw, b);
+  const uint32_t *aw = a.w;
+  mpfw::mul<NL>(r, a.sign, a.exp, aw, bsign, bexp, bw);
+  return r;
+}
+template <int NL>
 __global__ void __launch_bounds__(128)
 restore_P_kernel(const BandDesc *bands, int N, const limb_t *norms, int prec)
 {
@@ -599,14 +731,26 @@ restore_P_kernel(const BandDesc *bands, int N, const limb_t *norms, int prec)
       e += (long)gridDim.y * blockDim.x)
     {
       const int c = (int)(e / b.rows);
-      Num<NL> v, nrm;
-      ld(nrm, norms, c);
-      if(nrm.sign == 0)
+      const uint32_t *nrm = reinterpret_cast<const uint32_t *>(norms + (size_t)c * Fmt<NL>::ES);
+      if((int32_t)nrm[1] == 0)
         continue;
-      ld(v, b.P, e);
-      mpfx::div_2exp(v, v, (uint32_t)prec);
-      mpfx::mul(v, v, nrm);
-      st(b.P, e, v);
+      limb_t *elem = b.P + (size_t)e * Fmt<NL>::ES;
+      Reg<NL> v;
+      ldg_reg<NL>(v, elem);
+      if((prec & 63) == 0)
+        {
+          if(v.sign != 0)
+            v.exp -= prec >> 6;
+        }
+      else
+        {
+          Num<NL> t;
+          mpfw::to_num(t, v);
+          mpfx::div_2exp(t, t, (uint32_t)prec);
+          mpfw::from_num(v, t);
+        }
+      v = mul_nl<NL>(v, nrm);
+      stg_reg<NL>(elem, v);
     }
 }
 

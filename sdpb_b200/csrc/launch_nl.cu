@@ -189,9 +189,12 @@ template <int NL> struct Launch
       {
         dim3 g2(J, (unsigned)std::min<long>(((long)c->max_P * N + 127) / 128, 65535));
         c->kt_begin("normalize_kernel");
-        normalize_kernel<NL><<<g2, 128, 0, st>>>(c->d_bands, N, c->K, c->norms, c->recipN,
-                                                 c->prec, c->crt, c->R,
-                                                 c->d_flags);
+        const size_t nsmem = ((size_t)c->crt.np * NormGeom<NL>::NDP + ((c->crt.np + 1) & ~1)) * 4
+                             + (size_t)c->crt.np * 8;
+        CUDA_TRY(c, cudaFuncSetAttribute(normalize_kernel<NL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsmem));
+        normalize_kernel<NL><<<g2, 128, nsmem, st>>>(c->d_bands, N, c->NS, c->K, c->norms,
+                                                     c->recipN, c->prec, c->crt, c->R, c->d_flags);
         c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
       }
@@ -200,7 +203,7 @@ template <int NL> struct Launch
       const int nt = (N + 15) / 16;
       dim3 g3(nt * (nt + 1) / 2, c->crt.np);
       c->kt_begin("syrk_mod_kernel");
-      syrk_mod_kernel<64><<<g3, 256, 0, st>>>(c->R, c->K, N, c->d_primes, c->Qres);
+      syrk_mod_kernel<4><<<g3, 256, 0, st>>>(c->R, c->K, N, c->NS, c->d_primes, c->Qres);
       c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
     }

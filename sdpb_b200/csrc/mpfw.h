@@ -248,9 +248,91 @@ MPFW_D void mul_columns(uint32_t (&out)[2 * W - C0], const uint32_t *a, const ui
     }
   out[2 * W - 1 - C0] = t0;
 }
+// Same result as mul_columns<W, C0, C0>, formed by rows (operand scanning):
+// for each word a_i the products a_i b_j go into two sets of 64-bit lanes, the
+// ones with i+j even into `ev`, the ones with i+j odd into `od`, so that every
+// product is ONE IMAD.WIDE.U32.X whose carry feeds the next lane of the same
+// row (ptxas fuses each mad.lo.cc / madc.hi.cc pair).  No per-product carry
+// bookkeeping, and `a` is read one word at a time (it may live in shared
+// memory), which keeps the live registers at b + two lane sets.
+// Rows ascend, so the word a chain's final carry lands in has only ever
+// received carries: it cannot overflow.
+template <int W, int C0, class APtr>
+MPFW_D void mul_rows_short(uint32_t (&out)[2 * W - C0], APtr a, const uint32_t (&b)[W])
+{
+  static_assert((C0 & 1) == 0 && (W & 1) == 0, "lane pairing needs even W and C0");
+#if defined(__CUDA_ARCH__)
+  constexpr int NO = 2 * W - C0;
+  uint32_t ev[NO], od[NO]; // od[k] = word k+1
+#pragma unroll
+  for(int k = 0; k < NO; ++k)
+    ev[k] = od[k] = 0;
+#pragma unroll
+  for(int i = 0; i < W; ++i)
+    {
+      const uint32_t ai = a[i];
+      const int jmin = (C0 - i > 0) ? C0 - i : 0;
+      bool first = true;
+      int ctop = -1;
+#pragma unroll
+      for(int j = 0; j < W; ++j)
+        {
+          const int c = i + j - C0;
+          if(j < jmin || (c & 1))
+            continue;
+          if(first)
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                         : "+r"(ev[c]), "+r"(ev[c + 1])
+                         : "r"(ai), "r"(b[j]));
+          else
+            asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                         : "+r"(ev[c]), "+r"(ev[c + 1])
+                         : "r"(ai), "r"(b[j]));
+          first = false;
+          ctop = c;
+        }
+      if(ctop >= 0 && ctop + 2 < NO)
+        asm volatile("addc.u32 %0, %0, 0;" : "+r"(ev[ctop + 2]));
+      first = true;
+      ctop = -1;
+#pragma unroll
+      for(int j = 0; j < W; ++j)
+        {
+          const int c = i + j - C0;
+          if(j < jmin || !(c & 1))
+            continue;
+          if(first)
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                         : "+r"(od[c - 1]), "+r"(od[c])
+                         : "r"(ai), "r"(b[j]));
+          else
+            asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                         : "+r"(od[c - 1]), "+r"(od[c])
+                         : "r"(ai), "r"(b[j]));
+          first = false;
+          ctop = c;
+        }
+      if(ctop >= 0 && ctop + 1 < NO - 1)
+        asm volatile("addc.u32 %0, %0, 0;" : "+r"(od[ctop + 1]));
+    }
+  out[0] = ev[0];
+  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(out[1]) : "r"(ev[1]), "r"(od[0]));
+#pragma unroll
+  for(int q = 2; q < NO - 1; ++q)
+    asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(out[q]) : "r"(ev[q]), "r"(od[q - 1]));
+  asm volatile("addc.u32 %0, %1, %2;" : "=r"(out[NO - 1]) : "r"(ev[NO - 1]), "r"(od[NO - 2]));
+#else
+  uint32_t aw[W];
+  for(int i = 0; i < W; ++i)
+    aw[i] = a[i];
+  mul_columns<W, C0, C0>(out, aw, b);
+#endif
+}
+
 // the exact product, all columns (rare path; kept out of line, operands and
 // result by value so that the caller's arrays never have their address taken
-// and stay in registers)
+// and stay in registers; a pointer-based interface through a local buffer was
+// measured slower, profiles/mac_bench_r01_v2.jsonl)
 template <int NL> struct MulWords
 {
   uint32_t w[2 * NL];
@@ -267,17 +349,187 @@ MPFW_NOINLINE MulProd<NL> mul_full(MulWords<NL> a, MulWords<NL> b)
   return r;
 }
 
-// r = mpf_mul(a, b); a and b are the mantissa words w[0..2NL) of non-zero
-// operands (their lowest limb is ignored, as GMP does).
-template <int NL>
-MPFW_D void mul(Reg<NL> &r, int32_t asign, int32_t aexp, const uint32_t (&aw)[2 * NL],
-                int32_t bsign, int32_t bexp, const uint32_t (&bw)[2 * NL])
+// ---- radix-2^29 short product (the hot multiply) ---------------------------
+// On sm_100a IMAD.WIDE.U32 with a plain 64-bit accumulate issues at the full
+// 64 lanes/clk/SM, but every carry-using form (carry-out predicate, .X, or
+// IMAD.HI) runs at half that (profiles/imad_rate2_r01.jsonl).  So the product
+// is formed without carries: both operands are re-cut into 29-bit digits,
+// digit products (< 2^58) are summed in independent 64-bit column lanes (at
+// most 2^5 products per lane), and only the lanes are normalised afterwards.
+// Lanes below C0 are not formed; what they would add is below one unit of the
+// guard word GW, so the kept words are exact unless the guard word is all
+// ones (probability 2^-32), in which case the exact full product is used.
+template <int NL> struct Mul29Geom
 {
-  typedef MulGeom<NL> G;
-  constexpr int W = G::W, C0 = G::C0;
-  uint32_t p[G::NO];
-  mul_columns<W, C0, C0>(p, aw + 2, bw + 2);
-  if(C0 > 0 && p[1] >= 0xFFFFFF00u)
+  static constexpr int W = 2 * (NL - 1);       // operand words used
+  static constexpr int ND = (32 * W + 28) / 29; // 29-bit digits per operand
+  static constexpr int NLANE = 2 * ND - 1;
+  static constexpr bool SHORT = W > 6;
+  static constexpr int GW = SHORT ? W - 5 : 0; // guard word (product word index)
+  static constexpr int NOUT = 2 * W - GW;      // product words GW .. 2W-1
+  static constexpr int bits_of(int c) { return c == 0 ? 0 : 1 + bits_of(c >> 1); }
+  // largest c0 with c0 * 2^(29 c0 + 29) <= 2^(32 GW): omitted lanes < one unit of word GW
+  static constexpr int find_c0(int c)
+  {
+    return (29 * (c + 1) + 29 + bits_of(c + 1) <= 32 * GW) ? find_c0(c + 1) : c;
+  }
+  static constexpr int C0 = SHORT ? find_c0(0) : 0;
+  static constexpr int T = 32 * GW - 29 * C0; // bits of the lane stream below word GW
+  static constexpr int NL29 = NLANE - C0;     // lanes formed
+  static_assert(!SHORT || (29 * C0 + 29 + bits_of(C0) <= 32 * GW && T >= 0), "guard bound");
+};
+
+// digit k (29 bits) of the W-word integer w[0..W)
+template <int W, int K, class WPtr> MPFW_D uint32_t digit29(WPtr w)
+{
+  constexpr int bit = 29 * K, q = bit >> 5, r = bit & 31;
+  const uint32_t lo = w[q];
+  uint32_t v = lo >> r;
+  if constexpr(r > 3 && q + 1 < W)
+    v |= w[q + 1] << (32 - r);
+  return v & 0x1FFFFFFFu;
+}
+template <int W, int ND, int K = 0, class WPtr> MPFW_D void digits29(uint32_t (&d)[ND], WPtr w)
+{
+  if constexpr(K < ND)
+    {
+      d[K] = digit29<W, K>(w);
+      digits29<W, ND, K + 1>(d, w);
+    }
+}
+
+// one row of the digit product: lanes[i + j - C0] += a_i * b_j for i + j >= C0
+template <int NL, int I, class APtr>
+MPFW_D void mul29_rows(uint64_t (&lane)[Mul29Geom<NL>::NL29], APtr aw,
+                       const uint32_t (&bd)[Mul29Geom<NL>::ND])
+{
+  typedef Mul29Geom<NL> G;
+  if constexpr(I < G::ND)
+    {
+      const uint32_t ai = digit29<G::W, I>(aw);
+#pragma unroll
+      for(int j = 0; j < G::ND; ++j)
+        if(I + j >= G::C0)
+          lane[I + j - G::C0] += (uint64_t)ai * bd[j];
+      mul29_rows<NL, I + 1>(lane, aw, bd);
+    }
+}
+
+// out[k] = word GW + k of  sum_{i+j >= C0} a_i b_j 2^(29 (i+j)),  k in [0, NOUT)
+template <int NL, class APtr>
+MPFW_D void mul29_words(uint32_t (&out)[Mul29Geom<NL>::NOUT], APtr aw, const uint32_t (&bd)[Mul29Geom<NL>::ND])
+{
+  typedef Mul29Geom<NL> G;
+  uint64_t lane[G::NL29];
+#pragma unroll
+  for(int c = 0; c < G::NL29; ++c)
+    lane[c] = 0;
+  mul29_rows<NL, 0>(lane, aw, bd);
+  // normalise: 29-bit digits, the top one keeps everything that is left
+  uint32_t dg[G::NL29];
+  uint64_t carry = 0;
+#pragma unroll
+  for(int c = 0; c < G::NL29 - 1; ++c)
+    {
+      const uint64_t x = lane[c] + carry;
+      dg[c] = (uint32_t)x & 0x1FFFFFFFu;
+      carry = x >> 29;
+    }
+  const uint64_t top = lane[G::NL29 - 1] + carry;
+  // re-cut into 32-bit words starting T bits into the stream
+#pragma unroll
+  for(int k = 0; k < G::NOUT; ++k)
+    {
+      const int bit0 = G::T + 32 * k;
+      uint32_t v = 0;
+#pragma unroll
+      for(int q = 0; q < G::NL29; ++q)
+        {
+          const int s = 29 * q - bit0; // digit q sits s bits above the word's bit 0
+          if(q < G::NL29 - 1)
+            {
+              if(s >= 0 && s < 32)
+                v |= dg[q] << s;
+              else if(s < 0 && -s < 29)
+                v |= dg[q] >> (-s);
+            }
+          else
+            {
+              if(s >= 0 && s < 32)
+                v |= (uint32_t)(top << s);
+              else if(s < 0 && -s < 64)
+                v |= (uint32_t)(top >> (-s));
+            }
+        }
+      out[k] = v;
+    }
+}
+
+// assemble mpf_mul's result from product words GW.. (out) : top limb zero -> one limb lower
+template <int NL>
+MPFW_D void mul_finish(Reg<NL> &r, const uint32_t (&out)[Mul29Geom<NL>::NOUT], int32_t asign, int32_t aexp,
+                       int32_t bsign, int32_t bexp)
+{
+  typedef Mul29Geom<NL> G;
+  constexpr int W = G::W;
+  const bool adj = (out[G::NOUT - 1] | out[G::NOUT - 2]) == 0;
+#pragma unroll
+  for(int i = 0; i < 2 * NL; ++i)
+    {
+      const uint32_t hi = out[W - 2 + i - G::GW];
+      const uint32_t lo = out[W - 4 + i - G::GW];
+      r.w[i] = adj ? lo : hi;
+    }
+  r.exp = aexp + bexp - (adj ? 1 : 0);
+  r.sign = asign * bsign;
+}
+
+// r = mpf_mul(a, b); aw: the mantissa words w[0..2NL) of a (registers or
+// memory), bw likewise in registers; both non-zero (their lowest limb is
+// ignored, as GMP does).
+// Default form: operand scanning by rows with IMAD.WIDE.U32.X carry chains
+// (mul_rows_short), a's words read as the rows need them.  IMAD.WIDE issues at
+// 32 lanes/clk/SM on sm_100a whether or not it carries (profiles/
+// imad_rate4_r01.jsonl), so the carry-free radix-2^29 form (MPFW_MUL_RADIX29,
+// 26 % more partial products) loses; it and the column form (MPFW_MUL_COLUMNS)
+// are kept for A/B measurements only.
+template <int NL, class APtr>
+MPFW_D void mul(Reg<NL> &r, int32_t asign, int32_t aexp, APtr aw, int32_t bsign, int32_t bexp,
+                const uint32_t (&bw)[2 * NL])
+{
+  typedef Mul29Geom<NL> G;
+  uint32_t out[G::NOUT];
+  bool rare;
+#if defined(MPFW_MUL_RADIX29)
+  {
+    uint32_t bd[G::ND];
+    digits29<G::W, G::ND>(bd, bw + 2);
+    mul29_words<NL>(out, aw + 2, bd);
+    rare = G::SHORT && out[0] == 0xFFFFFFFFu;
+  }
+#else
+  {
+    uint32_t p[MulGeom<NL>::NO], br[G::W];
+#pragma unroll
+    for(int i = 0; i < G::W; ++i)
+      br[i] = bw[2 + i];
+#if defined(MPFW_MUL_COLUMNS)
+    uint32_t ar[G::W];
+#pragma unroll
+    for(int i = 0; i < G::W; ++i)
+      ar[i] = aw[2 + i];
+    mul_columns<G::W, MulGeom<NL>::C0, MulGeom<NL>::C0>(p, ar, br);
+#else
+    mul_rows_short<G::W, MulGeom<NL>::C0>(p, aw + 2, br);
+#endif
+#pragma unroll
+    for(int i = 0; i < G::NOUT; ++i)
+      out[i] = p[i + G::GW - MulGeom<NL>::C0];
+    // columns below C0 add less than 2^8 units of word GW - 1 ... conservatively: guard word near overflow
+    rare = G::SHORT && out[0] >= 0xFFFFFF00u;
+  }
+#endif
+  if(rare)
     {
 #ifdef MPFW_COUNT_RARE
       ++rare_mul_count;
@@ -289,23 +541,12 @@ MPFW_D void mul(Reg<NL> &r, int32_t asign, int32_t aexp, const uint32_t (&aw)[2 
           ca.w[i] = aw[i];
           cb.w[i] = bw[i];
         }
-      const MulProd<NL> full = mul_full<NL>(ca, cb);
+      const MulProd<NL> full = mul_full<NL>(ca, cb); // words from column MulGeom::C0 = GW - 1
 #pragma unroll
-      for(int i = 0; i < G::NO; ++i)
-        p[i] = full.p[i];
+      for(int i = 0; i < G::NOUT; ++i)
+        out[i] = full.p[i + G::GW - MulGeom<NL>::C0];
     }
-  // top limb of the 2P-limb product zero?  -> one limb lower, exponent - 1
-  const bool adj = (p[2 * W - 1 - C0] | p[2 * W - 2 - C0]) == 0;
-  // kept words start at product word W-2 (adj: W-4)
-#pragma unroll
-  for(int i = 0; i < 2 * NL; ++i)
-    {
-      const uint32_t hi = p[W - 2 + i - C0];
-      const uint32_t lo = p[W - 4 + i - C0];
-      r.w[i] = adj ? lo : hi;
-    }
-  r.exp = aexp + bexp - (adj ? 1 : 0);
-  r.sign = asign * bsign;
+  mul_finish<NL>(r, out, asign, aexp, bsign, bexp);
 }
 
 // ------------------------------------------------------------------ add/sub
@@ -515,14 +756,14 @@ MPFW_D void load_packed(int32_t &exp, int32_t &sign, uint32_t (&w)[2 * NL], cons
 template <int NL>
 MPFW_D void mac(Reg<NL> &acc, const uint32_t *a, const uint32_t *b, bool negate)
 {
-  int32_t aexp, asign, bexp, bsign;
-  uint32_t aw[2 * NL], bw[2 * NL];
-  load_packed<NL>(aexp, asign, aw, a);
+  int32_t bexp, bsign;
+  uint32_t bw[2 * NL];
   load_packed<NL>(bexp, bsign, bw, b);
+  const int32_t aexp = (int32_t)a[0], asign = (int32_t)a[1];
   if(asign == 0 || bsign == 0)
     return; // 0 * x = 0 and c + 0 = c exactly in mpf
   Reg<NL> p;
-  mul<NL>(p, asign, aexp, aw, bsign, bexp, bw);
+  mul<NL>(p, asign, aexp, a + 2, bsign, bexp, bw); // a's words are read from memory as the rows need them
   add_signed<NL>(acc, p, negate ? -p.sign : p.sign);
 }
 template <int NL>
@@ -531,7 +772,8 @@ MPFW_D void mac(Reg<NL> &acc, const Reg<NL> &a, const Reg<NL> &b, bool negate)
   if(a.sign == 0 || b.sign == 0)
     return;
   Reg<NL> p;
-  mul<NL>(p, a.sign, a.exp, a.w, b.sign, b.exp, b.w);
+  const uint32_t *aw = a.w;
+  mul<NL>(p, a.sign, a.exp, aw, b.sign, b.exp, b.w);
   add_signed<NL>(acc, p, negate ? -p.sign : p.sign);
 }
 

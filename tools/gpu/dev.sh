@@ -1,0 +1,3 @@
+set -x
+timeout 900 python tools/gpu/dev_check.py 2>&1 | tail -8
+timeout 600 python bench.py --kernels --steps 3 --warmup 3 --no-cpu 2>&1 | tail -25
