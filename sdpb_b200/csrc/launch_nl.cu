@@ -67,6 +67,38 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaGetLastError());
     return 0;
   }
+  // right-looking schedule (tile.cuh): the choice for a single large matrix
+  static int potrf_rl(sdpb_b200_ctx *c, const char *label, const PotrfDesc *d,
+                      const std::vector<int> &sizes, int *status, int nstatus)
+  {
+    if(sizes.empty() || nstatus == 0)
+      return 0;
+    if(int rc = smem_opt_in(c, potrf_diag_rl<NL>))
+      return rc;
+    if(int rc = smem_opt_in(c, potrf_panel_rl<NL>))
+      return rc;
+    if(int rc = smem_opt_in(c, potrf_trail_rl<NL>))
+      return rc;
+    CUDA_TRY(c, cudaMemsetAsync(status, 0xFF, (size_t)nstatus * sizeof(int), c->stream));
+    const int T = (sizes[0] + TS - 1) / TS;
+    c->kt_begin(label);
+    for(int Jt = 0; Jt < T; ++Jt)
+      {
+        const int n = alive(sizes, Jt), nbelow = alive(sizes, Jt + 1);
+        potrf_diag_rl<NL><<<n, 256, TILE_SMEM, c->stream>>>(d, Jt, status);
+        ++c->launches;
+        if(nbelow == 0)
+          continue;
+        const int tb = (sizes[0] - (Jt + 1) * TS + TS - 1) / TS; // tiles below / right of Jt
+        potrf_panel_rl<NL><<<dim3(nbelow, tb), 256, TILE_SMEM, c->stream>>>(d, Jt, status);
+        potrf_trail_rl<NL><<<dim3(nbelow, tb * (tb + 1) / 2), 256, TILE_SMEM, c->stream>>>(d, Jt, status);
+        c->launches += 2;
+      }
+    c->kt_end();
+    --c->launches;
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
   // batched X <- L^{-1} B, level-synchronous; sizes sorted descending
   static int trsm(sdpb_b200_ctx *c, const char *label, const TrsmTileDesc *d,
                   const std::vector<int> &sizes, int maxcols)
@@ -230,7 +262,7 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaGetLastError());
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[7], st));
-    rc = potrf(c, "potrf_Q", c->d_potrfQ, c->szQ, c->d_status + 5 * J, 1);
+    rc = potrf_rl(c, "potrf_Q", c->d_potrfQ, c->szQ, c->d_status + 5 * J, 1);
     if(rc)
       return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[8], st));

@@ -454,6 +454,98 @@ potrf_gemm_level(const PotrfDesc *descs, int Jt, const int *status)
     stg_reg<NL>(d.A + ((long)(It * TS + ti) * d.si + (long)(Jt * TS + tj) * d.sj) * G::ES, acc);
 }
 
+// ---- right-looking variant ------------------------------------------------
+// Same arithmetic (every element still receives its updates in ascending k),
+// different schedule: after block column Jt is finished, ALL tiles to its right
+// get its 16 updates at once.  The diagonal tile of the next level is then
+// ready the moment the level starts, so the serial chain of a level is only
+// factor(16 pivots) -> panel solve -> 16 updates, instead of also carrying the
+// J0-long update loop of the left-looking form.  That chain bounds the time of
+// a single large matrix (Cholesky of Q: N/16 levels).
+//   potrf_diag_rl   one CTA per matrix: factor the (already updated) diagonal tile
+//   potrf_panel_rl  one CTA per tile below it: X = A_tile L_JJ^{-T}
+//   potrf_trail_rl  one CTA per tile (It >= Kt > Jt): a_ij -= sum_{k in column Jt} l_ik l_jk
+template <int NL>
+__global__ void __launch_bounds__(256, 2)
+potrf_diag_rl(const PotrfDesc *descs, int Jt, int *status)
+{
+  typedef TileGeom<NL> G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
+  const PotrfDesc d = descs[blockIdx.x];
+  if(Jt * TS >= d.s || status[d.id] >= 0)
+    return;
+  tile_smem_init(sm);
+  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int J0 = Jt * TS, nd = min(TS, d.s - J0);
+  Reg<NL> acc;
+  if(ti < nd && tj < nd && ti >= tj)
+    ldg_reg<NL>(acc, d.A + ((long)(J0 + ti) * d.si + (long)(J0 + tj) * d.sj) * G::ES);
+  else
+    mpfw::set_zero(acc);
+  if(!potrf_diag_tile<NL>(acc, d, Jt, sm))
+    {
+      if(threadIdx.x == 0)
+        status[d.id] = sm.bad;
+    }
+}
+template <int NL>
+__global__ void __launch_bounds__(256, 2)
+potrf_panel_rl(const PotrfDesc *descs, int Jt, const int *status)
+{
+  typedef TileGeom<NL> G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
+  const PotrfDesc d = descs[blockIdx.x];
+  const int It = Jt + 1 + blockIdx.y;
+  if(It * TS >= d.s || status[d.id] >= 0)
+    return;
+  load_diag_tile<NL>(d.A, d.si, d.sj, d.recip, d.s, Jt, sm);
+  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  Reg<NL> acc;
+  if(It * TS + ti < d.s && Jt * TS + tj < d.s)
+    ldg_reg<NL>(acc, d.A + ((long)(It * TS + ti) * d.si + (long)(Jt * TS + tj) * d.sj) * G::ES);
+  else
+    mpfw::set_zero(acc);
+  potrf_row_tile_solve<NL>(acc, d, It, Jt, sm);
+}
+template <int NL>
+__global__ void __launch_bounds__(256, 2)
+potrf_trail_rl(const PotrfDesc *descs, int Jt, const int *status)
+{
+  typedef TileGeom<NL> G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
+  const PotrfDesc d = descs[blockIdx.x];
+  // blockIdx.y -> (a >= b) among the tiles right of Jt
+  int t = blockIdx.y, a = 0;
+  while(t > a)
+    {
+      t -= a + 1;
+      ++a;
+    }
+  const int It = Jt + 1 + a, Kt = Jt + 1 + t;
+  if(It * TS >= d.s || status[d.id] >= 0)
+    return;
+  tile_smem_init(sm);
+  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int I0 = It * TS, K0 = Kt * TS, J0 = Jt * TS;
+  const int ni = min(TS, d.s - I0), nk = min(TS, d.s - K0);
+  const bool active = ti < ni && tj < nk && (It > Kt || ti >= tj);
+  Reg<NL> acc;
+  uint64_t *mine = d.A + ((long)(I0 + ti) * d.si + (long)(K0 + tj) * d.sj) * G::ES;
+  if(active)
+    ldg_reg<NL>(acc, mine);
+  else
+    mpfw::set_zero(acc);
+  uint32_t it = 0;
+  Operand A{d.A + ((long)I0 * d.si + (long)J0 * d.sj) * G::ES, d.si, d.sj, ni};
+  Operand B{d.A + ((long)K0 * d.si + (long)J0 * d.sj) * G::ES, d.si, d.sj, nk};
+  tile_k_loop<NL>(acc, true, A, B, TS, sm, it, active); // a full block column: rows exist below it
+  if(active)
+    stg_reg<NL>(mine, acc);
+}
+
 template <int NL> struct DiagSmem
 {
   typedef TileGeom<NL> G;
