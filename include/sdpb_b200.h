@@ -161,6 +161,15 @@ int sdpb_b200_comm_get_unique_id(void *id);
 int sdpb_b200_comm_init(sdpb_b200_ctx *ctx, int rank, int world, const void *id,
                         int num_blocks_global, const int *global_block_index);
 
+/* Scheduling of a step on the device.  level 1 (default): the independent chains
+ * of the step -- chol(X) -> L_X^-1 V -> A_X_inv, Y V -> A_Y, chol(Y), and per block
+ * S_j -> chol(S_j) -> L_j^-1 B_j -> norm partials in interleaved groups of blocks --
+ * run on side streams, so the latency-bound tails of one chain are filled by the
+ * others.  level 0: every kernel on one stream in program order; this is the mode
+ * in which sdpb_b200_kernel_timings gives non-overlapping per-kernel durations
+ * (and the per-stage times below are exact).  Results are bit-identical. */
+int sdpb_b200_set_concurrency(sdpb_b200_ctx *ctx, int level);
+
 /* Device-side timing of the last step, milliseconds per stage (CUDA events):
  * [0] cholesky X+Y  [1] bilinear pairings  [2] S assembly  [3] cholesky S_j +
  * L^-1 B  [4] norms+normalise  [5] exact syrk  [6] restore  [7] Cholesky(Q)

@@ -67,6 +67,8 @@ def load_library():
     lib.sdpb_b200_schur_step_resident.argtypes = [ctypes.c_void_p]
     lib.sdpb_b200_download.restype = ctypes.c_int
     lib.sdpb_b200_download.argtypes = [ctypes.c_void_p] + [u64pp] * 6 + [u64p]
+    lib.sdpb_b200_set_concurrency.restype = ctypes.c_int
+    lib.sdpb_b200_set_concurrency.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.sdpb_b200_last_timings_ms.restype = ctypes.c_int
     lib.sdpb_b200_last_timings_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
     lib.sdpb_b200_kernel_launches.restype = ctypes.c_long
@@ -291,6 +293,10 @@ class SchurContext(StepContextBase):
             t = torch.frombuffer(bytearray(self.comm_unique_id()), dtype=torch.uint8).to(dev)
         dist.broadcast(t, 0)
         self.comm_init(rank, world, bytes(t.cpu().numpy().tobytes()), num_blocks_global, global_block_index)
+
+    def set_concurrency(self, level):
+        """0: one stream, program order (per-kernel timing mode); 1: concurrent chains (default)."""
+        self._check(self.lib.sdpb_b200_set_concurrency(self.handle, int(level)))
 
     def kernel_launches(self):
         return int(self.lib.sdpb_b200_kernel_launches(self.handle))

@@ -272,6 +272,13 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
     }                                                                         \
   while(0)
   TRY_C(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->cur = c->stream;
+  for(auto &a : c->aux)
+    TRY_C(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+  for(auto &e : c->evf)
+    TRY_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if(const char *env = getenv("SDPB_B200_CONCURRENCY"))
+    c->concurrency = atoi(env) != 0;
   TRY_C(cudaMalloc(&c->arena, c->arena_words * sizeof(limb_t)));
   TRY_C(cudaMemsetAsync(c->arena, 0, c->arena_words * sizeof(limb_t), c->stream));
   {
@@ -387,6 +394,48 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
   c->tiles_YV = sort_gemm(gYV);
   c->tiles_AY = sort_gemm(gAY);
   c->n_gemm = (int)gAX.size();
+  // the S chain in G interleaved groups (largest blocks dealt round-robin), each with its
+  // own sorted descriptor arrays, so that the groups can run on separate streams
+  {
+    // measured at c3 (profiles/r01_v5_summary.md): every level kernel already fills the
+    // CTA slots, so splitting the batch only multiplies the level count (G = 1: 145 ms,
+    // 2: 156, 4: 153); the mechanism stays for shapes with few, large blocks
+    int G = 1;
+    if(const char *env = getenv("SDPB_B200_GROUPS"))
+      G = atoi(env);
+    c->G = std::max(1, std::min(std::min(G, (int)sdpb_b200_ctx::MAXG), std::max(1, num_blocks)));
+    std::vector<int> order(num_blocks);
+    for(int j = 0; j < num_blocks; ++j)
+      order[j] = j;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return c->g[a].P > c->g[b].P; });
+    for(int g = 0; g < c->G; ++g)
+      {
+        std::vector<PotrfDesc> gp;
+        std::vector<TrsmTileDesc> gt;
+        std::vector<SchurDesc> gs;
+        std::vector<BandDesc> gb;
+        for(int k = g; k < num_blocks; k += c->G)
+          {
+            const int j = order[k];
+            const BlockGeom &b = c->g[j];
+            gp.push_back(PotrfDesc{c->S + c->oS[j], c->recipS + (size_t)b.row0 * rs, b.P, 1,
+                                   (long)b.P, j});
+            gt.push_back(TrsmTileDesc{c->S + c->oS[j], c->recipS + (size_t)b.row0 * rs,
+                                      c->Pband + c->oB[j], b.P, N});
+            gs.push_back(sd[j]);
+            gb.push_back(bd[j]);
+            c->szS_g[g].push_back(b.P);
+            c->szP_g[g].push_back(b.P);
+            c->maxP_g[g] = std::max(c->maxP_g[g], b.P);
+          }
+        c->nblk_g[g] = (int)gp.size();
+        TRY_C(upload(&c->d_potrfS_g[g], gp));
+        TRY_C(upload(&c->d_trsmP_g[g], gt));
+        TRY_C(upload(&c->d_schur_g[g], gs));
+        TRY_C(upload(&c->d_bands_g[g], gb));
+      }
+  }
   std::vector<PotrfDesc> pQ{PotrfDesc{c->Q, c->recipQ, N, (long)N, 1, 0}}; // upper: A = U^T U
   c->szQ.assign(1, N);
   TRY_C(upload(&c->d_potrfQ, pQ));
@@ -538,6 +587,18 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
   cudaFree(c->d_bands);
   cudaFree(c->d_status);
   cudaFree(c->d_flags);
+  for(int g = 0; g < sdpb_b200_ctx::MAXG; ++g)
+    {
+      cudaFree(c->d_potrfS_g[g]);
+      cudaFree(c->d_trsmP_g[g]);
+      cudaFree(c->d_schur_g[g]);
+      cudaFree(c->d_bands_g[g]);
+      if(c->aux[g])
+        cudaStreamDestroy(c->aux[g]);
+    }
+  for(auto &e : c->evf)
+    if(e)
+      cudaEventDestroy(e);
   if(c->pinned)
     cudaFreeHost(c->pinned);
   for(auto &k : c->kt)
@@ -613,9 +674,30 @@ static int dispatch_cholesky(sdpb_b200_ctx *c, int which)
 {
   return table_for(c->nl)->cholesky(c, which);
 }
-static int dispatch_pairings(sdpb_b200_ctx *c)
+// A_X_inv chain on `stream`, A_Y chain beside it; `from_event` (an index into evf, recorded by
+// the caller on `stream` when Y became ready) lets the side chain start before chol(X) ends
+static int dispatch_pairings(sdpb_b200_ctx *c, int y_ready_event = -1)
 {
-  return table_for(c->nl)->pairings(c);
+  cudaStream_t st = c->stream, sy = c->side(0);
+  if(sy != st)
+    {
+      if(y_ready_event < 0)
+        {
+          y_ready_event = 0;
+          CUDA_TRY(c, cudaEventRecord(c->evf[0], st));
+        }
+      CUDA_TRY(c, cudaStreamWaitEvent(sy, c->evf[y_ready_event], 0));
+    }
+  c->cur = sy;
+  int rc = table_for(c->nl)->pairings(c, 1);
+  c->cur = st;
+  if(rc)
+    return rc;
+  rc = table_for(c->nl)->pairings(c, 0);
+  if(rc)
+    return rc;
+  CUDA_TRY(c, c->after(sy, st, 1));
+  return 0;
 }
 static int dispatch_schur_and_Q(sdpb_b200_ctx *c)
 {
@@ -685,6 +767,7 @@ extern "C" int sdpb_b200_cholesky_decomposition(sdpb_b200_ctx *c, int which,
     return SDPB_B200_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->device));
   limb_t *dst = which == 0 ? c->X : c->LY;
+  c->cur = c->stream;
   if(which == 0)
     c->kt_used = 0;
   int rc = copy_blocks_in(c, A, dst);
@@ -917,16 +1000,24 @@ extern "C" int sdpb_b200_schur_step_resident(sdpb_b200_ctx *c)
       CUDA_TRY(c, cudaMemcpyAsync(c->Y, c->Yin, c->wXY * 8, cudaMemcpyDeviceToDevice, st));
       CUDA_TRY(c, cudaMemcpyAsync(c->LY, c->Yin, c->wXY * 8, cudaMemcpyDeviceToDevice, st));
     }
-  int rc = dispatch_cholesky(c, 0);
+  // chol(Y) on a side stream, the A_Y chain on another, chol(X) -> A_X_inv here
+  CUDA_TRY(c, cudaEventRecord(c->evf[2], st)); // X, Y, LY in place
+  cudaStream_t sl = c->side(3);
+  if(sl != st)
+    CUDA_TRY(c, cudaStreamWaitEvent(sl, c->evf[2], 0));
+  c->cur = sl;
+  int rc = dispatch_cholesky(c, 1);
+  c->cur = st;
   if(rc)
     return rc;
-  rc = dispatch_cholesky(c, 1);
+  rc = dispatch_cholesky(c, 0);
   if(rc)
     return rc;
   CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
-  rc = dispatch_pairings(c);
+  rc = dispatch_pairings(c, 2);
   if(rc)
     return rc;
+  CUDA_TRY(c, c->after(sl, st, 3));
   CUDA_TRY(c, cudaEventRecord(c->ev[1], st));
   rc = dispatch_schur_and_Q(c);
   if(rc)
@@ -1062,6 +1153,18 @@ extern "C" int sdpb_b200_schur_step(
   return 0;
 }
 
+// 0: every kernel on one stream in program order (the mode per-kernel timings are taken in);
+// 1 (default): independent chains on side streams, the S chain in interleaved groups
+extern "C" int sdpb_b200_set_concurrency(sdpb_b200_ctx *c, int level)
+{
+  if(!c || level < 0 || level > 1)
+    return SDPB_B200_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaDeviceSynchronize());
+  c->concurrency = level;
+  return 0;
+}
+
 extern "C" int sdpb_b200_last_timings_ms(const sdpb_b200_ctx *c, float *ms, int n)
 {
   if(!c || !ms)
@@ -1080,6 +1183,7 @@ extern "C" int sdpb_b200_scalar_op(sdpb_b200_ctx *c, int op, int k, long count,
     return SDPB_B200_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->device));
   c->kt_used = 0;
+  c->cur = c->stream;
   limb_t *da, *db, *dr;
   const size_t bytes = (size_t)count * c->es * 8;
   CUDA_TRY(c, cudaMalloc(&da, bytes));

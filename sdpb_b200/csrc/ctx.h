@@ -87,9 +87,37 @@ struct sdpb_b200_ctx
   limb_t *part_global = nullptr;
   int (*allreduce)(sdpb_b200_ctx *, void *buf, size_t count, int is_u64, const char *label) = nullptr;
 
+  // Concurrent schedule.  The step is a small dependency graph -- chol(X) ->
+  // L_X^-1 V -> A_X_inv | Y V -> A_Y | chol(Y) | per block: S_j -> chol(S_j) ->
+  // L_j^-1 B_j -> norm partials | restore_P beside the exact syrk -- and the
+  // batched factorisations are chains of short level kernels with latency-bound
+  // tails, so independent chains run on side streams and the S chain is cut
+  // into G interleaved groups of blocks.  concurrency == 0 puts everything back
+  // on `stream` in program order (what the per-kernel timeline is measured in).
+  static constexpr int MAXG = 4;
+  cudaStream_t cur = nullptr; // the stream the launch helpers enqueue on
+  cudaStream_t aux[MAXG] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evf[16] = {};
+  int concurrency = 1, G = 1;
+  PotrfDesc *d_potrfS_g[MAXG] = {};
+  TrsmTileDesc *d_trsmP_g[MAXG] = {};
+  SchurDesc *d_schur_g[MAXG] = {};
+  BandDesc *d_bands_g[MAXG] = {};
+  std::vector<int> szS_g[MAXG], szP_g[MAXG];
+  int nblk_g[MAXG] = {}, maxP_g[MAXG] = {};
+  cudaStream_t side(int k) const { return concurrency ? aux[k] : stream; }
+  // `to` waits for everything enqueued on `from` so far
+  cudaError_t after(cudaStream_t from, cudaStream_t to, int e)
+  {
+    if(from == to)
+      return cudaSuccess;
+    cudaError_t r = cudaEventRecord(evf[e], from);
+    return r != cudaSuccess ? r : cudaStreamWaitEvent(to, evf[e], 0);
+  }
+
   bool have_X_cholesky = false, have_pairings = false;
   long launches = 0; // kernels launched since creation
-  cudaEvent_t ev[12]; // 0,1 pairings; 2..8 Schur stages; 9,10,11 resident step
+  cudaEvent_t ev[12] = {}; // 0,1 pairings; 2..8 Schur stages; 9,10,11 resident step
   float stage_ms[9] = {0};
 
   // per-launch timeline of the last step: every kernel launch is bracketed by
@@ -112,12 +140,12 @@ struct sdpb_b200_ctx
         kt.push_back(s);
       }
     kt[kt_used].name = name;
-    cudaEventRecord(kt[kt_used].e0, stream);
+    cudaEventRecord(kt[kt_used].e0, cur);
     return kt_used;
   }
   void kt_end()
   {
-    cudaEventRecord(kt[kt_used].e1, stream);
+    cudaEventRecord(kt[kt_used].e1, cur);
     ++kt_used;
     ++launches;
   }
@@ -128,7 +156,7 @@ struct sdpb_b200_ctx
 struct LaunchTable
 {
   int (*cholesky)(sdpb_b200_ctx *, int which);
-  int (*pairings)(sdpb_b200_ctx *);
+  int (*pairings)(sdpb_b200_ctx *, int part); // 0: X chain (L_X^-1 V, A_X_inv); 1: Y chain (Y V, A_Y)
   int (*schur_and_Q)(sdpb_b200_ctx *);
   int (*scalar)(sdpb_b200_ctx *, int op, int k, long count, const limb_t *a,
                 const limb_t *b, limb_t *r);

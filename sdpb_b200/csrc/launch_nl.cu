@@ -31,7 +31,7 @@ template <int NL> struct Launch
   }
   // batched Cholesky, level-synchronous (tile.cuh); sizes sorted descending
   static int potrf(sdpb_b200_ctx *c, const char *label, const PotrfDesc *d,
-                   const std::vector<int> &sizes, int *status, int nstatus)
+                   const std::vector<int> &sizes, int *status, int nstatus, bool reset = true)
   {
     if(sizes.empty() || nstatus == 0)
       return 0;
@@ -41,13 +41,14 @@ template <int NL> struct Launch
       return rc;
     CUDA_TRY(c, cudaFuncSetAttribute(potrf_solve_level<NL>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-    CUDA_TRY(c, cudaMemsetAsync(status, 0xFF, (size_t)nstatus * sizeof(int), c->stream));
+    if(reset)
+      CUDA_TRY(c, cudaMemsetAsync(status, 0xFF, (size_t)nstatus * sizeof(int), c->cur));
     const int T = (sizes[0] + TS - 1) / TS;
     c->kt_begin(label);
     for(int Jt = 0; Jt < T; ++Jt)
       {
         const int n = alive(sizes, Jt), nbelow = alive(sizes, Jt + 1);
-        potrf_diag_level<NL><<<n, 256, TILE_SMEM, c->stream>>>(d, Jt, status);
+        potrf_diag_level<NL><<<n, 256, TILE_SMEM, c->cur>>>(d, Jt, status);
         ++c->launches;
         if(nbelow == 0)
           continue;
@@ -55,11 +56,11 @@ template <int NL> struct Launch
         if(Jt > 0)
           {
             dim3 g(nbelow, (rows_below + TS - 1) / TS);
-            potrf_gemm_level<NL><<<g, 256, TILE_SMEM, c->stream>>>(d, Jt, status);
+            potrf_gemm_level<NL><<<g, 256, TILE_SMEM, c->cur>>>(d, Jt, status);
             ++c->launches;
           }
         dim3 g2(nbelow, (rows_below + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
-        potrf_solve_level<NL><<<g2, ROWS_PER_CTA, DIAG_SMEM, c->stream>>>(d, Jt, status);
+        potrf_solve_level<NL><<<g2, ROWS_PER_CTA, DIAG_SMEM, c->cur>>>(d, Jt, status);
         ++c->launches;
       }
     c->kt_end();
@@ -79,19 +80,19 @@ template <int NL> struct Launch
       return rc;
     if(int rc = smem_opt_in(c, potrf_trail_rl<NL>))
       return rc;
-    CUDA_TRY(c, cudaMemsetAsync(status, 0xFF, (size_t)nstatus * sizeof(int), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(status, 0xFF, (size_t)nstatus * sizeof(int), c->cur));
     const int T = (sizes[0] + TS - 1) / TS;
     c->kt_begin(label);
     for(int Jt = 0; Jt < T; ++Jt)
       {
         const int n = alive(sizes, Jt), nbelow = alive(sizes, Jt + 1);
-        potrf_diag_rl<NL><<<n, 256, TILE_SMEM, c->stream>>>(d, Jt, status);
+        potrf_diag_rl<NL><<<n, 256, TILE_SMEM, c->cur>>>(d, Jt, status);
         ++c->launches;
         if(nbelow == 0)
           continue;
         const int tb = (sizes[0] - (Jt + 1) * TS + TS - 1) / TS; // tiles below / right of Jt
-        potrf_panel_rl<NL><<<dim3(nbelow, tb), 256, TILE_SMEM, c->stream>>>(d, Jt, status);
-        potrf_trail_rl<NL><<<dim3(nbelow, tb * (tb + 1) / 2), 256, TILE_SMEM, c->stream>>>(d, Jt, status);
+        potrf_panel_rl<NL><<<dim3(nbelow, tb), 256, TILE_SMEM, c->cur>>>(d, Jt, status);
+        potrf_trail_rl<NL><<<dim3(nbelow, tb * (tb + 1) / 2), 256, TILE_SMEM, c->cur>>>(d, Jt, status);
         c->launches += 2;
       }
     c->kt_end();
@@ -117,11 +118,11 @@ template <int NL> struct Launch
         if(It > 0)
           {
             dim3 g(n, (maxcols + TS - 1) / TS);
-            trsm_gemm_level<NL><<<g, 256, TILE_SMEM, c->stream>>>(d, It);
+            trsm_gemm_level<NL><<<g, 256, TILE_SMEM, c->cur>>>(d, It);
             ++c->launches;
           }
         dim3 g2(n, (maxcols + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
-        trsm_diag_level<NL><<<g2, ROWS_PER_CTA, DIAG_SMEM, c->stream>>>(d, It);
+        trsm_diag_level<NL><<<g2, ROWS_PER_CTA, DIAG_SMEM, c->cur>>>(d, It);
         ++c->launches;
       }
     c->kt_end();
@@ -137,7 +138,7 @@ template <int NL> struct Launch
     if(int rc = smem_opt_in(c, gemm_tile_kernel<NL>))
       return rc;
     c->kt_begin(label);
-    gemm_tile_kernel<NL><<<tiles, 256, TILE_SMEM, c->stream>>>(d, count);
+    gemm_tile_kernel<NL><<<tiles, 256, TILE_SMEM, c->cur>>>(d, count);
     c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
     return 0;
@@ -147,21 +148,21 @@ template <int NL> struct Launch
     return potrf(c, which == 0 ? "potrf_X" : "potrf_Y", which == 0 ? c->d_potrfX : c->d_potrfY,
                  c->szXY, c->d_status + which * 2 * c->J, 2 * c->J);
   }
-  static int pairings(sdpb_b200_ctx *c)
+  static int pairings(sdpb_b200_ctx *c, int part)
   {
     const int nb = 2 * c->J;
     if(nb == 0)
       return 0;
-    // T = V ; T <- L_X^{-1} T ; AX = T^T T
-    CUDA_TRY(c, cudaMemcpyAsync(c->T, c->V, c->wV * 8, cudaMemcpyDeviceToDevice,
-                                c->stream));
-    int rc = trsm(c, "trsm_LXinv_V", c->d_trsmT, c->szT, c->max_mn);
-    if(rc)
-      return rc;
-    rc = gemm(c, "gemm_A_X_inv", c->d_gemmAX, c->n_gemm, c->tiles_AX);
-    if(rc)
-      return rc;
-    rc = gemm(c, "gemm_YV", c->d_gemmYV, c->n_gemm, c->tiles_YV);
+    if(part == 0)
+      {
+        // T = V ; T <- L_X^{-1} T ; AX = T^T T
+        CUDA_TRY(c, cudaMemcpyAsync(c->T, c->V, c->wV * 8, cudaMemcpyDeviceToDevice, c->cur));
+        int rc = trsm(c, "trsm_LXinv_V", c->d_trsmT, c->szT, c->max_mn);
+        if(rc)
+          return rc;
+        return gemm(c, "gemm_A_X_inv", c->d_gemmAX, c->n_gemm, c->tiles_AX);
+      }
+    int rc = gemm(c, "gemm_YV", c->d_gemmYV, c->n_gemm, c->tiles_YV);
     if(rc)
       return rc;
     return gemm(c, "gemm_A_Y", c->d_gemmAY, c->n_gemm, c->tiles_AY);
@@ -170,44 +171,51 @@ template <int NL> struct Launch
   {
     const int J = c->J, N = c->N;
     cudaStream_t st = c->stream;
+    c->cur = st;
     CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
+    CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
+    const bool sharded = c->world > 1;
+    limb_t *part = sharded ? c->part_global : c->part;
+    const int Jsum = sharded ? c->J_global : J;
     if(J)
       {
-        dim3 grid(J, (unsigned)std::min<long>(((long)c->max_P * c->max_P + 127) / 128, 65535));
-        c->kt_begin("schur_kernel");
-        schur_kernel<NL><<<grid, 128, 0, st>>>(c->d_schur);
-        c->kt_end();
-    CUDA_TRY(c, cudaGetLastError());
+        CUDA_TRY(c, cudaMemsetAsync(c->d_status + 4 * J, 0xFF, (size_t)J * sizeof(int), st));
+        CUDA_TRY(c, cudaMemcpyAsync(c->Pband, c->B, c->wB * 8, cudaMemcpyDeviceToDevice, st));
       }
-    CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
-    // Cholesky(S_j), P = L^{-1} B
-    int rc = potrf(c, "potrf_S", c->d_potrfS, c->szS, c->d_status + 4 * J, J);
-    if(rc)
-      return rc;
-    if(J)
-      CUDA_TRY(c, cudaMemcpyAsync(c->Pband, c->B, c->wB * 8,
-                                  cudaMemcpyDeviceToDevice, st));
-    rc = trsm(c, "trsm_Linv_B", c->d_trsmP, c->szP, N);
-    if(rc)
-      return rc;
+    if(sharded) // rows of blocks owned elsewhere: exact zeros, so the sum below is a gather
+      CUDA_TRY(c, cudaMemsetAsync(part, 0, (size_t)Jsum * N * Fmt<NL>::ES * 8, st));
+    // per group of blocks: S_j -> Cholesky(S_j) -> P_j = L_j^{-1} B_j -> column-norm partials
+    for(int g = 0; g < c->G && J; ++g)
+      {
+        cudaStream_t sg = g == 0 ? st : c->side(g);
+        CUDA_TRY(c, c->after(st, sg, 4 + g));
+        c->cur = sg;
+        const int nb = c->nblk_g[g], mp = c->maxP_g[g];
+        dim3 grid(nb, (unsigned)std::min<long>(((long)mp * mp + 127) / 128, 65535));
+        c->kt_begin("schur_kernel");
+        schur_kernel<NL><<<grid, 128, 0, sg>>>(c->d_schur_g[g]);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+        int rc = potrf(c, "potrf_S", c->d_potrfS_g[g], c->szS_g[g], c->d_status + 4 * J, J, false);
+        if(rc)
+          return rc;
+        rc = trsm(c, "trsm_Linv_B", c->d_trsmP_g[g], c->szP_g[g], N);
+        if(rc)
+          return rc;
+        dim3 g1(nb, (N + 63) / 64);
+        c->kt_begin("norm_partial_kernel");
+        norm_partial_kernel<NL><<<g1, 64, 0, sg>>>(c->d_bands_g[g], N, part);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+      }
+    c->cur = st;
+    for(int g = 1; g < c->G && J; ++g)
+      CUDA_TRY(c, c->after(c->side(g), st, 8 + g));
     CUDA_TRY(c, cudaEventRecord(c->ev[4], st));
     // norms, normalise, residues
     const int init_flags[4] = {0, INT_MAX, 0, 0};
     CUDA_TRY(c, cudaMemcpyAsync(c->d_flags, init_flags, sizeof(init_flags),
                                 cudaMemcpyHostToDevice, st));
-    const bool sharded = c->world > 1;
-    limb_t *part = sharded ? c->part_global : c->part;
-    const int Jsum = sharded ? c->J_global : J;
-    if(sharded) // rows of blocks owned elsewhere: exact zeros, so the sum below is a gather
-      CUDA_TRY(c, cudaMemsetAsync(part, 0, (size_t)Jsum * N * Fmt<NL>::ES * 8, st));
-    if(J)
-      {
-        dim3 g1(J, (N + 63) / 64);
-        c->kt_begin("norm_partial_kernel");
-        norm_partial_kernel<NL><<<g1, 64, 0, st>>>(c->d_bands, N, part);
-        c->kt_end();
-    CUDA_TRY(c, cudaGetLastError());
-      }
     if(sharded)
       if(int rc2 = c->allreduce(c, part, (size_t)Jsum * N * Fmt<NL>::ES, 1, "nccl_allreduce_norm_partials"))
         return rc2;
@@ -231,6 +239,18 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaGetLastError());
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
+    if(J) // P = (P' >> prec) * norm needs only the norms: beside the exact syrk
+      {
+        cudaStream_t sr = c->side(1);
+        CUDA_TRY(c, c->after(st, sr, 12));
+        c->cur = sr;
+        dim3 g4(J, (unsigned)std::min<long>(((long)c->max_P * N + 127) / 128, 65535));
+        c->kt_begin("restore_P_kernel");
+        restore_P_kernel<NL><<<g4, 128, 0, sr>>>(c->d_bands, N, c->norms, c->prec);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+        c->cur = st;
+      }
     {
       const int nt = (N + 15) / 16;
       dim3 g3(nt * (nt + 1) / 2, c->crt.np);
@@ -253,18 +273,12 @@ template <int NL> struct Launch
       c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
     }
-    if(J)
-      {
-        dim3 g4(J, (unsigned)std::min<long>(((long)c->max_P * N + 127) / 128, 65535));
-        c->kt_begin("restore_P_kernel");
-        restore_P_kernel<NL><<<g4, 128, 0, st>>>(c->d_bands, N, c->norms, c->prec);
-        c->kt_end();
-    CUDA_TRY(c, cudaGetLastError());
-      }
     CUDA_TRY(c, cudaEventRecord(c->ev[7], st));
-    rc = potrf_rl(c, "potrf_Q", c->d_potrfQ, c->szQ, c->d_status + 5 * J, 1);
+    int rc = potrf_rl(c, "potrf_Q", c->d_potrfQ, c->szQ, c->d_status + 5 * J, 1);
     if(rc)
       return rc;
+    if(J)
+      CUDA_TRY(c, c->after(c->side(1), st, 13));
     CUDA_TRY(c, cudaEventRecord(c->ev[8], st));
     return 0;
   }
@@ -272,7 +286,7 @@ template <int NL> struct Launch
                     const limb_t *a, const limb_t *b, limb_t *r)
   {
     c->kt_begin("scalar_op_kernel");
-    scalar_op_kernel<NL><<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(
+    scalar_op_kernel<NL><<<(unsigned)((count + 127) / 128), 128, 0, c->cur>>>(
       op, k, count, a, b, r);
     c->kt_end();
     CUDA_TRY(c, cudaGetLastError());

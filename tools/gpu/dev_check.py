@@ -27,8 +27,9 @@ for prec, shapes, N in CASES:
     got = sdp.run_step(ctx)
     for k in KEYS:
         ol.assert_same(k, got[k], want[k])
+    ctx.set_concurrency(0)
     again = sdp.run_step(ctx)
     for k in KEYS:
-        ol.assert_same(k + " (2nd step)", again[k], want[k])
+        ol.assert_same(k + " (single stream)", again[k], want[k])
     ctx.close()
     print("parity ok", prec, shapes, N, flush=True)
