@@ -786,4 +786,48 @@ __global__ void scalar_op_kernel(int op, int k, long count, const limb_t *a,
     }
   st(r, e, z);
 }
+// test hook for the warp-cooperative pivot (coop.cuh): one warp per element.
+// op 8: r = mpf_sqrt(a);  op 9: r = [sign 1, exp 1, w0 = number of words in which the
+// cooperative reciprocal of sqrt(a) differs from mpfw::reciprocal_fast, other words 0]
+template <int NL>
+__global__ void __launch_bounds__(32) coop_test_kernel(int op, long count, const limb_t *a, limb_t *r)
+{
+  typedef TileGeom<NL> G;
+  extern __shared__ __align__(16) unsigned char coop_raw[];
+  coop::Work<NL> &ws = *reinterpret_cast<coop::Work<NL> *>(coop_raw);
+  uint32_t *slot = reinterpret_cast<uint32_t *>(coop_raw + ((sizeof(coop::Work<NL>) + 15) & ~(size_t)15));
+  uint32_t *R = slot + G::SW;
+  const long e = blockIdx.x;
+  if(e >= count)
+    return;
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(a + e * Fmt<NL>::ES);
+  for(int i = threadIdx.x; i < G::EW; i += 32)
+    slot[i] = src[i];
+  if(threadIdx.x == 0)
+    ws.flag = 0;
+  __syncwarp();
+  Reg<NL> out;
+  mpfw::set_zero(out);
+  if((int32_t)slot[1] > 0)
+    {
+      coop::pivot<NL>(ws, slot, R, nullptr);
+      if(threadIdx.x == 0)
+        {
+          mpfw::load<NL>(out, slot);
+          if(op == 9)
+            {
+              const RecipWords<NL> rw = recip_nl<NL>(out);
+              uint32_t bad = ws.flag; // a fallback counts as a mismatch: the fast path must close
+              for(int w = 0; w < G::RW; ++w)
+                bad += rw.w[w] != R[w];
+              mpfw::set_zero(out);
+              out.sign = 1;
+              out.exp = 1;
+              out.w[0] = bad;
+            }
+        }
+    }
+  if(threadIdx.x == 0)
+    stg_reg<NL>(r + e * Fmt<NL>::ES, out);
+}
 } // namespace sdpb_b200

@@ -285,6 +285,16 @@ template <int NL> struct Launch
   static int scalar(sdpb_b200_ctx *c, int op, int k, long count,
                     const limb_t *a, const limb_t *b, limb_t *r)
   {
+    if(op == 8 || op == 9)
+      {
+        const size_t sm = ((sizeof(coop::Work<NL>) + 15) & ~(size_t)15)
+                          + (TileGeom<NL>::SW + TileGeom<NL>::RS) * 4;
+        c->kt_begin("coop_test_kernel");
+        coop_test_kernel<NL><<<(unsigned)count, 32, sm, c->cur>>>(op, count, a, r);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+        return 0;
+      }
     c->kt_begin("scalar_op_kernel");
     scalar_op_kernel<NL><<<(unsigned)((count + 127) / 128), 128, 0, c->cur>>>(
       op, k, count, a, b, r);

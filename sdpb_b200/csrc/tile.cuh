@@ -17,6 +17,7 @@
 // HBM next to the factor (they are reused by the triangular solves).
 #pragma once
 #include "mpfw.h"
+#include "coop.cuh"
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -130,6 +131,7 @@ template <int NL> struct TileSmem
   uint32_t recip[TS * G::RS];     // reciprocals of the 16 pivots of `diag`
   uint64_t bar[2];
   int bad;
+  coop::Work<NL> work;            // workspace of the warp-cooperative pivot (coop.cuh)
 };
 
 // acc -+= sum_k A(ti,k) B(k,tj), k ascending in [0, K); `it` counts the chunks
@@ -283,29 +285,23 @@ __device__ __forceinline__ bool potrf_diag_tile(Reg<NL> &acc, const PotrfDesc &d
   const int nd = min(TS, d.s - J0);
   for(int kk = 0; kk < nd; ++kk)
     {
+      uint32_t *pslot = sm.diag + (kk * TS + kk) * G::SW;
       if(ti == kk && tj == kk)
         {
           if(acc.sign <= 0)
             sm.bad = J0 + kk;
           else
-            {
-              acc = sqrt_nl<NL>(acc);
-              const RecipWords<NL> rw = recip_nl<NL>(acc);
-              const uint32_t(&R)[G::RW] = rw.w;
-              uint32_t *rs = sm.recip + kk * G::RS;
-              uint32_t *rg = d.recip + (long)(J0 + kk) * G::RS;
-#pragma unroll
-              for(int w = 0; w < G::RW; ++w)
-                {
-                  rs[w] = R[w];
-                  rg[w] = R[w];
-                }
-              mpfw::store<NL>(sm.diag + (kk * TS + kk) * G::SW, acc);
-            }
+            mpfw::store<NL>(pslot, acc);
         }
       __syncthreads();
       if(sm.bad >= 0)
         return false;
+      // l_kk = sqrt(a_kk) and its reciprocal, by the 32 lanes of warp 0 together
+      if(threadIdx.x < 32)
+        coop::pivot<NL>(sm.work, pslot, sm.recip + kk * G::RS, d.recip + (long)(J0 + kk) * G::RS);
+      __syncthreads();
+      if(ti == kk && tj == kk)
+        mpfw::load<NL>(acc, pslot);
       if(tj == kk && ti > kk && ti < nd)
         {
           const uint32_t *piv = sm.diag + (kk * TS + kk) * G::SW;
