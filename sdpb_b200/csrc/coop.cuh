@@ -216,7 +216,7 @@ __device__ __forceinline__ void wmul(uint32_t *out, const uint32_t *a, int KA, c
 }
 
 // ------------------------------------------------------------------ workspace
-template <int NL> struct Work
+template <int NL> struct alignas(16) Work
 {
   static constexpr int P = NL - 1;
   static constexpr int NT = 4 * P;       // words of the sqrt radicand frame

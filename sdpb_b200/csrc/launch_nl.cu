@@ -35,10 +35,11 @@ template <int NL> struct Launch
   {
     if(sizes.empty() || nstatus == 0)
       return 0;
-    if(int rc = smem_opt_in(c, potrf_diag_level<NL>))
-      return rc;
     if(int rc = smem_opt_in(c, potrf_gemm_level<NL>))
       return rc;
+    constexpr size_t WARP_SMEM = DIAG_WARPS * sizeof(WarpTileSmem<NL>);
+    CUDA_TRY(c, cudaFuncSetAttribute(potrf_diag_warp<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)WARP_SMEM));
     CUDA_TRY(c, cudaFuncSetAttribute(potrf_solve_level<NL>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
     if(reset)
@@ -48,17 +49,19 @@ template <int NL> struct Launch
     for(int Jt = 0; Jt < T; ++Jt)
       {
         const int n = alive(sizes, Jt), nbelow = alive(sizes, Jt + 1);
-        potrf_diag_level<NL><<<n, 256, TILE_SMEM, c->cur>>>(d, Jt, status);
-        ++c->launches;
-        if(nbelow == 0)
-          continue;
-        const int rows_below = sizes[0] - (Jt + 1) * TS;
-        if(Jt > 0)
+        const int rows_from = sizes[0] - Jt * TS; // rows of the largest matrix in block column Jt
+        if(Jt > 0) // a_ij -= sum_{k < J0} l_ik l_jk for every tile of the block column
           {
-            dim3 g(nbelow, (rows_below + TS - 1) / TS);
+            dim3 g(n, (rows_from + TS - 1) / TS);
             potrf_gemm_level<NL><<<g, 256, TILE_SMEM, c->cur>>>(d, Jt, status);
             ++c->launches;
           }
+        potrf_diag_warp<NL><<<(n + DIAG_WARPS - 1) / DIAG_WARPS, 32 * DIAG_WARPS, WARP_SMEM, c->cur>>>(
+          d, n, Jt, status);
+        ++c->launches;
+        if(nbelow == 0)
+          continue;
+        const int rows_below = rows_from - TS;
         dim3 g2(nbelow, (rows_below + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
         potrf_solve_level<NL><<<g2, ROWS_PER_CTA, DIAG_SMEM, c->cur>>>(d, Jt, status);
         ++c->launches;

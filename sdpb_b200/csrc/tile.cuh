@@ -438,7 +438,7 @@ potrf_gemm_level(const PotrfDesc *descs, int Jt, const int *status)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
   const PotrfDesc d = descs[blockIdx.x];
-  const int It = Jt + 1 + blockIdx.y;
+  const int It = Jt + blockIdx.y; // the diagonal tile included (factored by potrf_diag_warp)
   if(It * TS >= d.s || status[d.id] >= 0)
     return;
   tile_smem_init(sm);
@@ -448,6 +448,123 @@ potrf_gemm_level(const PotrfDesc *descs, int Jt, const int *status)
   const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
   if(It * TS + ti < d.s && Jt * TS + tj < d.s)
     stg_reg<NL>(d.A + ((long)(It * TS + ti) * d.si + (long)(Jt * TS + tj) * d.sj) * G::ES, acc);
+}
+
+// ---- diagonal tiles of a BATCH: one warp per matrix ------------------------
+// Factoring a 16x16 diagonal tile is a chain of 16 pivots (sqrt, reciprocal,
+// column division, rank-1 update), ~0.5 ms of mostly serial work.  Giving it a
+// whole 256-thread CTA (potrf_diag_level / potrf_diag_rl) leaves two tiles in
+// flight per SM; here a tile lives in shared memory (packed lower triangle),
+// one warp owns it -- the pivot by all 32 lanes (coop.cuh), the column and the
+// trailing update one element per lane -- and eight tiles share an SM.
+template <int NL> struct alignas(128) WarpTileSmem
+{
+  typedef TileGeom<NL> G;
+  static constexpr int NE = TS * (TS + 1) / 2;
+  uint32_t el[NE * G::SW];
+  uint32_t recip[TS * G::RS];
+  coop::Work<NL> work;
+};
+constexpr int DIAG_WARPS = 4;
+__device__ __forceinline__ int tri_index(int i, int j) // i >= j, column-packed lower triangle
+{
+  return j * TS - j * (j - 1) / 2 + (i - j);
+}
+template <int NL>
+__global__ void __launch_bounds__(32 * DIAG_WARPS, 2)
+potrf_diag_warp(const PotrfDesc *descs, int count, int Jt, int *status)
+{
+  typedef TileGeom<NL> G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * DIAG_WARPS + warp;
+  if(m >= count)
+    return;
+  WarpTileSmem<NL> &sm = reinterpret_cast<WarpTileSmem<NL> *>(smem_raw)[warp];
+  const PotrfDesc d = descs[m];
+  const int J0 = Jt * TS;
+  if(J0 >= d.s || status[d.id] >= 0)
+    return;
+  const int nd = min(TS, d.s - J0);
+  if(lane == 0)
+    sm.work.flag = 0;
+  for(int e = lane; e < TS * TS; e += 32)
+    {
+      const int i = e & (TS - 1), j = e >> 4;
+      if(i >= j && i < nd)
+        {
+          const uint4 *src = reinterpret_cast<const uint4 *>(
+            d.A + ((long)(J0 + i) * d.si + (long)(J0 + j) * d.sj) * G::ES);
+          uint4 *dst = reinterpret_cast<uint4 *>(sm.el + tri_index(i, j) * G::SW);
+#pragma unroll
+          for(int w = 0; w < G::EB / 16; ++w)
+            dst[w] = src[w];
+        }
+    }
+  __syncwarp();
+  for(int kk = 0; kk < nd; ++kk)
+    {
+      uint32_t *pslot = sm.el + tri_index(kk, kk) * G::SW;
+      if((int32_t)pslot[1] <= 0)
+        {
+          if(lane == 0)
+            status[d.id] = J0 + kk;
+          return;
+        }
+      coop::pivot<NL>(sm.work, pslot, sm.recip + kk * G::RS, d.recip + (long)(J0 + kk) * G::RS);
+      {
+        const int i = kk + 1 + lane;
+        if(i < nd)
+          {
+            uint32_t *x = sm.el + tri_index(i, kk) * G::SW;
+            Reg<NL> acc;
+            mpfw::load<NL>(acc, x);
+            acc = div_nl<NL>(acc, pslot, sm.recip + kk * G::RS);
+            mpfw::store<NL>(x, acc);
+          }
+      }
+      __syncwarp();
+      const int r = nd - 1 - kk, cnt = r * (r + 1) / 2;
+      for(int e = lane; e < cnt; e += 32)
+        {
+          int jj = 0, rem = e; // e -> (ii >= jj) in the r x r lower triangle, column-packed
+          while(rem >= r - jj)
+            {
+              rem -= r - jj;
+              ++jj;
+            }
+          const int i = kk + 1 + jj + rem, j = kk + 1 + jj;
+          uint32_t *x = sm.el + tri_index(i, j) * G::SW;
+          Reg<NL> acc;
+          mpfw::load<NL>(acc, x);
+          acc = mac_nl<NL>(acc, sm.el + tri_index(i, kk) * G::SW, sm.el + tri_index(j, kk) * G::SW, true);
+          mpfw::store<NL>(x, acc);
+        }
+      __syncwarp();
+    }
+  // the factor below / on the diagonal, exact zeros above
+  for(int e = lane; e < TS * TS; e += 32)
+    {
+      const int i = e & (TS - 1), j = e >> 4;
+      if(i < nd && j < nd)
+        {
+          uint4 *dst = reinterpret_cast<uint4 *>(
+            d.A + ((long)(J0 + i) * d.si + (long)(J0 + j) * d.sj) * G::ES);
+          if(i >= j)
+            {
+              const uint4 *src = reinterpret_cast<const uint4 *>(sm.el + tri_index(i, j) * G::SW);
+#pragma unroll
+              for(int w = 0; w < G::EB / 16; ++w)
+                dst[w] = src[w];
+            }
+          else
+            {
+#pragma unroll
+              for(int w = 0; w < G::EB / 16; ++w)
+                dst[w] = make_uint4(0, 0, 0, 0);
+            }
+        }
+    }
 }
 
 // ---- right-looking variant ------------------------------------------------
