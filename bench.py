@@ -121,6 +121,48 @@ def algorithmic_bytes(kernel, prec, shapes, N):
     return tot
 
 
+def limb_macs(kernel, shapes, N):
+    """mpf multiply-accumulates of one launch (element updates)."""
+    tot = 0
+    for s in shapes:
+        P, mn = s.schur_size, s.pairing_size
+        for p in (0, 1):
+            sp = s.psd_size(p)
+            if kernel in ("potrf_X", "potrf_Y"):
+                tot += sp ** 3 / 3
+            elif kernel == "trsm_LXinv_V":
+                tot += sp * sp * mn / 2
+            elif kernel == "gemm_A_X_inv":
+                tot += mn * mn * sp / 2
+            elif kernel == "gemm_YV":
+                tot += sp * sp * mn
+            elif kernel == "gemm_A_Y":
+                tot += mn * mn * sp / 2
+        if kernel == "schur_kernel":
+            tot += 8 * P * P / 2
+        elif kernel == "potrf_S":
+            tot += P ** 3 / 3
+        elif kernel == "trsm_Linv_B":
+            tot += P * P * N / 2
+    if kernel == "potrf_Q":
+        tot = N ** 3 / 3
+    return tot
+
+
+# measured on this pool's B200 (profiles/imad_rate4_r01.jsonl): IMAD.WIDE.U32 with a 64-bit
+# accumulate, operands changing every instruction, 28.8 lanes/clk/SM x 148 SMs x 1.965 GHz
+IMAD_WIDE_PER_S = 28.77 * 148 * 1.965e9
+
+
+def imad_per_mac(prec):
+    """32x32->64 partial products of one mpf_mul at this precision (mpfw.h short product:
+    W = 2(NL-1) operand words, columns from C0 = W-6)."""
+    nl = (prec + 63) // 64 + 2
+    w = 2 * (nl - 1)
+    c0 = max(w - 6, 0)
+    return sum(1 for i in range(w) for j in range(w) if i + j >= c0)
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -263,11 +305,14 @@ def main():
 
     # ---- end to end through the C-ABI with host buffers -----------------
     pool = PinnedPool()
-    Xh, Yh = pool.like(sdp.X), pool.like(sdp.Y)
-    Xc = [pool.empty(x.shape) for x in sdp.X]
-    Yc = [pool.empty(x.shape) for x in sdp.X]
-    Lh = [pool.empty((s.schur_size, s.schur_size, ctx.ew)) for s in ctx.shapes]
-    Ph = [pool.empty((N, s.schur_size, ctx.ew)) for s in ctx.shapes]
+    # the caller's staging buffers: one pinned slab per block-diagonal object, blocks back to back
+    Xh, Yh = pool.slab([x.shape for x in sdp.X]), pool.slab([x.shape for x in sdp.Y])
+    for dst, src in zip(Xh + Yh, sdp.X + sdp.Y):
+        dst[...] = src
+    Xc = pool.slab([x.shape for x in sdp.X])
+    Yc = pool.slab([x.shape for x in sdp.X])
+    Lh = pool.slab([(s.schur_size, s.schur_size, ctx.ew) for s in ctx.shapes])
+    Ph = pool.slab([(N, s.schur_size, ctx.ew) for s in ctx.shapes])
     Qh = pool.empty((N, N, ctx.ew))
     h2d = sum(x.nbytes for x in Xh) + sum(x.nbytes for x in Yh)
     d2h = sum(x.nbytes for x in Xc + Yc + Lh + Ph) + Qh.nbytes
@@ -301,6 +346,13 @@ def main():
                 "timed_in": "single-stream pass (%.1f ms/step); the headline value overlaps independent "
                             "chains on side streams" % serial_step,
                 "note": "multi-limb contraction: the INT32 multiply pipe binds, not HBM (DESIGN.md §4)"}
+    macs = limb_macs(dom, ctx.shapes, N)
+    if macs:
+        rate = macs * imad_per_mac(prec) / (dom_ms * 1e-3)
+        roofline["int_pipe"] = {"unit": "IMAD.WIDE/s", "achieved": rate, "peak": IMAD_WIDE_PER_S,
+                                "frac": rate / IMAD_WIDE_PER_S, "mpf_macs_per_launch": macs / max(1, dom_launches),
+                                "imad_wide_per_mac": imad_per_mac(prec),
+                                "peak_source": "measured, profiles/imad_rate4_r01.jsonl"}
     if a.kernels:
         for k, (ms, n) in sorted(per_kernel.items(), key=lambda kv: -kv[1][0]):
             ab = algorithmic_bytes(k, prec, ctx.shapes, N)

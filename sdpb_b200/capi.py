@@ -153,6 +153,21 @@ class PinnedPool:
         buf = (ctypes.c_uint64 * (nbytes // 8)).from_address(p.value)
         return np.frombuffer(buf, dtype=np.uint64).reshape(shape)
 
+    def slab(self, shapes):
+        """Arrays of the given shapes carved back to back out of ONE page-locked allocation
+        (what a reference-side shim would pack El::BigFloat blocks into): the library then
+        moves adjacent blocks with a single DMA."""
+        sizes = [int(np.prod(s)) for s in shapes]
+        total = sum(sizes)
+        if total == 0:
+            return [np.zeros(s, dtype=np.uint64) for s in shapes]
+        flat = self.empty((total,))
+        out, pos = [], 0
+        for s, n in zip(shapes, sizes):
+            out.append(flat[pos:pos + n].reshape(s))
+            pos += n
+        return out
+
     def like(self, arrays):
         out = []
         for a in arrays:

@@ -277,6 +277,9 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
     TRY_C(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
   for(auto &e : c->evf)
     TRY_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  TRY_C(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+  for(auto &e : c->evd)
+    TRY_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if(const char *env = getenv("SDPB_B200_CONCURRENCY"))
     c->concurrency = atoi(env) != 0;
   TRY_C(cudaMalloc(&c->arena, c->arena_words * sizeof(limb_t)));
@@ -338,23 +341,28 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
             const int s = b.s[p];
             pX.push_back(PotrfDesc{c->X + c->oXY[q], c->recipX + rXY * rs, s, 1, (long)s, q});
             pY.push_back(PotrfDesc{c->LY + c->oXY[q], c->recipY + rXY * rs, s, 1, (long)s, q});
+            // bases_blocks[q] = I_m (x) v: diagonal blocks of h rows x n columns
+            const int hb = b.m > 1 ? s / b.m : 0, nbk = b.n;
             tT.push_back(TrsmTileDesc{c->X + c->oXY[q], c->recipX + rXY * rs, c->T + c->oV[q],
-                                      s, b.mn});
+                                      s, b.mn, hb, nbk});
             rXY += s;
             // AX = T^T T : A(i,l) = T(l,i), B(l,j) = T(l,j)
             gAX.push_back(GemmTileDesc{c->T + c->oV[q], c->T + c->oV[q], c->AX + c->oA[q],
-                                       (long)s, 1, 1, (long)s, b.mn, b.mn, s, 1, 0});
+                                       (long)s, 1, 1, (long)s, b.mn, b.mn, s, 1, 0,
+                                       hb ? 3 : 0, hb, nbk});
             // YV = Y V
             gYV.push_back(GemmTileDesc{c->Y + c->oXY[q], c->V + c->oV[q], c->YV + c->oV[q], 1,
-                                       (long)s, 1, (long)s, s, b.mn, s, 0, 0});
+                                       (long)s, 1, (long)s, s, b.mn, s, 0, 0,
+                                       hb ? 1 : 0, hb, nbk});
             // AY = V^T (YV)
             gAY.push_back(GemmTileDesc{c->V + c->oV[q], c->YV + c->oV[q], c->AY + c->oA[q],
-                                       (long)s, 1, 1, (long)s, b.mn, b.mn, s, 1, 0});
+                                       (long)s, 1, 1, (long)s, b.mn, b.mn, s, 1, 0,
+                                       hb ? 2 : 0, hb, nbk});
           }
         pS.push_back(PotrfDesc{c->S + c->oS[j], c->recipS + (size_t)b.row0 * rs, b.P, 1,
                                (long)b.P, j});
         tP.push_back(TrsmTileDesc{c->S + c->oS[j], c->recipS + (size_t)b.row0 * rs,
-                                  c->Pband + c->oB[j], b.P, N});
+                                  c->Pband + c->oB[j], b.P, N, 0, 0});
         sd.push_back(SchurDesc{{c->AX + c->oA[2 * j], c->AX + c->oA[2 * j + 1]},
                                {c->AY + c->oA[2 * j], c->AY + c->oA[2 * j + 1]},
                                c->S + c->oS[j], b.m, b.n});
@@ -422,7 +430,7 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
             gp.push_back(PotrfDesc{c->S + c->oS[j], c->recipS + (size_t)b.row0 * rs, b.P, 1,
                                    (long)b.P, j});
             gt.push_back(TrsmTileDesc{c->S + c->oS[j], c->recipS + (size_t)b.row0 * rs,
-                                      c->Pband + c->oB[j], b.P, N});
+                                      c->Pband + c->oB[j], b.P, N, 0, 0});
             gs.push_back(sd[j]);
             gb.push_back(bd[j]);
             c->szS_g[g].push_back(b.P);
@@ -599,6 +607,11 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
   for(auto &e : c->evf)
     if(e)
       cudaEventDestroy(e);
+  for(auto &e : c->evd)
+    if(e)
+      cudaEventDestroy(e);
+  if(c->copy)
+    cudaStreamDestroy(c->copy);
   if(c->pinned)
     cudaFreeHost(c->pinned);
   for(auto &k : c->kt)
@@ -752,10 +765,23 @@ static int copy_blocks_out(sdpb_b200_ctx *c, const limb_t *src,
 {
   if(!out)
     return 0;
-  for(int q = 0; q < count; ++q)
-    if(out[q] && elems[q])
-      CUDA_TRY(c, cudaMemcpyAsync(out[q], src + off[q], elems[q] * c->es * 8,
-                                  cudaMemcpyDeviceToHost, c->stream));
+  // blocks that are adjacent on both sides (the arena is packed in block order; a caller
+  // that packs its staging buffer the same way gets one DMA instead of one per block)
+  for(int q = 0; q < count;)
+    {
+      if(!out[q] || !elems[q])
+        {
+          ++q;
+          continue;
+        }
+      size_t words = elems[q] * c->es;
+      int r = q + 1;
+      while(r < count && out[r] && elems[r] && out[r] == out[q] + words
+            && off[r] == off[q] + words)
+        words += elems[r++] * c->es;
+      CUDA_TRY(c, cudaMemcpyAsync(out[q], src + off[q], words * 8, cudaMemcpyDeviceToHost, c->stream));
+      q = r;
+    }
   return 0;
 }
 
@@ -985,13 +1011,9 @@ extern "C" int sdpb_b200_upload_XY(sdpb_b200_ctx *c, const uint64_t *const *X,
 
 // The whole hot path from device-resident X, Y (sdpb_b200_upload_XY): every
 // kernel is enqueued back to back, one host synchronisation at the end.
-extern "C" int sdpb_b200_schur_step_resident(sdpb_b200_ctx *c)
+static int enqueue_step(sdpb_b200_ctx *c)
 {
-  if(!c)
-    return SDPB_B200_ERR_ARG;
-  CUDA_TRY(c, cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  const int J = c->J;
   c->kt_used = 0;
   CUDA_TRY(c, cudaEventRecord(c->ev[9], st));
   if(c->wXY)
@@ -1010,6 +1032,7 @@ extern "C" int sdpb_b200_schur_step_resident(sdpb_b200_ctx *c)
   c->cur = st;
   if(rc)
     return rc;
+  CUDA_TRY(c, cudaEventRecord(c->evd[0], sl));
   rc = dispatch_cholesky(c, 0);
   if(rc)
     return rc;
@@ -1022,7 +1045,16 @@ extern "C" int sdpb_b200_schur_step_resident(sdpb_b200_ctx *c)
   rc = dispatch_schur_and_Q(c);
   if(rc)
     return rc;
+  CUDA_TRY(c, cudaEventRecord(c->evd[1], c->side(1))); // restore_P was the last thing enqueued there
   CUDA_TRY(c, cudaEventRecord(c->ev[10], st));
+  return 0;
+}
+
+// wait for the step, read the status words back and turn them into the reference's errors
+static int finish_step(sdpb_b200_ctx *c)
+{
+  cudaStream_t st = c->stream;
+  const int J = c->J;
   std::vector<int> status(5 * J + 1);
   int flags[4];
   CUDA_TRY(c, cudaMemcpyAsync(status.data(), c->d_status, status.size() * sizeof(int),
@@ -1076,6 +1108,15 @@ extern "C" int sdpb_b200_schur_step_resident(sdpb_b200_ctx *c)
   return 0;
 }
 
+extern "C" int sdpb_b200_schur_step_resident(sdpb_b200_ctx *c)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int rc = enqueue_step(c);
+  return rc ? rc : finish_step(c);
+}
+
 // D2H of whichever outputs of the last step the caller wants (NULL = skip).
 extern "C" int sdpb_b200_download(
   sdpb_b200_ctx *c, uint64_t *const *X_cholesky, uint64_t *const *Y_cholesky,
@@ -1125,14 +1166,100 @@ extern "C" int sdpb_b200_schur_step(
   uint64_t *const *schur_complement_cholesky,
   uint64_t *const *schur_off_diagonal, uint64_t *Q, int32_t *block_timings_ms)
 {
-  int rc = sdpb_b200_upload_XY(c, X, Y);
+  // One pipeline: X, Y go up block by block straight from the caller's buffers, the whole
+  // step is enqueued without a host synchronisation, and every output is copied back on a
+  // separate stream as soon as the kernel that finishes it has run -- L_j while L_j^-1 B_j
+  // is still being solved, P (the largest, P x N) beside the exact syrk and Cholesky(Q).
+  if(!c || !X || !Y)
+    return SDPB_B200_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int J = c->J;
+  for(int which = 0; which < 2; ++which)
+    {
+      const uint64_t *const *A = which == 0 ? X : Y;
+      limb_t *dst = which == 0 ? c->Xin : c->Yin;
+      for(int q = 0; q < 2 * J;)
+        {
+          const int s = c->g[q / 2].s[q % 2];
+          if(s == 0)
+            {
+              ++q;
+              continue;
+            }
+          if(!A[q])
+            {
+              c->error = "null input block " + std::to_string(q);
+              return SDPB_B200_ERR_ARG;
+            }
+          size_t words = (size_t)s * s * c->es;
+          int r = q + 1; // merge blocks the caller stored back to back
+          while(r < 2 * J)
+            {
+              const size_t sr = c->g[r / 2].s[r % 2];
+              if(sr == 0 || A[r] != A[q] + words || c->oXY[r] != c->oXY[q] + words)
+                break;
+              words += sr * sr * c->es;
+              ++r;
+            }
+          CUDA_TRY(c, cudaMemcpyAsync(dst + c->oXY[q], A[q], words * 8, cudaMemcpyHostToDevice, c->stream));
+          q = r;
+        }
+    }
+  int rc = enqueue_step(c);
   if(rc)
     return rc;
-  rc = sdpb_b200_schur_step_resident(c);
-  if(rc)
-    return rc;
-  rc = sdpb_b200_download(c, X_cholesky, Y_cholesky, A_X_inv, A_Y,
-                          schur_complement_cholesky, schur_off_diagonal, Q);
+  {
+    std::vector<size_t> eXY(2 * J), eA(2 * J), eS(J), eP(J);
+    for(int q = 0; q < 2 * J; ++q)
+      {
+        eXY[q] = (size_t)c->g[q / 2].s[q % 2] * c->g[q / 2].s[q % 2];
+        eA[q] = (size_t)c->g[q / 2].mn * c->g[q / 2].mn;
+      }
+    for(int j = 0; j < J; ++j)
+      {
+        eS[j] = (size_t)c->g[j].P * c->g[j].P;
+        eP[j] = (size_t)c->g[j].P * c->N;
+      }
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->copy; // copy_blocks_out enqueues on c->stream
+    auto out = [&](cudaEvent_t ready, const limb_t *src, const std::vector<size_t> &off,
+                   uint64_t *const *dst, int count, const std::vector<size_t> &elems) -> int {
+      if(!dst)
+        return 0;
+      if(cudaStreamWaitEvent(c->copy, ready, 0) != cudaSuccess)
+        return SDPB_B200_ERR_CUDA;
+      return copy_blocks_out(c, src, off, dst, count, elems);
+    };
+    rc = out(c->ev[0], c->X, c->oXY, X_cholesky, 2 * J, eXY);
+    if(!rc)
+      rc = out(c->evd[0], c->LY, c->oXY, Y_cholesky, 2 * J, eXY);
+    if(!rc)
+      rc = out(c->ev[1], c->AX, c->oA, A_X_inv, 2 * J, eA);
+    if(!rc)
+      rc = out(c->ev[1], c->AY, c->oA, A_Y, 2 * J, eA);
+    if(!rc)
+      rc = out(c->ev[4], c->S, c->oS, schur_complement_cholesky, J, eS);
+    if(!rc)
+      rc = out(c->evd[1], c->Pband, c->oB, schur_off_diagonal, J, eP);
+    if(!rc && Q)
+      {
+        if(cudaStreamWaitEvent(c->copy, c->ev[10], 0) != cudaSuccess
+           || cudaMemcpyAsync(Q, c->Q, (size_t)c->N * c->N * c->es * 8, cudaMemcpyDeviceToHost, c->copy)
+                != cudaSuccess)
+          rc = SDPB_B200_ERR_CUDA;
+      }
+    c->stream = main_stream;
+    if(rc)
+      {
+        cudaStreamSynchronize(c->copy);
+        cudaStreamSynchronize(c->stream);
+        if(c->error.empty())
+          c->error = "CUDA failure while enqueueing the output copies";
+        return rc;
+      }
+  }
+  rc = finish_step(c);
+  CUDA_TRY(c, cudaStreamSynchronize(c->copy));
   if(rc)
     return rc;
   if(block_timings_ms)

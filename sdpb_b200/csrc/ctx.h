@@ -96,6 +96,8 @@ struct sdpb_b200_ctx
   // on `stream` in program order (what the per-kernel timeline is measured in).
   static constexpr int MAXG = 4;
   cudaStream_t cur = nullptr; // the stream the launch helpers enqueue on
+  cudaStream_t copy = nullptr; // D2H of finished outputs while the step is still running (schur_step)
+  cudaEvent_t evd[2] = {};     // [0] chol(Y) done, [1] restore_P done
   cudaStream_t aux[MAXG] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t evf[16] = {};
   int concurrency = 1, G = 1;

@@ -25,27 +25,6 @@ template <int NL> struct Fmt
   static constexpr int ES = (NL + 2) & ~1; // 64-bit words per element
 };
 
-struct MatDesc // one square matrix to factor in place
-{
-  limb_t *a;
-  int s;
-  int id; // reported on failure
-};
-struct TrsmDesc // B <- L^{-1} B
-{
-  const limb_t *L;
-  limb_t *B;
-  int p, ncols;
-};
-struct GemmDesc // C(i,j) = sum_l A(i,l) B(l,j), strides in elements
-{
-  const limb_t *A;
-  const limb_t *B;
-  limb_t *C;
-  long sa_i, sa_l, sb_l, sb_j;
-  int M, N, K;
-  int sym; // 1: compute i >= j only and mirror
-};
 struct SchurDesc
 {
   const limb_t *AX[2];
@@ -71,184 +50,6 @@ template <int NL>
 __device__ __forceinline__ void st(limb_t *base, size_t idx, const Num<NL> &x)
 {
   mpfx::store(base + idx * Fmt<NL>::ES, x);
-}
-
-// ------------------------------------------------------------------- potrf
-// One CTA per matrix, in place.  upper == 0: A = L L^T (lower); upper == 1:
-// A = U^T U stored in the upper triangle (same recurrence on the transposed
-// storage).  status[matrix] = -1 or the index of the first non-positive pivot
-// (the reference's El::Cholesky throws there: cholesky_decomposition.cxx:14-26,
-// compute_Q.cxx:29-39, initialize_schur_complement_solver.cxx:96-103).
-template <int NL>
-__global__ void __launch_bounds__(256)
-potrf_kernel(const MatDesc *descs, int upper, int *status)
-{
-  const MatDesc d = descs[blockIdx.x];
-  const int s = d.s;
-  if(s == 0)
-    {
-      if(threadIdx.x == 0)
-        status[blockIdx.x] = -1;
-      return;
-    }
-  limb_t *A = d.a;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  __shared__ int bad;
-  if(tid == 0)
-    bad = -1;
-  __syncthreads();
-  // logical (i,j), i >= j
-  auto idx = [&](int i, int j) -> size_t {
-    return upper ? (size_t)i * s + j : (size_t)j * s + i;
-  };
-  for(int j = 0; j < s; ++j)
-    {
-      if(tid == 0)
-        {
-          Num<NL> a;
-          ld(a, A, idx(j, j));
-          if(a.sign <= 0)
-            bad = j;
-          else
-            {
-              mpfx::sqrt(a, a);
-              st(A, idx(j, j), a);
-            }
-        }
-      __syncthreads();
-      if(bad >= 0)
-        {
-          if(tid == 0)
-            status[blockIdx.x] = bad;
-          return;
-        }
-      {
-        Num<NL> piv;
-        bool have = false;
-        for(int i = j + 1 + tid; i < s; i += nt)
-          {
-            if(!have)
-              {
-                ld(piv, A, idx(j, j));
-                have = true;
-              }
-            Num<NL> x;
-            ld(x, A, idx(i, j));
-            mpfx::div(x, x, piv);
-            st(A, idx(i, j), x);
-          }
-      }
-      __syncthreads();
-      const int r = s - 1 - j;
-      const int cnt = r * (r + 1) / 2;
-      for(int e = tid; e < cnt; e += nt)
-        {
-          // e -> (ii >= kk) in the r x r lower triangle
-          int ii = (int)((::sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-          while(ii * (ii + 1) / 2 > e)
-            --ii;
-          while((ii + 1) * (ii + 2) / 2 <= e)
-            ++ii;
-          const int kk = e - ii * (ii + 1) / 2;
-          const int i = j + 1 + ii, k = j + 1 + kk;
-          Num<NL> lij, lkj, a, p;
-          ld(lij, A, idx(i, j));
-          ld(lkj, A, idx(k, j));
-          ld(a, A, idx(i, k));
-          mpfx::mul(p, lij, lkj);
-          mpfx::sub(a, a, p);
-          st(A, idx(i, k), a);
-        }
-      __syncthreads();
-    }
-  // zero the other triangle
-  Num<NL> z;
-  mpfx::set_zero(z);
-  for(int e = tid; e < s * s; e += nt)
-    {
-      const int i = e % s, j = e / s; // storage (row i, col j)
-      const bool other = upper ? (i > j) : (i < j);
-      if(other)
-        st(A, (size_t)j * s + i, z);
-    }
-  if(tid == 0)
-    status[blockIdx.x] = -1;
-}
-
-// -------------------------------------------------------------------- trsm
-// B <- L^{-1} B, right-looking: for k: x_k = b_k / l_kk ; b_i -= l_ik x_k
-// (i > k).  grid = (matrices, column slabs of `slab` columns), one CTA each.
-template <int NL>
-__global__ void __launch_bounds__(256)
-trsm_kernel(const TrsmDesc *descs, int slab)
-{
-  const TrsmDesc d = descs[blockIdx.x];
-  const int c0 = blockIdx.y * slab;
-  if(c0 >= d.ncols || d.p == 0)
-    return;
-  const int nc = min(slab, d.ncols - c0);
-  const int p = d.p;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const limb_t *L = d.L;
-  limb_t *B = d.B;
-  for(int k = 0; k < p; ++k)
-    {
-      for(int c = tid; c < nc; c += nt)
-        {
-          Num<NL> x, piv;
-          ld(piv, L, (size_t)k * p + k);
-          ld(x, B, (size_t)(c0 + c) * p + k);
-          mpfx::div(x, x, piv);
-          st(B, (size_t)(c0 + c) * p + k, x);
-        }
-      __syncthreads();
-      const int r = p - 1 - k;
-      for(int e = tid; e < r * nc; e += nt)
-        {
-          const int i = k + 1 + e % r, c = c0 + e / r;
-          Num<NL> l, x, b, pr;
-          ld(l, L, (size_t)k * p + i);
-          ld(x, B, (size_t)c * p + k);
-          ld(b, B, (size_t)c * p + i);
-          mpfx::mul(pr, l, x);
-          mpfx::sub(b, b, pr);
-          st(B, (size_t)c * p + i, b);
-        }
-      __syncthreads();
-    }
-}
-
-// -------------------------------------------------------------------- gemm
-// C(i,j) = sum_l A(i,l) B(l,j), l ascending from an exact zero; one thread
-// per output.  sym: only i >= j is computed, result mirrored.
-template <int NL>
-__global__ void __launch_bounds__(128) gemm_kernel(const GemmDesc *descs)
-{
-  const GemmDesc d = descs[blockIdx.x];
-  const long total = (long)d.M * d.N;
-  for(long e = (long)blockIdx.y * blockDim.x + threadIdx.x; e < total;
-      e += (long)gridDim.y * blockDim.x)
-    {
-      const int i = (int)(e % d.M), j = (int)(e / d.M);
-      if(d.sym && i < j)
-        continue;
-      Num<NL> acc, a, b, p;
-      mpfx::set_zero(acc);
-      for(int l = 0; l < d.K; ++l)
-        {
-          ld(a, d.A, (size_t)(i * d.sa_i + l * d.sa_l));
-          if(a.sign == 0)
-            continue; // 0 * x = 0 and c + 0 = c exactly in mpf
-          ld(b, d.B, (size_t)(l * d.sb_l + j * d.sb_j));
-          if(b.sign == 0)
-            continue;
-          mpfx::mul(p, a, b);
-          mpfx::add(acc, acc, p);
-        }
-      st(d.C, (size_t)j * d.M + i, acc);
-      if(d.sym && i != j)
-        st(d.C, (size_t)i * d.M + j, acc);
-    }
 }
 
 // ------------------------------------------------------------ Schur assembly

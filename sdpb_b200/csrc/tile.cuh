@@ -216,7 +216,33 @@ struct GemmTileDesc // C(i,j) = sum_l A(i,l) B(l,j); strides in elements
   int M, N, K;
   int sym;   // 1: only tiles/elements with i >= j, result mirrored
   int tile0; // first linear tile index of this matrix in the launch
+  // Block structure of bases_blocks = I_m (x) v (SDP/set_bases_blocks.cxx:3-22): with hb rows
+  // and nb columns per diagonal block, an operand entry (l, x) is an exact zero unless
+  // l / hb == x / nb (band 1: the B operand, 2: the A operand), or -- for T = L_X^-1 V, whose
+  // columns start with the zeros of V -- unless l >= (x / nb) hb (band 3: both operands).
+  // A multiply-accumulate with an exact zero leaves the accumulator untouched
+  // (mpf: 0 * x = 0, c + 0 = c), so only the k-range that can hold non-zeros is visited.
+  int band, hb, nb;
 };
+// k-range [klo, khi) of the products that can be non-zero for an output tile
+__device__ __forceinline__ void band_range(const GemmTileDesc &d, int i0, int i1, int j0, int j1,
+                                           int &klo, int &khi)
+{
+  klo = 0;
+  khi = d.K;
+  if(d.band == 1)
+    {
+      klo = (j0 / d.nb) * d.hb;
+      khi = min(d.K, ((j1 - 1) / d.nb + 1) * d.hb);
+    }
+  else if(d.band == 2)
+    {
+      klo = (i0 / d.nb) * d.hb;
+      khi = min(d.K, ((i1 - 1) / d.nb + 1) * d.hb);
+    }
+  else if(d.band == 3)
+    klo = max(i0 / d.nb, j0 / d.nb) * d.hb;
+}
 
 // grid.x = total number of 16x16 tiles over all matrices (host prefix sums in
 // `tile0`); the matrix of a tile is found by binary search.
@@ -249,9 +275,13 @@ gemm_tile_kernel(const GemmTileDesc *descs, int count)
   Reg<NL> acc;
   mpfw::set_zero(acc);
   uint32_t it = 0;
-  Operand A{d.A + (long)It * TS * d.sa_i * G::ES, d.sa_i, d.sa_l, min(TS, d.M - It * TS)};
-  Operand B{d.B + (long)Jt * TS * d.sb_j * G::ES, d.sb_j, d.sb_l, min(TS, d.N - Jt * TS)};
-  tile_k_loop<NL>(acc, false, A, B, d.K, sm, it, active);
+  int klo, khi;
+  band_range(d, It * TS, min(d.M, It * TS + TS), Jt * TS, min(d.N, Jt * TS + TS), klo, khi);
+  Operand A{d.A + ((long)It * TS * d.sa_i + (long)klo * d.sa_l) * G::ES, d.sa_i, d.sa_l,
+            min(TS, d.M - It * TS)};
+  Operand B{d.B + ((long)Jt * TS * d.sb_j + (long)klo * d.sb_l) * G::ES, d.sb_j, d.sb_l,
+            min(TS, d.N - Jt * TS)};
+  tile_k_loop<NL>(acc, false, A, B, max(0, khi - klo), sm, it, active);
   if(active)
     {
       stg_reg<NL>(d.C + ((long)j * d.M + i) * G::ES, acc);
@@ -403,33 +433,15 @@ __device__ __forceinline__ void potrf_tile_update(Reg<NL> &acc, const PotrfDesc 
 
 // ---- level-synchronous batched Cholesky --------------------------------
 // Block column Jt of every matrix of the batch is finished by three launches:
-//   potrf_diag_level   one CTA per matrix: update + factor the diagonal tile
-//   potrf_gemm_level   one CTA per tile below it: a_ij -= sum_{k<J0} l_ik l_jk
+//   potrf_gemm_level   one CTA per tile of the block column, the diagonal one
+//                      included: a_ij -= sum_{k<J0} l_ik l_jk
+//   potrf_diag_warp    one WARP per matrix: factor the diagonal tile (below)
 //   potrf_solve_level  one THREAD per row below it: the 16 unknowns of that row
 //                      against the factored diagonal tile (16 divisions and 120
 //                      multiply-accumulates, sequential by nature, so rows are
 //                      the parallel dimension)
 // `descs` is sorted by size (largest first); grid.x covers the prefix of
 // matrices that still have a block column Jt.
-template <int NL>
-__global__ void __launch_bounds__(256, 2)
-potrf_diag_level(const PotrfDesc *descs, int Jt, int *status)
-{
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
-  const PotrfDesc d = descs[blockIdx.x];
-  if(Jt * TS >= d.s || status[d.id] >= 0)
-    return;
-  tile_smem_init(sm);
-  uint32_t it = 0;
-  Reg<NL> acc;
-  potrf_tile_update<NL>(acc, d, Jt, Jt, sm, it);
-  if(!potrf_diag_tile<NL>(acc, d, Jt, sm))
-    {
-      if(threadIdx.x == 0)
-        status[d.id] = sm.bad;
-    }
-}
 template <int NL>
 __global__ void __launch_bounds__(256, 2)
 potrf_gemm_level(const PotrfDesc *descs, int Jt, const int *status)
@@ -732,6 +744,9 @@ struct TrsmTileDesc // X <- L^{-1} B in place, L lower p x p (column-major)
   const uint32_t *recip; // reciprocals of diag(L)
   uint64_t *B;           // p x ncols, column-major, ld = p
   int p, ncols;
+  // right-hand sides that are bases_blocks (see GemmTileDesc): column c is zero above row
+  // (c / nb) hb, and so is the solution; hb == 0: dense
+  int hb, nb;
 };
 
 // Row tile It of every solve of the batch (sorted by p, largest first):
@@ -747,6 +762,10 @@ __global__ void __launch_bounds__(256, 2) trsm_gemm_level(const TrsmTileDesc *de
   const int c0 = blockIdx.y * TS, I0 = It * TS;
   if(I0 >= d.p || c0 >= d.ncols)
     return;
+  // leading zeros of these columns (block structure): rows above klo hold exact zeros
+  const int klo = d.hb ? ((c0 / d.nb) * d.hb) & ~(KC - 1) : 0;
+  if(I0 <= klo)
+    return; // nothing above this tile can be non-zero: no update
   tile_smem_init(sm);
   const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
   const int nc = min(TS, d.ncols - c0), ni = min(TS, d.p - I0);
@@ -758,9 +777,9 @@ __global__ void __launch_bounds__(256, 2) trsm_gemm_level(const TrsmTileDesc *de
   else
     mpfw::set_zero(acc);
   uint32_t it = 0;
-  Operand A{d.L + (long)I0 * G::ES, 1, d.p, ni};
-  Operand B{d.B + (long)c0 * d.p * G::ES, d.p, 1, nc};
-  tile_k_loop<NL>(acc, true, A, B, I0, sm, it, active);
+  Operand A{d.L + ((long)I0 + (long)klo * d.p) * G::ES, 1, d.p, ni};
+  Operand B{d.B + ((long)c0 * d.p + klo) * G::ES, d.p, 1, nc};
+  tile_k_loop<NL>(acc, true, A, B, I0 - klo, sm, it, active);
   if(active)
     stg_reg<NL>(mine, acc);
 }

@@ -70,6 +70,25 @@ def test_device_scalar_arithmetic_matches_libgmp(prec):
     ctx.close()
 
 
+@pytest.mark.parametrize("prec", [128, 448, 768, 960, 1536])
+def test_cooperative_pivot_matches_libgmp(prec):
+    """coop.cuh: sqrt and pivot reciprocal by one warp (ops 8, 9 of the scalar hook) --
+    sqrt against libgmp's mpf_sqrt, the reciprocal words against the single-thread routine,
+    whose own fast path must not have fallen back."""
+    ctx = sdpb_b200.SchurContext(prec, [(1, 2)], 1)
+    a, _ = _adversarial_operands(prec, 2048, 23)
+    a[:, 0] = (a[:, 0] & np.uint64(0xFFFFFFFF)) | (np.uint64(1) << np.uint64(32))  # a > 0
+    nl = (prec + 63) // 64 + 2
+    a[a[:, nl] == 0, nl] = 1
+    got = ctx.scalar_op(8, a, a)
+    want = ol.scalar_op(prec, 4, a, a)
+    bad = np.argwhere((got != want).any(axis=1))
+    assert len(bad) == 0, f"cooperative sqrt: {len(bad)} mismatches, first index {bad[0]}"
+    got = ctx.scalar_op(9, a, a)
+    assert int((got[:, 1] & np.uint64(0xFFFFFFFF)).max()) == 0, "cooperative reciprocal differs"
+    ctx.close()
+
+
 CASES = [
     # prec, [(m, n)...], N
     (128, [(1, 4), (2, 3), (1, 1)], 3),
@@ -92,10 +111,29 @@ def test_schur_step_bit_exact(prec, shapes, N):
     got = sdp.run_step(ctx)
     for k in KEYS:
         ol.assert_same(k, got[k], want[k])
-    # second step on the same context must reproduce itself (state is reset)
+    # second step on the same context must reproduce itself (state is reset), here with
+    # every kernel on one stream instead of the concurrent schedule
+    ctx.set_concurrency(0)
     again = sdp.run_step(ctx)
     for k in KEYS:
-        ol.assert_same(k + " (2nd step)", again[k], want[k])
+        ol.assert_same(k + " (2nd step, single stream)", again[k], want[k])
+    ctx.close()
+
+
+def test_block_groups_on_side_streams_bit_exact(monkeypatch):
+    """The S chain cut into interleaved groups of blocks on separate streams
+    (SDPB_B200_GROUPS) must not change a bit."""
+    prec, shapes, N = 768, [(1, 9), (2, 5), (1, 17), (1, 4), (2, 9), (1, 12), (1, 3)], 9
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=8)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    want = sdp.run_step(ref)
+    monkeypatch.setenv("SDPB_B200_GROUPS", "3")
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    got = sdp.run_step(ctx)
+    for k in KEYS:
+        ol.assert_same(k, got[k], want[k])
     ctx.close()
 
 
