@@ -163,6 +163,22 @@ def imad_per_mac(prec):
     return sum(1 for i in range(w) for j in range(w) if i + j >= c0)
 
 
+def recorded_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of all launches behind `kernel`'s label in one
+    step, from the committed `ncu --set full` capture (profiles/traffic_*.json), or None."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json"))):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            if d.get("workload") == workload and d.get("label") == kernel:
+                best = float(d["dram_bytes"])
+        except Exception:
+            pass
+    return best
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -341,7 +357,7 @@ def main():
     abytes = algorithmic_bytes(dom, prec, ctx.shapes, N) / max(1, dom_launches)
     achieved = abytes / (dom_ms / max(1, dom_launches) * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": which,
+                "frac": achieved / peak, "traffic": recorded_traffic(a.workload, dom), "peak_source": which,
                 "share_of_step": dom_ms / serial_step,
                 "timed_in": "single-stream pass (%.1f ms/step); the headline value overlaps independent "
                             "chains on side streams" % serial_step,

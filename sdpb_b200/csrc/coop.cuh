@@ -41,9 +41,19 @@ __device__ __forceinline__ void wzero(uint32_t *dst, int n)
   __syncwarp();
 }
 
+// Carries of a 32-word chunk in one step.  g: lanes whose word overflowed, p: lanes whose
+// word is all ones (a carry coming in passes through), cin: carry into lane 0.  A carry is
+// injected above every g lane; adding the inject mask to the propagate mask lets the integer
+// adder ripple it through each run of p lanes.  Bit i of the result = carry into lane i,
+// bit 32 = carry out of the chunk.  (g and p exclude each other: x + y = 2^32 + 0xFFFFFFFF
+// is impossible.)
+__device__ __forceinline__ uint64_t carry_lookahead(uint32_t g, uint32_t p, uint32_t cin)
+{
+  const uint64_t inject = ((uint64_t)g << 1) | cin, prop = p;
+  return inject | ((prop + inject) ^ prop ^ inject);
+}
+
 // r = a + b + cin (n words, r may alias a or b); returns the carry out (0/1), uniform.
-// Words are added per lane; carries are then pushed upward until none is left
-// (one or two rounds in practice, n rounds for a run of all-ones words).
 __device__ __forceinline__ uint32_t wadd(uint32_t *r, const uint32_t *a, const uint32_t *b, int n,
                                          uint32_t cin = 0)
 {
@@ -53,34 +63,17 @@ __device__ __forceinline__ uint32_t wadd(uint32_t *r, const uint32_t *a, const u
     {
       const int i = base + l;
       const bool on = i < n;
-      uint32_t x = on ? a[i] : 0u, y = on ? b[i] : 0u;
+      const uint32_t x = on ? a[i] : 0u, y = on ? b[i] : 0u;
       uint32_t s = x + y;
-      uint32_t cy = s < x ? 1u : 0u;
-      uint32_t top = 0; // carry leaving this chunk
-      uint32_t in = __shfl_up_sync(FULL, cy, 1);
-      if(l == 0)
-        in = carry_in;
-      top += __shfl_sync(FULL, cy, 31);
-      while(__any_sync(FULL, in != 0))
-        {
-          const uint32_t s2 = s + in;
-          cy = s2 < s ? 1u : 0u;
-          s = s2;
-          in = __shfl_up_sync(FULL, cy, 1);
-          if(l == 0)
-            in = 0;
-          top += __shfl_sync(FULL, cy, 31);
-        }
+      const uint32_t g = __ballot_sync(FULL, s < x), p = __ballot_sync(FULL, s == 0xFFFFFFFFu);
+      const uint64_t c = carry_lookahead(g, p, carry_in);
+      s += (uint32_t)(c >> l) & 1u;
       __syncwarp();
       if(on)
         r[i] = s;
-      // carry leaving word n-1: in a partial last chunk the lanes beyond n hold zeros, so
-      // it shows up as a 1 in the first of them; in a full chunk it is what left lane 31
-      const int last = n - base;
-      if(last < 32)
-        carry_in = __shfl_sync(FULL, s, last) != 0 ? 1u : 0u;
-      else
-        carry_in = top;
+      // lanes beyond n hold zeros: the carry leaving word n-1 is the one entering lane n - base
+      const int last = n - base < 32 ? n - base : 32;
+      carry_in = (uint32_t)(c >> last) & 1u;
     }
   __syncwarp();
   return carry_in;
@@ -103,6 +96,15 @@ __device__ __forceinline__ void wneg(uint32_t *r, int n, uint32_t *scratch, uint
 __device__ __forceinline__ void wsub_small(uint32_t *r, int n, uint32_t k, uint32_t *scratch,
                                            uint32_t *scratch2)
 {
+  __syncwarp();
+  if(r[0] >= k) // no borrow leaves word 0 (all but 2^-30 of the time)
+    {
+      __syncwarp();
+      if(lane_id() == 0)
+        r[0] -= k;
+      __syncwarp();
+      return;
+    }
   for(int i = lane_id(); i < n; i += 32)
     scratch2[i] = i == 0 ? k : 0u;
   __syncwarp();
@@ -193,21 +195,16 @@ __device__ __forceinline__ void wmul(uint32_t *out, const uint32_t *a, int KA, c
         }
       if(l == 0)
         s += carry_in;
-      uint32_t w = (uint32_t)s, cy = (uint32_t)(s >> 32); // cy <= 3
-      uint32_t top = __shfl_sync(FULL, cy, 31);
+      uint32_t w = (uint32_t)s;
+      const uint32_t cy = (uint32_t)(s >> 32); // <= 3: goes to the next lane
       uint32_t in = __shfl_up_sync(FULL, cy, 1);
       if(l == 0)
         in = 0;
-      while(__any_sync(FULL, in != 0))
-        {
-          const uint32_t w2 = w + in;
-          cy = w2 < w ? 1u : 0u;
-          w = w2;
-          in = __shfl_up_sync(FULL, cy, 1);
-          if(l == 0)
-            in = 0;
-          top += __shfl_sync(FULL, cy, 31);
-        }
+      const uint32_t w2 = w + in;
+      const uint32_t g = __ballot_sync(FULL, w2 < w), p = __ballot_sync(FULL, w2 == 0xFFFFFFFFu);
+      const uint64_t c = carry_lookahead(g, p, 0u);
+      w = w2 + ((uint32_t)(c >> l) & 1u);
+      const uint32_t top = __shfl_sync(FULL, cy, 31) + ((uint32_t)(c >> 32) & 1u);
       if(on && C0 + k >= FROM)
         out[C0 + k - FROM] = w;
       carry_in = top;

@@ -122,31 +122,39 @@ __global__ void __launch_bounds__(64) norm_partial_kernel(const BandDesc *bands,
       stg_reg<NL>(part + ((size_t)b.gidx * N + c) * Fmt<NL>::ES, acc);
     }
 }
+// one warp per column: lane 0 adds the per-block partials in block order (the canonical,
+// sequential sum), then the warp takes sqrt and its reciprocal together (coop.cuh)
 template <int NL>
-__global__ void norm_final_kernel(const limb_t *part, int J, int N,
-                                  limb_t *norms, uint32_t *recip)
+__global__ void __launch_bounds__(32) norm_final_kernel(const limb_t *part, int J, int N,
+                                                       limb_t *norms, uint32_t *recip)
 {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  typedef TileGeom<NL> G;
+  extern __shared__ __align__(16) unsigned char coop_raw[];
+  coop::Work<NL> &ws = *reinterpret_cast<coop::Work<NL> *>(coop_raw);
+  uint32_t *slot = reinterpret_cast<uint32_t *>(coop_raw + ((sizeof(coop::Work<NL>) + 15) & ~(size_t)15));
+  const int c = blockIdx.x;
   if(c >= N)
     return;
-  Num<NL> acc, v;
-  mpfx::set_zero(acc);
-  for(int j = 0; j < J; ++j)
+  if(threadIdx.x == 0)
     {
-      ld(v, part, (size_t)j * N + c);
-      mpfx::add(acc, acc, v);
-    }
-  if(acc.sign > 0)
-    {
+      Num<NL> acc, v;
+      mpfx::set_zero(acc);
+      for(int j = 0; j < J; ++j)
+        {
+          ld(v, part, (size_t)j * N + c);
+          mpfx::add(acc, acc, v);
+        }
       Reg<NL> r;
       mpfw::from_num(r, acc);
-      r = sqrt_nl<NL>(r);
-      const RecipWords<NL> rw = recip_nl<NL>(r);
-      for(int w = 0; w < TileGeom<NL>::RW; ++w)
-        recip[(size_t)c * TileGeom<NL>::RS + w] = rw.w[w];
-      mpfw::to_num(acc, r);
+      mpfw::store<NL>(slot, r);
+      ws.flag = 0;
     }
-  st(norms, c, acc);
+  __syncwarp();
+  if((int32_t)slot[1] > 0)
+    coop::pivot<NL>(ws, slot, nullptr, recip + (size_t)c * G::RS);
+  uint32_t *dst = reinterpret_cast<uint32_t *>(norms + (size_t)c * Fmt<NL>::ES);
+  for(int i = threadIdx.x; i < G::EW; i += 32)
+    dst[i] = slot[i];
 }
 
 // residue tables for the CRT syrk
@@ -589,7 +597,7 @@ __global__ void scalar_op_kernel(int op, int k, long count, const limb_t *a,
 }
 // test hook for the warp-cooperative pivot (coop.cuh): one warp per element.
 // op 8: r = mpf_sqrt(a);  op 9: r = [sign 1, exp 1, w0 = number of words in which the
-// cooperative reciprocal of sqrt(a) differs from mpfw::reciprocal_fast, other words 0]
+// cooperative reciprocal of sqrt(a) differs from mpfw::reciprocal (Knuth), other words 0]
 template <int NL>
 __global__ void __launch_bounds__(32) coop_test_kernel(int op, long count, const limb_t *a, limb_t *r)
 {
@@ -617,10 +625,13 @@ __global__ void __launch_bounds__(32) coop_test_kernel(int op, long count, const
           mpfw::load<NL>(out, slot);
           if(op == 9)
             {
-              const RecipWords<NL> rw = recip_nl<NL>(out);
-              uint32_t bad = ws.flag; // a fallback counts as a mismatch: the fast path must close
+              Num<NL> x;
+              mpfw::to_num(x, out);
+              uint32_t rw[2 * NL + 4];
+              mpfw::reciprocal<NL>(rw, x); // Knuth long division: independent of the Newton code
+              uint32_t bad = ws.flag;      // a fallback counts as a mismatch: the fast path must close
               for(int w = 0; w < G::RW; ++w)
-                bad += rw.w[w] != R[w];
+                bad += rw[w] != R[w];
               mpfw::set_zero(out);
               out.sign = 1;
               out.exp = 1;

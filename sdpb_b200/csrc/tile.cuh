@@ -57,23 +57,6 @@ __device__ __noinline__ Reg<NL> div_nl(Reg<NL> x, const uint32_t *piv, const uin
   mpfw::div_recip<NL>(x, (int32_t)piv[1], (int32_t)piv[0], piv + 2, R);
   return x;
 }
-template <int NL> __device__ __noinline__ Reg<NL> sqrt_nl(Reg<NL> a)
-{
-  Reg<NL> r;
-  mpfw::sqrt_fast<NL>(r, a);
-  return r;
-}
-template <int NL> struct RecipWords
-{
-  uint32_t w[2 * NL + 4];
-};
-template <int NL> __device__ __noinline__ RecipWords<NL> recip_nl(Reg<NL> a)
-{
-  RecipWords<NL> r;
-  mpfw::reciprocal_fast<NL>(r.w, a);
-  return r;
-}
-
 // ------------------------------------------------------------ TMA / mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -436,10 +419,8 @@ __device__ __forceinline__ void potrf_tile_update(Reg<NL> &acc, const PotrfDesc 
 //   potrf_gemm_level   one CTA per tile of the block column, the diagonal one
 //                      included: a_ij -= sum_{k<J0} l_ik l_jk
 //   potrf_diag_warp    one WARP per matrix: factor the diagonal tile (below)
-//   potrf_solve_level  one THREAD per row below it: the 16 unknowns of that row
-//                      against the factored diagonal tile (16 divisions and 120
-//                      multiply-accumulates, sequential by nature, so rows are
-//                      the parallel dimension)
+//   potrf_panel_rl     one CTA per tile below it: X = A_tile L_JJ^{-T}, the 16
+//                      unknowns of a row shared by 16 threads
 // `descs` is sorted by size (largest first); grid.x covers the prefix of
 // matrices that still have a block column Jt.
 template <int NL>
@@ -703,39 +684,6 @@ __device__ __forceinline__ void load_diag(DiagSmem<NL> &sm, const uint64_t *A, l
 }
 
 constexpr int ROWS_PER_CTA = 128;
-template <int NL>
-__global__ void __launch_bounds__(ROWS_PER_CTA, 4)
-potrf_solve_level(const PotrfDesc *descs, int Jt, const int *status)
-{
-  typedef TileGeom<NL> G;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  DiagSmem<NL> &sm = *reinterpret_cast<DiagSmem<NL> *>(smem_raw);
-  const PotrfDesc d = descs[blockIdx.x];
-  const int J0 = Jt * TS;
-  const int row0 = J0 + TS + blockIdx.y * ROWS_PER_CTA;
-  if(row0 >= d.s || status[d.id] >= 0)
-    return;
-  load_diag<NL>(sm, d.A, d.si, d.sj, d.recip, d.s, Jt);
-  const int row = row0 + threadIdx.x;
-  if(row >= d.s)
-    return;
-  Reg<NL> z;
-  mpfw::set_zero(z);
-  for(int kk = 0; kk < TS; ++kk) // the diagonal tile is full here (rows exist below it)
-    {
-      uint64_t *mine = d.A + ((long)row * d.si + (long)(J0 + kk) * d.sj) * G::ES;
-      Reg<NL> acc;
-      ldg_reg<NL>(acc, mine);
-      for(int k = 0; k < kk; ++k)
-        acc = mac_nl<NL>(acc,
-                         reinterpret_cast<const uint32_t *>(
-                           d.A + ((long)row * d.si + (long)(J0 + k) * d.sj) * G::ES),
-                         sm.diag + (k * TS + kk) * G::SW, true);
-      acc = div_nl<NL>(acc, sm.diag + (kk * TS + kk) * G::SW, sm.recip + kk * G::RS);
-      stg_reg<NL>(mine, acc);
-      stg_reg<NL>(d.A + ((long)(J0 + kk) * d.si + (long)row * d.sj) * G::ES, z);
-    }
-}
 
 // -------------------------------------------------------- triangular solve
 struct TrsmTileDesc // X <- L^{-1} B in place, L lower p x p (column-major)

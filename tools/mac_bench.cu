@@ -8,6 +8,25 @@
 #include <vector>
 using namespace sdpb_b200;
 
+// the single-thread Newton routines of mpfw.h (the library itself now takes pivots with the
+// warp-cooperative coop::pivot; these stay here as the baseline they are measured against)
+template <int NL> __device__ __noinline__ Reg<NL> sqrt_nl(Reg<NL> a)
+{
+  Reg<NL> r;
+  mpfw::sqrt_fast<NL>(r, a);
+  return r;
+}
+template <int NL> struct RecipWords
+{
+  uint32_t w[2 * NL + 4];
+};
+template <int NL> __device__ __noinline__ RecipWords<NL> recip_nl(Reg<NL> a)
+{
+  RecipWords<NL> r;
+  mpfw::reciprocal_fast<NL>(r.w, a);
+  return r;
+}
+
 template <int NL, int OP>
 __global__ void __launch_bounds__(256, 2) bench(const uint32_t *A, uint32_t *O, int K, long long *clk)
 {
