@@ -347,6 +347,8 @@ def main():
         ms_step, e2e_s, wall = [float(x) for x in t.tolist()]
     if rank != 0:
         pool.close()
+        ctx.close()
+        dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel -------------------------------
@@ -395,6 +397,8 @@ def main():
     print(json.dumps(line), flush=True)
     pool.close()
     ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def _mix(shapes):

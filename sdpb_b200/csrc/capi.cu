@@ -433,6 +433,7 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
                                       c->Pband + c->oB[j], b.P, N, 0, 0});
             gs.push_back(sd[j]);
             gb.push_back(bd[j]);
+            c->blocks_g[g].push_back(j);
             c->szS_g[g].push_back(b.P);
             c->szP_g[g].push_back(b.P);
             c->maxP_g[g] = std::max(c->maxP_g[g], b.P);
@@ -474,13 +475,29 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
 // Two exchanges remain inside initialize_schur_complement_solver: the per-block
 // column-norm partials (Matrix_Normalizer.cxx:131 is an MPI AllReduce) and the
 // exact integer Q' partial sums (restore_and_reduce.cxx:137-212 is a ring of
-// SendRecv); both are one ncclAllReduce here.  Cholesky(Q) is replicated.
+// SendRecv); both are one ncclAllReduce here.  Cholesky(Q): replicated for small N, by
+// broadcast panels from qdist_min_N on (launch_nl.cu potrf_rl).
 static int nccl_allreduce(sdpb_b200_ctx *c, void *buf, size_t count, int is_u64, const char *label)
 {
   NcclApi &api = nccl_api();
   c->kt_begin(label);
   const ncclResult_t r = api.AllReduce(buf, buf, count, is_u64 ? ncclUint64 : ncclUint32, ncclSum,
                                        (ncclComm_t)c->comm, c->stream);
+  c->kt_end();
+  --c->launches; // NCCL's kernel, not one of ours
+  if(r != ncclSuccess)
+    {
+      c->error = std::string("NCCL: ") + api.GetErrorString(r) + " in " + label;
+      return SDPB_B200_ERR_CUDA;
+    }
+  return 0;
+}
+
+static int nccl_bcast(sdpb_b200_ctx *c, void *buf, size_t bytes, int root, const char *label)
+{
+  NcclApi &api = nccl_api();
+  c->kt_begin(label);
+  const ncclResult_t r = api.Broadcast(buf, buf, bytes, ncclUint8, root, (ncclComm_t)c->comm, c->stream);
   c->kt_end();
   --c->launches; // NCCL's kernel, not one of ours
   if(r != ncclSuccess)
@@ -532,6 +549,15 @@ extern "C" int sdpb_b200_comm_init(sdpb_b200_ctx *c, int rank, int world, const 
   if(c->J)
     CUDA_TRY(c, cudaMemcpy(c->d_bands, c->h_bands.data(), c->h_bands.size() * sizeof(BandDesc),
                            cudaMemcpyHostToDevice));
+  for(int g = 0; g < c->G; ++g) // the per-group copies of the band descriptors carry gidx too
+    {
+      std::vector<BandDesc> gb;
+      for(int j : c->blocks_g[g])
+        gb.push_back(c->h_bands[j]);
+      if(!gb.empty())
+        CUDA_TRY(c, cudaMemcpy(c->d_bands_g[g], gb.data(), gb.size() * sizeof(BandDesc),
+                               cudaMemcpyHostToDevice));
+    }
   CUDA_TRY(c, cudaMalloc(&c->part_global, (size_t)std::max(1, num_blocks_global) * c->N * c->es * 8));
   NcclApi &api = nccl_api();
   if(!api.load())
@@ -553,6 +579,10 @@ extern "C" int sdpb_b200_comm_init(sdpb_b200_ctx *c, int rank, int world, const 
   c->world = world;
   c->J_global = num_blocks_global;
   c->allreduce = &nccl_allreduce;
+  c->bcast = &nccl_bcast;
+  CUDA_TRY(c, cudaMalloc(&c->qpanel, ((size_t)c->N * TS * c->es + 2) * 8));
+  if(const char *env = getenv("SDPB_B200_QDIST_MIN_N"))
+    c->qdist_min_N = atoi(env);
   return 0;
 }
 
@@ -567,6 +597,7 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
       nccl_api().CommDestroy((ncclComm_t)c->comm);
     }
   cudaFree(c->part_global);
+  cudaFree(c->qpanel);
   cudaFree(c->arena);
   cudaFree(c->R);
   cudaFree(c->Qres);

@@ -86,6 +86,13 @@ struct sdpb_b200_ctx
   int rank = 0, world = 1, J_global = 0;
   limb_t *part_global = nullptr;
   int (*allreduce)(sdpb_b200_ctx *, void *buf, size_t count, int is_u64, const char *label) = nullptr;
+  // Cholesky(Q) by panels over the ranks (block-cyclic tile columns) from this N on: the owner of
+  // a block column factors it and broadcasts it (NCCL over NVLink), every rank applies it to the
+  // tile columns it owns.  Below the threshold the N pivots' serial chain dominates and every
+  // rank factors its own copy of Q.
+  int (*bcast)(sdpb_b200_ctx *, void *buf, size_t bytes, int root, const char *label) = nullptr;
+  limb_t *qpanel = nullptr; // one packed block column of Q + its status word
+  int qdist_min_N = 512;
 
   // Concurrent schedule.  The step is a small dependency graph -- chol(X) ->
   // L_X^-1 V -> A_X_inv | Y V -> A_Y | chol(Y) | per block: S_j -> chol(S_j) ->
@@ -105,7 +112,7 @@ struct sdpb_b200_ctx
   TrsmTileDesc *d_trsmP_g[MAXG] = {};
   SchurDesc *d_schur_g[MAXG] = {};
   BandDesc *d_bands_g[MAXG] = {};
-  std::vector<int> szS_g[MAXG], szP_g[MAXG];
+  std::vector<int> szS_g[MAXG], szP_g[MAXG], blocks_g[MAXG]; // blocks_g: local block indices of a group
   int nblk_g[MAXG] = {}, maxP_g[MAXG] = {};
   cudaStream_t side(int k) const { return concurrency ? aux[k] : stream; }
   // `to` waits for everything enqueued on `from` so far

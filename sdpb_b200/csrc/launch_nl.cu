@@ -87,18 +87,53 @@ template <int NL> struct Launch
       return rc;
     CUDA_TRY(c, cudaMemsetAsync(status, 0xFF, (size_t)nstatus * sizeof(int), c->cur));
     const int T = (sizes[0] + TS - 1) / TS;
+    // one matrix, several ranks, N large enough: block columns dealt round-robin over the ranks
+    const bool dist = c->world > 1 && sizes.size() == 1 && sizes[0] >= c->qdist_min_N && c->bcast;
+    const int mod = dist ? c->world : 1, me = dist ? c->rank : 0;
     c->kt_begin(label);
     for(int Jt = 0; Jt < T; ++Jt)
       {
         const int n = alive(sizes, Jt), nbelow = alive(sizes, Jt + 1);
-        potrf_diag_rl<NL><<<n, 256, TILE_SMEM, c->cur>>>(d, Jt, status);
-        ++c->launches;
+        const int tb = (sizes[0] - (Jt + 1) * TS + TS - 1) / TS; // tiles below / right of Jt
+        const bool mine = Jt % mod == me;
+        if(mine)
+          {
+            potrf_diag_rl<NL><<<n, 256, TILE_SMEM, c->cur>>>(d, Jt, status);
+            ++c->launches;
+            if(nbelow)
+              {
+                potrf_panel_rl<NL><<<dim3(nbelow, tb), 256, TILE_SMEM, c->cur>>>(d, Jt, status);
+                ++c->launches;
+              }
+          }
+        if(dist)
+          {
+            // the finished block column (and the owner's status) to every rank
+            const int rows = sizes[0] - Jt * TS;
+            const size_t bytes = ((size_t)sizes[0] * TS * Fmt<NL>::ES + 1) * 8;
+            const int pg = std::min(592, (rows * TS + 127) / 128);
+            c->kt_end();
+            --c->launches; // a span boundary, not a launch
+            if(mine)
+              {
+                c->kt_begin("panel_pack");
+                panel_pack<NL><<<pg, 128, 0, c->cur>>>(d, Jt, c->qpanel, status, 0);
+                c->kt_end();
+              }
+            if(int rc = c->bcast(c, c->qpanel, bytes, Jt % mod, "nccl_broadcast_Q_panel"))
+              return rc;
+            if(!mine)
+              {
+                c->kt_begin("panel_pack");
+                panel_pack<NL><<<pg, 128, 0, c->cur>>>(d, Jt, c->qpanel, status, 1);
+                c->kt_end();
+              }
+            c->kt_begin(label);
+          }
         if(nbelow == 0)
           continue;
-        const int tb = (sizes[0] - (Jt + 1) * TS + TS - 1) / TS; // tiles below / right of Jt
-        potrf_panel_rl<NL><<<dim3(nbelow, tb), 256, TILE_SMEM, c->cur>>>(d, Jt, status);
-        potrf_trail_rl<NL><<<dim3(nbelow, tb * (tb + 1) / 2), 256, TILE_SMEM, c->cur>>>(d, Jt, status);
-        c->launches += 2;
+        potrf_trail_rl<NL><<<dim3(nbelow, tb * (tb + 1) / 2), 256, TILE_SMEM, c->cur>>>(d, Jt, status, mod, me);
+        ++c->launches;
       }
     c->kt_end();
     --c->launches;

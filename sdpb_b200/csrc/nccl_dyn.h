@@ -1,7 +1,8 @@
 // NCCL, bound at run time: the single-GPU path (and a machine without NCCL)
 // never loads it; a multi-GPU context dlopens libnccl.so.2 — inside a process
 // that already imported torch this resolves to the copy torch loaded.  Only the
-// entry points the Schur step uses are bound (nccl.h 2.27: :146,160,181,215,392).
+// entry points the Schur step uses are bound (nccl.h 2.27: ncclGetUniqueId, ncclCommInitRank,
+// ncclCommDestroy, ncclGetErrorString, ncclAllReduce, ncclBroadcast).
 #pragma once
 #include <dlfcn.h>
 #include <nccl.h>
@@ -17,6 +18,8 @@ struct NcclApi
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t)
+    = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)
     = nullptr;
   std::string error;
   bool load()
@@ -46,6 +49,7 @@ struct NcclApi
     SDPB_BIND(CommDestroy, "ncclCommDestroy")
     SDPB_BIND(GetErrorString, "ncclGetErrorString")
     SDPB_BIND(AllReduce, "ncclAllReduce")
+    SDPB_BIND(Broadcast, "ncclBroadcast")
 #undef SDPB_BIND
     return true;
   }

@@ -615,9 +615,47 @@ potrf_panel_rl(const PotrfDesc *descs, int Jt, const int *status)
     mpfw::set_zero(acc);
   potrf_row_tile_solve<NL>(acc, d, It, Jt, sm);
 }
+// block column Jt (rows J0.., its 16 columns) <-> a contiguous buffer, for the broadcast of the
+// panel-distributed Cholesky; the last word carries the matrix's status (a failed pivot on the
+// owner must stop every rank)
+template <int NL>
+__global__ void panel_pack(const PotrfDesc *descs, int Jt, uint64_t *buf, int *status, int unpack)
+{
+  typedef TileGeom<NL> G;
+  const PotrfDesc d = descs[0];
+  const int J0 = Jt * TS, nd = min(TS, d.s - J0), rows = d.s - J0;
+  const long total = (long)rows * nd;
+  for(long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x)
+    {
+      const int j = (int)(e % nd), i = (int)(e / nd);
+      uint4 *g = reinterpret_cast<uint4 *>(d.A + ((long)(J0 + i) * d.si + (long)(J0 + j) * d.sj) * G::ES);
+      uint4 *b = reinterpret_cast<uint4 *>(buf + e * G::ES);
+#pragma unroll
+      for(int w = 0; w < G::EB / 16; ++w)
+        {
+          if(unpack)
+            g[w] = b[w];
+          else
+            b[w] = g[w];
+        }
+    }
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+    {
+      uint64_t *sw = buf + (long)d.s * TS * G::ES; // fixed slot past the largest panel
+      if(unpack)
+        {
+          if((int)(int64_t)*sw >= 0)
+            status[d.id] = (int)(int64_t)*sw;
+        }
+      else
+        *sw = (uint64_t)(int64_t)status[d.id];
+    }
+}
+
+// cyc_mod > 1: only the tile columns Kt with Kt % cyc_mod == cyc_rem (this rank's share)
 template <int NL>
 __global__ void __launch_bounds__(256, 2)
-potrf_trail_rl(const PotrfDesc *descs, int Jt, const int *status)
+potrf_trail_rl(const PotrfDesc *descs, int Jt, const int *status, int cyc_mod, int cyc_rem)
 {
   typedef TileGeom<NL> G;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -631,7 +669,7 @@ potrf_trail_rl(const PotrfDesc *descs, int Jt, const int *status)
       ++a;
     }
   const int It = Jt + 1 + a, Kt = Jt + 1 + t;
-  if(It * TS >= d.s || status[d.id] >= 0)
+  if(It * TS >= d.s || status[d.id] >= 0 || (cyc_mod > 1 && Kt % cyc_mod != cyc_rem))
     return;
   tile_smem_init(sm);
   const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;

@@ -4,6 +4,7 @@
 MODE = oracle : gloo, CPU.  The blocks are split with sdpb_b200.partition; each rank runs the oracle's
                 staged model on its share and the two exchanges of DESIGN.md §7 go through
                 torch.distributed (all_gather).  Checks the sharding logic and exchange semantics.
+MODE = b200q  : as b200, with Cholesky(Q) forced onto the panel-distributed path (N = 41).
 MODE = b200   : nccl, one GPU per rank.  Each rank creates a SchurContext with its blocks, joins the
                 library's NCCL communicator (sdpb_b200_comm_init) and runs the collective step.
 Either way every rank compares its outputs bit for bit with the UNSHARDED oracle on the whole SDP."""
@@ -26,7 +27,14 @@ SHAPES = [(1, 6), (2, 4), (1, 9), (1, 5), (2, 3), (1, 8), (1, 4)]
 
 
 def main():
+    global N
     mode = sys.argv[1]
+    if mode == "b200q":
+        # Cholesky(Q) by broadcast panels (block columns dealt over the ranks): force the
+        # distributed path at a size with three block columns, two of them on rank 0
+        os.environ["SDPB_B200_QDIST_MIN_N"] = "1"
+        N = 41
+        mode = "b200"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if mode == "b200":
@@ -78,7 +86,7 @@ def main():
     ol.assert_same("L", L, [want["L"][j] for j in mine])
     ol.assert_same("P", P, [want["P"][j] for j in mine])
     dist.barrier()
-    print(f"rank {rank}/{world} mode {mode}: blocks {mine} match the unsharded oracle bit for bit", flush=True)
+    print(f"rank {rank}/{world} mode {sys.argv[1]}: blocks {mine} match the unsharded oracle bit for bit", flush=True)
     ctx.close()
     dist.destroy_process_group()
 

@@ -183,3 +183,52 @@ def test_calls_out_of_order_are_rejected():
         ctx.compute_bilinear_pairings(ctx.alloc_psd_blocks())
     assert ei.value.code == 5
     ctx.close()
+
+
+def test_c3_sample_full_width_bit_exact():
+    """The bench workload's own shapes at its full width (N = 300 columns, P_j = 40 / 120, 768 bits;
+    24 of the 600 blocks so that the CPU oracle finishes in seconds): every output bit for bit,
+    through the host-buffer pipeline (sdpb_b200_schur_step) and through the split calls."""
+    from sdpb_b200.synthetic import WORKLOADS
+    prec, shapes, N = WORKLOADS["c3-sample"]
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=1)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    want = sdp.run_step(ref)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    got = sdp.run_step(ctx)
+    for k in KEYS:
+        ol.assert_same(k, got[k], want[k])
+    ctx.close()
+
+
+def test_full_c3_properties():
+    """BASELINE config c3 at full size (J = 600, N = 300, 768 bits) through size-independent
+    properties: (1) idempotence -- two steps from the same X, Y give identical bytes, in the
+    concurrent and in the single-stream schedule; (2) the per-block outputs of blocks that also
+    occur in a small SDP (same seed => same data) do not depend on the other 576 blocks up to the
+    stage where the column norms couple them: X/Y Cholesky factors, pairings and L_j are compared
+    bit for bit with the oracle run on the 24-block sub-problem."""
+    from sdpb_b200.synthetic import WORKLOADS
+    prec, shapes, N = WORKLOADS["c3"]
+    pick = list(range(0, 6)) + list(range(150, 168))  # 6 blocks m=2, 18 blocks m=1
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=1)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    got = sdp.run_step(ctx)
+    ctx.set_concurrency(0)
+    again = sdp.run_step(ctx)
+    for k in KEYS:
+        ol.assert_same(k + " (idempotence / schedule)", again[k], got[k])
+    ctx.close()
+    sub_shapes = [shapes[j] for j in pick]
+    sub = ol.SyntheticSDP(prec, sub_shapes, N, seed=1, block_ids=pick)
+    for a, j in zip(sub.B, pick):
+        assert np.array_equal(a, sdp.B[j])
+    ref = ol.OracleContext(prec, sub_shapes, N)
+    sub.upload(ref)
+    want = sub.run_step(ref)
+    for k in ("X_chol", "Y_chol", "A_X_inv", "A_Y"):
+        ol.assert_same(k, [got[k][2 * j + p] for j in pick for p in (0, 1)], want[k])
+    ol.assert_same("L", [got["L"][j] for j in pick], want["L"])

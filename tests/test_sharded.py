@@ -55,3 +55,11 @@ def test_sharded_b200_nccl_world2():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     _launch("b200", 2)
+
+
+@pytest.mark.gpu
+def test_sharded_b200_panel_distributed_Q_world2():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    _launch("b200q", 2)
