@@ -110,7 +110,7 @@ def algorithmic_bytes(kernel, prec, shapes, N):
             tot += (P * P // 2 + 2 * P * N) * E
         elif kernel in ("norm_partial_kernel",):
             tot += P * N * E
-        elif kernel in ("normalize_kernel", "restore_P_kernel"):
+        elif kernel == "normalize_kernel":  # reads P, writes the restored P (+ residues, not counted)
             tot += 2 * P * N * E
     if kernel == "syrk_mod_kernel":  # exact integer syrk
         tot = K * N * 8 * L + N * (N + 1) // 2 * 8 * (2 * L + 1)

@@ -1076,7 +1076,7 @@ static int enqueue_step(sdpb_b200_ctx *c)
   rc = dispatch_schur_and_Q(c);
   if(rc)
     return rc;
-  CUDA_TRY(c, cudaEventRecord(c->evd[1], c->side(1))); // restore_P was the last thing enqueued there
+  // (the P bands are final after normalize_kernel, which restores them in the same pass: ev[5])
   CUDA_TRY(c, cudaEventRecord(c->ev[10], st));
   return 0;
 }
@@ -1271,7 +1271,7 @@ extern "C" int sdpb_b200_schur_step(
     if(!rc)
       rc = out(c->ev[4], c->S, c->oS, schur_complement_cholesky, J, eS);
     if(!rc)
-      rc = out(c->evd[1], c->Pband, c->oB, schur_off_diagonal, J, eP);
+      rc = out(c->ev[5], c->Pband, c->oB, schur_off_diagonal, J, eP);
     if(!rc && Q)
       {
         if(cudaStreamWaitEvent(c->copy, c->ev[10], 0) != cudaSuccess

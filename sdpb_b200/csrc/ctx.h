@@ -96,7 +96,7 @@ struct sdpb_b200_ctx
 
   // Concurrent schedule.  The step is a small dependency graph -- chol(X) ->
   // L_X^-1 V -> A_X_inv | Y V -> A_Y | chol(Y) | per block: S_j -> chol(S_j) ->
-  // L_j^-1 B_j -> norm partials | restore_P beside the exact syrk -- and the
+  // L_j^-1 B_j -> norm partials -- and the
   // batched factorisations are chains of short level kernels with latency-bound
   // tails, so independent chains run on side streams and the S chain is cut
   // into G interleaved groups of blocks.  concurrency == 0 puts everything back
@@ -104,7 +104,7 @@ struct sdpb_b200_ctx
   static constexpr int MAXG = 4;
   cudaStream_t cur = nullptr; // the stream the launch helpers enqueue on
   cudaStream_t copy = nullptr; // D2H of finished outputs while the step is still running (schur_step)
-  cudaEvent_t evd[2] = {};     // [0] chol(Y) done, [1] restore_P done
+  cudaEvent_t evd[2] = {};     // [0] chol(Y) done
   cudaStream_t aux[MAXG] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t evf[16] = {};
   int concurrency = 1, G = 1;

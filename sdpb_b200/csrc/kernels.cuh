@@ -122,6 +122,11 @@ __global__ void __launch_bounds__(64) norm_partial_kernel(const BandDesc *bands,
       stg_reg<NL>(part + ((size_t)b.gidx * N + c) * Fmt<NL>::ES, acc);
     }
 }
+template <int NL> __device__ __noinline__ Reg<NL> add_nl(Reg<NL> acc, Reg<NL> v)
+{
+  mpfw::add_signed<NL>(acc, v, v.sign);
+  return acc;
+}
 // one warp per column: lane 0 adds the per-block partials in block order (the canonical,
 // sequential sum), then the warp takes sqrt and its reciprocal together (coop.cuh)
 template <int NL>
@@ -137,16 +142,15 @@ __global__ void __launch_bounds__(32) norm_final_kernel(const limb_t *part, int 
     return;
   if(threadIdx.x == 0)
     {
-      Num<NL> acc, v;
-      mpfx::set_zero(acc);
+      // J grows with the number of GPUs (one row per GLOBAL block): register-form mpf_add
+      Reg<NL> acc, v;
+      mpfw::set_zero(acc);
       for(int j = 0; j < J; ++j)
         {
-          ld(v, part, (size_t)j * N + c);
-          mpfx::add(acc, acc, v);
+          ldg_reg<NL>(v, part + ((size_t)j * N + c) * Fmt<NL>::ES);
+          acc = add_nl<NL>(acc, v);
         }
-      Reg<NL> r;
-      mpfw::from_num(r, acc);
-      mpfw::store<NL>(slot, r);
+      mpfw::store<NL>(slot, acc);
       ws.flag = 0;
     }
   __syncwarp();
@@ -183,7 +187,7 @@ __device__ __forceinline__ uint32_t barrett_mod(uint64_t x, uint32_t p, uint64_t
   return r;
 }
 
-// P' = (P / norm) << prec, in place (Matrix_Normalizer.cxx:174-190), plus the
+// P' = (P / norm) << prec (Matrix_Normalizer.cxx:174-190) held in registers, the
 // residues of trunc(P') (fmpz_set_mpf truncates toward zero,
 // fmpz_BigFloat_convert.hxx:13) modulo every prime:
 // R[(p*K + row)*NS + col], NS = row stride (N rounded up to 16; the pad
@@ -194,6 +198,22 @@ __device__ __forceinline__ uint32_t barrett_mod(uint64_t x, uint32_t p, uint64_t
 // either way).  The integer part is cut into 28-bit digits held in registers;
 // a residue is sum_k digit_k * (2^(28k) mod p) -- IMAD.WIDE against a table in
 // shared memory -- followed by one Barrett reduction.
+template <int NL>
+__device__ __noinline__ Reg<NL> mul_nl(Reg<NL> a, const uint32_t *b)
+{
+  Reg<NL> r;
+  if(a.sign == 0 || (int32_t)b[1] == 0)
+    {
+      mpfw::set_zero(r);
+      return r;
+    }
+  int32_t bexp, bsign;
+  uint32_t bw[2 * NL];
+  mpfw::load_packed<NL>(bexp, bsign, bw, b);
+  const uint32_t *aw = a.w;
+  mpfw::mul<NL>(r, a.sign, a.exp, aw, bsign, bexp, bw);
+  return r;
+}
 template <int NL> struct NormGeom
 {
   static constexpr int ND = (64 * (NL - 2) + 2 + 27) / 28; // digits of an integer below 2^(prec+2), prec <= 64 (NL-2)
@@ -246,7 +266,23 @@ normalize_kernel(const BandDesc *bands, int N, int NS, long K, const limb_t *nor
               mpfx::mul_2exp(t, t, (uint32_t)prec);
               mpfw::from_num(v, t);
             }
-          stg_reg<NL>(elem, v);
+          // restore_P (Matrix_Normalizer.cxx:210-226) fused: the stored band goes straight to
+          // P = (P' >> prec) * norm; P' itself is only needed for the residues below
+          Reg<NL> back = v;
+          if((prec & 63) == 0)
+            {
+              if(back.sign != 0)
+                back.exp -= prec >> 6;
+            }
+          else
+            {
+              Num<NL> t;
+              mpfw::to_num(t, back);
+              mpfx::div_2exp(t, t, (uint32_t)prec);
+              mpfw::from_num(back, t);
+            }
+          back = mul_nl<NL>(back, nrm);
+          stg_reg<NL>(elem, back);
         }
       // integer part: the mantissa shifted right by NL - exp limbs
       uint32_t iw[2 * NL];
@@ -511,56 +547,6 @@ crt_restore_kernel(const uint32_t *__restrict__ Qres, int N, int prec,
   mpfx::mul(q, q, ni);
   mpfx::mul(q, q, nj);
   st(Q, (size_t)j * N + i, q);
-}
-
-// restore_P (Matrix_Normalizer.cxx:210-226): P = (P' >> prec) * norm
-template <int NL>
-__device__ __noinline__ Reg<NL> mul_nl(Reg<NL> a, const uint32_t *b)
-{
-  Reg<NL> r;
-  if(a.sign == 0 || (int32_t)b[1] == 0)
-    {
-      mpfw::set_zero(r);
-      return r;
-    }
-  int32_t bexp, bsign;
-  uint32_t bw[2 * NL];
-  mpfw::load_packed<NL>(bexp, bsign, bw, b);
-  const uint32_t *aw = a.w;
-  mpfw::mul<NL>(r, a.sign, a.exp, aw, bsign, bexp, bw);
-  return r;
-}
-template <int NL>
-__global__ void __launch_bounds__(128)
-restore_P_kernel(const BandDesc *bands, int N, const limb_t *norms, int prec)
-{
-  const BandDesc b = bands[blockIdx.x];
-  const long total = (long)b.rows * N;
-  for(long e = (long)blockIdx.y * blockDim.x + threadIdx.x; e < total;
-      e += (long)gridDim.y * blockDim.x)
-    {
-      const int c = (int)(e / b.rows);
-      const uint32_t *nrm = reinterpret_cast<const uint32_t *>(norms + (size_t)c * Fmt<NL>::ES);
-      if((int32_t)nrm[1] == 0)
-        continue;
-      limb_t *elem = b.P + (size_t)e * Fmt<NL>::ES;
-      Reg<NL> v;
-      ldg_reg<NL>(v, elem);
-      if((prec & 63) == 0)
-        {
-          if(v.sign != 0)
-            v.exp -= prec >> 6;
-        }
-      else
-        {
-          Num<NL> t;
-          mpfw::to_num(t, v);
-          mpfx::div_2exp(t, t, (uint32_t)prec);
-          mpfw::from_num(v, t);
-        }
-      v = mul_nl<NL>(v, nrm);
-      stg_reg<NL>(elem, v);
-    }
 }
 
 // scalar-op kernel for device-vs-libgmp parity tests (same op codes as

@@ -282,18 +282,6 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaGetLastError());
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
-    if(J) // P = (P' >> prec) * norm needs only the norms: beside the exact syrk
-      {
-        cudaStream_t sr = c->side(1);
-        CUDA_TRY(c, c->after(st, sr, 12));
-        c->cur = sr;
-        dim3 g4(J, (unsigned)std::min<long>(((long)c->max_P * N + 127) / 128, 65535));
-        c->kt_begin("restore_P_kernel");
-        restore_P_kernel<NL><<<g4, 128, 0, sr>>>(c->d_bands, N, c->norms, c->prec);
-        c->kt_end();
-        CUDA_TRY(c, cudaGetLastError());
-        c->cur = st;
-      }
     {
       const int nt = (N + 15) / 16;
       dim3 g3(nt * (nt + 1) / 2, c->crt.np);
@@ -320,8 +308,6 @@ template <int NL> struct Launch
     int rc = potrf_rl(c, "potrf_Q", c->d_potrfQ, c->szQ, c->d_status + 5 * J, 1);
     if(rc)
       return rc;
-    if(J)
-      CUDA_TRY(c, c->after(c->side(1), st, 13));
     CUDA_TRY(c, cudaEventRecord(c->ev[8], st));
     return 0;
   }
