@@ -88,6 +88,20 @@ def algorithmic_bytes(kernel, prec, shapes, N):
     E = 8 * (L + 1) + 8
     tot = 0
     K = sum(s.schur_size for s in shapes)
+    if kernel in ("trsm_Linv_B/gemm", "trsm_Linv_B/diag"):
+        # per level It (16 rows): gemm reads the L strip (ni x I0), the solved rows above
+        # (I0 x N) and reads + writes the tile row (ni x N); diag reads the 16x16 diagonal
+        # tile and reads + writes the tile row
+        for s in shapes:
+            P = s.schur_size
+            for I0 in range(0, P, 16):
+                ni = min(16, P - I0)
+                if kernel.endswith("gemm"):
+                    if I0:
+                        tot += (ni * I0 + I0 * N + 2 * ni * N) * E
+                else:
+                    tot += (ni * (ni + 1) // 2 + 2 * ni * N) * E
+        return tot
     for s in shapes:
         P, mn = s.schur_size, s.pairing_size
         for p in (0, 1):
@@ -124,6 +138,13 @@ def algorithmic_bytes(kernel, prec, shapes, N):
 def limb_macs(kernel, shapes, N):
     """mpf multiply-accumulates of one launch (element updates)."""
     tot = 0
+    if kernel in ("trsm_Linv_B/gemm", "trsm_Linv_B/diag"):
+        for s in shapes:
+            P = s.schur_size
+            for I0 in range(0, P, 16):
+                ni = min(16, P - I0)
+                tot += (ni * I0 * N) if kernel.endswith("gemm") else (ni * (ni - 1) // 2 * N)
+        return tot
     for s in shapes:
         P, mn = s.schur_size, s.pairing_size
         for p in (0, 1):
@@ -372,6 +393,14 @@ def main():
                                 "imad_wide_per_mac": imad_per_mac(prec),
                                 "peak_source": "measured, profiles/imad_rate4_r01.jsonl"}
     if a.kernels:
+        groups = {}
+        for k, (ms, n) in per_kernel.items():
+            if "/" in k:
+                g0 = groups.setdefault(k.split("/")[0], [0.0, 0])
+                g0[0] += ms
+                g0[1] += n
+        for k, (ms, n) in sorted(groups.items(), key=lambda kv: -kv[1][0]):
+            log(f"  [{k:22s}] {ms:10.3f} ms/step  x{n}  (sum of its launch kinds below)")
         for k, (ms, n) in sorted(per_kernel.items(), key=lambda kv: -kv[1][0]):
             ab = algorithmic_bytes(k, prec, ctx.shapes, N)
             log(f"  {k:24s} {ms:10.3f} ms/step  x{n}  {ab / 1e6:10.1f} MB  {ab / (ms * 1e-3) / 1e9 if ms else 0:8.1f} GB/s")

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <set>
 
 #ifndef SDPB_NL
 #error "compile with -DSDPB_NL=<n>"
@@ -21,6 +22,12 @@ template <int NL> struct Launch
     return 0;
   }
   static constexpr size_t DIAG_SMEM = sizeof(DiagSmem<NL>);
+  // "<label>/<part>": one timeline name per kind of launch inside a batched factorisation
+  static const char *sub(const char *label, const char *part)
+  {
+    static std::set<std::string> pool;
+    return pool.insert(std::string(label) + "/" + part).first->c_str();
+  }
   // matrices of a batch (sorted, largest first) that still have tile index `t`
   static int alive(const std::vector<int> &sizes, int t)
   {
@@ -45,7 +52,7 @@ template <int NL> struct Launch
     if(reset)
       CUDA_TRY(c, cudaMemsetAsync(status, 0xFF, (size_t)nstatus * sizeof(int), c->cur));
     const int T = (sizes[0] + TS - 1) / TS;
-    c->kt_begin(label);
+    const char *l_gemm = sub(label, "gemm"), *l_diag = sub(label, "diag"), *l_panel = sub(label, "panel");
     for(int Jt = 0; Jt < T; ++Jt)
       {
         const int n = alive(sizes, Jt), nbelow = alive(sizes, Jt + 1);
@@ -53,23 +60,24 @@ template <int NL> struct Launch
         if(Jt > 0) // a_ij -= sum_{k < J0} l_ik l_jk for every tile of the block column
           {
             dim3 g(n, (rows_from + TS - 1) / TS);
+            c->kt_begin(l_gemm);
             potrf_gemm_level<NL><<<g, 256, TILE_SMEM, c->cur>>>(d, Jt, status);
-            ++c->launches;
+            c->kt_end();
           }
+        c->kt_begin(l_diag);
         potrf_diag_warp<NL><<<(n + DIAG_WARPS - 1) / DIAG_WARPS, 32 * DIAG_WARPS, WARP_SMEM, c->cur>>>(
           d, n, Jt, status);
-        ++c->launches;
+        c->kt_end();
         if(nbelow == 0)
           continue;
         // tiles below the diagonal one: X = A_tile L_JJ^{-T}, one CTA per tile, the 16 steps of a
         // row shared by 16 threads (0.1 ms of latency instead of 0.45 for one thread per row)
         const int rows_below = rows_from - TS;
         dim3 g2(nbelow, (rows_below + TS - 1) / TS);
+        c->kt_begin(l_panel);
         potrf_panel_rl<NL><<<g2, 256, TILE_SMEM, c->cur>>>(d, Jt, status);
-        ++c->launches;
+        c->kt_end();
       }
-    c->kt_end();
-    --c->launches; // kt_end counted one
     CUDA_TRY(c, cudaGetLastError());
     return 0;
   }
@@ -90,7 +98,7 @@ template <int NL> struct Launch
     // one matrix, several ranks, N large enough: block columns dealt round-robin over the ranks
     const bool dist = c->world > 1 && sizes.size() == 1 && sizes[0] >= c->qdist_min_N && c->bcast;
     const int mod = dist ? c->world : 1, me = dist ? c->rank : 0;
-    c->kt_begin(label);
+    const char *l_diag = sub(label, "diag"), *l_panel = sub(label, "panel"), *l_trail = sub(label, "trail");
     for(int Jt = 0; Jt < T; ++Jt)
       {
         const int n = alive(sizes, Jt), nbelow = alive(sizes, Jt + 1);
@@ -98,12 +106,14 @@ template <int NL> struct Launch
         const bool mine = Jt % mod == me;
         if(mine)
           {
+            c->kt_begin(l_diag);
             potrf_diag_rl<NL><<<n, 256, TILE_SMEM, c->cur>>>(d, Jt, status);
-            ++c->launches;
+            c->kt_end();
             if(nbelow)
               {
+                c->kt_begin(l_panel);
                 potrf_panel_rl<NL><<<dim3(nbelow, tb), 256, TILE_SMEM, c->cur>>>(d, Jt, status);
-                ++c->launches;
+                c->kt_end();
               }
           }
         if(dist)
@@ -112,8 +122,6 @@ template <int NL> struct Launch
             const int rows = sizes[0] - Jt * TS;
             const size_t bytes = ((size_t)sizes[0] * TS * Fmt<NL>::ES + 1) * 8;
             const int pg = std::min(592, (rows * TS + 127) / 128);
-            c->kt_end();
-            --c->launches; // a span boundary, not a launch
             if(mine)
               {
                 c->kt_begin("panel_pack");
@@ -128,15 +136,13 @@ template <int NL> struct Launch
                 panel_pack<NL><<<pg, 128, 0, c->cur>>>(d, Jt, c->qpanel, status, 1);
                 c->kt_end();
               }
-            c->kt_begin(label);
           }
         if(nbelow == 0)
           continue;
+        c->kt_begin(l_trail);
         potrf_trail_rl<NL><<<dim3(nbelow, tb * (tb + 1) / 2), 256, TILE_SMEM, c->cur>>>(d, Jt, status, mod, me);
-        ++c->launches;
+        c->kt_end();
       }
-    c->kt_end();
-    --c->launches;
     CUDA_TRY(c, cudaGetLastError());
     return 0;
   }
@@ -151,22 +157,22 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaFuncSetAttribute(trsm_diag_level<NL>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
     const int T = (sizes[0] + TS - 1) / TS;
-    c->kt_begin(label);
+    const char *l_gemm = sub(label, "gemm"), *l_diag = sub(label, "diag");
     for(int It = 0; It < T; ++It)
       {
         const int n = alive(sizes, It);
         if(It > 0)
           {
             dim3 g(n, (maxcols + TS - 1) / TS);
+            c->kt_begin(l_gemm);
             trsm_gemm_level<NL><<<g, 256, TILE_SMEM, c->cur>>>(d, It);
-            ++c->launches;
+            c->kt_end();
           }
         dim3 g2(n, (maxcols + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
+        c->kt_begin(l_diag);
         trsm_diag_level<NL><<<g2, ROWS_PER_CTA, DIAG_SMEM, c->cur>>>(d, It);
-        ++c->launches;
+        c->kt_end();
       }
-    c->kt_end();
-    --c->launches;
     CUDA_TRY(c, cudaGetLastError());
     return 0;
   }

@@ -29,6 +29,13 @@ using mpfw::Reg;
 constexpr int TS = 16; // tile side
 constexpr int KC = 4;  // k-chunk
 
+// Thread -> output element of the 16x16 tile.  A warp covers 8 ROWS x 4 COLUMNS (even warps
+// rows 0-7, odd warps rows 8-15; warp pair w/2 columns 4(w/2)..4(w/2)+3), so that a ragged
+// tile -- 8 valid rows of a 40-row block, 12 valid columns of N = 300 -- leaves whole warps
+// without work instead of half-filling every warp: their issue slots go to the other CTA.
+__device__ __forceinline__ int tile_ti() { return (threadIdx.x & 7) + ((threadIdx.x >> 2) & 8); }
+__device__ __forceinline__ int tile_tj() { return ((threadIdx.x >> 3) & 3) + ((threadIdx.x >> 4) & 12); }
+
 template <int NL> struct TileGeom
 {
   static constexpr int ES = (NL + 2) & ~1;                  // 64-bit words / element
@@ -127,7 +134,7 @@ __device__ __forceinline__ void tile_k_loop(Reg<NL> &acc, bool negate, const Ope
 {
   typedef TileGeom<NL> G;
   const int t = threadIdx.x;
-  const int ti = t & (TS - 1), tj = t >> 4;
+  const int ti = tile_ti(), tj = tile_tj();
   const int nchunks = (K + KC - 1) / KC;
   if(nchunks == 0)
     return;
@@ -252,7 +259,7 @@ gemm_tile_kernel(const GemmTileDesc *descs, int count)
   if(Jt * TS >= d.N || (d.sym && It < Jt))
     return;
   tile_smem_init(sm);
-  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int ti = tile_ti(), tj = tile_tj();
   const int i = It * TS + ti, j = Jt * TS + tj;
   const bool active = i < d.M && j < d.N && (!d.sym || i >= j);
   Reg<NL> acc;
@@ -293,7 +300,7 @@ __device__ __forceinline__ bool potrf_diag_tile(Reg<NL> &acc, const PotrfDesc &d
                                                 TileSmem<NL> &sm)
 {
   typedef TileGeom<NL> G;
-  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int ti = tile_ti(), tj = tile_tj();
   const int J0 = Jt * TS;
   const int nd = min(TS, d.s - J0);
   for(int kk = 0; kk < nd; ++kk)
@@ -347,7 +354,7 @@ __device__ __forceinline__ void potrf_row_tile_solve(Reg<NL> &acc, const PotrfDe
                                                      int Jt, TileSmem<NL> &sm)
 {
   typedef TileGeom<NL> G;
-  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int ti = tile_ti(), tj = tile_tj();
   const int J0 = Jt * TS, I0 = It * TS;
   const int nd = min(TS, d.s - J0), ni = min(TS, d.s - I0);
   for(int kk = 0; kk < nd; ++kk)
@@ -401,7 +408,7 @@ __device__ __forceinline__ void potrf_tile_update(Reg<NL> &acc, const PotrfDesc 
                                                   TileSmem<NL> &sm, uint32_t &it)
 {
   typedef TileGeom<NL> G;
-  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int ti = tile_ti(), tj = tile_tj();
   const int I0 = It * TS, J0 = Jt * TS;
   const int ni = min(TS, d.s - I0), nj = min(TS, d.s - J0);
   const bool active = ti < ni && tj < nj && (It > Jt || ti >= tj);
@@ -438,7 +445,7 @@ potrf_gemm_level(const PotrfDesc *descs, int Jt, const int *status)
   uint32_t it = 0;
   Reg<NL> acc;
   potrf_tile_update<NL>(acc, d, It, Jt, sm, it);
-  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int ti = tile_ti(), tj = tile_tj();
   if(It * TS + ti < d.s && Jt * TS + tj < d.s)
     stg_reg<NL>(d.A + ((long)(It * TS + ti) * d.si + (long)(Jt * TS + tj) * d.sj) * G::ES, acc);
 }
@@ -582,7 +589,7 @@ potrf_diag_rl(const PotrfDesc *descs, int Jt, int *status)
   if(Jt * TS >= d.s || status[d.id] >= 0)
     return;
   tile_smem_init(sm);
-  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int ti = tile_ti(), tj = tile_tj();
   const int J0 = Jt * TS, nd = min(TS, d.s - J0);
   Reg<NL> acc;
   if(ti < nd && tj < nd && ti >= tj)
@@ -607,7 +614,7 @@ potrf_panel_rl(const PotrfDesc *descs, int Jt, const int *status)
   if(It * TS >= d.s || status[d.id] >= 0)
     return;
   load_diag_tile<NL>(d.A, d.si, d.sj, d.recip, d.s, Jt, sm);
-  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int ti = tile_ti(), tj = tile_tj();
   Reg<NL> acc;
   if(It * TS + ti < d.s && Jt * TS + tj < d.s)
     ldg_reg<NL>(acc, d.A + ((long)(It * TS + ti) * d.si + (long)(Jt * TS + tj) * d.sj) * G::ES);
@@ -672,7 +679,7 @@ potrf_trail_rl(const PotrfDesc *descs, int Jt, const int *status, int cyc_mod, i
   if(It * TS >= d.s || status[d.id] >= 0 || (cyc_mod > 1 && Kt % cyc_mod != cyc_rem))
     return;
   tile_smem_init(sm);
-  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int ti = tile_ti(), tj = tile_tj();
   const int I0 = It * TS, K0 = Kt * TS, J0 = Jt * TS;
   const int ni = min(TS, d.s - I0), nk = min(TS, d.s - K0);
   const bool active = ti < ni && tj < nk && (It > Kt || ti >= tj);
@@ -753,7 +760,7 @@ __global__ void __launch_bounds__(256, 2) trsm_gemm_level(const TrsmTileDesc *de
   if(I0 <= klo)
     return; // nothing above this tile can be non-zero: no update
   tile_smem_init(sm);
-  const int ti = threadIdx.x & (TS - 1), tj = threadIdx.x >> 4;
+  const int ti = tile_ti(), tj = tile_tj();
   const int nc = min(TS, d.ncols - c0), ni = min(TS, d.p - I0);
   const bool active = ti < ni && tj < nc;
   Reg<NL> acc;
