@@ -56,7 +56,7 @@ __device__ __forceinline__ void st(limb_t *base, size_t idx, const Num<NL> &x)
 // compute_schur_complement.cxx:31-124, lower triangle + mirror; one thread per
 // element, the eight products in the order the reference spells out.
 template <int NL>
-__global__ void __launch_bounds__(128) schur_kernel(const SchurDesc *descs)
+__global__ void __launch_bounds__(128, 4) schur_kernel(const SchurDesc *descs)
 {
   const SchurDesc d = descs[blockIdx.x];
   const int n = d.n, m = d.m, mn = m * n;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) schur_kernel(const SchurDesc *descs)
 // Matrix_Normalizer.cxx:75-139.  part[j*N + c] = sum over the rows of band j
 // of v^2 (rows ascending); norms[c] = sqrt(sum_j part) in block order.
 template <int NL>
-__global__ void __launch_bounds__(64) norm_partial_kernel(const BandDesc *bands, int N, limb_t *part)
+__global__ void __launch_bounds__(64, 8) norm_partial_kernel(const BandDesc *bands, int N, limb_t *part)
 {
   const BandDesc b = bands[blockIdx.x];
   for(int c = blockIdx.y * blockDim.x + threadIdx.x; c < N;
@@ -220,7 +220,7 @@ template <int NL> struct NormGeom
   static constexpr int NDP = (ND + 3) & ~3;
 };
 template <int NL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 normalize_kernel(const BandDesc *bands, int N, int NS, long K, const limb_t *norms,
                  const uint32_t *recip, int prec, CrtTables T, uint32_t *R, int *flags)
 {
