@@ -244,6 +244,32 @@ def cpu_sample(workload, steps, warmup):
     return {"value": full, "unit": "s/step", "cores": cores, "kind": "port", "sample": sample}, wall
 
 
+def cpu_solve_sample(workload):
+    """solve_schur_complement_equation by the CPU restatement on the block sample (after one
+    sample step), per-block work scaled to the full block list."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from sdpb_b200.synthetic import WORKLOADS, SyntheticSDP, solve_rhs
+    prec, shapes, N = WORKLOADS[workload]
+    sname = workload + "-sample" if workload + "-sample" in WORKLOADS else workload
+    sprec, sshapes, sN = WORKLOADS[sname]
+    scale = len(shapes) / len(sshapes)
+    sdp = SyntheticSDP(sprec, sshapes, sN, seed=1)
+    ref = ol.OracleContext(sprec, sshapes, sN)
+    sdp.upload(ref)
+    ref.schur_step(sdp.X, sdp.Y)
+    best = None
+    for _ in range(3):
+        dx, dy = solve_rhs(sprec, ref.shapes, sN, seed=7)
+        t0 = time.perf_counter()
+        ref.solve_schur_complement_equation(dx, dy)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": best * scale * 1e3, "unit": "ms/solve", "cores": ol.load_oracle().oracle_num_threads(),
+            "kind": "port", "sample": f"{len(sshapes)} of {len(shapes)} blocks, {best * 1e3:.1f} ms, scaled x{scale:g} "
+                                      "(the N x N solve with chol(Q), ~10 % of the sample, is scaled too)"}
+
+
 # --------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -361,11 +387,44 @@ def main():
     barrier()
     e2e_s = (time.perf_counter() - e0) / a.steps
 
+    # ---- solve_schur_complement_equation on the resident factors ----
+    # (called twice per Newton iteration: predictor and corrector).  With the solves on the
+    # device the step no longer has to bring L_j^-1 B_j (P x N elements) back to the host.
+    from sdpb_b200.synthetic import solve_rhs
+    rx, ry = solve_rhs(prec, ctx.shapes, N, seed=7 + rank)
+    dxh = pool.slab([x.shape for x in rx])
+    dyh = pool.empty(ry.shape)
+    solve_dev, solve_k = [], {}
+    for it in range(2 + a.steps):
+        for dst, src in zip(dxh + [dyh], rx + [ry]):
+            dst[...] = src
+        if it == 2:
+            barrier()
+            s0 = time.perf_counter()
+        ctx.solve_schur_complement_equation(dxh, dyh)
+        if it >= 2:
+            solve_dev.append(ctx.last_solve_ms())
+            for name, ms in ctx.kernel_timings():
+                solve_k.setdefault(name, []).append(ms)
+    barrier()
+    solve_api_s = (time.perf_counter() - s0) / a.steps
+    solve_dev_ms = float(np.mean(solve_dev))
+    # the step as the host solver now calls it: P stays in HBM
+    d2h_np = d2h - sum(x.nbytes for x in Ph)
+    ctx.schur_step(Xh, Yh, Xc, Yc, None, None, Lh, None, Qh)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(a.steps):
+        ctx.schur_step(Xh, Yh, Xc, Yc, None, None, Lh, None, Qh)
+    barrier()
+    e2e_np_s = (time.perf_counter() - e0) / a.steps
+
     # ---- max over ranks -------------------------------------------------
     if world > 1:
-        t = torch.tensor([ms_step, e2e_s, wall], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_step, e2e_s, wall, solve_dev_ms, solve_api_s, e2e_np_s], device="cuda",
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, e2e_s, wall = [float(x) for x in t.tolist()]
+        ms_step, e2e_s, wall, solve_dev_ms, solve_api_s, e2e_np_s = [float(x) for x in t.tolist()]
     if rank != 0:
         pool.close()
         ctx.close()
@@ -405,9 +464,16 @@ def main():
             ab = algorithmic_bytes(k, prec, ctx.shapes, N)
             log(f"  {k:24s} {ms:10.3f} ms/step  x{n}  {ab / 1e6:10.1f} MB  {ab / (ms * 1e-3) / 1e9 if ms else 0:8.1f} GB/s")
         log(f"  stages(ms) {[round(x, 3) for x in stages]}")
+        for k, v in solve_k.items():
+            log(f"  [solve] {k:24s} {float(np.mean(v)):10.3f} ms")
 
     cpu = None
+    solve_cpu = None
     if not a.no_cpu:
+        try:
+            solve_cpu = cpu_solve_sample(a.workload)
+        except Exception as e:
+            solve_cpu = {"value": None, "sample": f"unavailable: {e}"}
         try:
             cpu, _ = cpu_sample(a.workload, 1, 0)
         except Exception as e:  # the product arm does not depend on the oracle
@@ -420,6 +486,16 @@ def main():
             "e2e": {"value": e2e_s, "unit": "s/step", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "serial_ms_per_step": serial_step,
+            "schur_solve": {"what": "solve_schur_complement_equation on the resident L_j, L_j^-1 B_j, chol(Q) "
+                                    "(SURVEY 8f N1); called twice per Newton iteration",
+                            "device_ms": solve_dev_ms, "api_ms_host_buffers": solve_api_s * 1e3,
+                            "bytes_each_way": int(sum(x.nbytes for x in rx) + ry.nbytes),
+                            "kernels_ms": {k: round(float(np.mean(v)), 4) for k, v in solve_k.items()},
+                            "cpu": solve_cpu},
+            "e2e_resident_factors": {"what": "sdpb_b200_schur_step without the D2H of L_j^-1 B_j, plus two solves "
+                                             "through the C-ABI with host buffers",
+                                     "value": e2e_np_s + 2 * solve_api_s, "unit": "s/iteration",
+                                     "step_s": e2e_np_s, "d2h_bytes_per_step": int(d2h_np)},
             "stages_ms": {n: round(float(v), 4) for n, v in zip(
                 ["chol_XY", "pairings", "schur_assembly", "chol_S+trsm", "normalize", "exact_syrk", "restore",
                  "chol_Q", "step"], stages)}}

@@ -116,6 +116,25 @@ int sdpb_b200_initialize_schur_complement_solver(
   sdpb_b200_ctx *ctx, uint64_t *const *schur_complement_cholesky,
   uint64_t *const *schur_off_diagonal, uint64_t *Q, int32_t *block_timings_ms);
 
+/* solve_schur_complement_equation
+ * (run/step/compute_search_direction/solve_schur_complement_equation.cxx:16-79;
+ * called twice per iteration, compute_search_direction.cxx:62, for the predictor
+ * and the corrector): with the device-resident L_j, L_j^-1 B_j and chol(Q) of the
+ * preceding initialize_schur_complement_solver / schur_step,
+ *     dx_j <- L_j^-1 dx_j ;  dy <- dy - sum_j (L_j^-1 B_j)^T dx_j ;
+ *     dy <- Q^-1 dy ;  dx_j <- dx_j + (L_j^-1 B_j) dy ;  dx_j <- L_j^-T dx_j .
+ * dx[j]: P_j packed elements of local block j (in: r_x, out: dx); dy: N packed
+ * elements (in: r_y, out: dy; the same on every rank).  With a communicator the
+ * per-block partial sums of the dy update are exchanged over NCCL and added in
+ * GLOBAL block order, so the result does not depend on the sharding.  Keeping
+ * these solves next to the factors removes the largest device->host copy of a
+ * step (schur_off_diagonal, P x N elements). */
+int sdpb_b200_solve_schur_complement_equation(sdpb_b200_ctx *ctx,
+                                              uint64_t *const *dx, uint64_t *dy);
+
+/* Device time of the last sdpb_b200_solve_schur_complement_equation, ms (CUDA events). */
+float sdpb_b200_last_solve_ms(const sdpb_b200_ctx *ctx);
+
 /* The whole hot path of one Newton iteration in one call:
  * cholesky_decomposition(X), cholesky_decomposition(Y),
  * compute_bilinear_pairings, initialize_schur_complement_solver, with a

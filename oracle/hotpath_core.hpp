@@ -483,4 +483,121 @@ inline void compute_Q_and_factor(const std::vector<Matrix> &S,
                   .count()
                 - out.cholesky_Q_ms;
 }
+
+// ---- solve_schur_complement_equation -------------------
+// Reference: compute_search_direction/solve_schur_complement_equation.cxx:16-79
+// (lower_triangular_solve :23, Gemv TRANSPOSE -1 per block and the dy sum
+// :31-60, cholesky::SolveAfter(UPPER, Q) :64-65, Gemv NORMAL +1 :69-75,
+// lower_triangular_transpose_solve :78).  Trsv/Gemv/SolveAfter live in the
+// un-vendored Elemental fork, so the order inside them is this repo's canonical
+// one: dot products start from an exact zero and ascend; a
+// substitution applies the solved unknowns in the order they become available
+// (forward: k ascending, backward: k descending), then divides by the pivot.
+//
+// stage A, per local block: dx_j <- L_j^{-1} dx_j ; part_j[c] = -(sum_r P_j(r,c) dx_j(r))
+inline void schur_solve_forward(const SchurOutputs &f, std::vector<Matrix> &dx, int N,
+                                std::vector<std::vector<BigFloat>> &part)
+{
+  const size_t J = dx.size();
+  part.assign(J, std::vector<BigFloat>(N));
+#pragma omp parallel for schedule(dynamic)
+  for(size_t j = 0; j < J; ++j)
+    {
+      const Matrix &L = f.schur_complement_cholesky[j], &P = f.schur_off_diagonal[j];
+      Matrix &x = dx[j];
+      BigFloat prod, acc;
+      for(int i = 0; i < x.h; ++i)
+        {
+          for(int k = 0; k < i; ++k)
+            {
+              prod = L(i, k);
+              prod *= x(k, 0);
+              x(i, 0) -= prod;
+            }
+          x(i, 0) /= L(i, i);
+        }
+      for(int c = 0; c < N; ++c)
+        {
+          acc.zero();
+          for(int r = 0; r < P.h; ++r)
+            {
+              prod = P(r, c);
+              prod *= x(r, 0);
+              acc += prod;
+            }
+          part[j][c] = -acc;
+        }
+    }
+}
+// stage B, replicated: dy += part_j in GLOBAL block order; dy <- U^{-1} U^{-T} dy, Q = U^T U
+inline void schur_solve_Q(const Matrix &U, const std::vector<std::vector<BigFloat>> &part_global,
+                          Matrix &dy)
+{
+  const int n = U.h;
+  for(size_t j = 0; j < part_global.size(); ++j)
+    for(int c = 0; c < n; ++c)
+      dy(c, 0) += part_global[j][c];
+  BigFloat prod;
+  for(int i = 0; i < n; ++i)
+    {
+      for(int k = 0; k < i; ++k)
+        {
+          prod = U(k, i);
+          prod *= dy(k, 0);
+          dy(i, 0) -= prod;
+        }
+      dy(i, 0) /= U(i, i);
+    }
+  for(int i = n - 1; i >= 0; --i)
+    {
+      for(int k = n - 1; k > i; --k)
+        {
+          prod = U(i, k);
+          prod *= dy(k, 0);
+          dy(i, 0) -= prod;
+        }
+      dy(i, 0) /= U(i, i);
+    }
+}
+// stage C, per local block: dx_j += P_j dy ; dx_j <- L_j^{-T} dx_j
+inline void schur_solve_backward(const SchurOutputs &f, const Matrix &dy, std::vector<Matrix> &dx)
+{
+  const size_t J = dx.size();
+  const int N = dy.h;
+#pragma omp parallel for schedule(dynamic)
+  for(size_t j = 0; j < J; ++j)
+    {
+      const Matrix &L = f.schur_complement_cholesky[j], &P = f.schur_off_diagonal[j];
+      Matrix &x = dx[j];
+      BigFloat prod, acc;
+      for(int r = 0; r < P.h; ++r)
+        {
+          acc.zero();
+          for(int c = 0; c < N; ++c)
+            {
+              prod = P(r, c);
+              prod *= dy(c, 0);
+              acc += prod;
+            }
+          x(r, 0) += acc;
+        }
+      for(int i = x.h - 1; i >= 0; --i)
+        {
+          for(int k = x.h - 1; k > i; --k)
+            {
+              prod = L(k, i);
+              prod *= x(k, 0);
+              x(i, 0) -= prod;
+            }
+          x(i, 0) /= L(i, i);
+        }
+    }
+}
+inline void solve_schur_complement_equation(const SchurOutputs &f, std::vector<Matrix> &dx, Matrix &dy)
+{
+  std::vector<std::vector<BigFloat>> part;
+  schur_solve_forward(f, dx, dy.h, part);
+  schur_solve_Q(f.Q, part, dy);
+  schur_solve_backward(f, dy, dx);
+}
 } // namespace oracle

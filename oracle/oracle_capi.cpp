@@ -27,7 +27,7 @@ struct oracle_ctx
   std::vector<Matrix> AX, AY;          // 2J
   std::string error;
   double stage_ms[9];
-  SchurOutputs shard; // state between the stages of the sharded model
+  SchurOutputs shard; // state between the stages of the sharded model; after a step: L_j, P_j, chol(Q)
 };
 
 static void pack_out(const Matrix &m, uint64_t *out)
@@ -182,7 +182,8 @@ int oracle_initialize_schur_complement_solver(
   c->stage_ms[2] = std::chrono::duration<double, std::milli>(
                      std::chrono::steady_clock::now() - t0)
                      .count();
-  SchurOutputs out;
+  c->shard = SchurOutputs();
+  SchurOutputs &out = c->shard; // kept: oracle_solve_schur_complement_equation reads L_j, P_j, chol(Q)
   compute_Q_and_factor(S, c->B, c->N, out);
   c->stage_ms[3] = out.block_ms;
   c->stage_ms[5] = out.syrk_ms;
@@ -357,6 +358,78 @@ int oracle_shard_stage3(oracle_ctx *c, int nparts, const uint64_t *const *qprime
     }
   if(Q)
     pack_out(c->shard.Q, Q);
+  return 0;
+}
+
+// ---- solve_schur_complement_equation (row N1) -----------------------------
+// dx[j]: P_j elements (in: r_x, out: dx), dy: N elements (in: r_y, out: dy);
+// uses L_j, L_j^-1 B_j and chol(Q) of the last initialize_schur_complement_solver
+// (or oracle_shard_stage3) on this context.
+static int unpack_dx(oracle_ctx *c, uint64_t *const *dx, std::vector<Matrix> &x)
+{
+  if((int)c->shard.schur_complement_cholesky.size() != c->J || c->shard.Q.h != c->N)
+    {
+      c->error = "solve_schur_complement_equation before initialize_schur_complement_solver";
+      return 5;
+    }
+  x.resize(c->J);
+  for(int j = 0; j < c->J; ++j)
+    unpack_matrix(x[j], c->shapes[j].schur_size(), 1, dx[j]);
+  return 0;
+}
+int oracle_solve_schur_complement_equation(oracle_ctx *c, uint64_t *const *dx, uint64_t *dy)
+{
+  sdpb_host::set_precision(c->prec);
+  std::vector<Matrix> x;
+  if(int rc = unpack_dx(c, dx, x))
+    return rc;
+  Matrix y;
+  unpack_matrix(y, c->N, 1, dy);
+  solve_schur_complement_equation(c->shard, x, y);
+  for(int j = 0; j < c->J; ++j)
+    pack_out(x[j], dx[j]);
+  pack_out(y, dy);
+  return 0;
+}
+// sharded model: stage A on the local blocks (dx updated in place, one row of N
+// partials per local block), the caller gathers the rows in global block order,
+// then stage B+C with the gathered rows.
+int oracle_shard_solve_stage1(oracle_ctx *c, uint64_t *const *dx, uint64_t *part)
+{
+  sdpb_host::set_precision(c->prec);
+  std::vector<Matrix> x;
+  if(int rc = unpack_dx(c, dx, x))
+    return rc;
+  std::vector<std::vector<BigFloat>> p;
+  schur_solve_forward(c->shard, x, c->N, p);
+  const int ew = elem_words();
+  for(int j = 0; j < c->J; ++j)
+    {
+      pack_out(x[j], dx[j]);
+      for(int col = 0; col < c->N; ++col)
+        sdpb_host::pack(p[j][col], part + ((size_t)j * c->N + col) * ew);
+    }
+  return 0;
+}
+int oracle_shard_solve_stage2(oracle_ctx *c, const uint64_t *part_global, int J_global,
+                              uint64_t *const *dx, uint64_t *dy)
+{
+  sdpb_host::set_precision(c->prec);
+  std::vector<Matrix> x;
+  if(int rc = unpack_dx(c, dx, x))
+    return rc;
+  const int ew = elem_words(), N = c->N;
+  std::vector<std::vector<BigFloat>> p(J_global, std::vector<BigFloat>(N));
+  for(int j = 0; j < J_global; ++j)
+    for(int col = 0; col < N; ++col)
+      sdpb_host::unpack(p[j][col], part_global + ((size_t)j * N + col) * ew);
+  Matrix y;
+  unpack_matrix(y, N, 1, dy);
+  schur_solve_Q(c->shard.Q, p, y);
+  schur_solve_backward(c->shard, y, x);
+  for(int j = 0; j < c->J; ++j)
+    pack_out(x[j], dx[j]);
+  pack_out(y, dy);
   return 0;
 }
 

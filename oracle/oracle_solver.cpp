@@ -23,6 +23,7 @@ int oracle_compute_bilinear_pairings(oracle_ctx *c, const uint64_t *const *Y, ui
 int oracle_initialize_schur_complement_solver(oracle_ctx *c, uint64_t *const *schur_complement_cholesky,
                                               uint64_t *const *schur_off_diagonal, uint64_t *Q,
                                               int32_t *block_timings_ms);
+int oracle_solve_schur_complement_equation(oracle_ctx *c, uint64_t *const *dx, uint64_t *dy);
 }
 
 using namespace sdpb_host;
@@ -48,6 +49,9 @@ static Hot_Path_Table oracle_table(const Block_Info &bi, const SDP &sdp, int pre
     = [](void *x, uint64_t *const *L, uint64_t *const *P, uint64_t *Q, int32_t *ms) {
         return oracle_initialize_schur_complement_solver((oracle_ctx *)x, L, P, Q, ms);
       };
+  t.solve_schur_complement_equation = [](void *x, uint64_t *const *dx, uint64_t *dy) {
+    return oracle_solve_schur_complement_equation((oracle_ctx *)x, dx, dy);
+  };
   t.last_error = [](const void *x) { return oracle_last_error((const oracle_ctx *)x); };
   t.destroy = [](void *x) { oracle_destroy((oracle_ctx *)x); };
   t.name = "cpu-oracle(libgmp)";

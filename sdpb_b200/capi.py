@@ -58,6 +58,10 @@ def load_library():
     lib.sdpb_b200_initialize_schur_complement_solver.restype = ctypes.c_int
     lib.sdpb_b200_initialize_schur_complement_solver.argtypes = [
         ctypes.c_void_p, u64pp, u64pp, u64p, ctypes.POINTER(ctypes.c_int32)]
+    lib.sdpb_b200_solve_schur_complement_equation.restype = ctypes.c_int
+    lib.sdpb_b200_solve_schur_complement_equation.argtypes = [ctypes.c_void_p, u64pp, u64p]
+    lib.sdpb_b200_last_solve_ms.restype = ctypes.c_float
+    lib.sdpb_b200_last_solve_ms.argtypes = [ctypes.c_void_p]
     lib.sdpb_b200_schur_step.restype = ctypes.c_int
     lib.sdpb_b200_schur_step.argtypes = [ctypes.c_void_p] + [u64pp] * 8 + [
         u64p, ctypes.POINTER(ctypes.c_int32)]
@@ -202,6 +206,9 @@ class StepContextBase:
     def alloc_pairing_blocks(self):
         return [self.empty(s.pairing_size, s.pairing_size) for s in self.shapes for p in (0, 1)]
 
+    def alloc_solve_vectors(self):
+        return [self.empty(s.schur_size, 1) for s in self.shapes], self.empty(self.N, 1)
+
     def alloc_schur_outputs(self):
         L = [self.empty(s.schur_size, s.schur_size) for s in self.shapes]
         P = [self.empty(s.schur_size, self.N) for s in self.shapes]
@@ -260,6 +267,14 @@ class SchurContext(StepContextBase):
             ptr_array(L) if L is not None else None,
             ptr_array(P) if P is not None else None,
             _ptr(Q) if Q is not None else None, bt))
+
+    def solve_schur_complement_equation(self, dx, dy):
+        """In place: dx[j] (1, P_j, ew) holds r_x -> dx, dy (1, N, ew) holds r_y -> dy
+        (solve_schur_complement_equation.cxx:16-79) on the device-resident factors."""
+        self._check(self.lib.sdpb_b200_solve_schur_complement_equation(self.handle, ptr_array(dx), _ptr(dy)))
+
+    def last_solve_ms(self):
+        return float(self.lib.sdpb_b200_last_solve_ms(self.handle))
 
     def schur_step(self, X, Y, X_chol=None, Y_chol=None, A_X_inv=None, A_Y=None, L=None, P=None, Q=None,
                    block_timings_ms=None):

@@ -445,6 +445,17 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
         TRY_C(upload(&c->d_bands_g[g], gb));
       }
   }
+  {
+    // triangular systems of the Schur solves: every L_j (largest first), and Q = U^T U read as U^T
+    std::vector<SolveTriDesc> sS, sQ{SolveTriDesc{c->Q, c->recipQ, (long)N, 1, N, 0}};
+    for(const PotrfDesc &d : pS)
+      sS.push_back(SolveTriDesc{d.A, d.recip, 1, (long)d.s, d.s, c->g[d.id].row0});
+    TRY_C(upload(&c->d_solveS, sS));
+    TRY_C(upload(&c->d_solveQ, sQ));
+    TRY_C(cudaMalloc(&c->sol_x, std::max<size_t>(16, (size_t)c->K * es * 8)));
+    TRY_C(cudaMalloc(&c->sol_y, std::max<size_t>(16, (size_t)N * es * 8)));
+    TRY_C(cudaMallocHost(&c->sol_pinned, std::max<size_t>(16, (size_t)(c->K + N) * es * 8)));
+  }
   std::vector<PotrfDesc> pQ{PotrfDesc{c->Q, c->recipQ, N, (long)N, 1, 0}}; // upper: A = U^T U
   c->szQ.assign(1, N);
   TRY_C(upload(&c->d_potrfQ, pQ));
@@ -580,7 +591,7 @@ extern "C" int sdpb_b200_comm_init(sdpb_b200_ctx *c, int rank, int world, const 
   c->J_global = num_blocks_global;
   c->allreduce = &nccl_allreduce;
   c->bcast = &nccl_bcast;
-  CUDA_TRY(c, cudaMalloc(&c->qpanel, ((size_t)c->N * TS * c->es + 2) * 8));
+  CUDA_TRY(c, cudaMalloc(&c->qpanel, ((size_t)c->N * TS * c->es + 2) * 8 + (size_t)TS * (2 * c->nl + 8) * 4));
   if(const char *env = getenv("SDPB_B200_QDIST_MIN_N"))
     c->qdist_min_N = atoi(env);
   return 0;
@@ -611,6 +622,11 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
   cudaFree(c->d_potrfX);
   cudaFree(c->d_potrfY);
   cudaFree(c->d_potrfS);
+  cudaFree(c->d_solveS);
+  cudaFree(c->d_solveQ);
+  cudaFree(c->sol_x);
+  cudaFree(c->sol_y);
+  cudaFreeHost(c->sol_pinned);
   cudaFree(c->d_potrfQ);
   cudaFree(c->recipX);
   cudaFree(c->recipY);
@@ -746,6 +762,10 @@ static int dispatch_pairings(sdpb_b200_ctx *c, int y_ready_event = -1)
 static int dispatch_schur_and_Q(sdpb_b200_ctx *c)
 {
   return table_for(c->nl)->schur_and_Q(c);
+}
+static int dispatch_schur_solve(sdpb_b200_ctx *c)
+{
+  return table_for(c->nl)->schur_solve(c);
 }
 static int dispatch_scalar(sdpb_b200_ctx *c, int op, int k, long count,
                            const limb_t *a, const limb_t *b, limb_t *r)
@@ -912,6 +932,7 @@ extern "C" int sdpb_b200_initialize_schur_complement_solver(
       return SDPB_B200_ERR_STATE;
     }
   CUDA_TRY(c, cudaSetDevice(c->device));
+  c->have_factors = false;
   int rc = dispatch_schur_and_Q(c);
   if(rc)
     return rc;
@@ -953,6 +974,7 @@ extern "C" int sdpb_b200_initialize_schur_complement_solver(
                  + std::to_string(qstat);
       return SDPB_B200_ERR_NOT_HPD;
     }
+  c->have_factors = true;
   {
     std::vector<size_t> eS(c->J), eP(c->J);
     for(int j = 0; j < c->J; ++j)
@@ -993,6 +1015,61 @@ extern "C" int sdpb_b200_initialize_schur_complement_solver(
     }
   return 0;
 }
+
+// ------------------------------------------- solve_schur_complement_equation
+// (solve_schur_complement_equation.cxx:16-79) on the resident factors.  The
+// right-hand sides travel through one pinned staging buffer: one H2D and one
+// D2H of (P + N) elements per solve.
+extern "C" int sdpb_b200_solve_schur_complement_equation(sdpb_b200_ctx *c, uint64_t *const *dx,
+                                                         uint64_t *dy)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  if(!c->have_factors)
+    {
+      c->error = "solve_schur_complement_equation called before a successful "
+                 "initialize_schur_complement_solver";
+      return SDPB_B200_ERR_STATE;
+    }
+  if(!dy || (c->J && !dx))
+    {
+      c->error = "solve_schur_complement_equation: null argument";
+      return SDPB_B200_ERR_ARG;
+    }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const size_t es = (size_t)c->es;
+  for(int j = 0; j < c->J; ++j)
+    {
+      if(c->g[j].P && !dx[j])
+        {
+          c->error = "solve_schur_complement_equation: dx[" + std::to_string(j) + "] is null";
+          return SDPB_B200_ERR_ARG;
+        }
+      memcpy(c->sol_pinned + (size_t)c->g[j].row0 * es, dx[j], (size_t)c->g[j].P * es * 8);
+    }
+  memcpy(c->sol_pinned + (size_t)c->K * es, dy, (size_t)c->N * es * 8);
+  if(c->K)
+    CUDA_TRY(c, cudaMemcpyAsync(c->sol_x, c->sol_pinned, (size_t)c->K * es * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->sol_y, c->sol_pinned + (size_t)c->K * es, (size_t)c->N * es * 8,
+                              cudaMemcpyHostToDevice, st));
+  c->kt_used = 0;
+  CUDA_TRY(c, cudaEventRecord(c->ev[9], st));
+  if(int rc = dispatch_schur_solve(c))
+    return rc;
+  CUDA_TRY(c, cudaEventRecord(c->ev[10], st));
+  if(c->K)
+    CUDA_TRY(c, cudaMemcpyAsync(c->sol_pinned, c->sol_x, (size_t)c->K * es * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->sol_pinned + (size_t)c->K * es, c->sol_y, (size_t)c->N * es * 8,
+                              cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&c->solve_ms, c->ev[9], c->ev[10]);
+  for(int j = 0; j < c->J; ++j)
+    memcpy(dx[j], c->sol_pinned + (size_t)c->g[j].row0 * es, (size_t)c->g[j].P * es * 8);
+  memcpy(dy, c->sol_pinned + (size_t)c->K * es, (size_t)c->N * es * 8);
+  return 0;
+}
+extern "C" float sdpb_b200_last_solve_ms(const sdpb_b200_ctx *c) { return c ? c->solve_ms : 0.f; }
 
 // ----------------------------------------------------- resident step
 // H2D of X and Y through one pinned staging buffer (two large copies instead
@@ -1046,6 +1123,7 @@ static int enqueue_step(sdpb_b200_ctx *c)
 {
   cudaStream_t st = c->stream;
   c->kt_used = 0;
+  c->have_factors = false;
   CUDA_TRY(c, cudaEventRecord(c->ev[9], st));
   if(c->wXY)
     {
@@ -1135,7 +1213,7 @@ static int finish_step(sdpb_b200_ctx *c)
                  + std::to_string(status[5 * J]);
       return SDPB_B200_ERR_NOT_HPD;
     }
-  c->have_X_cholesky = c->have_pairings = true;
+  c->have_X_cholesky = c->have_pairings = c->have_factors = true;
   return 0;
 }
 

@@ -3,6 +3,7 @@
 #pragma once
 #include "../../include/sdpb_b200.h"
 #include "kernels.cuh"
+#include "solve.cuh"
 
 #include <string>
 #include <vector>
@@ -125,6 +126,12 @@ struct sdpb_b200_ctx
   }
 
   bool have_X_cholesky = false, have_pairings = false;
+  // solve_schur_complement_equation on the resident factors (solve.cuh)
+  bool have_factors = false; // L_j, L_j^-1 B_j and chol(Q) of a successful step are in place
+  SolveTriDesc *d_solveS = nullptr, *d_solveQ = nullptr; // S blocks largest first; the one Q system
+  limb_t *sol_x = nullptr, *sol_y = nullptr;             // stacked dx (K elements), dy (N elements)
+  uint64_t *sol_pinned = nullptr;                        // host staging, (K + N) elements
+  float solve_ms = 0;                                    // device time of the last solve
   long launches = 0; // kernels launched since creation
   cudaEvent_t ev[12] = {}; // 0,1 pairings; 2..8 Schur stages; 9,10,11 resident step
   float stage_ms[9] = {0};
@@ -167,6 +174,7 @@ struct LaunchTable
   int (*cholesky)(sdpb_b200_ctx *, int which);
   int (*pairings)(sdpb_b200_ctx *, int part); // 0: X chain (L_X^-1 V, A_X_inv); 1: Y chain (Y V, A_Y)
   int (*schur_and_Q)(sdpb_b200_ctx *);
+  int (*schur_solve)(sdpb_b200_ctx *); // solve.cuh, on sol_x / sol_y
   int (*scalar)(sdpb_b200_ctx *, int op, int k, long count, const limb_t *a,
                 const limb_t *b, limb_t *r);
 };

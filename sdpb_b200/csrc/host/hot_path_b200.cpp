@@ -34,6 +34,9 @@ static Hot_Path_Table b200_table(const Block_Info &bi, const SDP &sdp, int prec,
     = [](void *x, uint64_t *const *L, uint64_t *const *P, uint64_t *Q, int32_t *ms) {
         return sdpb_b200_initialize_schur_complement_solver((sdpb_b200_ctx *)x, L, P, Q, ms);
       };
+  t.solve_schur_complement_equation = [](void *x, uint64_t *const *dx, uint64_t *dy) {
+    return sdpb_b200_solve_schur_complement_equation((sdpb_b200_ctx *)x, dx, dy);
+  };
   t.last_error = [](const void *x) { return sdpb_b200_last_error((const sdpb_b200_ctx *)x); };
   t.destroy = [](void *x) { sdpb_b200_destroy((sdpb_b200_ctx *)x); };
   t.name = "sm_100a(libsdpb_b200.so)";

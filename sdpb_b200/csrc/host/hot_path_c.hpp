@@ -18,6 +18,7 @@ struct Hot_Path_Table
     = nullptr;
   int (*initialize_schur_complement_solver)(void *, uint64_t *const *, uint64_t *const *, uint64_t *, int32_t *)
     = nullptr;
+  int (*solve_schur_complement_equation)(void *, uint64_t *const *, uint64_t *) = nullptr;
   const char *(*last_error)(const void *) = nullptr;
   void (*destroy)(void *) = nullptr;
   std::string name;
@@ -29,8 +30,8 @@ class Hot_Path_C : public Hot_Path
   const Block_Info &bi;
   int N;
   typedef std::vector<uint64_t> Buf;
-  std::vector<Buf> in2J, out2J, outJ_L, outJ_P;
-  Buf outQ;
+  std::vector<Buf> in2J, out2J, outJ_L, ioJ_dx;
+  Buf outQ, io_dy;
   std::vector<int32_t> block_timings_ms;
 
   static std::vector<const uint64_t *> cptrs(const std::vector<Buf> &v)
@@ -73,7 +74,7 @@ public:
     in2J.resize(2 * J);
     out2J.resize(2 * J);
     outJ_L.resize(J);
-    outJ_P.resize(J);
+    ioJ_dx.resize(J);
     block_timings_ms.assign(J, 0);
     for(int j = 0; j < J; ++j)
       {
@@ -150,22 +151,41 @@ public:
       {
         const size_t Pj = (size_t)bi.schur_block_size(j);
         outJ_L[j].resize(Pj * Pj * ew);
-        outJ_P[j].resize(Pj * (size_t)N * ew);
       }
     const auto pl = ptrs(outJ_L);
-    const auto pp = ptrs(outJ_P);
-    check(t.initialize_schur_complement_solver(t.ctx, pl.data(), pp.data(), outQ.data(),
+    // L_j and chol(Q) come back for the condition numbers (update_cond_numbers, step.cxx:187-189); L_j^-1 B_j is
+    // read only by the Schur solve and stays with the implementation
+    check(t.initialize_schur_complement_solver(t.ctx, pl.data(), nullptr, outQ.data(),
                                                block_timings_ms.data()));
     L.resize(J);
-    P.resize(J);
+    P.clear();
 #pragma omp parallel for schedule(dynamic)
     for(int j = 0; j < J; ++j)
       {
         const int Pj = bi.schur_block_size(j);
         unpack_matrix(L[j], Pj, Pj, outJ_L[j].data());
-        unpack_matrix(P[j], Pj, N, outJ_P[j].data());
       }
     unpack_matrix(Q, N, N, outQ.data());
+  }
+
+  void solve_schur_complement_equation(std::vector<Matrix> &dx, Matrix &dy) override
+  {
+    const size_t ew = (size_t)elem_words();
+    const int J = bi.num_blocks();
+    for(int j = 0; j < J; ++j)
+      {
+        ioJ_dx[j].resize(dx[j].a.size() * ew + 1);
+        if(!dx[j].a.empty())
+          pack_matrix(dx[j], ioJ_dx[j].data());
+      }
+    io_dy.resize((size_t)N * ew + 1);
+    pack_matrix(dy, io_dy.data());
+    const auto px = ptrs(ioJ_dx);
+    check(t.solve_schur_complement_equation(t.ctx, px.data(), io_dy.data()));
+    for(int j = 0; j < J; ++j)
+      if(!dx[j].a.empty())
+        unpack_matrix(dx[j], dx[j].h, 1, ioJ_dx[j].data());
+    unpack_matrix(dy, N, 1, io_dy.data());
   }
 };
 } // namespace sdpb_host

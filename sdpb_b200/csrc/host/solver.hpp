@@ -32,9 +32,15 @@ struct Hot_Path
   // (only the Schur assembly reads it); A_Y[b] = V^T Y V, (m n) x (m n).
   virtual void compute_bilinear_pairings(const std::vector<Matrix> &Y, std::vector<Matrix> &A_Y) = 0;
   // initialize_schur_complement_solver.cxx:62-104
+  // schur_off_diagonal may come back empty: it is read only by the Schur solve below, which
+  // the implementation runs on its own resident copy.
   virtual void initialize_schur_complement_solver(std::vector<Matrix> &schur_complement_cholesky,
                                                   std::vector<Matrix> &schur_off_diagonal, Matrix &Q)
     = 0;
+  // solve_schur_complement_equation.cxx:16-79 with the L_j, L_j^-1 B_j and
+  // chol(Q) of the preceding initialize_schur_complement_solver, which stay with the
+  // implementation: dx[j] (P_j x 1) and dy (N x 1) hold r_x, r_y on entry, the solution on exit.
+  virtual void solve_schur_complement_equation(std::vector<Matrix> &dx, Matrix &dy) = 0;
   virtual std::string name() const = 0;
 };
 
@@ -621,53 +627,6 @@ public:
       }
   }
 
-  // solve_schur_complement_equation.cxx:16-79
-  void solve_schur_complement_equation(const std::vector<Matrix> &L, const std::vector<Matrix> &P,
-                                       const Matrix &Q, std::vector<Matrix> &dx, Matrix &dy) const
-  {
-    const int J = block_info.num_blocks(), N = sdp.N();
-    std::vector<Matrix> part(J);
-#pragma omp parallel for schedule(dynamic)
-    for(int j = 0; j < J; ++j)
-      {
-        trsm_lower_left(L[j], dx[j]); // dx = L^{-1} dx
-        part[j].resize(N, 1);
-        BigFloat acc, t;
-        for(int c = 0; c < N; ++c) // - P^T dx
-          {
-            acc.zero();
-            for(int r = 0; r < P[j].h; ++r)
-              {
-                t = P[j](r, c);
-                t *= dx[j](r, 0);
-                acc += t;
-              }
-            part[j](c, 0) = -acc;
-          }
-      }
-    for(int j = 0; j < J; ++j)
-      for(int c = 0; c < N; ++c)
-        dy(c, 0) += part[j](c, 0);
-    cholesky_upper_solve(Q, dy); // dy = Q^{-1} dy
-#pragma omp parallel for schedule(dynamic)
-    for(int j = 0; j < J; ++j)
-      {
-        BigFloat acc, t;
-        for(int r = 0; r < P[j].h; ++r) // dx += P dy
-          {
-            acc.zero();
-            for(int c = 0; c < N; ++c)
-              {
-                t = P[j](r, c);
-                t *= dy(c, 0);
-                acc += t;
-              }
-            dx[j](r, 0) += acc;
-          }
-        trsm_lower_transpose_left(L[j], dx[j]); // dx = L^{-T} dx
-      }
-  }
-
   // compute_search_direction.cxx:44-90
   void compute_search_direction(const std::vector<Matrix> &minus_XY, const std::vector<Matrix> &L,
                                 const std::vector<Matrix> &P, const Matrix &Q,
@@ -694,7 +653,7 @@ public:
       symmetrize(blk);
     compute_schur_RHS(Z, dx);
     dy = primal_residue_p;
-    solve_schur_complement_equation(L, P, Q, dx, dy);
+    hot.solve_schur_complement_equation(dx, dy); // solve_schur_complement_equation.cxx:16-79
     // dX = PrimalResidues + sum_p A_p dx[p]
     constraint_matrix_weighted_sum(dx, dX);
     for(size_t b = 0; b < dX.size(); ++b)

@@ -120,7 +120,7 @@ template <int NL> struct Launch
           {
             // the finished block column (and the owner's status) to every rank
             const int rows = sizes[0] - Jt * TS;
-            const size_t bytes = ((size_t)sizes[0] * TS * Fmt<NL>::ES + 1) * 8;
+            const size_t bytes = ((size_t)sizes[0] * TS * Fmt<NL>::ES + 2) * 8 + (size_t)TS * TileGeom<NL>::RS * 4;
             const int pg = std::min(592, (rows * TS + 127) / 128);
             if(mine)
               {
@@ -317,6 +317,71 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaEventRecord(c->ev[8], st));
     return 0;
   }
+  // one CTA per triangular system; unknowns in shared memory when the largest system fits
+  template <bool BACK>
+  static int solve_tri(sdpb_b200_ctx *c, const char *label, const SolveTriDesc *d, int count, int maxp,
+                       limb_t *x)
+  {
+    if(count == 0 || maxp == 0)
+      return 0;
+    const size_t need = (size_t)maxp * TileGeom<NL>::SW * 4;
+    const int use_smem = need <= 200 * 1024;
+    const size_t smem = use_smem ? need : 0;
+    CUDA_TRY(c, cudaFuncSetAttribute(solve_tri_kernel<NL, BACK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)std::max<size_t>(smem, 1024)));
+    const int threads = std::min(SOLVE_MAX_THREADS, std::max(32, (maxp + 31) & ~31));
+    c->kt_begin(label);
+    solve_tri_kernel<NL, BACK><<<count, threads, smem, c->cur>>>(d, x, use_smem);
+    c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
+  // solve_schur_complement_equation.cxx:16-79 on sol_x (stacked dx) and sol_y (dy)
+  static int schur_solve(sdpb_b200_ctx *c)
+  {
+    const int J = c->J, N = c->N;
+    cudaStream_t st = c->stream;
+    c->cur = st;
+    const bool sharded = c->world > 1;
+    limb_t *part = sharded ? c->part_global : c->part;
+    const int Jsum = sharded ? c->J_global : J;
+    // dx_j <- L_j^-1 dx_j
+    if(int rc = solve_tri<false>(c, "solve_Linv_dx", c->d_solveS, J, c->max_P, c->sol_x))
+      return rc;
+    // dy -= sum_j P_j^T dx_j: per-block partial rows, added in GLOBAL block order
+    if(sharded)
+      CUDA_TRY(c, cudaMemsetAsync(part, 0, (size_t)Jsum * N * Fmt<NL>::ES * 8, st));
+    if(J)
+      {
+        dim3 g(J, (N + 63) / 64);
+        c->kt_begin("solve_gemvT_kernel");
+        solve_gemvT_kernel<NL><<<g, 64, 0, st>>>(c->d_bands, N, c->sol_x, part);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+      }
+    if(sharded)
+      if(int rc = c->allreduce(c, part, (size_t)Jsum * N * Fmt<NL>::ES, 1, "nccl_allreduce_dy_partials"))
+        return rc;
+    c->kt_begin("solve_dysum_kernel");
+    solve_dysum_kernel<NL><<<(N + 31) / 32, 32, 0, st>>>(part, Jsum, N, c->sol_y);
+    c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
+    // dy <- U^-1 U^-T dy
+    if(int rc = solve_tri<false>(c, "solve_Q_forward", c->d_solveQ, 1, N, c->sol_y))
+      return rc;
+    if(int rc = solve_tri<true>(c, "solve_Q_backward", c->d_solveQ, 1, N, c->sol_y))
+      return rc;
+    // dx_j += P_j dy ; dx_j <- L_j^-T dx_j
+    if(J)
+      {
+        dim3 g(J, (c->max_P + 63) / 64);
+        c->kt_begin("solve_gemv_kernel");
+        solve_gemv_kernel<NL><<<g, 64, 0, st>>>(c->d_bands, N, c->sol_y, c->sol_x);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+      }
+    return solve_tri<true>(c, "solve_LinvT_dx", c->d_solveS, J, c->max_P, c->sol_x);
+  }
   static int scalar(sdpb_b200_ctx *c, int op, int k, long count,
                     const limb_t *a, const limb_t *b, limb_t *r)
   {
@@ -344,4 +409,4 @@ template <int NL> struct Launch
 #define SDPB_CAT(a, b) SDPB_CAT2(a, b)
 extern "C" __attribute__((visibility("default"))) const LaunchTable
   SDPB_CAT(sdpb_b200_launch_nl, SDPB_NL) = {&Launch<SDPB_NL>::cholesky, &Launch<SDPB_NL>::pairings,
-     &Launch<SDPB_NL>::schur_and_Q, &Launch<SDPB_NL>::scalar};
+     &Launch<SDPB_NL>::schur_and_Q, &Launch<SDPB_NL>::schur_solve, &Launch<SDPB_NL>::scalar};

@@ -646,6 +646,19 @@ __global__ void panel_pack(const PotrfDesc *descs, int Jt, uint64_t *buf, int *s
             b[w] = g[w];
         }
     }
+  // the pivots' reciprocals travel with the panel (the Schur solves divide by them on every rank)
+  if(blockIdx.x == 0)
+    {
+      uint32_t *rb = reinterpret_cast<uint32_t *>(buf + (long)d.s * TS * G::ES + 2);
+      uint32_t *rg = d.recip + (long)J0 * G::RS;
+      for(int w = threadIdx.x; w < nd * G::RS; w += blockDim.x)
+        {
+          if(unpack)
+            rg[w] = rb[w];
+          else
+            rb[w] = rg[w];
+        }
+    }
   if(blockIdx.x == 0 && threadIdx.x == 0)
     {
       uint64_t *sw = buf + (long)d.s * TS * G::ES; // fixed slot past the largest panel

@@ -77,3 +77,10 @@ class SyntheticSDP:
 
     def input_bytes(self):
         return sum(a.nbytes for a in self.X) + sum(a.nbytes for a in self.Y)
+
+
+def solve_rhs(prec, shapes, N, seed=7):
+    """Right-hand sides (r_x per block, r_y) for solve_schur_complement_equation, U(-1,1)."""
+    rng = np.random.Generator(np.random.PCG64(0x5D9B1000 + seed))
+    shapes = [s if isinstance(s, BlockShape) else BlockShape(*s) for s in shapes]
+    return [random_matrix(rng, prec, s.schur_size, 1) for s in shapes], random_matrix(rng, prec, N, 1)

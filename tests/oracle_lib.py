@@ -43,6 +43,12 @@ def load_oracle():
     lib.oracle_shard_stage3.restype = ctypes.c_int
     lib.oracle_shard_stage3.argtypes = [ctypes.c_void_p, ctypes.c_int, u64pp, u64pp, u64pp, u64p]
     lib.oracle_last_error.argtypes = [ctypes.c_void_p]
+    lib.oracle_solve_schur_complement_equation.restype = ctypes.c_int
+    lib.oracle_solve_schur_complement_equation.argtypes = [ctypes.c_void_p, u64pp, u64p]
+    lib.oracle_shard_solve_stage1.restype = ctypes.c_int
+    lib.oracle_shard_solve_stage1.argtypes = [ctypes.c_void_p, u64pp, u64p]
+    lib.oracle_shard_solve_stage2.restype = ctypes.c_int
+    lib.oracle_shard_solve_stage2.argtypes = [ctypes.c_void_p, u64p, ctypes.c_int, u64pp, u64p]
     lib.oracle_set_block.argtypes = [ctypes.c_void_p, ctypes.c_int, u64p, u64p, u64p]
     lib.oracle_cholesky_decomposition.argtypes = [ctypes.c_void_p, ctypes.c_int, u64pp, u64pp]
     lib.oracle_compute_bilinear_pairings.argtypes = [ctypes.c_void_p, u64pp, u64pp, u64pp]
@@ -121,6 +127,21 @@ class OracleContext(StepContextBase):
         self._check(self.lib.oracle_schur_step(
             self.handle, ptr_array(X), ptr_array(Y), opt(X_chol), opt(Y_chol), opt(A_X_inv), opt(A_Y),
             opt(L), opt(P), _ptr(Q) if Q is not None else None, None))
+
+    def solve_schur_complement_equation(self, dx, dy):
+        self._check(self.lib.oracle_solve_schur_complement_equation(self.handle, ptr_array(dx), _ptr(dy)))
+
+    # sharded Schur solve: stage 1 local (dx in place, partial rows out), the caller gathers the
+    # rows in global block order, stage 2 finishes dy (replicated) and the local dx
+    def shard_solve_stage1(self, dx):
+        part = np.zeros((self.J, self.N, self.ew), dtype=np.uint64)
+        self._check(self.lib.oracle_shard_solve_stage1(self.handle, ptr_array(dx), _ptr(part)))
+        return part
+
+    def shard_solve_stage2(self, part_global, dx, dy):
+        part_global = np.ascontiguousarray(part_global, dtype=np.uint64)
+        self._check(self.lib.oracle_shard_solve_stage2(self.handle, _ptr(part_global), part_global.shape[0],
+                                                       ptr_array(dx), _ptr(dy)))
 
     # sharded model (oracle_shard_stage1..3): the caller does the two exchanges
     def shard_stage1(self, X, Y):
@@ -204,6 +225,7 @@ class SyntheticSDP:
         self.B, self.bases = [], []
         self.X, self.Y = [], []
         ids = list(block_ids) if block_ids is not None else list(range(len(self.shapes)))
+        self.block_ids = ids
         for j, s in zip(ids, self.shapes):
             base = seed * 1000003 + j * 101
             self.B.append(random_matrix(prec, s.schur_size, N, base + 1))
@@ -212,6 +234,14 @@ class SyntheticSDP:
             for p in (0, 1):
                 self.X.append(random_spd(prec, s.psd_size(p), base + 10 + p))
                 self.Y.append(random_spd(prec, s.psd_size(p), base + 20 + p))
+
+    def solve_rhs(self, seed=7):
+        """Seeded right-hand sides (r_x per block, r_y) for solve_schur_complement_equation; the
+        data of a block depends only on its global index."""
+        ids = self.block_ids
+        dx = [random_matrix(self.prec, s.schur_size, 1, seed * 7919 + 31 * j + 5) for j, s in zip(ids, self.shapes)]
+        dy = random_matrix(self.prec, self.N, 1, seed * 7919 + 3)
+        return dx, dy
 
     def upload(self, ctx):
         for j in range(len(self.shapes)):

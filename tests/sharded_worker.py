@@ -52,6 +52,9 @@ def main():
     ref = ol.OracleContext(PREC, SHAPES, N)
     full.upload(ref)
     want = full.run_step(ref)
+    # ... and the Schur solve (solve_schur_complement_equation) on its factors
+    want_dx, want_dy = full.solve_rhs()
+    ref.solve_schur_complement_equation(want_dx, want_dy)
 
     sdp = ol.SyntheticSDP(PREC, shapes, N, seed=5, block_ids=mine)
     for a, j in zip(sdp.B, mine):
@@ -70,6 +73,16 @@ def main():
         qs = [torch.zeros(q.shape, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(qs, torch.from_numpy(q.view(np.int64)))
         L, P, Q = ctx.shard_stage3([t.numpy().view(np.uint64) for t in qs])
+        # the Schur solve, staged: local forward part, partial rows gathered in global block order
+        dx, dy = sdp.solve_rhs()
+        spart = ctx.shard_solve_stage1(dx)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (mine, spart))
+        spart_global = np.zeros((len(SHAPES), N, ctx.ew), dtype=np.uint64)
+        for ids, p in gathered:
+            for k, j in enumerate(ids):
+                spart_global[j] = p[k]
+        ctx.shard_solve_stage2(spart_global, dx, dy)
     else:
         import sdpb_b200
         ctx = sdpb_b200.SchurContext(PREC, shapes, N, device=local)
@@ -82,9 +95,13 @@ def main():
         # a second step on the same communicator (buffers are reused)
         got2 = sdp.run_step(ctx)
         ol.assert_same("Q(second step)", got2["Q"], want["Q"])
+        dx, dy = sdp.solve_rhs()
+        ctx.solve_schur_complement_equation(dx, dy)
     ol.assert_same("Q", Q, want["Q"])
     ol.assert_same("L", L, [want["L"][j] for j in mine])
     ol.assert_same("P", P, [want["P"][j] for j in mine])
+    ol.assert_same("dy", dy, want_dy)
+    ol.assert_same("dx", dx, [want_dx[j] for j in mine])
     dist.barrier()
     print(f"rank {rank}/{world} mode {sys.argv[1]}: blocks {mine} match the unsharded oracle bit for bit", flush=True)
     ctx.close()

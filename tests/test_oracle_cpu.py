@@ -78,3 +78,42 @@ def test_non_pd_X_names_block_and_parity():
     with pytest.raises(ol.OracleError) as ei:
         sdp.run_step(ctx)
     assert "block index = 1, parity = 1" in str(ei.value)
+
+
+@pytest.mark.parametrize("prec,shapes,N", [
+    (128, [(1, 4), (2, 3), (1, 1)], 3),
+    (768, [(1, 5), (2, 4), (1, 7)], 4),
+])
+def test_schur_solve_satisfies_the_block_system(prec, shapes, N):
+    """solve_schur_complement_equation.cxx:16-79 solves {{S, -B}, {B^T, 0}} {dx, dy} = {r_x, r_y}
+    (compute_schur_RHS.cxx:3-7): check S_j dx_j - B_j dy = r_x_j and sum_j B_j^T dx_j = r_y in double."""
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=11)
+    ctx = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ctx)
+    out = sdp.run_step(ctx)
+    rx, ry = sdp.solve_rhs()
+    dx, dy = [a.copy() for a in rx], ry.copy()
+    ctx.solve_schur_complement_equation(dx, dy)
+    dyf = _to_float(prec, dy)
+    acc = np.zeros((N, 1))
+    for j in range(len(shapes)):
+        Lf, Bf = _to_float(prec, out["L"][j]), _to_float(prec, sdp.B[j])
+        dxf = _to_float(prec, dx[j])
+        assert np.allclose(Lf @ (Lf.T @ dxf) - Bf @ dyf, _to_float(prec, rx[j]), rtol=1e-8, atol=1e-8)
+        acc += Bf.T @ dxf
+    assert np.allclose(acc, _to_float(prec, ry), rtol=1e-8, atol=1e-8)
+    # the staged (sharded) model with one rank is the same computation
+    dx2, dy2 = [a.copy() for a in rx], ry.copy()
+    part = ctx.shard_solve_stage1(dx2)
+    ctx.shard_solve_stage2(part, dx2, dy2)
+    ol.assert_same("dx", dx2, dx)
+    ol.assert_same("dy", dy2, dy)
+
+
+def test_schur_solve_needs_the_factors():
+    prec, shapes, N = 128, [(1, 4)], 2
+    ctx = ol.OracleContext(prec, shapes, N)
+    dx, dy = ctx.alloc_solve_vectors()
+    with pytest.raises(ol.OracleError) as ei:
+        ctx.solve_schur_complement_equation(dx, dy)
+    assert ei.value.code == 5

@@ -120,6 +120,61 @@ def test_schur_step_bit_exact(prec, shapes, N):
     ctx.close()
 
 
+SOLVE_CASES = CASES + [
+    (768, [(1, 40), (2, 40), (1, 33), (2, 17)], 37),   # several 16-row tiles, more rows than a warp
+    (1536, [(1, 9), (2, 4)], 6),
+]
+
+
+@pytest.mark.parametrize("prec,shapes,N", SOLVE_CASES)
+def test_schur_solve_bit_exact(prec, shapes, N):
+    """solve_schur_complement_equation.cxx:16-79 on the device-resident L_j, L_j^-1 B_j, chol(Q)
+     against the oracle's restatement, every limb of dx and dy; twice with
+    different right-hand sides (the predictor and the corrector of one iteration)."""
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=3)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    sdp.run_step(ref)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    sdp.run_step(ctx)
+    for seed in (7, 8):
+        want_dx, want_dy = sdp.solve_rhs(seed)
+        ref.solve_schur_complement_equation(want_dx, want_dy)
+        dx, dy = sdp.solve_rhs(seed)
+        ctx.solve_schur_complement_equation(dx, dy)
+        ol.assert_same("dy", dy, want_dy)
+        ol.assert_same("dx", dx, want_dx)
+    assert ctx.last_solve_ms() > 0
+    # zero right-hand side: exact zeros stay exact zeros
+    dx, dy = ctx.alloc_solve_vectors()
+    ctx.solve_schur_complement_equation(dx, dy)
+    assert not any(a.any() for a in dx) and not dy.any()
+    ctx.close()
+
+
+def test_schur_solve_after_resident_step_and_state():
+    prec, shapes, N = 768, [(1, 12), (2, 7)], 9
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=4)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    sdp.run_step(ref)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    dx, dy = sdp.solve_rhs()
+    with pytest.raises(sdpb_b200.SdpbB200Error) as ei:
+        ctx.solve_schur_complement_equation(dx, dy)   # no factors yet
+    assert ei.value.code == 5
+    ctx.upload_XY(sdp.X, sdp.Y)
+    ctx.schur_step_resident()
+    ctx.solve_schur_complement_equation(dx, dy)
+    want_dx, want_dy = sdp.solve_rhs()
+    ref.solve_schur_complement_equation(want_dx, want_dy)
+    ol.assert_same("dy", dy, want_dy)
+    ol.assert_same("dx", dx, want_dx)
+    ctx.close()
+
+
 def test_block_groups_on_side_streams_bit_exact(monkeypatch):
     """The S chain cut into interleaved groups of blocks on separate streams
     (SDPB_B200_GROUPS) must not change a bit."""
@@ -200,6 +255,12 @@ def test_c3_sample_full_width_bit_exact():
     got = sdp.run_step(ctx)
     for k in KEYS:
         ol.assert_same(k, got[k], want[k])
+    want_dx, want_dy = sdp.solve_rhs()
+    ref.solve_schur_complement_equation(want_dx, want_dy)
+    dx, dy = sdp.solve_rhs()
+    ctx.solve_schur_complement_equation(dx, dy)
+    ol.assert_same("dy", dy, want_dy)
+    ol.assert_same("dx", dx, want_dx)
     ctx.close()
 
 
