@@ -147,6 +147,8 @@ __global__ void __launch_bounds__(32) norm_final_kernel(const limb_t *part, int 
       mpfw::set_zero(acc);
       for(int j = 0; j < J; ++j)
         {
+          if(j + 8 < J) // sequential sum, but the loads need not wait for it
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(part + ((size_t)(j + 8) * N + c) * Fmt<NL>::ES));
           ldg_reg<NL>(v, part + ((size_t)j * N + c) * Fmt<NL>::ES);
           acc = add_nl<NL>(acc, v);
         }

@@ -267,6 +267,53 @@ MPFW_D void mul_rows_short(uint32_t (&out)[2 * W - C0], APtr a, const uint32_t (
 #pragma unroll
   for(int k = 0; k < NO; ++k)
     ev[k] = od[k] = 0;
+#if !defined(MPFW_MUL_MANYCHAINS)
+  // ONE carry chain through the whole product.  A row's chain ends in a word that has only
+  // ever received carries (or past the top word), so its carry-out is always zero; handing
+  // that zero to the next chain as its carry-in changes nothing arithmetically, but it makes
+  // every chain depend on the previous one.  ptxas then keeps a single carry predicate live
+  // instead of interleaving ~20 independent chains and spilling their predicates into a
+  // bit-mask register (3 LOP3 per product and a serial dependency through that register):
+  // mac_nl inside trsm_gemm_level 1604 -> 1501 instructions, LOP3 215 -> 74; step 118.8 ->
+  // 117.2 ms at c3.  Four warps per scheduler hide the chain's latency: the microbenchmark
+  // (tools/mac_bench.cu) measures the same rate for both forms.  MPFW_MUL_MANYCHAINS keeps
+  // the independent-chain form for A/B measurements.
+  bool started = false;
+#pragma unroll
+  for(int i = 0; i < W; ++i)
+    {
+      const uint32_t ai = a[i];
+      const int jmin = (C0 - i > 0) ? C0 - i : 0;
+#pragma unroll
+      for(int par = 0; par < 2; ++par)
+        {
+          int ctop = -1;
+#pragma unroll
+          for(int j = 0; j < W; ++j)
+            {
+              const int c = i + j - C0;
+              if(j < jmin || (c & 1) != par)
+                continue;
+              uint32_t &lo = par ? od[c - 1] : ev[c];
+              uint32_t &hi = par ? od[c] : ev[c + 1];
+              if(!started)
+                asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                             : "+r"(lo), "+r"(hi)
+                             : "r"(ai), "r"(b[j]));
+              else
+                asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                             : "+r"(lo), "+r"(hi)
+                             : "r"(ai), "r"(b[j]));
+              started = true;
+              ctop = c;
+            }
+          if(par == 0 && ctop >= 0 && ctop + 2 < NO)
+            asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(ev[ctop + 2]));
+          if(par == 1 && ctop >= 0 && ctop + 1 < NO - 1)
+            asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(od[ctop + 1]));
+        }
+    }
+#else
 #pragma unroll
   for(int i = 0; i < W; ++i)
     {
@@ -315,6 +362,7 @@ MPFW_D void mul_rows_short(uint32_t (&out)[2 * W - C0], APtr a, const uint32_t (
       if(ctop >= 0 && ctop + 1 < NO - 1)
         asm volatile("addc.u32 %0, %0, 0;" : "+r"(od[ctop + 1]));
     }
+#endif
   out[0] = ev[0];
   asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(out[1]) : "r"(ev[1]), "r"(od[0]));
 #pragma unroll

@@ -135,6 +135,10 @@ __global__ void __launch_bounds__(32) solve_dysum_kernel(const limb_t *part, int
   ldg_reg<NL>(acc, dy + (size_t)c * Fmt<NL>::ES);
   for(int j = 0; j < J; ++j)
     {
+      // the sum is sequential by definition (its order is part of the result); the loads are
+      // not: keep the next rows' lines on their way (J grows with the number of GPUs)
+      if(j + 8 < J)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(part + ((size_t)(j + 8) * N + c) * Fmt<NL>::ES));
       ldg_reg<NL>(v, part + ((size_t)j * N + c) * Fmt<NL>::ES);
       acc = add_nl<NL>(acc, v);
     }

@@ -57,6 +57,17 @@ __device__ __noinline__ Reg<NL> mac_nl(Reg<NL> acc, const uint32_t *a, const uin
   mpfw::mac<NL>(acc, a, b, negate);
   return acc;
 }
+// the same for operands that both live in shared memory (the k-loop of the tile kernels): telling
+// the compiler so turns the generic LD.E of the operand words into LDS
+template <int NL>
+__device__ __noinline__ Reg<NL> mac_ss_nl(Reg<NL> acc, const uint32_t *a, const uint32_t *b,
+                                          bool negate)
+{
+  __builtin_assume(__isShared(a));
+  __builtin_assume(__isShared(b));
+  mpfw::mac<NL>(acc, a, b, negate);
+  return acc;
+}
 // x / pivot, pivot given as a packed element, R its reciprocal
 template <int NL>
 __device__ __noinline__ Reg<NL> div_nl(Reg<NL> x, const uint32_t *piv, const uint32_t *R)
@@ -169,7 +180,7 @@ __device__ __forceinline__ void tile_k_loop(Reg<NL> &acc, bool negate, const Ope
         {
           const uint32_t *pa = sm.a[s] + ti * G::SW, *pb = sm.b[s] + tj * G::SW;
           for(int kk = 0; kk < kcnt; ++kk)
-            acc = mac_nl<NL>(acc, pa + kk * TS * G::SW, pb + kk * TS * G::SW, negate);
+            acc = mac_ss_nl<NL>(acc, pa + kk * TS * G::SW, pb + kk * TS * G::SW, negate);
         }
       __syncthreads();
     }

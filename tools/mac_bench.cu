@@ -48,6 +48,12 @@ __global__ void __launch_bounds__(256, 2) bench(const uint32_t *A, uint32_t *O, 
         {
           mpfw::mac<NL>(acc, a, b, (kk & 3) == 0);
         }
+      else if(OP >= 10) // the tile kernels' k-loop: a CTA-wide barrier every OP-10 operations
+        {
+          acc = mac_nl<NL>(acc, a, b, (kk & 3) == 0);
+          if((kk + 1) % (OP - 10) == 0)
+            __syncthreads();
+        }
       else if(OP == 2)
         acc = div_nl<NL>(acc, a, O + 8 * (kk & 1)); // reciprocal words: arbitrary (timing only)
       else if(OP == 3)
@@ -133,6 +139,10 @@ int main(int argc, char **argv)
   run<14, 0>("mac_noinline full chip 148x256", 148, 256, 200);
   run<14, 0>("mac_noinline full chip 296x256", 296, 256, 200);
   run<14, 1>("mac_inline full chip 296x256", 296, 256, 200);
+  run<14, 14>("mac + __syncthreads every 4, 296x256", 296, 256, 200);
+  run<14, 18>("mac + __syncthreads every 8, 296x256", 296, 256, 200);
+  run<14, 26>("mac + __syncthreads every 16, 296x256", 296, 256, 208);
+  run<14, 11>("mac + __syncthreads every 1, 296x256", 296, 256, 200);
   if(quick)
     return 0;
 #ifndef MAC_BENCH_QUICK
