@@ -270,6 +270,28 @@ def cpu_solve_sample(workload):
                                       "(the N x N solve with chol(Q), ~10 % of the sample, is scaled too)"}
 
 
+def cpu_sma_sample(workload):
+    """scale_multiply_add(-1, X, Y, 0, C) by the CPU restatement on the block sample, scaled."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from sdpb_b200.synthetic import WORKLOADS, SyntheticSDP
+    prec, shapes, N = WORKLOADS[workload]
+    sname = workload + "-sample" if workload + "-sample" in WORKLOADS else workload
+    sprec, sshapes, sN = WORKLOADS[sname]
+    scale = len(shapes) / len(sshapes)
+    sdp = SyntheticSDP(sprec, sshapes, sN, seed=1)
+    ref = ol.OracleContext(sprec, sshapes, sN)
+    C = [x.copy() for x in sdp.X]
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ref.scale_multiply_add(-1, sdp.X, sdp.Y, 0, C)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": best * scale * 1e3, "unit": "ms/call", "cores": ol.load_oracle().oracle_num_threads(),
+            "kind": "port", "sample": f"{len(sshapes)} of {len(shapes)} blocks, {best * 1e3:.1f} ms, scaled x{scale:g}"}
+
+
 # --------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -419,6 +441,19 @@ def main():
     barrier()
     e2e_np_s = (time.perf_counter() - e0) / a.steps
 
+    # ---- scale_multiply_add (-X Y and the other block GEMMs of step()) ----
+    Ch = pool.slab([x.shape for x in sdp.X])
+    sma_k = {}
+    ctx.scale_multiply_add(-1, Xh, Yh, 0, Ch)
+    barrier()
+    s0 = time.perf_counter()
+    for _ in range(a.steps):
+        ctx.scale_multiply_add(-1, Xh, Yh, 0, Ch)
+        for name, ms in ctx.kernel_timings():
+            sma_k.setdefault(name, []).append(ms)
+    barrier()
+    sma_api_s = (time.perf_counter() - s0) / a.steps
+
     # ---- max over ranks -------------------------------------------------
     if world > 1:
         t = torch.tensor([ms_step, e2e_s, wall, solve_dev_ms, solve_api_s, e2e_np_s], device="cuda",
@@ -469,7 +504,12 @@ def main():
 
     cpu = None
     solve_cpu = None
+    sma_cpu = None
     if not a.no_cpu:
+        try:
+            sma_cpu = cpu_sma_sample(a.workload)
+        except Exception as e:
+            sma_cpu = {"value": None, "sample": f"unavailable: {e}"}
         try:
             solve_cpu = cpu_solve_sample(a.workload)
         except Exception as e:
@@ -492,6 +532,12 @@ def main():
                             "bytes_each_way": int(sum(x.nbytes for x in rx) + ry.nbytes),
                             "kernels_ms": {k: round(float(np.mean(v)), 4) for k, v in solve_k.items()},
                             "cpu": solve_cpu},
+            "scale_multiply_add": {"what": "C = -X Y on the 2J PSD-shaped blocks through the C-ABI with host buffers "
+                                           "(SURVEY 8f N2; scale_multiply_add.cxx:4-16)",
+                                   "api_ms_host_buffers": sma_api_s * 1e3,
+                                   "kernels_ms": {k: round(float(np.mean(v)), 4) for k, v in sma_k.items()},
+                                   "bytes_h2d": int(2 * sum(x.nbytes for x in Xh)),
+                                   "bytes_d2h": int(sum(x.nbytes for x in Ch)), "cpu": sma_cpu},
             "e2e_resident_factors": {"what": "sdpb_b200_schur_step without the D2H of L_j^-1 B_j, plus two solves "
                                              "through the C-ABI with host buffers",
                                      "value": e2e_np_s + 2 * solve_api_s, "unit": "s/iteration",

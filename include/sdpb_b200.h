@@ -132,6 +132,19 @@ int sdpb_b200_initialize_schur_complement_solver(
 int sdpb_b200_solve_schur_complement_equation(sdpb_b200_ctx *ctx,
                                               uint64_t *const *dx, uint64_t *dy);
 
+/* scale_multiply_add
+ * (run/step/compute_search_direction/scale_multiply_add.cxx:4-16, forward-declared at
+ * step.cxx:7 and compute_search_direction.cxx:19): per block-parity b = 2*j + parity
+ *     C_b = alpha * A_b * B_b + beta * C_b
+ * on s x s blocks, s = psd_matrix_block_size (the shape of X, Y, dX, dY, R, Z).
+ * alpha is 1 or -1 and beta 0 or 1 -- the reference's call sites: -X Y (step.cxx:137),
+ * (1, 0) (compute_search_direction.cxx:28), (-1, 1) (:60).  A, B, C: host pointers as for
+ * cholesky_decomposition; C is read only when beta != 0. */
+int sdpb_b200_scale_multiply_add(sdpb_b200_ctx *ctx, int alpha,
+                                 const uint64_t *const *A,
+                                 const uint64_t *const *B, int beta,
+                                 uint64_t *const *C);
+
 /* Device time of the last sdpb_b200_solve_schur_complement_equation, ms (CUDA events). */
 float sdpb_b200_last_solve_ms(const sdpb_b200_ctx *ctx);
 

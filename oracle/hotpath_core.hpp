@@ -600,4 +600,36 @@ inline void solve_schur_complement_equation(const SchurOutputs &f, std::vector<M
   schur_solve_Q(f.Q, part, dy);
   schur_solve_backward(f, dy, dx);
 }
+
+// ---- scale_multiply_add (the block GEMMs of step() / compute_search_direction)
+// Reference: compute_search_direction/scale_multiply_add.cxx:4-16 -- per block
+// El::Gemm(NORMAL, NORMAL, alpha, A_b, B_b, beta, C_b); call sites step.cxx:137 (-X Y),
+// compute_search_direction.cxx:28 (1, 0) and :60 (-1, 1).  Canonical order (Gemm is
+// Elemental's): the dot product from an exact zero with l ascending, then `acc *= alpha`,
+// then C = acc (beta == 0) or `C *= beta; C += acc`.
+inline void scale_multiply_add_block(const BigFloat &alpha, const Matrix &A, const Matrix &B,
+                                     const BigFloat &beta, Matrix &C)
+{
+  BigFloat acc, prod;
+  const bool beta_zero = beta.sgn() == 0;
+  for(int j = 0; j < B.w; ++j)
+    for(int i = 0; i < A.h; ++i)
+      {
+        acc.zero();
+        for(int l = 0; l < A.w; ++l)
+          {
+            prod = A(i, l);
+            prod *= B(l, j);
+            acc += prod;
+          }
+        acc *= alpha;
+        if(beta_zero)
+          C(i, j) = acc;
+        else
+          {
+            C(i, j) *= beta;
+            C(i, j) += acc;
+          }
+      }
+}
 } // namespace oracle

@@ -433,6 +433,38 @@ int oracle_shard_solve_stage2(oracle_ctx *c, const uint64_t *part_global, int J_
   return 0;
 }
 
+// ---- scale_multiply_add (row N2) ------------------------------------------
+// C_b = alpha A_b B_b + beta C_b for the 2J PSD-shaped blocks (s x s each); alpha in {1,-1},
+// beta in {0,1} (the reference's call sites)
+int oracle_scale_multiply_add(oracle_ctx *c, int alpha, const uint64_t *const *A, const uint64_t *const *B,
+                              int beta, uint64_t *const *C)
+{
+  sdpb_host::set_precision(c->prec);
+  if((alpha != 1 && alpha != -1) || (beta != 0 && beta != 1))
+    {
+      c->error = "scale_multiply_add: alpha must be 1 or -1, beta 0 or 1";
+      return 1;
+    }
+  const BigFloat al(alpha), be(beta);
+#pragma omp parallel for schedule(dynamic)
+  for(int b = 0; b < 2 * c->J; ++b)
+    {
+      const int s = c->shapes[b / 2].psd_size(b % 2);
+      if(s == 0)
+        continue;
+      Matrix Am, Bm, Cm;
+      unpack_matrix(Am, s, s, A[b]);
+      unpack_matrix(Bm, s, s, B[b]);
+      if(beta)
+        unpack_matrix(Cm, s, s, C[b]);
+      else
+        Cm.resize(s, s);
+      scale_multiply_add_block(al, Am, Bm, be, Cm);
+      pack_out(Cm, C[b]);
+    }
+  return 0;
+}
+
 // ---- single-kernel entry points for unit parity tests -----------------
 int oracle_potrf(int prec, int s, int upper, const uint64_t *A, uint64_t *L)
 {

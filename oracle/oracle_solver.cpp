@@ -24,6 +24,8 @@ int oracle_initialize_schur_complement_solver(oracle_ctx *c, uint64_t *const *sc
                                               uint64_t *const *schur_off_diagonal, uint64_t *Q,
                                               int32_t *block_timings_ms);
 int oracle_solve_schur_complement_equation(oracle_ctx *c, uint64_t *const *dx, uint64_t *dy);
+int oracle_scale_multiply_add(oracle_ctx *c, int alpha, const uint64_t *const *A, const uint64_t *const *B, int beta,
+                              uint64_t *const *C);
 }
 
 using namespace sdpb_host;
@@ -52,6 +54,8 @@ static Hot_Path_Table oracle_table(const Block_Info &bi, const SDP &sdp, int pre
   t.solve_schur_complement_equation = [](void *x, uint64_t *const *dx, uint64_t *dy) {
     return oracle_solve_schur_complement_equation((oracle_ctx *)x, dx, dy);
   };
+  t.scale_multiply_add = [](void *x, int al, const uint64_t *const *A, const uint64_t *const *B, int be,
+                            uint64_t *const *C) { return oracle_scale_multiply_add((oracle_ctx *)x, al, A, B, be, C); };
   t.last_error = [](const void *x) { return oracle_last_error((const oracle_ctx *)x); };
   t.destroy = [](void *x) { oracle_destroy((oracle_ctx *)x); };
   t.name = "cpu-oracle(libgmp)";

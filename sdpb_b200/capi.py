@@ -60,6 +60,8 @@ def load_library():
         ctypes.c_void_p, u64pp, u64pp, u64p, ctypes.POINTER(ctypes.c_int32)]
     lib.sdpb_b200_solve_schur_complement_equation.restype = ctypes.c_int
     lib.sdpb_b200_solve_schur_complement_equation.argtypes = [ctypes.c_void_p, u64pp, u64p]
+    lib.sdpb_b200_scale_multiply_add.restype = ctypes.c_int
+    lib.sdpb_b200_scale_multiply_add.argtypes = [ctypes.c_void_p, ctypes.c_int, u64pp, u64pp, ctypes.c_int, u64pp]
     lib.sdpb_b200_last_solve_ms.restype = ctypes.c_float
     lib.sdpb_b200_last_solve_ms.argtypes = [ctypes.c_void_p]
     lib.sdpb_b200_schur_step.restype = ctypes.c_int
@@ -272,6 +274,12 @@ class SchurContext(StepContextBase):
         """In place: dx[j] (1, P_j, ew) holds r_x -> dx, dy (1, N, ew) holds r_y -> dy
         (solve_schur_complement_equation.cxx:16-79) on the device-resident factors."""
         self._check(self.lib.sdpb_b200_solve_schur_complement_equation(self.handle, ptr_array(dx), _ptr(dy)))
+
+    def scale_multiply_add(self, alpha, A, B, beta, C):
+        """C[b] = alpha A[b] B[b] + beta C[b] on the PSD-shaped blocks (scale_multiply_add.cxx:4-16);
+        alpha in (1, -1), beta in (0, 1); C is overwritten."""
+        self._check(self.lib.sdpb_b200_scale_multiply_add(self.handle, int(alpha), ptr_array(A), ptr_array(B),
+                                                          int(beta), ptr_array(C)))
 
     def last_solve_ms(self):
         return float(self.lib.sdpb_b200_last_solve_ms(self.handle))

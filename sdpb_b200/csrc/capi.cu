@@ -446,6 +446,23 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
       }
   }
   {
+    // scale_multiply_add: C_b = A_b B_b on s x s blocks, column-major
+    const size_t bytes = std::max<size_t>(16, c->wXY * 8);
+    TRY_C(cudaMalloc(&c->smaA, bytes));
+    TRY_C(cudaMalloc(&c->smaB, bytes));
+    TRY_C(cudaMalloc(&c->smaT, bytes));
+    TRY_C(cudaMalloc(&c->smaC, bytes));
+    std::vector<GemmTileDesc> gS;
+    for(int q = 0; q < 2 * num_blocks; ++q)
+      {
+        const int s = c->g[q / 2].s[q % 2];
+        gS.push_back(GemmTileDesc{c->smaA + c->oXY[q], c->smaB + c->oXY[q], c->smaT + c->oXY[q], 1, (long)s,
+                                  1, (long)s, s, s, s, 0, 0, 0, 0, 0});
+      }
+    c->tiles_SMA = sort_gemm(gS);
+    TRY_C(upload(&c->d_gemmSMA, gS));
+  }
+  {
     // triangular systems of the Schur solves: every L_j (largest first), and Q = U^T U read as U^T
     std::vector<SolveTriDesc> sS, sQ{SolveTriDesc{c->Q, c->recipQ, (long)N, 1, N, 0}};
     for(const PotrfDesc &d : pS)
@@ -623,6 +640,11 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
   cudaFree(c->d_potrfY);
   cudaFree(c->d_potrfS);
   cudaFree(c->d_solveS);
+  cudaFree(c->smaA);
+  cudaFree(c->smaB);
+  cudaFree(c->smaT);
+  cudaFree(c->smaC);
+  cudaFree(c->d_gemmSMA);
   cudaFree(c->d_solveQ);
   cudaFree(c->sol_x);
   cudaFree(c->sol_y);
@@ -794,18 +816,27 @@ static int first_bad(sdpb_b200_ctx *c, const int *d_status, int count, int *pivo
 
 static int copy_blocks_in(sdpb_b200_ctx *c, const uint64_t *const *A, limb_t *dst)
 {
-  for(int q = 0; q < 2 * c->J; ++q)
+  const int n = 2 * c->J;
+  auto words_of = [&](int q) { return (size_t)c->g[q / 2].s[q % 2] * c->g[q / 2].s[q % 2] * c->es; };
+  for(int q = 0; q < n;)
     {
-      const int s = c->g[q / 2].s[q % 2];
-      if(s == 0)
-        continue;
+      size_t words = words_of(q);
+      if(words == 0)
+        {
+          ++q;
+          continue;
+        }
       if(!A || !A[q])
         {
           c->error = "null input block " + std::to_string(q);
           return SDPB_B200_ERR_ARG;
         }
-      CUDA_TRY(c, cudaMemcpyAsync(dst + c->oXY[q], A[q], (size_t)s * s * c->es * 8,
-                                  cudaMemcpyHostToDevice, c->stream));
+      // blocks the caller packed back to back (as the arena is): one DMA for the run
+      int r = q + 1;
+      while(r < n && (words_of(r) == 0 || (A[r] == A[q] + words && c->oXY[r] == c->oXY[q] + words)))
+        words += words_of(r++);
+      CUDA_TRY(c, cudaMemcpyAsync(dst + c->oXY[q], A[q], words * 8, cudaMemcpyHostToDevice, c->stream));
+      q = r;
     }
   return 0;
 }
@@ -1070,6 +1101,44 @@ extern "C" int sdpb_b200_solve_schur_complement_equation(sdpb_b200_ctx *c, uint6
   return 0;
 }
 extern "C" float sdpb_b200_last_solve_ms(const sdpb_b200_ctx *c) { return c ? c->solve_ms : 0.f; }
+
+// ---------------------------------------------------------- scale_multiply_add
+extern "C" int sdpb_b200_scale_multiply_add(sdpb_b200_ctx *c, int alpha, const uint64_t *const *A,
+                                            const uint64_t *const *B, int beta, uint64_t *const *C)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  if((alpha != 1 && alpha != -1) || (beta != 0 && beta != 1) || !C)
+    {
+      c->error = "scale_multiply_add: alpha must be 1 or -1, beta 0 or 1, C non-null";
+      return SDPB_B200_ERR_ARG;
+    }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rc = copy_blocks_in(c, A, c->smaA);
+  if(rc)
+    return rc;
+  rc = copy_blocks_in(c, B, c->smaB);
+  if(rc)
+    return rc;
+  if(beta)
+    {
+      rc = copy_blocks_in(c, C, c->smaC);
+      if(rc)
+        return rc;
+    }
+  c->kt_used = 0;
+  rc = table_for(c->nl)->scale_multiply_add(c, alpha, beta);
+  if(rc)
+    return rc;
+  std::vector<size_t> elems(2 * c->J);
+  for(int q = 0; q < 2 * c->J; ++q)
+    elems[q] = (size_t)c->g[q / 2].s[q % 2] * c->g[q / 2].s[q % 2];
+  rc = copy_blocks_out(c, c->smaC, c->oXY, C, 2 * c->J, elems);
+  if(rc)
+    return rc;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
 
 // ----------------------------------------------------- resident step
 // H2D of X and Y through one pinned staging buffer (two large copies instead

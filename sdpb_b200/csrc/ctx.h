@@ -132,6 +132,10 @@ struct sdpb_b200_ctx
   limb_t *sol_x = nullptr, *sol_y = nullptr;             // stacked dx (K elements), dy (N elements)
   uint64_t *sol_pinned = nullptr;                        // host staging, (K + N) elements
   float solve_ms = 0;                                    // device time of the last solve
+  // scale_multiply_add (row N2): operands, product and result as block-diagonal objects
+  limb_t *smaA = nullptr, *smaB = nullptr, *smaT = nullptr, *smaC = nullptr; // wXY words each
+  GemmTileDesc *d_gemmSMA = nullptr;
+  int tiles_SMA = 0;
   long launches = 0; // kernels launched since creation
   cudaEvent_t ev[12] = {}; // 0,1 pairings; 2..8 Schur stages; 9,10,11 resident step
   float stage_ms[9] = {0};
@@ -175,6 +179,7 @@ struct LaunchTable
   int (*pairings)(sdpb_b200_ctx *, int part); // 0: X chain (L_X^-1 V, A_X_inv); 1: Y chain (Y V, A_Y)
   int (*schur_and_Q)(sdpb_b200_ctx *);
   int (*schur_solve)(sdpb_b200_ctx *); // solve.cuh, on sol_x / sol_y
+  int (*scale_multiply_add)(sdpb_b200_ctx *, int alpha, int beta); // smaC = alpha smaA smaB + beta smaC
   int (*scalar)(sdpb_b200_ctx *, int op, int k, long count, const limb_t *a,
                 const limb_t *b, limb_t *r);
 };

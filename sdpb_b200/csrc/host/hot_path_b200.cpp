@@ -37,6 +37,10 @@ static Hot_Path_Table b200_table(const Block_Info &bi, const SDP &sdp, int prec,
   t.solve_schur_complement_equation = [](void *x, uint64_t *const *dx, uint64_t *dy) {
     return sdpb_b200_solve_schur_complement_equation((sdpb_b200_ctx *)x, dx, dy);
   };
+  t.scale_multiply_add = [](void *x, int al, const uint64_t *const *A, const uint64_t *const *B, int be,
+                            uint64_t *const *C) {
+    return sdpb_b200_scale_multiply_add((sdpb_b200_ctx *)x, al, A, B, be, C);
+  };
   t.last_error = [](const void *x) { return sdpb_b200_last_error((const sdpb_b200_ctx *)x); };
   t.destroy = [](void *x) { sdpb_b200_destroy((sdpb_b200_ctx *)x); };
   t.name = "sm_100a(libsdpb_b200.so)";

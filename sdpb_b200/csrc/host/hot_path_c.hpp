@@ -19,6 +19,8 @@ struct Hot_Path_Table
   int (*initialize_schur_complement_solver)(void *, uint64_t *const *, uint64_t *const *, uint64_t *, int32_t *)
     = nullptr;
   int (*solve_schur_complement_equation)(void *, uint64_t *const *, uint64_t *) = nullptr;
+  int (*scale_multiply_add)(void *, int, const uint64_t *const *, const uint64_t *const *, int, uint64_t *const *)
+    = nullptr;
   const char *(*last_error)(const void *) = nullptr;
   void (*destroy)(void *) = nullptr;
   std::string name;
@@ -30,7 +32,7 @@ class Hot_Path_C : public Hot_Path
   const Block_Info &bi;
   int N;
   typedef std::vector<uint64_t> Buf;
-  std::vector<Buf> in2J, out2J, outJ_L, ioJ_dx;
+  std::vector<Buf> in2J, inB2J, out2J, outJ_L, ioJ_dx;
   Buf outQ, io_dy;
   std::vector<int32_t> block_timings_ms;
 
@@ -72,6 +74,7 @@ public:
     const int J = bi.num_blocks();
     const size_t ew = (size_t)elem_words();
     in2J.resize(2 * J);
+    inB2J.resize(2 * J);
     out2J.resize(2 * J);
     outJ_L.resize(J);
     ioJ_dx.resize(J);
@@ -166,6 +169,35 @@ public:
         unpack_matrix(L[j], Pj, Pj, outJ_L[j].data());
       }
     unpack_matrix(Q, N, N, outQ.data());
+  }
+
+  void scale_multiply_add(int alpha, const std::vector<Matrix> &A, const std::vector<Matrix> &B, int beta,
+                          std::vector<Matrix> &C) override
+  {
+    const size_t ew = (size_t)elem_words();
+    pack_psd(A);
+#pragma omp parallel for schedule(dynamic)
+    for(size_t b = 0; b < B.size(); ++b)
+      {
+        inB2J[b].resize(B[b].a.size() * ew);
+        if(!B[b].a.empty())
+          pack_matrix(B[b], inB2J[b].data());
+        out2J[b].resize(A[b].a.size() * ew);
+        if(beta && !C[b].a.empty())
+          pack_matrix(C[b], out2J[b].data());
+      }
+    const auto pa = cptrs(in2J), pb = cptrs(inB2J);
+    const auto pc = ptrs(out2J);
+    check(t.scale_multiply_add(t.ctx, alpha, pa.data(), pb.data(), beta, pc.data()));
+    C.resize(A.size());
+#pragma omp parallel for schedule(dynamic)
+    for(size_t b = 0; b < A.size(); ++b)
+      {
+        if(A[b].h)
+          unpack_matrix(C[b], A[b].h, A[b].w, out2J[b].data());
+        else
+          C[b].resize(0, 0);
+      }
   }
 
   void solve_schur_complement_equation(std::vector<Matrix> &dx, Matrix &dy) override

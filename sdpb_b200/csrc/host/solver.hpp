@@ -41,6 +41,12 @@ struct Hot_Path
   // chol(Q) of the preceding initialize_schur_complement_solver, which stay with the
   // implementation: dx[j] (P_j x 1) and dy (N x 1) hold r_x, r_y on entry, the solution on exit.
   virtual void solve_schur_complement_equation(std::vector<Matrix> &dx, Matrix &dy) = 0;
+  // scale_multiply_add.cxx:4-16: C_b = alpha A_b B_b + beta C_b on the PSD-shaped
+  // blocks; alpha is 1 or -1, beta 0 or 1 at every call site (step.cxx:137,
+  // compute_search_direction.cxx:28,60).
+  virtual void scale_multiply_add(int alpha, const std::vector<Matrix> &A, const std::vector<Matrix> &B, int beta,
+                                  std::vector<Matrix> &C)
+    = 0;
   virtual std::string name() const = 0;
 };
 
@@ -574,13 +580,11 @@ public:
         trsm_lower_transpose_left(L[b], Z[b]);
       }
   }
-  // C = alpha A B + beta C per block (scale_multiply_add.cxx)
-  static void scale_multiply_add(const BigFloat &alpha, const std::vector<Matrix> &A,
-                                 const std::vector<Matrix> &B, const BigFloat &beta, std::vector<Matrix> &C)
+  // C = alpha A B + beta C per block (scale_multiply_add.cxx): through the hot-path seam
+  void scale_multiply_add(int alpha, const std::vector<Matrix> &A, const std::vector<Matrix> &B, int beta,
+                          std::vector<Matrix> &C) const
   {
-#pragma omp parallel for schedule(dynamic)
-    for(size_t b = 0; b < A.size(); ++b)
-      gemm_nn(alpha, A[b], B[b], beta, C[b]);
+    hot.scale_multiply_add(alpha, A, B, beta, C);
   }
 
   // compute_schur_RHS.cxx:21-86: dx = -dual_residues - Tr(A_p Z)
@@ -637,14 +641,14 @@ public:
   {
     std::vector<Matrix> R(minus_XY);
     if(is_corrector_phase)
-      scale_multiply_add(BigFloat(-1), dX, dY, BigFloat(1), R);
+      scale_multiply_add(-1, dX, dY, 1, R);
     const BigFloat bm = beta * mu;
     for(auto &blk : R)
       for(int i = 0; i < blk.h; ++i)
         blk(i, i) += bm;
     // Z = Symmetrize(X^{-1} (PrimalResidues Y - R))
     std::vector<Matrix> Z(X);
-    scale_multiply_add(BigFloat(1), primal_residues, Y, BigFloat(0), Z);
+    scale_multiply_add(1, primal_residues, Y, 0, Z);
     for(size_t b = 0; b < Z.size(); ++b)
       for(size_t i = 0; i < Z[b].a.size(); ++i)
         Z[b].a[i] -= R[b].a[i];
@@ -660,7 +664,7 @@ public:
       for(size_t i = 0; i < dX[b].a.size(); ++i)
         dX[b].a[i] += primal_residues[b].a[i];
     // dY = Symmetrize(X^{-1} (R - dX Y))
-    scale_multiply_add(BigFloat(1), dX, Y, BigFloat(0), dY);
+    scale_multiply_add(1, dX, Y, 0, dY);
     for(size_t b = 0; b < dY.size(); ++b)
       for(size_t i = 0; i < dY[b].a.size(); ++i)
         dY[b].a[i] -= R[b].a[i];
@@ -732,7 +736,7 @@ public:
       hot_path_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
       std::vector<Matrix> minus_XY(X);
-      scale_multiply_add(BigFloat(-1), X, Y, BigFloat(0), minus_XY);
+      scale_multiply_add(-1, X, Y, 0, minus_XY);
       {
         BigFloat tr;
         for(const auto &blk : minus_XY)

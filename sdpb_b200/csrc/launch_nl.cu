@@ -382,6 +382,22 @@ template <int NL> struct Launch
       }
     return solve_tri<true>(c, "solve_LinvT_dx", c->d_solveS, J, c->max_P, c->sol_x);
   }
+  // scale_multiply_add.cxx:4-16 on the resident operands smaA, smaB (-> smaT) and smaC
+  static int scale_multiply_add(sdpb_b200_ctx *c, int alpha, int beta)
+  {
+    c->cur = c->stream;
+    if(int rc = gemm(c, "gemm_scale_multiply_add", c->d_gemmSMA, c->n_gemm, c->tiles_SMA))
+      return rc;
+    const long count = (long)(c->wXY / Fmt<NL>::ES);
+    if(count == 0)
+      return 0;
+    c->kt_begin("sma_epilogue_kernel");
+    sma_epilogue_kernel<NL><<<(unsigned)std::min<long>((count + 127) / 128, 148 * 16), 128, 0, c->cur>>>(
+      c->smaT, c->smaC, count, alpha, beta);
+    c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
   static int scalar(sdpb_b200_ctx *c, int op, int k, long count,
                     const limb_t *a, const limb_t *b, limb_t *r)
   {
@@ -409,4 +425,5 @@ template <int NL> struct Launch
 #define SDPB_CAT(a, b) SDPB_CAT2(a, b)
 extern "C" __attribute__((visibility("default"))) const LaunchTable
   SDPB_CAT(sdpb_b200_launch_nl, SDPB_NL) = {&Launch<SDPB_NL>::cholesky, &Launch<SDPB_NL>::pairings,
-     &Launch<SDPB_NL>::schur_and_Q, &Launch<SDPB_NL>::schur_solve, &Launch<SDPB_NL>::scalar};
+     &Launch<SDPB_NL>::schur_and_Q, &Launch<SDPB_NL>::schur_solve, &Launch<SDPB_NL>::scale_multiply_add,
+     &Launch<SDPB_NL>::scalar};

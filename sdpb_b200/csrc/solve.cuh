@@ -165,4 +165,28 @@ solve_gemv_kernel(const BandDesc *bands, int N, const limb_t *dy, limb_t *x)
       stg_reg<NL>(xe, v);
     }
 }
+
+// epilogue of scale_multiply_add (scale_multiply_add.cxx:4-16): T holds sum_l A(i,l) B(l,j);
+// C = alpha T (beta == 0) or C = C + alpha T (beta == 1: `C *= 1` is the identity in mpf)
+template <int NL>
+__global__ void __launch_bounds__(128)
+sma_epilogue_kernel(const limb_t *T, limb_t *C, long count, int alpha, int beta)
+{
+  for(long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long)gridDim.x * blockDim.x)
+    {
+      Reg<NL> t;
+      ldg_reg<NL>(t, T + e * Fmt<NL>::ES);
+      if(alpha < 0)
+        t.sign = -t.sign; // mpf_mul by -1: exact
+      if(beta)
+        {
+          Reg<NL> c;
+          ldg_reg<NL>(c, C + e * Fmt<NL>::ES);
+          c = add_nl<NL>(c, t);
+          stg_reg<NL>(C + e * Fmt<NL>::ES, c);
+        }
+      else
+        stg_reg<NL>(C + e * Fmt<NL>::ES, t);
+    }
+}
 } // namespace sdpb_b200

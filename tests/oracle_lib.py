@@ -45,6 +45,8 @@ def load_oracle():
     lib.oracle_last_error.argtypes = [ctypes.c_void_p]
     lib.oracle_solve_schur_complement_equation.restype = ctypes.c_int
     lib.oracle_solve_schur_complement_equation.argtypes = [ctypes.c_void_p, u64pp, u64p]
+    lib.oracle_scale_multiply_add.restype = ctypes.c_int
+    lib.oracle_scale_multiply_add.argtypes = [ctypes.c_void_p, ctypes.c_int, u64pp, u64pp, ctypes.c_int, u64pp]
     lib.oracle_shard_solve_stage1.restype = ctypes.c_int
     lib.oracle_shard_solve_stage1.argtypes = [ctypes.c_void_p, u64pp, u64p]
     lib.oracle_shard_solve_stage2.restype = ctypes.c_int
@@ -130,6 +132,10 @@ class OracleContext(StepContextBase):
 
     def solve_schur_complement_equation(self, dx, dy):
         self._check(self.lib.oracle_solve_schur_complement_equation(self.handle, ptr_array(dx), _ptr(dy)))
+
+    def scale_multiply_add(self, alpha, A, B, beta, C):
+        self._check(self.lib.oracle_scale_multiply_add(self.handle, int(alpha), ptr_array(A), ptr_array(B),
+                                                       int(beta), ptr_array(C)))
 
     # sharded Schur solve: stage 1 local (dx in place, partial rows out), the caller gathers the
     # rows in global block order, stage 2 finishes dy (replicated) and the local dx

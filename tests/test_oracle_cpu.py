@@ -117,3 +117,21 @@ def test_schur_solve_needs_the_factors():
     with pytest.raises(ol.OracleError) as ei:
         ctx.solve_schur_complement_equation(dx, dy)
     assert ei.value.code == 5
+
+
+def test_scale_multiply_add_in_double():
+    """scale_multiply_add.cxx:4-16: C = alpha A B + beta C per block, the three (alpha, beta) the
+    reference uses (step.cxx:137, compute_search_direction.cxx:28,60)."""
+    prec, shapes, N = 256, [(1, 5), (2, 3), (1, 1)], 2
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=13)
+    ctx = ol.OracleContext(prec, shapes, N)
+    for alpha, beta in ((-1, 0), (1, 0), (-1, 1)):
+        C = [a.copy() for a in sdp.Y]
+        ctx.scale_multiply_add(alpha, sdp.X, sdp.Y, beta, C)
+        for a, b, c0, c in zip(sdp.X, sdp.Y, sdp.Y, C):
+            if a.size == 0:
+                continue
+            want = alpha * (_to_float(prec, a) @ _to_float(prec, b)) + beta * _to_float(prec, c0)
+            assert np.allclose(_to_float(prec, c), want, rtol=1e-12, atol=1e-12)
+    with pytest.raises(ol.OracleError):
+        ctx.scale_multiply_add(2, sdp.X, sdp.Y, 0, [a.copy() for a in sdp.Y])

@@ -175,6 +175,26 @@ def test_schur_solve_after_resident_step_and_state():
     ctx.close()
 
 
+@pytest.mark.parametrize("prec,shapes,N", [CASES[0], CASES[2], CASES[3], (1536, [(1, 9), (2, 4)], 6),
+                                           (768, [(2, 40), (1, 40), (1, 33), (2, 17)], 3)])
+def test_scale_multiply_add_bit_exact(prec, shapes, N):
+    """scale_multiply_add.cxx:4-16 for the reference's three (alpha, beta):
+    -X Y (step.cxx:137), (1, 0) and (-1, 1) (compute_search_direction.cxx:28,60)."""
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=6)
+    ref = ol.OracleContext(prec, shapes, N)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    for alpha, beta in ((-1, 0), (1, 0), (-1, 1)):
+        want = [a.copy() for a in sdp.X]
+        ref.scale_multiply_add(alpha, sdp.X, sdp.Y, beta, want)
+        got = [a.copy() for a in sdp.X]
+        ctx.scale_multiply_add(alpha, sdp.X, sdp.Y, beta, got)
+        ol.assert_same(f"C (alpha={alpha}, beta={beta})", got, want)
+    with pytest.raises(sdpb_b200.SdpbB200Error) as ei:
+        ctx.scale_multiply_add(3, sdp.X, sdp.Y, 0, got)
+    assert ei.value.code == 1
+    ctx.close()
+
+
 def test_block_groups_on_side_streams_bit_exact(monkeypatch):
     """The S chain cut into interleaved groups of blocks on separate streams
     (SDPB_B200_GROUPS) must not change a bit."""
