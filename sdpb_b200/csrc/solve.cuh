@@ -167,7 +167,11 @@ solve_gemv_kernel(const BandDesc *bands, int N, const limb_t *dy, limb_t *x)
 }
 
 // epilogue of scale_multiply_add (scale_multiply_add.cxx:4-16): T holds sum_l A(i,l) B(l,j);
-// C = alpha T (beta == 0) or C = C + alpha T (beta == 1: `C *= 1` is the identity in mpf)
+// C = alpha T (beta == 0) or C = (C * 1) + alpha T.  Multiplying by +-1 is NOT the identity in
+// mpf: mpf_mul reads only the top `prec` limbs of its operands (mpf/mul.c), so a full
+// (prec+1)-limb value loses its lowest limb -- in the top-aligned element format: the lowest
+// stored limb becomes zero (nothing else changes: 1 has one limb, the product's top limb is
+// zero and is stripped again).
 template <int NL>
 __global__ void __launch_bounds__(128)
 sma_epilogue_kernel(const limb_t *T, limb_t *C, long count, int alpha, int beta)
@@ -176,12 +180,14 @@ sma_epilogue_kernel(const limb_t *T, limb_t *C, long count, int alpha, int beta)
     {
       Reg<NL> t;
       ldg_reg<NL>(t, T + e * Fmt<NL>::ES);
+      t.w[0] = t.w[1] = 0; // acc *= alpha
       if(alpha < 0)
-        t.sign = -t.sign; // mpf_mul by -1: exact
+        t.sign = -t.sign;
       if(beta)
         {
           Reg<NL> c;
           ldg_reg<NL>(c, C + e * Fmt<NL>::ES);
+          c.w[0] = c.w[1] = 0; // C *= beta
           c = add_nl<NL>(c, t);
           stg_reg<NL>(C + e * Fmt<NL>::ES, c);
         }

@@ -64,3 +64,16 @@ def test_create_fails_loudly_without_gpu():
 def test_unsupported_precision_is_rejected():
     with pytest.raises(sdpb_b200.SdpbB200Error):
         sdpb_b200.SchurContext(64 * 40, [(1, 4)], 3)
+
+
+def test_makefile_tracks_every_kernel_header():
+    """A header missing from HDRS means `make` keeps stale objects after an edit (the GPU box then
+    runs old kernels): every .h / .cuh next to the kernels must be a dependency."""
+    import os
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sdpb_b200", "csrc")
+    text = open(os.path.join(csrc, "Makefile")).read()
+    hdrs = re.search(r"^HDRS := (.*)$", text, re.M).group(1).split()
+    for name in os.listdir(csrc):
+        if name.endswith((".h", ".cuh")):
+            assert name in hdrs, f"{name} is not listed in HDRS of sdpb_b200/csrc/Makefile"
