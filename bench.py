@@ -306,6 +306,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # NCCL writes its version / debug lines to stdout by default; stdout carries the ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
 
     from sdpb_b200.synthetic import WORKLOADS, SyntheticSDP
