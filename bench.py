@@ -308,6 +308,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     # NCCL writes its version / debug lines to stdout by default; stdout carries the ONE JSON line
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # the VERSION banner is a bare printf to stdout
     warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
 
     from sdpb_b200.synthetic import WORKLOADS, SyntheticSDP

@@ -18,6 +18,7 @@ WORKLOADS = {
     "c3": (768, [(2, 40)] * 150 + [(1, 40)] * 450, 300),
     "c3-sample": (768, [(2, 40)] * 6 + [(1, 40)] * 18, 300),
     "c4": (960, [(2, 40)] * 250 + [(1, 40)] * 750, 1000),
+    "c4-sample": (960, [(2, 40)] * 6 + [(1, 40)] * 18, 1000),
     "tiny": (768, [(1, 6), (2, 4), (1, 9)], 5),
 }
 
