@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <set>
 
 #ifndef SDPB_NL
@@ -325,7 +326,13 @@ template <int NL> struct Launch
     if(count == 0 || maxp == 0)
       return 0;
     const size_t need = (size_t)maxp * TileGeom<NL>::SW * 4;
-    const int use_smem = need <= 200 * 1024;
+    // the unknowns stay in shared memory up to 200 KB (1422 rows at 768 bits); larger systems
+    // substitute on the global vector itself.  SDPB_B200_SOLVE_SMEM_MAX (bytes) moves the limit
+    // (tests force the global path with 0).
+    size_t smem_max = 200 * 1024;
+    if(const char *env = getenv("SDPB_B200_SOLVE_SMEM_MAX"))
+      smem_max = std::min<size_t>(smem_max, (size_t)atol(env));
+    const int use_smem = need <= smem_max;
     const size_t smem = use_smem ? need : 0;
     CUDA_TRY(c, cudaFuncSetAttribute(solve_tri_kernel<NL, BACK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)std::max<size_t>(smem, 1024)));

@@ -153,6 +153,31 @@ def test_schur_solve_bit_exact(prec, shapes, N):
     ctx.close()
 
 
+def test_schur_solve_wide_Q_and_global_memory_path(monkeypatch):
+    """N = 530 > 512 threads: several rows per thread in the substitution with chol(Q) (the c4 shape
+    class, N = 1000); then the same solve with the unknowns in global instead of shared memory
+    (what systems beyond 200 KB of unknowns use)."""
+    prec, shapes, N = 448, [(2, 40)] * 5, 530
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=9)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    sdp.run_step(ref)
+    want_dx, want_dy = sdp.solve_rhs()
+    ref.solve_schur_complement_equation(want_dx, want_dy)
+    for smem_max in (None, "0"):
+        if smem_max is not None:
+            monkeypatch.setenv("SDPB_B200_SOLVE_SMEM_MAX", smem_max)
+        ctx = sdpb_b200.SchurContext(prec, shapes, N)
+        sdp.upload(ctx)
+        ctx.upload_XY(sdp.X, sdp.Y)
+        ctx.schur_step_resident()
+        dx, dy = sdp.solve_rhs()
+        ctx.solve_schur_complement_equation(dx, dy)
+        ol.assert_same(f"dy (smem_max={smem_max})", dy, want_dy)
+        ol.assert_same(f"dx (smem_max={smem_max})", dx, want_dx)
+        ctx.close()
+
+
 def test_schur_solve_after_resident_step_and_state():
     prec, shapes, N = 768, [(1, 12), (2, 7)], 9
     sdp = ol.SyntheticSDP(prec, shapes, N, seed=4)
