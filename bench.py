@@ -405,11 +405,15 @@ def main():
     Qh = pool.empty((N, N, ctx.ew))
     h2d = sum(x.nbytes for x in Xh) + sum(x.nbytes for x in Yh)
     d2h = sum(x.nbytes for x in Xc + Yc + Lh + Ph) + Qh.nbytes
-    ctx.schur_step(Xh, Yh, Xc, Yc, None, None, Lh, Ph, Qh)
+    # the block-pointer tables are built once, as a C++ caller's would be (ctypes needs ~5 us per
+    # pointer: 6000 pointers per call would put 20-30 ms of Python into the timed region)
+    from sdpb_b200.capi import ptr_array
+    pX, pY, pXc, pYc, pL, pP = (ptr_array(v) for v in (Xh, Yh, Xc, Yc, Lh, Ph))
+    ctx.schur_step(pX, pY, pXc, pYc, None, None, pL, pP, Qh)
     barrier()
     e0 = time.perf_counter()
     for _ in range(a.steps):
-        ctx.schur_step(Xh, Yh, Xc, Yc, None, None, Lh, Ph, Qh)
+        ctx.schur_step(pX, pY, pXc, pYc, None, None, pL, pP, Qh)
     barrier()
     e2e_s = (time.perf_counter() - e0) / a.steps
 
@@ -421,38 +425,41 @@ def main():
     dxh = pool.slab([x.shape for x in rx])
     dyh = pool.empty(ry.shape)
     solve_dev, solve_k = [], {}
+    pdx = ptr_array(dxh)
+    solve_wall = []
     for it in range(2 + a.steps):
-        for dst, src in zip(dxh + [dyh], rx + [ry]):
+        for dst, src in zip(dxh + [dyh], rx + [ry]):  # fresh right-hand sides (untimed)
             dst[...] = src
-        if it == 2:
-            barrier()
-            s0 = time.perf_counter()
-        ctx.solve_schur_complement_equation(dxh, dyh)
+        barrier()
+        s0 = time.perf_counter()
+        ctx.solve_schur_complement_equation(pdx, dyh)  # synchronous: returns with dx, dy on the host
         if it >= 2:
+            solve_wall.append(time.perf_counter() - s0)
             solve_dev.append(ctx.last_solve_ms())
             for name, ms in ctx.kernel_timings():
                 solve_k.setdefault(name, []).append(ms)
     barrier()
-    solve_api_s = (time.perf_counter() - s0) / a.steps
+    solve_api_s = float(np.mean(solve_wall))
     solve_dev_ms = float(np.mean(solve_dev))
     # the step as the host solver now calls it: P stays in HBM
     d2h_np = d2h - sum(x.nbytes for x in Ph)
-    ctx.schur_step(Xh, Yh, Xc, Yc, None, None, Lh, None, Qh)
+    ctx.schur_step(pX, pY, pXc, pYc, None, None, pL, None, Qh)
     barrier()
     e0 = time.perf_counter()
     for _ in range(a.steps):
-        ctx.schur_step(Xh, Yh, Xc, Yc, None, None, Lh, None, Qh)
+        ctx.schur_step(pX, pY, pXc, pYc, None, None, pL, None, Qh)
     barrier()
     e2e_np_s = (time.perf_counter() - e0) / a.steps
 
     # ---- scale_multiply_add (-X Y and the other block GEMMs of step()) ----
     Ch = pool.slab([x.shape for x in sdp.X])
     sma_k = {}
-    ctx.scale_multiply_add(-1, Xh, Yh, 0, Ch)
+    pC = ptr_array(Ch)
+    ctx.scale_multiply_add(-1, pX, pY, 0, pC)
     barrier()
     s0 = time.perf_counter()
     for _ in range(a.steps):
-        ctx.scale_multiply_add(-1, Xh, Yh, 0, Ch)
+        ctx.scale_multiply_add(-1, pX, pY, 0, pC)
         for name, ms in ctx.kernel_timings():
             sma_k.setdefault(name, []).append(ms)
     barrier()

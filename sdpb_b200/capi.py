@@ -133,7 +133,11 @@ def _ptr(a):
 
 
 def ptr_array(arrays):
-    """C array of uint64_t* from a list of numpy arrays (None / empty -> NULL)."""
+    """C array of uint64_t* from a list of numpy arrays (None / empty -> NULL).  A ctypes array
+    built by an earlier call passes through: marshalling 1200 block pointers costs milliseconds of
+    Python, which a caller that reuses its buffers (every solver iteration does) pays once."""
+    if isinstance(arrays, ctypes.Array):
+        return arrays
     arr = (u64p * max(1, len(arrays)))()
     for i, a in enumerate(arrays):
         arr[i] = _ptr(a) if a is not None else None
