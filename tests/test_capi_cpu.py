@@ -77,3 +77,15 @@ def test_makefile_tracks_every_kernel_header():
     for name in os.listdir(csrc):
         if name.endswith((".h", ".cuh")):
             assert name in hdrs, f"{name} is not listed in HDRS of sdpb_b200/csrc/Makefile"
+
+
+def test_ptr_array_passes_prebuilt_tables_through():
+    import ctypes
+    import numpy as np
+    from sdpb_b200.capi import ptr_array
+    blocks = [np.zeros((2, 2, 4), dtype=np.uint64), np.zeros((0, 0, 4), dtype=np.uint64), None]
+    table = ptr_array(blocks)
+    assert isinstance(table, ctypes.Array) and len(table) == 3
+    assert ctypes.addressof(table[0].contents) == blocks[0].ctypes.data
+    assert not table[1] and not table[2]          # empty / missing block -> NULL
+    assert ptr_array(table) is table              # built once, reused by every later call
