@@ -5,6 +5,7 @@
 #include "hotpath_core.hpp"
 
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <memory>
 
@@ -561,6 +562,196 @@ int oracle_num_threads()
 #endif
 }
 } // extern "C"
+
+
+// ---- the reference's own formulation of the exact syrk (row a9), on the CPU ----------
+// bigint_syrk/Readme.md:27-55: residues of trunc(P') modulo primes chosen as in
+// fmpz/Fmpz_Comb.cxx:22-68 (adapted there from FLINT's fmpz_mat/mul_blas.c), stored as symmetric
+// doubles (fmpz_mul_blas_util.hxx:16-25), one fp64 dsyrk per prime (the caller supplies the BLAS:
+// tests/oracle_lib.py uses scipy's OpenBLAS), CRT back to the integer.  Used (a) to check that the
+// direct mpz sum above and the CRT route give the same Q' bit for bit, as the reference's own
+// calculate_matrix_square.test.cxx:44-86 does against fmpz_mat_mul_blas, and (b) as the second CPU
+// syrk variant SURVEY §8d asks bench.py to time.
+extern "C" {
+unsigned long __gmpz_fdiv_ui(mpz_srcptr, unsigned long);
+void __gmpz_mul_ui(mpz_ptr, mpz_srcptr, unsigned long);
+void __gmpz_addmul_ui(mpz_ptr, mpz_srcptr, unsigned long);
+void __gmpz_divexact_ui(mpz_ptr, mpz_srcptr, unsigned long);
+void __gmpz_mod(mpz_ptr, mpz_srcptr, mpz_srcptr);
+void __gmpz_sub(mpz_ptr, mpz_srcptr, mpz_srcptr);
+int __gmpz_cmp(mpz_srcptr, mpz_srcptr);
+void __gmpz_mul_2exp(mpz_ptr, mpz_srcptr, unsigned long);
+}
+struct syrk_crt_state
+{
+  int prec, N;
+  long K;
+  std::vector<__mpz_struct> z; // trunc(P'), column-major K x N
+};
+static bool small_prime(uint64_t n)
+{
+  if(n < 2 || n % 2 == 0)
+    return n == 2;
+  for(uint64_t d = 3; d * d <= n; d += 2)
+    if(n % d == 0)
+      return false;
+  return true;
+}
+static uint64_t inv_mod(uint64_t a, uint64_t p) // p prime
+{
+  int64_t t = 0, nt = 1, r = (int64_t)p, nr = (int64_t)(a % p);
+  while(nr)
+    {
+      const int64_t q = r / nr;
+      int64_t x = t - q * nt;
+      t = nt;
+      nt = x;
+      x = r - q * nr;
+      r = nr;
+      nr = x;
+    }
+  return (uint64_t)(t < 0 ? t + (int64_t)p : t);
+}
+extern "C" {
+// Fmpz_Comb.cxx:22-68 with bits = 2 prec + bits(k) + 1 (calculate_output_bits :14-18)
+int oracle_syrk_crt_primes(int prec_bits, long k, uint64_t *primes, int max)
+{
+  int kbits = 0;
+  for(long t = k; t; t >>= 1)
+    ++kbits;
+  const long bits = 2L * prec_bits + kbits + 1;
+  uint64_t root = (uint64_t)std::sqrt((double)(((uint64_t)1 << 53) - 1) / (double)k);
+  while(root * root > (((uint64_t)1 << 53) - 1) / (uint64_t)k)
+    --root;
+  uint64_t p = 2 + 2 * root;
+  if(bits > 200 && p > 1664544)
+    p = 1664544;
+  mpz_t prod;
+  mpz_init(prod);
+  mpz_set_ui(prod, 1);
+  int n = 0;
+  do
+    {
+      do
+        {
+          if(p < 1000)
+            {
+              mpz_clear(prod);
+              return 0;
+            }
+          --p;
+        }
+      while(!small_prime(p));
+      if(n >= max)
+        {
+          mpz_clear(prod);
+          return -1;
+        }
+      primes[n++] = p;
+      __gmpz_mul_ui(prod, prod, p);
+    }
+  while((long)mpz_sizeinbase(prod, 2) <= bits);
+  mpz_clear(prod);
+  return n;
+}
+// BigFloat -> integer once (fmpz_BigFloat_convert.hxx:13: truncation toward zero)
+syrk_crt_state *oracle_syrk_crt_begin(int prec, long K, int N, const uint64_t *Pn)
+{
+  sdpb_host::set_precision(prec);
+  auto *st = new syrk_crt_state{prec, N, K, {}};
+  st->z.resize((size_t)K * N);
+  const int ew = elem_words();
+#pragma omp parallel
+  {
+    BigFloat x;
+#pragma omp for schedule(static)
+    for(long e = 0; e < K * (long)N; ++e)
+      {
+        sdpb_host::unpack(x, Pn + (size_t)e * ew);
+        mpz_init(&st->z[e]);
+        mpz_set_f(&st->z[e], x.v);
+      }
+  }
+  return st;
+}
+// residues modulo p as symmetric doubles in (-p/2, p/2], column-major K x N
+int oracle_syrk_crt_residues(const syrk_crt_state *st, uint64_t p, double *out)
+{
+#pragma omp parallel for schedule(static)
+  for(long e = 0; e < st->K * (long)st->N; ++e)
+    {
+      const uint64_t r = __gmpz_fdiv_ui(&st->z[e], p);
+      out[e] = r > p / 2 ? (double)((int64_t)r - (int64_t)p) : (double)r;
+    }
+  return 0;
+}
+void oracle_syrk_crt_end(syrk_crt_state *st)
+{
+  for(auto &q : st->z)
+    mpz_clear(&q);
+  delete st;
+}
+// res[k][i + j*N] = (dsyrk result for prime k)(i,j) mod p_k in [0, p_k), upper triangle used;
+// Q'(i,j) = symmetric lift of the CRT value, converted like fmpz_get_mpf (:9)
+int oracle_syrk_crt_reconstruct(int prec, int N, int np, const uint64_t *primes, const int64_t *res,
+                                uint64_t *Qout)
+{
+  sdpb_host::set_precision(prec);
+  mpz_t M, half;
+  mpz_init(M);
+  mpz_init(half);
+  mpz_set_ui(M, 1);
+  for(int k = 0; k < np; ++k)
+    __gmpz_mul_ui(M, M, primes[k]);
+  std::vector<__mpz_struct> coef(np);
+  for(int k = 0; k < np; ++k)
+    {
+      mpz_init(&coef[k]);
+      __gmpz_divexact_ui(&coef[k], M, primes[k]);
+      const uint64_t inv = inv_mod(__gmpz_fdiv_ui(&coef[k], primes[k]), primes[k]);
+      __gmpz_mul_ui(&coef[k], &coef[k], inv);
+    }
+  Matrix Q(N, N);
+#pragma omp parallel
+  {
+    mpz_t x, twice;
+    mpz_init(x);
+    mpz_init(twice);
+#pragma omp for schedule(dynamic, 1)
+    for(int j = 0; j < N; ++j)
+      for(int i = 0; i <= j; ++i)
+        {
+          mpz_set_ui(x, 0);
+          for(int k = 0; k < np; ++k)
+            __gmpz_addmul_ui(x, &coef[k], (unsigned long)res[(size_t)k * N * N + (size_t)j * N + i]);
+          __gmpz_mod(x, x, M);
+          __gmpz_mul_2exp(twice, x, 1);
+          if(__gmpz_cmp(twice, M) > 0)
+            __gmpz_sub(x, x, M);
+          mpf_set_z(Q(i, j).v, x);
+        }
+    mpz_clear(x);
+    mpz_clear(twice);
+  }
+  pack_out(Q, Qout);
+  for(auto &q : coef)
+    mpz_clear(&q);
+  mpz_clear(M);
+  mpz_clear(half);
+  return 0;
+}
+// the direct mpz sum on the same input, for comparison and timing
+int oracle_syrk_direct(int prec, long K, int N, const uint64_t *Pn, uint64_t *Qout)
+{
+  sdpb_host::set_precision(prec);
+  std::vector<Matrix> blocks(1);
+  unpack_matrix(blocks[0], (int)K, N, Pn);
+  Matrix Q;
+  exact_syrk_upper(blocks, N, Q);
+  pack_out(Q, Qout);
+  return 0;
+}
+}
 
 // ---- deterministic synthetic inputs (seeded) ---------------
 static inline uint64_t splitmix64(uint64_t &s)

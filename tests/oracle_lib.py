@@ -45,6 +45,16 @@ def load_oracle():
     lib.oracle_last_error.argtypes = [ctypes.c_void_p]
     lib.oracle_solve_schur_complement_equation.restype = ctypes.c_int
     lib.oracle_solve_schur_complement_equation.argtypes = [ctypes.c_void_p, u64pp, u64p]
+    lib.oracle_syrk_crt_primes.restype = ctypes.c_int
+    lib.oracle_syrk_crt_primes.argtypes = [ctypes.c_int, ctypes.c_long, u64p, ctypes.c_int]
+    lib.oracle_syrk_crt_begin.restype = ctypes.c_void_p
+    lib.oracle_syrk_crt_begin.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, u64p]
+    lib.oracle_syrk_crt_residues.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double)]
+    lib.oracle_syrk_crt_end.restype = None
+    lib.oracle_syrk_crt_end.argtypes = [ctypes.c_void_p]
+    lib.oracle_syrk_crt_reconstruct.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, u64p,
+                                                ctypes.POINTER(ctypes.c_int64), u64p]
+    lib.oracle_syrk_direct.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_int, u64p, u64p]
     lib.oracle_scale_multiply_add.restype = ctypes.c_int
     lib.oracle_scale_multiply_add.argtypes = [ctypes.c_void_p, ctypes.c_int, u64pp, u64pp, ctypes.c_int, u64pp]
     lib.oracle_shard_solve_stage1.restype = ctypes.c_int
@@ -214,6 +224,62 @@ def scalar_op(prec, op, a, b, k=0):
     r = np.zeros_like(a)
     load_oracle().oracle_scalar_op(prec, op, k, a.size // elem_words(prec), _ptr(a), _ptr(b), _ptr(r))
     return r
+
+
+def syrk_crt_primes(prec, k):
+    buf = np.zeros(4096, dtype=np.uint64)
+    n = load_oracle().oracle_syrk_crt_primes(prec, k, _ptr(buf), len(buf))
+    assert n > 0
+    return buf[:n].copy()
+
+
+def syrk_direct(prec, Pn):
+    """Q' = trunc(P')^T trunc(P') by the direct mpz sum; Pn: (N, K, ew) packed, integer-valued."""
+    N, K, _ = Pn.shape
+    Q = np.zeros((N, N, elem_words(prec)), dtype=np.uint64)
+    load_oracle().oracle_syrk_direct(prec, K, N, _ptr(Pn), _ptr(Q))
+    return Q
+
+
+def syrk_crt_blas(prec, Pn, timings=None):
+    """The same Q' the way the reference computes it (bigint_syrk/Readme.md:27-55): residues modulo
+    the primes of Fmpz_Comb.cxx:22-68 as symmetric doubles, one fp64 dsyrk per prime (scipy's
+    OpenBLAS), CRT.  timings: optional dict receiving seconds per phase."""
+    import time
+    from scipy.linalg.blas import dsyrk
+    lib = load_oracle()
+    N, K, _ = Pn.shape
+    primes = syrk_crt_primes(prec, K)
+    t0 = time.perf_counter()
+    st = lib.oracle_syrk_crt_begin(prec, K, N, _ptr(Pn))
+    t_conv = time.perf_counter() - t0
+    res = np.zeros((len(primes), N, N), dtype=np.int64)
+    A = np.zeros((K, N), dtype=np.float64, order="F")
+    t_res = t_blas = 0.0
+    for k, p in enumerate(primes):
+        t0 = time.perf_counter()
+        lib.oracle_syrk_crt_residues(st, int(p), A.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        t1 = time.perf_counter()
+        C = dsyrk(1.0, A, trans=1, lower=0)             # upper triangle of A^T A, exact in fp64
+        res[k] = np.mod(C.T.astype(np.int64), int(p))   # res[k][j][i] = C(i, j): column-major (i + j N)
+        t2 = time.perf_counter()
+        t_res += t1 - t0
+        t_blas += t2 - t1
+    lib.oracle_syrk_crt_end(st)
+    t0 = time.perf_counter()
+    Q = np.zeros((N, N, elem_words(prec)), dtype=np.uint64)
+    lib.oracle_syrk_crt_reconstruct(prec, N, len(primes), _ptr(primes),
+                                    res.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _ptr(Q))
+    t_crt = time.perf_counter() - t0
+    if timings is not None:
+        timings.update(convert=t_conv, residues=t_res, dsyrk_and_mod=t_blas, crt=t_crt, primes=len(primes))
+    return Q
+
+
+def integer_valued_matrix(prec, K, N, seed):
+    """K x N with entries uniform in (-2^prec, 2^prec): what normalize_and_shift hands to the syrk."""
+    a = random_matrix(prec, K, N, seed)
+    return scalar_op(prec, 5, a.reshape(-1, elem_words(prec)), a.reshape(-1, elem_words(prec)), prec).reshape(a.shape)
 
 
 class SyntheticSDP:

@@ -135,3 +135,22 @@ def test_scale_multiply_add_in_double():
             assert np.allclose(_to_float(prec, c), want, rtol=1e-12, atol=1e-12)
     with pytest.raises(ol.OracleError):
         ctx.scale_multiply_add(2, sdp.X, sdp.Y, 0, [a.copy() for a in sdp.Y])
+
+
+@pytest.mark.parametrize("prec,K,N", [(256, 37, 5), (768, 90, 11)])
+def test_exact_syrk_direct_equals_the_references_crt_blas_route(prec, K, N):
+    """Row a9: the oracle's direct mpz sum and the reference's formulation (residues modulo the
+    primes of Fmpz_Comb.cxx:22-68, fp64 dsyrk per prime, CRT) give the same Q' to the last limb --
+    the check the reference's calculate_matrix_square.test.cxx:44-86 makes against fmpz_mat_mul_blas."""
+    Pn = ol.integer_valued_matrix(prec, K, N, seed=17)
+    primes = ol.syrk_crt_primes(prec, K)
+    assert all(int(p) < 1664544 for p in primes) and len(set(primes.tolist())) == len(primes)
+    prod = 1
+    for p in primes:
+        prod *= int(p)
+    assert prod.bit_length() > 2 * prec + K.bit_length() + 1
+    want = ol.syrk_direct(prec, Pn)
+    got = ol.syrk_crt_blas(prec, Pn)
+    iu = np.triu_indices(N)
+    assert np.array_equal(got[iu[1], iu[0]], want[iu[1], iu[0]])  # (col j, row i), i <= j
+    assert want[iu[1], iu[0]].any()
