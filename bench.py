@@ -245,7 +245,7 @@ def cpu_sample(workload, steps, warmup):
     # both CPU formulations of the exact syrk on the sample's K x N integer matrix -- the
     # direct mpz sum the restatement uses, and the reference's own route (residues modulo the primes
     # of Fmpz_Comb.cxx, one fp64 dsyrk per prime through scipy's OpenBLAS, CRT); they agree bit for bit
-    # (tests/test_oracle_cpu.py).  `value` uses the reference's route, `value_direct_syrk` the other.
+    # (tests/test_oracle_cpu.py).
     try:
         K = sum(s.schur_size for s in ref.shapes)
         Pn = ol.integer_valued_matrix(sprec, K, sN, 5)
@@ -259,10 +259,13 @@ def cpu_sample(workload, steps, warmup):
         out["syrk_variants"] = {"rows": K, "direct_mpz_s": t_direct, "crt_dsyrk_s": t_crt,
                                 "crt_phases_s": {k: round(v, 4) for k, v in tm.items() if k != "primes"},
                                 "primes": tm.get("primes")}
-        # the headline CPU number uses the reference's own formulation of the syrk
+        # the headline CPU number takes whichever formulation is faster on this host (on the B200
+        # box's 16 cores the direct sum wins, 0.54 s against 0.88 s for the sample; on 8 slower
+        # cores the CRT route does)
         out["value_direct_syrk"] = full
-        out["value"] = full + (t_crt - t_direct) * scale
-        out["sample"] += "; exact syrk timed as the reference formulates it (CRT + fp64 dsyrk), see syrk_variants"
+        out["value_crt_syrk"] = full + (t_crt - t_direct) * scale
+        out["value"] = min(out["value_direct_syrk"], out["value_crt_syrk"])
+        out["sample"] += "; exact syrk: the faster of the direct mpz sum and the reference's CRT + fp64 dsyrk route (syrk_variants)"
     except Exception as e:  # scipy's BLAS missing: the direct variant stands alone
         out["syrk_variants"] = {"unavailable": str(e)}
     return out, wall
