@@ -14,12 +14,17 @@ are the column-norm partials and the exact-syrk residues.
 `value`  = seconds per step with X and Y already resident in HBM, timed with
            CUDA events on the library's stream, max over ranks.
 `e2e`    = the same step through the reference-facing call sdpb_b200_schur_step
-           with HOST buffers: X, Y uploaded from pinned memory and every output the
-           reference's downstream code consumes (X/Y Cholesky factors, L_j,
-           L_j^-1 B_j, Cholesky(Q)) copied back, inside the timed region.
+           with HOST buffers: X, Y uploaded from pinned memory and, inside the
+           timed region, everything the host side of the solver consumes copied
+           back: the Cholesky factors of X and Y and the diagonals of L_j and
+           chol(Q) (update_cond_numbers).  L_j, L_j^-1 B_j and chol(Q) themselves
+           stay in HBM, where sdpb_b200_solve_schur_complement_equation uses them
+           (`e2e_with_two_solves` adds the two solves of an iteration;
+           `e2e_all_outputs` is the old contract: every output copied back).
 `--impl reference` times the CPU restatement of the reference algorithm
-(oracle/, libgmp mpf, OpenMP on all host cores) on a bounded sample of the same
-workload and extrapolates per stage; the reference binary itself cannot be
+(oracle/, libgmp mpf, OpenMP on every host core the process may run on) on the
+FULL block list of the same workload -- under weak scaling the blocks of all N
+ranks -- and reports the measured seconds; the reference binary itself cannot be
 built in this image.
 """
 import argparse
@@ -88,20 +93,6 @@ def algorithmic_bytes(kernel, prec, shapes, N):
     E = 8 * (L + 1) + 8
     tot = 0
     K = sum(s.schur_size for s in shapes)
-    if kernel in ("trsm_Linv_B/gemm", "trsm_Linv_B/diag"):
-        # per level It (16 rows): gemm reads the L strip (ni x I0), the solved rows above
-        # (I0 x N) and reads + writes the tile row (ni x N); diag reads the 16x16 diagonal
-        # tile and reads + writes the tile row
-        for s in shapes:
-            P = s.schur_size
-            for I0 in range(0, P, 16):
-                ni = min(16, P - I0)
-                if kernel.endswith("gemm"):
-                    if I0:
-                        tot += (ni * I0 + I0 * N + 2 * ni * N) * E
-                else:
-                    tot += (ni * (ni + 1) // 2 + 2 * ni * N) * E
-        return tot
     for s in shapes:
         P, mn = s.schur_size, s.pairing_size
         for p in (0, 1):
@@ -138,13 +129,6 @@ def algorithmic_bytes(kernel, prec, shapes, N):
 def limb_macs(kernel, shapes, N):
     """mpf multiply-accumulates of one launch (element updates)."""
     tot = 0
-    if kernel in ("trsm_Linv_B/gemm", "trsm_Linv_B/diag"):
-        for s in shapes:
-            P = s.schur_size
-            for I0 in range(0, P, 16):
-                ni = min(16, P - I0)
-                tot += (ni * I0 * N) if kernel.endswith("gemm") else (ni * (ni - 1) // 2 * N)
-        return tot
     for s in shapes:
         P, mn = s.schur_size, s.pairing_size
         for p in (0, 1):
@@ -209,73 +193,93 @@ def peaks():
 
 
 # ------------------------------------------------------------------ CPU arm
-def cpu_sample(workload, steps, warmup):
-    """Time the CPU restatement (oracle/) on the bounded sample of `workload`
-    and extrapolate per stage to the full block list."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def oracle_all_cores():
+    """The oracle library with its OpenMP team set to every core this process may use (torchrun
+    exports OMP_NUM_THREADS=1 to its workers, which would silently make the baseline single-core)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
+    lib = ol.load_oracle()
+    lib.oracle_set_num_threads(host_cores())
+    return ol, lib.oracle_num_threads()
+
+
+def cpu_full(workload, steps, warmup, world=1, budget_s=None):
+    """Seconds per step of the CPU restatement (oracle/) on the FULL block list of `workload`,
+    measured.  Under weak scaling the N-GPU job owns `world` copies of the block list; every stage
+    but Cholesky(Q) is linear in the blocks (the exact syrk accumulates over the stacked rows), so
+    the CPU processes them as `world` passes over one copy.  The number of timed steps is cut to
+    what fits `budget_s` (reported); if not even one full step fits, the bounded block sample is
+    timed instead and scaled, and the line says so."""
+    ol, cores = oracle_all_cores()
     from sdpb_b200.synthetic import WORKLOADS, SyntheticSDP
+    if budget_s is None:
+        budget_s = float(os.environ.get("SDPB_B200_CPU_BUDGET_S", "200"))
     prec, shapes, N = WORKLOADS[workload]
-    sname = workload + "-sample" if workload + "-sample" in WORKLOADS else workload
-    sprec, sshapes, sN = WORKLOADS[sname]
-    assert (sprec, sN) == (prec, N)
-    scale = len(shapes) / len(sshapes)
-    sdp = SyntheticSDP(sprec, sshapes, sN, seed=1)
-    ref = ol.OracleContext(sprec, sshapes, sN)
-    sdp.upload(ref)
-    L, P, Q = ref.alloc_schur_outputs()
-    per_step = []
-    for it in range(warmup + steps):
+    out = {"unit": "s/step", "cores": cores, "kind": "port"}
+    # a short sample first: warms the library up and predicts the cost of the full step
+    sname = workload + "-sample" if workload + "-sample" in WORKLOADS else None
+    est = None
+    if sname:
+        sprec, sshapes, sN = WORKLOADS[sname]
+        sdp = SyntheticSDP(sprec, sshapes, sN, seed=1)
+        ref = ol.OracleContext(sprec, sshapes, sN)
+        sdp.upload(ref)
         t0 = time.perf_counter()
-        ref.schur_step(sdp.X, sdp.Y, None, None, None, None, L, P, Q)
-        wall = time.perf_counter() - t0
+        ref.schur_step(sdp.X, sdp.Y)
+        t_sample = time.perf_counter() - t0
         ms = ref.stage_ms()
-        # stages 0-5 scale with the block count; Cholesky(Q) (7) does not
-        blocks_ms = ms[0] + ms[1] + ms[2] + ms[3] + ms[5]
-        full = (blocks_ms * scale + ms[7]) / 1e3
-        if it >= warmup:
-            per_step.append((wall, full))
-        log(f"[cpu] sample step {it}: wall {wall:.2f}s stages(ms) {[round(x) for x in ms]} -> full-size estimate {full:.1f}s")
-    cores = ol.load_oracle().oracle_num_threads()
-    full = float(np.mean([f for _, f in per_step]))
-    wall = float(np.mean([w for w, _ in per_step]))
-    sample = (f"{len(sshapes)} of {len(shapes)} blocks (same m,n mix), N={N}, prec={prec}; per-block stages scaled x{scale:g}, "
-              f"Cholesky(Q) counted once; {wall:.2f}s of CPU per sample step")
-    out = {"value": full, "unit": "s/step", "cores": cores, "kind": "port", "sample": sample}
-    # SURVEY 8d: both CPU formulations of the exact syrk on the sample's K x N integer matrix -- the
-    # direct mpz sum the restatement uses, and the reference's own route (residues modulo the primes
-    # of Fmpz_Comb.cxx, one fp64 dsyrk per prime through scipy's OpenBLAS, CRT); they agree bit for bit
-    # (tests/test_oracle_cpu.py).
-    try:
-        K = sum(s.schur_size for s in ref.shapes)
-        Pn = ol.integer_valued_matrix(sprec, K, sN, 5)
+        scale = len(shapes) / len(sshapes)
+        est = ((ms[0] + ms[1] + ms[2] + ms[3] + ms[5]) * scale * world + ms[7]) / 1e3
+        out["sample_estimate"] = {"value": est, "sample_wall_s": t_sample,
+                                  "what": f"{len(sshapes)} of {len(shapes)} blocks, per-block stages scaled "
+                                          f"x{scale * world:g}, Cholesky(Q) counted once"}
+        log(f"[cpu] {sname}: {t_sample:.2f}s -> full-size estimate {est:.1f}s per step on {cores} cores")
+        ref.close()
+        if est > budget_s:
+            out.update(value=est, extrapolated=True, steps=0, warmup=0,
+                       sample=f"EXTRAPOLATED from {out['sample_estimate']['what']}: one full step would take "
+                              f"{est:.0f}s > budget {budget_s:.0f}s")
+            return out
+    sdp = SyntheticSDP(prec, shapes, N, seed=1)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    sdp.B = None
+    walls = []
+    t_start = time.perf_counter()
+    n_warm = 0
+    if warmup > 0 and est is not None and 2 * est < budget_s:
+        ref.schur_step(sdp.X, sdp.Y)
+        n_warm = 1
+    for it in range(max(1, steps)):
         t0 = time.perf_counter()
-        ol.syrk_direct(sprec, Pn)
-        t_direct = time.perf_counter() - t0
-        tm = {}
-        t0 = time.perf_counter()
-        ol.syrk_crt_blas(sprec, Pn, tm)
-        t_crt = time.perf_counter() - t0
-        out["syrk_variants"] = {"rows": K, "direct_mpz_s": t_direct, "crt_dsyrk_s": t_crt,
-                                "crt_phases_s": {k: round(v, 4) for k, v in tm.items() if k != "primes"},
-                                "primes": tm.get("primes")}
-        # the headline CPU number takes whichever formulation is faster on this host (on the B200
-        # box's 16 cores the direct sum wins, 0.54 s against 0.88 s for the sample; on 8 slower
-        # cores the CRT route does)
-        out["value_direct_syrk"] = full
-        out["value_crt_syrk"] = full + (t_crt - t_direct) * scale
-        out["value"] = min(out["value_direct_syrk"], out["value_crt_syrk"])
-        out["sample"] += "; exact syrk: the faster of the direct mpz sum and the reference's CRT + fp64 dsyrk route (syrk_variants)"
-    except Exception as e:  # scipy's BLAS missing: the direct variant stands alone
-        out["syrk_variants"] = {"unavailable": str(e)}
-    return out, wall
+        for _ in range(world):
+            ref.schur_step(sdp.X, sdp.Y)
+        walls.append(time.perf_counter() - t0)
+        log(f"[cpu] full step {it}: {walls[-1]:.2f}s ({world} pass(es) over {len(shapes)} blocks) "
+            f"stages(ms) of the last pass {[round(x) for x in ref.stage_ms()]}")
+        used = time.perf_counter() - t_start
+        if used + walls[-1] > budget_s:
+            break
+    ref.close()
+    out.update(value=float(np.mean(walls)), extrapolated=False, steps=len(walls), warmup=n_warm,
+               sample=f"FULL block list, measured: {len(shapes)} blocks x {world} rank(s), N={N}, prec={prec}; "
+                      f"{len(walls)} timed step(s) of {float(np.mean(walls)):.1f}s after {n_warm} warm-up(s); "
+                      f"exact syrk = direct mpz sum (the faster CPU formulation on this class of host, "
+                      f"profiles/cpu_syrk_variants_r01_box.json)")
+    return out
 
 
 def cpu_solve_sample(workload):
     """solve_schur_complement_equation by the CPU restatement on the block sample (after one
     sample step), per-block work scaled to the full block list."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as ol
+    ol, _ = oracle_all_cores()
     from sdpb_b200.synthetic import WORKLOADS, SyntheticSDP, solve_rhs
     prec, shapes, N = WORKLOADS[workload]
     sname = workload + "-sample" if workload + "-sample" in WORKLOADS else workload
@@ -299,8 +303,7 @@ def cpu_solve_sample(workload):
 
 def cpu_sma_sample(workload):
     """scale_multiply_add(-1, X, Y, 0, C) by the CPU restatement on the block sample, scaled."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as ol
+    ol, _ = oracle_all_cores()
     from sdpb_b200.synthetic import WORKLOADS, SyntheticSDP
     prec, shapes, N = WORKLOADS[workload]
     sname = workload + "-sample" if workload + "-sample" in WORKLOADS else workload
@@ -319,6 +322,27 @@ def cpu_sma_sample(workload):
             "kind": "port", "sample": f"{len(sshapes)} of {len(shapes)} blocks, {best * 1e3:.1f} ms, scaled x{scale:g}"}
 
 
+def bind_to_gpu_numa_node(device):
+    """Run this process (and therefore place its pinned staging buffers, first-touch) on the CPUs
+    NVML reports as local to `device`.  Eight ranks that all stage through socket 0 share one
+    memory controller and the inter-socket link; this is what a launcher's --bind-to does for the
+    reference's MPI ranks."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": len(cpus), "first": min(cpus), "last": max(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:80]}
+    return {"unavailable": "empty affinity mask"}
+
+
 # --------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -328,6 +352,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("SDPB_B200_WORKLOAD", "c3"))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-all-outputs", action="store_true",
+                    help="skip the extra e2e pass that copies every output (L_j, L_j^-1 B_j, chol(Q)) back")
     ap.add_argument("--kernels", action="store_true", help="print the per-kernel timeline to stderr")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -349,15 +375,18 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        cb, wall = cpu_sample(a.workload, a.steps, a.warmup)
+        cb = cpu_full(a.workload, a.steps, a.warmup, world=max(1, a.gpus))
         line = {"impl": "reference", "metric": "sec_per_newton_step_hot_path", "value": cb["value"], "unit": "s/step",
-                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["value"] * 1e3,
+                "n_gpus": a.gpus, "steps": cb["steps"], "warmup": cb["warmup"],
+                "steps_requested": a.steps, "warmup_requested": a.warmup,
+                "ms_per_step": cb["value"] * 1e3,
                 "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "mpf%d" % prec,
                 "data": "synthetic", "config": cfg, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "s/step", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
 
+    numa = bind_to_gpu_numa_node(local)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -427,26 +456,31 @@ def main():
         dst[...] = src
     Xc = pool.slab([x.shape for x in sdp.X])
     Yc = pool.slab([x.shape for x in sdp.X])
-    Lh = pool.slab([(s.schur_size, s.schur_size, ctx.ew) for s in ctx.shapes])
-    Ph = pool.slab([(N, s.schur_size, ctx.ew) for s in ctx.shapes])
-    Qh = pool.empty((N, N, ctx.ew))
+    Ktot = sum(s.schur_size for s in ctx.shapes)
+    Sdiag, Qdiag = pool.empty((Ktot, ctx.ew)), pool.empty((N, ctx.ew))
     h2d = sum(x.nbytes for x in Xh) + sum(x.nbytes for x in Yh)
-    d2h = sum(x.nbytes for x in Xc + Yc + Lh + Ph) + Qh.nbytes
+    d2h = sum(x.nbytes for x in Xc + Yc) + Sdiag.nbytes + Qdiag.nbytes
     # the block-pointer tables are built once, as a C++ caller's would be (ctypes needs ~5 us per
     # pointer: 6000 pointers per call would put 20-30 ms of Python into the timed region)
     from sdpb_b200.capi import ptr_array
-    pX, pY, pXc, pYc, pL, pP = (ptr_array(v) for v in (Xh, Yh, Xc, Yc, Lh, Ph))
-    ctx.schur_step(pX, pY, pXc, pYc, None, None, pL, pP, Qh)
+    pX, pY, pXc, pYc = (ptr_array(v) for v in (Xh, Yh, Xc, Yc))
+
+    def e2e_step():
+        # L_j, L_j^-1 B_j and chol(Q) stay in HBM for the Schur solves; the host gets the factors of
+        # X and Y (step_length, cholesky_solve) and the diagonals update_cond_numbers reads
+        ctx.schur_step(pX, pY, pXc, pYc, None, None, None, None, None)
+        ctx.cholesky_diagonals(None, None, Sdiag, Qdiag)
+
+    e2e_step()
     barrier()
     e0 = time.perf_counter()
     for _ in range(a.steps):
-        ctx.schur_step(pX, pY, pXc, pYc, None, None, pL, pP, Qh)
+        e2e_step()
     barrier()
     e2e_s = (time.perf_counter() - e0) / a.steps
 
     # ---- solve_schur_complement_equation on the resident factors ----
-    # (called twice per Newton iteration: predictor and corrector).  With the solves on the
-    # device the step no longer has to bring L_j^-1 B_j (P x N elements) back to the host.
+    # (called twice per Newton iteration: predictor and corrector)
     from sdpb_b200.synthetic import solve_rhs
     rx, ry = solve_rhs(prec, ctx.shapes, N, seed=7 + rank)
     dxh = pool.slab([x.shape for x in rx])
@@ -468,15 +502,22 @@ def main():
     barrier()
     solve_api_s = float(np.mean(solve_wall))
     solve_dev_ms = float(np.mean(solve_dev))
-    # the step as the host solver now calls it: P stays in HBM
-    d2h_np = d2h - sum(x.nbytes for x in Ph)
-    ctx.schur_step(pX, pY, pXc, pYc, None, None, pL, None, Qh)
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(a.steps):
-        ctx.schur_step(pX, pY, pXc, pYc, None, None, pL, None, Qh)
-    barrier()
-    e2e_np_s = (time.perf_counter() - e0) / a.steps
+
+    # ---- the round-1 contract for comparison: EVERY output copied back (L_j, L_j^-1 B_j, chol(Q)) ----
+    e2e_all_s, d2h_all = None, None
+    if not a.no_all_outputs:
+        Lh = pool.slab([(s.schur_size, s.schur_size, ctx.ew) for s in ctx.shapes])
+        Ph = pool.slab([(N, s.schur_size, ctx.ew) for s in ctx.shapes])
+        Qh = pool.empty((N, N, ctx.ew))
+        pL, pP = ptr_array(Lh), ptr_array(Ph)
+        d2h_all = sum(x.nbytes for x in Xc + Yc + Lh + Ph) + Qh.nbytes
+        ctx.schur_step(pX, pY, pXc, pYc, None, None, pL, pP, Qh)
+        barrier()
+        e0 = time.perf_counter()
+        for _ in range(a.steps):
+            ctx.schur_step(pX, pY, pXc, pYc, None, None, pL, pP, Qh)
+        barrier()
+        e2e_all_s = (time.perf_counter() - e0) / a.steps
 
     # ---- scale_multiply_add (-X Y and the other block GEMMs of step()) ----
     Ch = pool.slab([x.shape for x in sdp.X])
@@ -494,29 +535,45 @@ def main():
 
     # ---- max over ranks -------------------------------------------------
     if world > 1:
-        t = torch.tensor([ms_step, e2e_s, wall, solve_dev_ms, solve_api_s, e2e_np_s], device="cuda",
+        t = torch.tensor([ms_step, e2e_s, wall, solve_dev_ms, solve_api_s, e2e_all_s or 0.0], device="cuda",
                          dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, e2e_s, wall, solve_dev_ms, solve_api_s, e2e_np_s = [float(x) for x in t.tolist()]
+        ms_step, e2e_s, wall, solve_dev_ms, solve_api_s, e2e_all_max = [float(x) for x in t.tolist()]
+        if e2e_all_s is not None:
+            e2e_all_s = e2e_all_max
     if rank != 0:
         pool.close()
         ctx.close()
         dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel -------------------------------
+    # ---- roofline of the dominant stage ---------------------------------
+    # A stage of SURVEY 8d's table is one label of the timeline; a label with sub-launches
+    # ("trsm_Linv_B/gemm", "/diag": the levels of one batched triangular solve) is summed, and the
+    # algorithmic bytes are the table's figure for the WHOLE stage -- (P_j^2/2 + 2 P_j N) E for the
+    # solve, whatever the schedule re-reads -- divided by the launches it took.
     per_kernel = {k: (float(np.mean(v)) * len(v) / a.steps, len(v) // a.steps) for k, v in ktimes.items()}
-    dom = max(per_kernel, key=lambda k: per_kernel[k][0])
-    dom_ms, dom_launches = per_kernel[dom]
+    per_stage = {}
+    for k, (ms, n) in per_kernel.items():
+        g0 = per_stage.setdefault(k.split("/")[0], [0.0, 0])
+        g0[0] += ms
+        g0[1] += n
+    dom = max(per_stage, key=lambda k: per_stage[k][0])
+    dom_ms, dom_launches = per_stage[dom]
     peak, which = peaks()
-    abytes = algorithmic_bytes(dom, prec, ctx.shapes, N) / max(1, dom_launches)
+    stage_bytes = algorithmic_bytes(dom, prec, ctx.shapes, N)
+    abytes = stage_bytes / max(1, dom_launches)
     achieved = abytes / (dom_ms / max(1, dom_launches) * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": recorded_traffic(a.workload, dom), "peak_source": which,
-                "share_of_step": dom_ms / serial_step,
+    traffic = recorded_traffic(a.workload, dom)
+    roofline = {"bound": "hbm", "kernel": dom, "launches_per_step": dom_launches,
+                "algorithmic_bytes_per_step": stage_bytes,
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic / max(1, dom_launches) if traffic else None,
+                "peak_source": which, "share_of_step": dom_ms / serial_step, "ms_per_step": dom_ms,
                 "timed_in": "single-stream pass (%.1f ms/step); the headline value overlaps independent "
                             "chains on side streams" % serial_step,
-                "note": "multi-limb contraction: the INT32 multiply pipe binds, not HBM (DESIGN.md §4)"}
+                "note": "bytes = SURVEY 8d's figure for the stage; multi-limb contraction: the INT32 multiply "
+                        "pipe binds, not HBM (DESIGN.md §4), hence int_pipe beside it"}
     macs = limb_macs(dom, ctx.shapes, N)
     if macs:
         rate = macs * imad_per_mac(prec) / (dom_ms * 1e-3)
@@ -525,17 +582,14 @@ def main():
                                 "imad_wide_per_mac": imad_per_mac(prec),
                                 "peak_source": "measured, profiles/imad_rate4_r01.jsonl"}
     if a.kernels:
-        groups = {}
-        for k, (ms, n) in per_kernel.items():
-            if "/" in k:
-                g0 = groups.setdefault(k.split("/")[0], [0.0, 0])
-                g0[0] += ms
-                g0[1] += n
-        for k, (ms, n) in sorted(groups.items(), key=lambda kv: -kv[1][0]):
-            log(f"  [{k:22s}] {ms:10.3f} ms/step  x{n}  (sum of its launch kinds below)")
-        for k, (ms, n) in sorted(per_kernel.items(), key=lambda kv: -kv[1][0]):
+        for k, (ms, n) in sorted(per_stage.items(), key=lambda kv: -kv[1][0]):
             ab = algorithmic_bytes(k, prec, ctx.shapes, N)
-            log(f"  {k:24s} {ms:10.3f} ms/step  x{n}  {ab / 1e6:10.1f} MB  {ab / (ms * 1e-3) / 1e9 if ms else 0:8.1f} GB/s")
+            mc = limb_macs(k, ctx.shapes, N)
+            log(f"  [{k:22s}] {ms:10.3f} ms/step  x{n}  {ab / 1e6:10.1f} MB  {ab / (ms * 1e-3) / 1e9 if ms else 0:8.1f} GB/s"
+                f"  int_pipe {mc * imad_per_mac(prec) / (ms * 1e-3) / IMAD_WIDE_PER_S if ms else 0:6.3f}")
+        for k, (ms, n) in sorted(per_kernel.items(), key=lambda kv: -kv[1][0]):
+            if "/" in k:
+                log(f"      {k:24s} {ms:10.3f} ms/step  x{n}")
         log(f"  stages(ms) {[round(x, 3) for x in stages]}")
         for k, v in solve_k.items():
             log(f"  [solve] {k:24s} {float(np.mean(v)):10.3f} ms")
@@ -553,7 +607,7 @@ def main():
         except Exception as e:
             solve_cpu = {"value": None, "sample": f"unavailable: {e}"}
         try:
-            cpu, _ = cpu_sample(a.workload, 1, 0)
+            cpu = cpu_full(a.workload, 1, 0, world=1, budget_s=60.0)
         except Exception as e:  # the product arm does not depend on the oracle
             cpu = {"value": None, "unit": "s/step", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
 
@@ -576,10 +630,13 @@ def main():
                                    "kernels_ms": {k: round(float(np.mean(v)), 4) for k, v in sma_k.items()},
                                    "bytes_h2d": int(2 * sum(x.nbytes for x in Xh)),
                                    "bytes_d2h": int(sum(x.nbytes for x in Ch)), "cpu": sma_cpu},
-            "e2e_resident_factors": {"what": "sdpb_b200_schur_step without the D2H of L_j^-1 B_j, plus two solves "
-                                             "through the C-ABI with host buffers",
-                                     "value": e2e_np_s + 2 * solve_api_s, "unit": "s/iteration",
-                                     "step_s": e2e_np_s, "d2h_bytes_per_step": int(d2h_np)},
+            "e2e_with_two_solves": {"what": "one Newton iteration's device work through the C-ABI with host "
+                                            "buffers: the e2e step plus the predictor and corrector Schur solves",
+                                    "value": e2e_s + 2 * solve_api_s, "unit": "s/iteration"},
+            "e2e_all_outputs": {"what": "round-1 contract: sdpb_b200_schur_step with EVERY output copied back "
+                                        "(X/Y factors, L_j, L_j^-1 B_j, chol(Q))",
+                                "value": e2e_all_s, "unit": "s/step", "d2h_bytes_per_step": d2h_all},
+            "numa": numa,
             "stages_ms": {n: round(float(v), 4) for n, v in zip(
                 ["chol_XY", "pairings", "schur_assembly", "chol_S+trsm", "normalize", "exact_syrk", "restore",
                  "chol_Q", "step"], stages)}}

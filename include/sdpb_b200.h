@@ -124,7 +124,12 @@ int sdpb_b200_initialize_schur_complement_solver(
  *     dx_j <- L_j^-1 dx_j ;  dy <- dy - sum_j (L_j^-1 B_j)^T dx_j ;
  *     dy <- Q^-1 dy ;  dx_j <- dx_j + (L_j^-1 B_j) dy ;  dx_j <- L_j^-T dx_j .
  * dx[j]: P_j packed elements of local block j (in: r_x, out: dx); dy: N packed
- * elements (in: r_y, out: dy; the same on every rank).  With a communicator the
+ * elements (in: r_y, out: dy; the same on every rank).  On entry dy must be the FULLY
+ * REDUCED right-hand side: the reference stores one share per block (dy.blocks[j] =
+ * -B_j^T x_j, plus b on global block 0, compute_primal_residues_and_error_p_b_Bx.cxx) and
+ * lets solve_schur_complement_equation.cxx:26-60 sum the shares over blocks and ranks; a
+ * caller of this ABI forms r_y = sum_j dy.blocks[j] itself and all-reduces it over its ranks
+ * (INTEGRATION.md shows the shim) -- every rank passes the same N values.  With a communicator the
  * per-block partial sums of the dy update are exchanged over NCCL and added in
  * GLOBAL block order, so the result does not depend on the sharding.  Keeping
  * these solves next to the factors removes the largest device->host copy of a
@@ -144,6 +149,15 @@ int sdpb_b200_scale_multiply_add(sdpb_b200_ctx *ctx, int alpha,
                                  const uint64_t *const *A,
                                  const uint64_t *const *B, int beta,
                                  uint64_t *const *C);
+
+/* The diagonals of the Cholesky factors the last step left in HBM -- all that
+ * update_cond_numbers (run/step/step.cxx:187-189, sdpb_util/cholesky_condition_number.hxx:8-36)
+ * reads of them.  With solve_schur_complement_equation on the device, L_j (sum P_j^2 elements)
+ * and L_j^-1 B_j (P x N) never have to cross PCIe: a step's device->host traffic drops from
+ * gigabytes to these vectors.  X_diag / Y_diag: stacked over b = 2j + parity; S_diag: stacked
+ * over local blocks j (P elements in all); Q_diag: N elements.  Any of them may be NULL. */
+int sdpb_b200_cholesky_diagonals(sdpb_b200_ctx *ctx, uint64_t *X_diag, uint64_t *Y_diag,
+                                 uint64_t *S_diag, uint64_t *Q_diag);
 
 /* Device time of the last sdpb_b200_solve_schur_complement_equation, ms (CUDA events). */
 float sdpb_b200_last_solve_ms(const sdpb_b200_ctx *ctx);
@@ -192,6 +206,15 @@ int sdpb_b200_download(sdpb_b200_ctx *ctx, uint64_t *const *X_cholesky,
 int sdpb_b200_comm_get_unique_id(void *id);
 int sdpb_b200_comm_init(sdpb_b200_ctx *ctx, int rank, int world, const void *id,
                         int num_blocks_global, const int *global_block_index);
+
+/* The same sharding with every rank inside ONE process on ONE device: ctxs[r] (r < world) are
+ * contexts created on the same device, each holding rank r's blocks and driven by its own host
+ * thread; the exchanges go through device memory instead of NCCL.  This is how the sharded code
+ * path (global-order sums, exact residue sums, panel-distributed Cholesky(Q), sharded Schur solve)
+ * is exercised on a single GPU.  Collective calls block until all `world` contexts have made
+ * them.  Call once, from one thread, before the first step. */
+int sdpb_b200_comm_init_local(sdpb_b200_ctx *const *ctxs, int world, int num_blocks_global,
+                              const int *const *global_block_index);
 
 /* Scheduling of a step on the device.  level 1 (default): the independent chains
  * of the step -- chol(X) -> L_X^-1 V -> A_X_inv, Y V -> A_Y, chol(Y), and per block

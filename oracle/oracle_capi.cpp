@@ -561,6 +561,17 @@ int oracle_num_threads()
   return 1;
 #endif
 }
+// torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm of bench.py sets the thread
+// count explicitly so that the baseline always uses every host core it is allowed to run on
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if(n > 0)
+    omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 } // extern "C"
 
 

@@ -91,6 +91,11 @@ def load_library():
     lib.sdpb_b200_comm_init.restype = ctypes.c_int
     lib.sdpb_b200_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                         ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.sdpb_b200_comm_init_local.restype = ctypes.c_int
+    lib.sdpb_b200_comm_init_local.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
+                                              ctypes.POINTER(ctypes.POINTER(ctypes.c_int))]
+    lib.sdpb_b200_cholesky_diagonals.restype = ctypes.c_int
+    lib.sdpb_b200_cholesky_diagonals.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, u64p]
     lib.sdpb_b200_scalar_op.restype = ctypes.c_int
     lib.sdpb_b200_scalar_op.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_long, u64p, u64p, u64p]
     _lib = lib
@@ -335,6 +340,25 @@ class SchurContext(StepContextBase):
             t = torch.frombuffer(bytearray(self.comm_unique_id()), dtype=torch.uint8).to(dev)
         dist.broadcast(t, 0)
         self.comm_init(rank, world, bytes(t.cpu().numpy().tobytes()), num_blocks_global, global_block_index)
+
+    @staticmethod
+    def comm_init_local(contexts, num_blocks_global, global_block_index):
+        """All ranks inside this process on one device (sdpb_b200_comm_init_local): contexts[r]
+        holds the blocks global_block_index[r].  Collective calls must then be made from one host
+        thread per context at the same time."""
+        lib = load_library()
+        world = len(contexts)
+        handles = (ctypes.c_void_p * world)(*[c.handle for c in contexts])
+        keep = [(ctypes.c_int * max(1, len(ix)))(*ix) for ix in global_block_index]
+        idx = (ctypes.POINTER(ctypes.c_int) * world)(*[ctypes.cast(k, ctypes.POINTER(ctypes.c_int)) for k in keep])
+        rc = lib.sdpb_b200_comm_init_local(handles, world, num_blocks_global, idx)
+        if rc != 0:
+            raise SdpbB200Error(rc, lib.sdpb_b200_last_error(contexts[0].handle).decode())
+
+    def cholesky_diagonals(self, X_diag=None, Y_diag=None, S_diag=None, Q_diag=None):
+        """Diagonals of the resident Cholesky factors (all update_cond_numbers reads of them)."""
+        self._check(self.lib.sdpb_b200_cholesky_diagonals(self.handle, _ptr(X_diag), _ptr(Y_diag), _ptr(S_diag),
+                                                          _ptr(Q_diag)))
 
     def set_concurrency(self, level):
         """0: one stream, program order (per-kernel timing mode); 1: concurrent chains (default)."""

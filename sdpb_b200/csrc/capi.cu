@@ -5,14 +5,20 @@
 #include "nccl_dyn.h"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
+#include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
 static const LaunchTable *table_for(int nl);
 static bool nl_supported(int nl) { return table_for(nl) != nullptr; }
+static std::string g_module_error; // why the kernels of a precision could not be loaded (module_table)
 
 // ------------------------------------------------------------ CRT tables
 static uint64_t powmod(uint64_t a, uint64_t e, uint64_t m)
@@ -184,11 +190,9 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
   if(!out || num_blocks < 0 || N <= 0 || prec_bits < 64)
     return fail(SDPB_B200_ERR_ARG, "sdpb_b200_create: bad argument");
   const int nl = mpfx::stored_limbs(prec_bits);
-  if(!nl_supported(nl))
-    return fail(SDPB_B200_ERR_ARG,
-                "sdpb_b200_create: precision " + std::to_string(prec_bits)
-                  + " (NL=" + std::to_string(nl)
-                  + ") has no compiled kernels; see SDPB_FOR_EACH_NL");
+  if(nl < 3 || nl > 34)
+    return fail(SDPB_B200_ERR_ARG, "sdpb_b200_create: precision " + std::to_string(prec_bits)
+                                     + " is outside the supported range (64 ... 2048 bits)");
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if(ce != cudaSuccess || ndev == 0)
@@ -198,6 +202,13 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
                   + "); this library has no CPU fallback");
   if(device < 0 || device >= ndev)
     return fail(SDPB_B200_ERR_ARG, "sdpb_b200_create: bad device ordinal");
+  // only now: a precision whose kernels are not linked in is built on demand (module_table),
+  // which needs nvcc and minutes -- pointless on a host that cannot run them
+  if(!nl_supported(nl))
+    return fail(SDPB_B200_ERR_ARG,
+                "sdpb_b200_create: precision " + std::to_string(prec_bits)
+                  + " (NL=" + std::to_string(nl)
+                  + ") has no compiled kernels: " + g_module_error);
   auto *c = new sdpb_b200_ctx();
   c->prec = prec_bits;
   c->nl = nl;
@@ -489,6 +500,42 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
   TRY_C(upload(&c->d_bands, bd));
   TRY_C(cudaMalloc(&c->d_status, (size_t)(5 * num_blocks + 8) * sizeof(int)));
   TRY_C(cudaMalloc(&c->d_flags, 4 * sizeof(int)));
+  TRY_C(cudaMalloc(&c->d_fail, 4 * sizeof(int)));
+  TRY_C(cudaMemset(c->d_fail, 0, 4 * sizeof(int)));
+  {
+    // sdpb_b200_cholesky_diagonals: [X factors | Y factors | L_j | chol(Q)]
+    std::vector<DiagDesc> dd;
+    long off = 0;
+    c->diag_off[0] = off;
+    for(int q = 0; q < 2 * num_blocks; ++q)
+      {
+        const int s = c->g[q / 2].s[q % 2];
+        dd.push_back(DiagDesc{c->X + c->oXY[q], s, (long)s, off});
+        off += s;
+      }
+    c->diag_off[1] = off;
+    for(int q = 0; q < 2 * num_blocks; ++q)
+      {
+        const int s = c->g[q / 2].s[q % 2];
+        dd.push_back(DiagDesc{c->LY + c->oXY[q], s, (long)s, off});
+        off += s;
+      }
+    c->diag_off[2] = off;
+    for(int j = 0; j < num_blocks; ++j)
+      {
+        dd.push_back(DiagDesc{c->S + c->oS[j], c->g[j].P, (long)c->g[j].P, off});
+        off += c->g[j].P;
+      }
+    c->diag_off[3] = off;
+    dd.push_back(DiagDesc{c->Q, N, (long)N, off});
+    off += N;
+    c->diag_total = off;
+    TRY_C(upload(&c->d_diag, dd));
+    TRY_C(cudaMalloc(&c->diag_buf, (size_t)off * es * 8));
+  }
+  c->gidx.resize(num_blocks);
+  for(int j = 0; j < num_blocks; ++j)
+    c->gidx[j] = j;
   for(auto &e : c->ev)
     TRY_C(cudaEventCreate(&e));
   TRY_C(cudaStreamSynchronize(c->stream));
@@ -548,18 +595,18 @@ extern "C" int sdpb_b200_comm_get_unique_id(void *id)
   return 0;
 }
 
-extern "C" int sdpb_b200_comm_init(sdpb_b200_ctx *c, int rank, int world, const void *id,
-                                   int num_blocks_global, const int *global_block_index)
+// what both communicators share: the global block indices, the buffer of per-GLOBAL-block
+// partial rows, the panel buffer of the distributed Cholesky(Q)
+static int comm_common(sdpb_b200_ctx *c, int rank, int world, int num_blocks_global,
+                       const int *global_block_index)
 {
-  if(!c)
-    return SDPB_B200_ERR_ARG;
-  if(world < 1 || world > 16 || rank < 0 || rank >= world || !id || num_blocks_global < c->J
+  if(world < 1 || world > 16 || rank < 0 || rank >= world || num_blocks_global < c->J
      || (c->J && !global_block_index))
     {
       c->error = "sdpb_b200_comm_init: bad argument (1 <= world <= 16: u32 residue sums must not overflow)";
       return SDPB_B200_ERR_ARG;
     }
-  if(c->comm)
+  if(c->comm || c->local)
     {
       c->error = "sdpb_b200_comm_init: communicator already initialised";
       return SDPB_B200_ERR_STATE;
@@ -572,6 +619,7 @@ extern "C" int sdpb_b200_comm_init(sdpb_b200_ctx *c, int rank, int world, const 
           return SDPB_B200_ERR_ARG;
         }
       c->h_bands[j].gidx = global_block_index[j];
+      c->gidx[j] = global_block_index[j];
     }
   CUDA_TRY(c, cudaSetDevice(c->device));
   if(c->J)
@@ -586,13 +634,36 @@ extern "C" int sdpb_b200_comm_init(sdpb_b200_ctx *c, int rank, int world, const 
         CUDA_TRY(c, cudaMemcpy(c->d_bands_g[g], gb.data(), gb.size() * sizeof(BandDesc),
                                cudaMemcpyHostToDevice));
     }
+  // one row of partial sums per GLOBAL block: used whenever a communicator exists (also with
+  // world == 1, where the global indices need not be 0..J-1)
   CUDA_TRY(c, cudaMalloc(&c->part_global, (size_t)std::max(1, num_blocks_global) * c->N * c->es * 8));
+  CUDA_TRY(c, cudaMalloc(&c->qpanel, ((size_t)c->N * TS * c->es + 2) * 8 + (size_t)TS * (2 * c->nl + 8) * 4));
+  c->rank = rank;
+  c->world = world;
+  c->J_global = num_blocks_global;
+  if(const char *env = getenv("SDPB_B200_QDIST_MIN_N"))
+    c->qdist_min_N = atoi(env);
+  return 0;
+}
+
+extern "C" int sdpb_b200_comm_init(sdpb_b200_ctx *c, int rank, int world, const void *id,
+                                   int num_blocks_global, const int *global_block_index)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  if(!id)
+    {
+      c->error = "sdpb_b200_comm_init: null communicator id";
+      return SDPB_B200_ERR_ARG;
+    }
   NcclApi &api = nccl_api();
   if(!api.load())
     {
       c->error = api.error;
       return SDPB_B200_ERR_CUDA;
     }
+  if(int rc = comm_common(c, rank, world, num_blocks_global, global_block_index))
+    return rc;
   ncclUniqueId u;
   memcpy(u.internal, id, NCCL_UNIQUE_ID_BYTES);
   ncclComm_t comm;
@@ -603,14 +674,158 @@ extern "C" int sdpb_b200_comm_init(sdpb_b200_ctx *c, int rank, int world, const 
       return SDPB_B200_ERR_CUDA;
     }
   c->comm = comm;
-  c->rank = rank;
-  c->world = world;
-  c->J_global = num_blocks_global;
   c->allreduce = &nccl_allreduce;
   c->bcast = &nccl_bcast;
-  CUDA_TRY(c, cudaMalloc(&c->qpanel, ((size_t)c->N * TS * c->es + 2) * 8 + (size_t)TS * (2 * c->nl + 8) * 4));
-  if(const char *env = getenv("SDPB_B200_QDIST_MIN_N"))
-    c->qdist_min_N = atoi(env);
+  return 0;
+}
+
+// ---- in-process communicator ------------------------------------------------
+// Several contexts of ONE process on ONE device, each driven by its own host thread, exchange
+// through device memory: the sharded code path (global-order sums, exact residue sums, the
+// panel-distributed Cholesky(Q), the sharded Schur solve) then runs -- and can be checked against
+// the unsharded oracle -- on a single GPU.  Same hooks as the NCCL communicator.
+struct LocalGroup
+{
+  int world = 0;
+  std::mutex m;
+  std::condition_variable cv;
+  int arrived = 0;
+  long generation = 0;
+  bool broken = false;
+  std::vector<void *> ptr;
+  void *tmp = nullptr;
+  size_t tmp_bytes = 0;
+  ~LocalGroup() { cudaFree(tmp); }
+  // false: a peer did not arrive within the time limit (it failed before the exchange)
+  bool barrier()
+  {
+    std::unique_lock<std::mutex> lock(m);
+    if(broken)
+      return false;
+    const long gen = generation;
+    if(++arrived == world)
+      {
+        arrived = 0;
+        ++generation;
+        cv.notify_all();
+        return true;
+      }
+    if(!cv.wait_for(lock, std::chrono::seconds(120), [&] { return generation != gen || broken; }))
+      {
+        broken = true;
+        cv.notify_all();
+        return false;
+      }
+    return !broken;
+  }
+};
+struct LocalPtrs
+{
+  const void *p[16];
+};
+template <typename T> __global__ void local_sum_kernel(LocalPtrs src, int world, size_t count, T *out)
+{
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+    {
+      T s = 0;
+      for(int r = 0; r < world; ++r)
+        s += static_cast<const T *>(src.p[r])[i];
+      out[i] = s;
+    }
+}
+static int local_fail(sdpb_b200_ctx *c, const char *label)
+{
+  c->error = std::string("in-process communicator: a peer context did not reach ") + label;
+  return SDPB_B200_ERR_STATE;
+}
+static int local_allreduce(sdpb_b200_ctx *c, void *buf, size_t count, int is_u64, const char *label)
+{
+  LocalGroup &g = *c->local;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  {
+    std::lock_guard<std::mutex> lock(g.m);
+    g.ptr[c->rank] = buf;
+  }
+  if(!g.barrier())
+    return local_fail(c, label);
+  if(c->rank == 0)
+    {
+      const size_t bytes = count * (is_u64 ? 8 : 4);
+      if(g.tmp_bytes < bytes)
+        {
+          cudaFree(g.tmp);
+          g.tmp = nullptr;
+          g.tmp_bytes = 0;
+          CUDA_TRY(c, cudaMalloc(&g.tmp, bytes));
+          g.tmp_bytes = bytes;
+        }
+      LocalPtrs src{};
+      for(int r = 0; r < g.world; ++r)
+        src.p[r] = g.ptr[r];
+      const unsigned blocks = (unsigned)std::min<size_t>((count + 255) / 256, 148 * 8);
+      c->cur = c->stream;
+      c->kt_begin(label);
+      if(is_u64)
+        local_sum_kernel<uint64_t><<<blocks, 256, 0, c->stream>>>(src, g.world, count, (uint64_t *)g.tmp);
+      else
+        local_sum_kernel<uint32_t><<<blocks, 256, 0, c->stream>>>(src, g.world, count, (uint32_t *)g.tmp);
+      c->kt_end();
+      CUDA_TRY(c, cudaGetLastError());
+      for(int r = 0; r < g.world; ++r)
+        CUDA_TRY(c, cudaMemcpyAsync(g.ptr[r], g.tmp, bytes, cudaMemcpyDeviceToDevice, c->stream));
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+  if(!g.barrier())
+    return local_fail(c, label);
+  return 0;
+}
+static int local_bcast(sdpb_b200_ctx *c, void *buf, size_t bytes, int root, const char *label)
+{
+  LocalGroup &g = *c->local;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  {
+    std::lock_guard<std::mutex> lock(g.m);
+    g.ptr[c->rank] = buf;
+  }
+  if(!g.barrier())
+    return local_fail(c, label);
+  if(c->rank != root)
+    {
+      CUDA_TRY(c, cudaMemcpyAsync(buf, g.ptr[root], bytes, cudaMemcpyDeviceToDevice, c->stream));
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+  if(!g.barrier())
+    return local_fail(c, label);
+  return 0;
+}
+
+extern "C" int sdpb_b200_comm_init_local(sdpb_b200_ctx *const *ctxs, int world, int num_blocks_global,
+                                         const int *const *global_block_index)
+{
+  if(!ctxs || world < 1 || world > 16)
+    return SDPB_B200_ERR_ARG;
+  for(int r = 0; r < world; ++r)
+    if(!ctxs[r])
+      return SDPB_B200_ERR_ARG;
+  for(int r = 1; r < world; ++r)
+    if(ctxs[r]->device != ctxs[0]->device || ctxs[r]->prec != ctxs[0]->prec || ctxs[r]->N != ctxs[0]->N)
+      {
+        ctxs[0]->error = ctxs[r]->error
+          = "sdpb_b200_comm_init_local: the contexts must share device, precision and N";
+        return SDPB_B200_ERR_ARG;
+      }
+  auto group = std::make_shared<LocalGroup>();
+  group->world = world;
+  group->ptr.assign(world, nullptr);
+  for(int r = 0; r < world; ++r)
+    {
+      sdpb_b200_ctx *c = ctxs[r];
+      if(int rc = comm_common(c, r, world, num_blocks_global, global_block_index ? global_block_index[r] : nullptr))
+        return rc;
+      c->local = group;
+      c->allreduce = &local_allreduce;
+      c->bcast = &local_bcast;
+    }
   return 0;
 }
 
@@ -664,6 +879,9 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
   cudaFree(c->d_bands);
   cudaFree(c->d_status);
   cudaFree(c->d_flags);
+  cudaFree(c->d_fail);
+  cudaFree(c->d_diag);
+  cudaFree(c->diag_buf);
   for(int g = 0; g < sdpb_b200_ctx::MAXG; ++g)
     {
       cudaFree(c->d_potrfS_g[g]);
@@ -742,15 +960,79 @@ extern "C" int sdpb_b200_set_block(sdpb_b200_ctx *c, int j, const uint64_t *B,
   return 0;
 }
 
-static const LaunchTable *table_for(int nl)
+static const LaunchTable *builtin_table(int nl)
 {
   switch(nl)
     {
-#define F(n) case n: return &sdpb_b200_launch_nl##n;
+#define F(n) case n: return &sdpb_b200_launch_nl##n; // null if this build left the precision out (weak)
       SDPB_FOR_EACH_NL(F)
 #undef F
     default: return nullptr;
     }
+}
+// Any --precision (Environment.cxx:29-36 accepts any): the kernels of a stored-limb count that is
+// not linked into libsdpb_b200.so live in libsdpb_b200_nl<NL>.so next to it; when that file does
+// not exist yet it is built on the spot from csrc/launch_nl.cu (`make nl NL=<n>`, nvcc for
+// sm_100a, one to ten minutes depending on the precision) and kept for the next run.
+// SDPB_B200_JIT=0 forbids the build.
+static std::map<int, const LaunchTable *> g_modules;
+static std::mutex g_modules_guard;
+static const LaunchTable *module_table(int nl)
+{
+  std::lock_guard<std::mutex> lock(g_modules_guard);
+  auto it = g_modules.find(nl);
+  if(it != g_modules.end())
+    return it->second;
+  g_module_error.clear();
+  if(nl < 3 || nl > 34)
+    {
+      g_module_error = "stored limbs out of range (precisions from 64 to 2048 bits)";
+      return nullptr;
+    }
+  Dl_info info;
+  if(!dladdr((void *)&sdpb_b200_elem_words, &info) || !info.dli_fname)
+    {
+      g_module_error = "cannot locate libsdpb_b200.so on disk";
+      return nullptr;
+    }
+  std::string dir(info.dli_fname);
+  dir = dir.substr(0, dir.find_last_of('/') == std::string::npos ? 0 : dir.find_last_of('/'));
+  if(dir.empty())
+    dir = ".";
+  const std::string so = dir + "/libsdpb_b200_nl" + std::to_string(nl) + ".so";
+  void *h = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+  if(!h)
+    {
+      const char *jit = getenv("SDPB_B200_JIT");
+      if(jit && atoi(jit) == 0)
+        {
+          g_module_error = so + " is missing and SDPB_B200_JIT=0 forbids building it";
+          return nullptr;
+        }
+      const std::string log = so + ".log";
+      const std::string cmd = "make -C '" + dir + "/csrc' nl NL=" + std::to_string(nl) + " > '" + log + "' 2>&1";
+      fprintf(stderr, "sdpb_b200: building the kernels for %d stored limbs (%s)\n", nl, cmd.c_str());
+      const int rc = system(cmd.c_str());
+      h = rc == 0 ? dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL) : nullptr;
+      if(!h)
+        {
+          g_module_error = "building " + so + " failed (see " + log + ")";
+          return nullptr;
+        }
+    }
+  const std::string sym = "sdpb_b200_launch_nl" + std::to_string(nl);
+  const LaunchTable *t = static_cast<const LaunchTable *>(dlsym(h, sym.c_str()));
+  if(!t)
+    g_module_error = so + " lacks " + sym;
+  else
+    g_modules[nl] = t;
+  return t;
+}
+static const LaunchTable *table_for(int nl)
+{
+  if(const LaunchTable *t = builtin_table(nl))
+    return t;
+  return module_table(nl);
 }
 static int dispatch_cholesky(sdpb_b200_ctx *c, int which)
 {
@@ -795,6 +1077,28 @@ static int dispatch_scalar(sdpb_b200_ctx *c, int op, int k, long count,
   return table_for(c->nl)->scalar(c, op, k, count, a, b, r);
 }
 
+// block_timings (compute_Q.cxx:40,52 feed the reference's block_mapping on restart): the time of
+// cholesky_j + solve_j is one batched stage here, split over the blocks by the reference's own
+// cost model P^3/3 + P^2 N/2 (bigint_syrk/Readme.md:327-346); never less than 1 ms per block, so
+// that a later block_mapping does not see zero-cost blocks
+static void add_block_timings(const sdpb_b200_ctx *c, int32_t *block_timings_ms)
+{
+  if(!block_timings_ms)
+    return;
+  double tot = 0;
+  for(int j = 0; j < c->J; ++j)
+    {
+      const double P = c->g[j].P;
+      tot += P * P * P / 3 + P * P * c->N / 2;
+    }
+  for(int j = 0; j < c->J; ++j)
+    {
+      const double P = c->g[j].P;
+      const double share = c->stage_ms[3] * (P * P * P / 3 + P * P * c->N / 2) / (tot > 0 ? tot : 1);
+      block_timings_ms[j] += (int32_t)std::max(1L, std::lround(share));
+    }
+}
+
 // read status words; returns index of first failing matrix or -1
 static int first_bad(sdpb_b200_ctx *c, const int *d_status, int count, int *pivot)
 {
@@ -818,6 +1122,12 @@ static int copy_blocks_in(sdpb_b200_ctx *c, const uint64_t *const *A, limb_t *ds
 {
   const int n = 2 * c->J;
   auto words_of = [&](int q) { return (size_t)c->g[q / 2].s[q % 2] * c->g[q / 2].s[q % 2] * c->es; };
+  for(int q = 0; q < n; ++q) // checked before anything is enqueued
+    if(words_of(q) && (!A || !A[q]))
+      {
+        c->error = "null input block " + std::to_string(q);
+        return SDPB_B200_ERR_ARG;
+      }
   for(int q = 0; q < n;)
     {
       size_t words = words_of(q);
@@ -825,11 +1135,6 @@ static int copy_blocks_in(sdpb_b200_ctx *c, const uint64_t *const *A, limb_t *ds
         {
           ++q;
           continue;
-        }
-      if(!A || !A[q])
-        {
-          c->error = "null input block " + std::to_string(q);
-          return SDPB_B200_ERR_ARG;
         }
       // blocks the caller packed back to back (as the arena is): one DMA for the run
       int r = q + 1;
@@ -883,7 +1188,10 @@ extern "C" int sdpb_b200_cholesky_decomposition(sdpb_b200_ctx *c, int which,
     return rc;
   rc = dispatch_cholesky(c, which);
   if(rc)
-    return rc;
+    {
+      cudaStreamSynchronize(c->stream);
+      return rc;
+    }
   int pivot = 0;
   const int bad = first_bad(c, c->d_status + which * 2 * c->J, 2 * c->J, &pivot);
   if(bad == -2)
@@ -896,7 +1204,7 @@ extern "C" int sdpb_b200_cholesky_decomposition(sdpb_b200_ctx *c, int which,
       c->error = std::string("Error when computing Cholesky decomposition of "
                              "Block_Diagonal_Matrix ")
                  + (which == 0 ? "X" : "Y")
-                 + ", block index = " + std::to_string(bad / 2)
+                 + ", block index = " + std::to_string(c->gidx[bad / 2])
                  + ", parity = " + std::to_string(bad % 2)
                  + ": non-positive pivot " + std::to_string(pivot);
       return SDPB_B200_ERR_NOT_HPD;
@@ -933,7 +1241,10 @@ extern "C" int sdpb_b200_compute_bilinear_pairings(sdpb_b200_ctx *c,
   CUDA_TRY(c, cudaEventRecord(c->ev[0], c->stream));
   rc = dispatch_pairings(c);
   if(rc)
-    return rc;
+    {
+      cudaStreamSynchronize(c->stream);
+      return rc;
+    }
   CUDA_TRY(c, cudaEventRecord(c->ev[1], c->stream));
   std::vector<size_t> elems(2 * c->J);
   for(int q = 0; q < 2 * c->J; ++q)
@@ -977,7 +1288,7 @@ extern "C" int sdpb_b200_initialize_schur_complement_solver(
   if(bad >= 0)
     {
       c->error = "Error when computing Cholesky decomposition of block_"
-                 + std::to_string(bad) + ": non-positive pivot "
+                 + std::to_string(c->gidx[bad]) + ": non-positive pivot "
                  + std::to_string(pivot);
       return SDPB_B200_ERR_NOT_HPD;
     }
@@ -1005,6 +1316,18 @@ extern "C" int sdpb_b200_initialize_schur_complement_solver(
                  + std::to_string(qstat);
       return SDPB_B200_ERR_NOT_HPD;
     }
+  if(c->sharded())
+    {
+      int fail0 = 0;
+      CUDA_TRY(c, cudaMemcpyAsync(&fail0, c->d_fail, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      if(fail0 > 0)
+        {
+          c->error = "Schur-complement step failed on " + std::to_string(fail0)
+                     + " peer rank(s) (their last_error names the block); Q is not usable";
+          return SDPB_B200_ERR_NOT_HPD;
+        }
+    }
   c->have_factors = true;
   {
     std::vector<size_t> eS(c->J), eP(c->J);
@@ -1027,23 +1350,7 @@ extern "C" int sdpb_b200_initialize_schur_complement_solver(
   for(int k = 2; k < 8; ++k)
     cudaEventElapsedTime(&c->stage_ms[k], c->ev[k], c->ev[k + 1]);
   cudaEventElapsedTime(&c->stage_ms[8], c->ev[2], c->ev[8]);
-  if(block_timings_ms)
-    {
-      // cholesky_j + solve_j share of stage 3, split by the cost model
-      // P^3/3 + P^2 N / 2 (reference cost: bigint_syrk/Readme.md:327-346)
-      double tot = 0;
-      for(int j = 0; j < c->J; ++j)
-        {
-          const double P = c->g[j].P;
-          tot += P * P * P / 3 + P * P * c->N / 2;
-        }
-      for(int j = 0; j < c->J; ++j)
-        {
-          const double P = c->g[j].P;
-          block_timings_ms[j] += (int32_t)(
-            c->stage_ms[3] * (P * P * P / 3 + P * P * c->N / 2) / (tot > 0 ? tot : 1));
-        }
-    }
+  add_block_timings(c, block_timings_ms);
   return 0;
 }
 
@@ -1115,21 +1422,18 @@ extern "C" int sdpb_b200_scale_multiply_add(sdpb_b200_ctx *c, int alpha, const u
     }
   CUDA_TRY(c, cudaSetDevice(c->device));
   int rc = copy_blocks_in(c, A, c->smaA);
-  if(rc)
-    return rc;
-  rc = copy_blocks_in(c, B, c->smaB);
-  if(rc)
-    return rc;
-  if(beta)
-    {
-      rc = copy_blocks_in(c, C, c->smaC);
-      if(rc)
-        return rc;
-    }
+  if(!rc)
+    rc = copy_blocks_in(c, B, c->smaB);
+  if(!rc && beta)
+    rc = copy_blocks_in(c, C, c->smaC);
   c->kt_used = 0;
-  rc = table_for(c->nl)->scale_multiply_add(c, alpha, beta);
+  if(!rc)
+    rc = table_for(c->nl)->scale_multiply_add(c, alpha, beta);
   if(rc)
-    return rc;
+    {
+      cudaStreamSynchronize(c->stream); // earlier uploads may still read the caller's buffers
+      return rc;
+    }
   std::vector<size_t> elems(2 * c->J);
   for(int q = 0; q < 2 * c->J; ++q)
     elems[q] = (size_t)c->g[q / 2].s[q % 2] * c->g[q / 2].s[q % 2];
@@ -1234,10 +1538,12 @@ static int finish_step(sdpb_b200_ctx *c)
   cudaStream_t st = c->stream;
   const int J = c->J;
   std::vector<int> status(5 * J + 1);
-  int flags[4];
+  int flags[4], fail[4] = {0, 0, 0, 0};
   CUDA_TRY(c, cudaMemcpyAsync(status.data(), c->d_status, status.size() * sizeof(int),
                               cudaMemcpyDeviceToHost, st));
   CUDA_TRY(c, cudaMemcpyAsync(flags, c->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  if(c->sharded())
+    CUDA_TRY(c, cudaMemcpyAsync(fail, c->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(c, cudaStreamSynchronize(st));
   cudaEventElapsedTime(&c->stage_ms[0], c->ev[9], c->ev[0]);
   cudaEventElapsedTime(&c->stage_ms[1], c->ev[0], c->ev[1]);
@@ -1251,7 +1557,7 @@ static int finish_step(sdpb_b200_ctx *c)
           c->error = std::string("Error when computing Cholesky decomposition of "
                                  "Block_Diagonal_Matrix ")
                      + (which == 0 ? "X" : "Y")
-                     + ", block index = " + std::to_string(q / 2)
+                     + ", block index = " + std::to_string(c->gidx[q / 2])
                      + ", parity = " + std::to_string(q % 2)
                      + ": non-positive pivot "
                      + std::to_string(status[which * 2 * J + q]);
@@ -1261,7 +1567,7 @@ static int finish_step(sdpb_b200_ctx *c)
     if(status[4 * J + j] >= 0)
       {
         c->error = "Error when computing Cholesky decomposition of block_"
-                   + std::to_string(j) + ": non-positive pivot "
+                   + std::to_string(c->gidx[j]) + ": non-positive pivot "
                    + std::to_string(status[4 * J + j]);
         return SDPB_B200_ERR_NOT_HPD;
       }
@@ -1280,6 +1586,14 @@ static int finish_step(sdpb_b200_ctx *c)
     {
       c->error = "Error when computing Cholesky(Q): non-positive pivot "
                  + std::to_string(status[5 * J]);
+      return SDPB_B200_ERR_NOT_HPD;
+    }
+  if(fail[0] > 0)
+    {
+      // this rank's blocks are fine, but a peer's failed: its contributions to the column norms
+      // and to Q are garbage, so Q is on every rank
+      c->error = "Schur-complement step failed on " + std::to_string(fail[0])
+                 + " peer rank(s) (their last_error names the block); Q is not usable";
       return SDPB_B200_ERR_NOT_HPD;
     }
   c->have_X_cholesky = c->have_pairings = c->have_factors = true;
@@ -1352,6 +1666,15 @@ extern "C" int sdpb_b200_schur_step(
     return SDPB_B200_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->device));
   const int J = c->J;
+  // every pointer is checked before the first copy is enqueued: an error return must not leave
+  // DMA from the caller's buffers in flight
+  for(int which = 0; which < 2; ++which)
+    for(int q = 0; q < 2 * J; ++q)
+      if(c->g[q / 2].s[q % 2] && !(which == 0 ? X : Y)[q])
+        {
+          c->error = "null input block " + std::to_string(q);
+          return SDPB_B200_ERR_ARG;
+        }
   for(int which = 0; which < 2; ++which)
     {
       const uint64_t *const *A = which == 0 ? X : Y;
@@ -1363,11 +1686,6 @@ extern "C" int sdpb_b200_schur_step(
             {
               ++q;
               continue;
-            }
-          if(!A[q])
-            {
-              c->error = "null input block " + std::to_string(q);
-              return SDPB_B200_ERR_ARG;
             }
           size_t words = (size_t)s * s * c->es;
           int r = q + 1; // merge blocks the caller stored back to back
@@ -1385,7 +1703,10 @@ extern "C" int sdpb_b200_schur_step(
     }
   int rc = enqueue_step(c);
   if(rc)
-    return rc;
+    {
+      cudaStreamSynchronize(c->stream); // the uploads still read the caller's buffers
+      return rc;
+    }
   {
     std::vector<size_t> eXY(2 * J), eA(2 * J), eS(J), eP(J);
     for(int q = 0; q < 2 * J; ++q)
@@ -1440,21 +1761,41 @@ extern "C" int sdpb_b200_schur_step(
   CUDA_TRY(c, cudaStreamSynchronize(c->copy));
   if(rc)
     return rc;
-  if(block_timings_ms)
+  add_block_timings(c, block_timings_ms);
+  return 0;
+}
+
+// The diagonals of the Cholesky factors of the last step, which is all that
+// update_cond_numbers (step.cxx:187-189, sdpb_util/cholesky_condition_number.hxx:8-36) reads of
+// L_j and chol(Q): with the Schur solves on the device (solve_schur_complement_equation above)
+// neither L_j (sum P_j^2 elements) nor L_j^-1 B_j (P x N) has to cross PCIe any more.
+// X_diag / Y_diag: stacked over b = 2j + parity (sum of psd sizes); S_diag: stacked over j (P
+// elements); Q_diag: N elements.  Each may be NULL.
+extern "C" int sdpb_b200_cholesky_diagonals(sdpb_b200_ctx *c, uint64_t *X_diag, uint64_t *Y_diag,
+                                            uint64_t *S_diag, uint64_t *Q_diag)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  if(!c->have_factors)
     {
-      double tot = 0;
-      for(int j = 0; j < c->J; ++j)
-        {
-          const double P = c->g[j].P;
-          tot += P * P * P / 3 + P * P * c->N / 2;
-        }
-      for(int j = 0; j < c->J; ++j)
-        {
-          const double P = c->g[j].P;
-          block_timings_ms[j] += (int32_t)(
-            c->stage_ms[3] * (P * P * P / 3 + P * P * c->N / 2) / (tot > 0 ? tot : 1));
-        }
+      c->error = "cholesky_diagonals called before a successful Schur-complement step";
+      return SDPB_B200_ERR_STATE;
     }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int count = 4 * c->J + 1;
+  diag_gather_kernel<<<std::min(count, 148 * 8), 128, 0, st>>>(c->d_diag, count, c->es, c->diag_buf);
+  ++c->launches;
+  CUDA_TRY(c, cudaGetLastError());
+  uint64_t *dst[4] = {X_diag, Y_diag, S_diag, Q_diag};
+  for(int k = 0; k < 4; ++k)
+    {
+      const long n = (k < 3 ? c->diag_off[k + 1] : c->diag_total) - c->diag_off[k];
+      if(dst[k] && n)
+        CUDA_TRY(c, cudaMemcpyAsync(dst[k], c->diag_buf + (size_t)c->diag_off[k] * c->es, (size_t)n * c->es * 8,
+                                    cudaMemcpyDeviceToHost, st));
+    }
+  CUDA_TRY(c, cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -1489,21 +1830,30 @@ extern "C" int sdpb_b200_scalar_op(sdpb_b200_ctx *c, int op, int k, long count,
   CUDA_TRY(c, cudaSetDevice(c->device));
   c->kt_used = 0;
   c->cur = c->stream;
-  limb_t *da, *db, *dr;
-  const size_t bytes = (size_t)count * c->es * 8;
+  limb_t *da = nullptr, *db = nullptr, *dr = nullptr;
+  const size_t bytes = std::max<size_t>(16, (size_t)count * c->es * 8);
+  struct Guard // frees the temporaries on every return path
+  {
+    limb_t *&a, *&b, *&r;
+    cudaStream_t st;
+    ~Guard()
+    {
+      cudaStreamSynchronize(st);
+      cudaFree(a);
+      cudaFree(b);
+      cudaFree(r);
+    }
+  } guard{da, db, dr, c->stream};
   CUDA_TRY(c, cudaMalloc(&da, bytes));
   CUDA_TRY(c, cudaMalloc(&db, bytes));
   CUDA_TRY(c, cudaMalloc(&dr, bytes));
-  CUDA_TRY(c, cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, c->stream));
-  CUDA_TRY(c, cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(da, a, (size_t)count * c->es * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(db, b, (size_t)count * c->es * 8, cudaMemcpyHostToDevice, c->stream));
   int rc = dispatch_scalar(c, op, k, count, da, db, dr);
   if(rc)
     return rc;
-  CUDA_TRY(c, cudaMemcpyAsync(r, dr, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(r, dr, (size_t)count * c->es * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  cudaFree(da);
-  cudaFree(db);
-  cudaFree(dr);
   return 0;
 }
 

@@ -5,10 +5,12 @@
 #include "kernels.cuh"
 #include "solve.cuh"
 
+#include <memory>
 #include <string>
 #include <vector>
 
 using namespace sdpb_b200;
+struct LocalGroup; // in-process communicator (capi.cu): several contexts on one device
 
 #define CUDA_TRY(c, expr)                                                     \
   do                                                                          \
@@ -94,6 +96,14 @@ struct sdpb_b200_ctx
   int (*bcast)(sdpb_b200_ctx *, void *buf, size_t bytes, int root, const char *label) = nullptr;
   limb_t *qpanel = nullptr; // one packed block column of Q + its status word
   int qdist_min_N = 512;
+  std::shared_ptr<LocalGroup> local; // sdpb_b200_comm_init_local: the exchanges stay inside the process
+  std::vector<int> gidx;             // global index of each local block (error texts name global blocks)
+  int *d_fail = nullptr;             // [0] this rank failed, summed over the ranks at the end of a step
+  bool sharded() const { return part_global != nullptr; }
+  // sdpb_b200_cholesky_diagonals: descriptors [2J X | 2J Y | J S | Q] and the gathered diagonals
+  DiagDesc *d_diag = nullptr;
+  limb_t *diag_buf = nullptr;
+  long diag_off[4] = {0, 0, 0, 0}, diag_total = 0; // element offsets of the four groups in diag_buf
 
   // Concurrent schedule.  The step is a small dependency graph -- chol(X) ->
   // L_X^-1 V -> A_X_inv | Y V -> A_Y | chol(Y) | per block: S_j -> chol(S_j) ->

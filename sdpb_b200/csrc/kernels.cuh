@@ -12,6 +12,7 @@
 #include "mpfx.h"
 #include "tile.cuh"
 
+#include <climits>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -549,6 +550,43 @@ crt_restore_kernel(const uint32_t *__restrict__ Qres, int N, int prec,
   mpfx::mul(q, q, ni);
   mpfx::mul(q, q, nj);
   st(Q, (size_t)j * N + i, q);
+}
+
+// fail[0] = 1 if any status word of this rank's step reports a failed pivot, or the residue
+// overflow / Q-diagonal flags are raised (summed over the ranks afterwards)
+static __global__ void fail_flag_kernel(const int *status, int n, const int *flags, int *fail)
+{
+  __shared__ int bad;
+  if(threadIdx.x == 0)
+    bad = (flags[0] != 0 || flags[1] != INT_MAX) ? 1 : 0;
+  __syncthreads();
+  for(int i = threadIdx.x; i < n; i += blockDim.x)
+    if(status[i] >= 0)
+      bad = 1;
+  __syncthreads();
+  if(threadIdx.x == 0)
+    fail[0] = bad;
+}
+// out[e] = element (i, i) of matrix m for the stacked diagonal index e; per matrix: base pointer,
+// size, and the element offset of its first diagonal entry in `out`
+struct DiagDesc
+{
+  const limb_t *A;
+  int s;
+  long ld;   // elements between consecutive columns
+  long out0; // first output element
+};
+static __global__ void diag_gather_kernel(const DiagDesc *descs, int count, int es, limb_t *out)
+{
+  for(int m = blockIdx.x; m < count; m += gridDim.x)
+    {
+      const DiagDesc d = descs[m];
+      for(int e = threadIdx.x; e < d.s * es; e += blockDim.x)
+        {
+          const int i = e / es, w = e % es;
+          out[(d.out0 + i) * es + w] = d.A[((long)i * d.ld + i) * es + w];
+        }
+    }
 }
 
 // scalar-op kernel for device-vs-libgmp parity tests (same op codes as

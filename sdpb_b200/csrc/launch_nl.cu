@@ -5,7 +5,9 @@
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
+#include <mutex>
 #include <set>
+#include <string>
 
 #ifndef SDPB_NL
 #error "compile with -DSDPB_NL=<n>"
@@ -26,7 +28,10 @@ template <int NL> struct Launch
   // "<label>/<part>": one timeline name per kind of launch inside a batched factorisation
   static const char *sub(const char *label, const char *part)
   {
+    // shared by every context of the process (one host thread per GPU may be in here at once)
     static std::set<std::string> pool;
+    static std::mutex guard;
+    std::lock_guard<std::mutex> lock(guard);
     return pool.insert(std::string(label) + "/" + part).first->c_str();
   }
   // matrices of a batch (sorted, largest first) that still have tile index `t`
@@ -153,6 +158,36 @@ template <int NL> struct Launch
   {
     if(sizes.empty() || sizes[0] == 0 || maxcols == 0)
       return 0;
+    // default: the whole solve in one launch (trsm_walk_kernel); SDPB_B200_TRSM=levels keeps the
+    // level-synchronous pair of kernels for A/B measurements
+    static const bool levels = [] {
+      const char *env = getenv("SDPB_B200_TRSM");
+      return env && std::string(env) == "levels";
+    }();
+    if(!levels)
+      {
+        // block = 16 TC threads owning ~16 TC columns: the largest TC whose padding of the
+        // column count stays within 3 % of the best one
+        int best_waste = INT_MAX;
+        for(int tc = 4; tc <= 16; ++tc)
+          best_waste = std::min(best_waste, ((maxcols + 16 * tc - 1) / (16 * tc)) * 16 * tc - maxcols);
+        int TC = 4;
+        for(int tc = 4; tc <= 16; ++tc)
+          if(((maxcols + 16 * tc - 1) / (16 * tc)) * 16 * tc - maxcols <= best_waste + maxcols * 3 / 100)
+            TC = tc;
+        while(TC > 4 && WalkGeom<NL>::bytes(TC) > 227 * 1024)
+          --TC;
+        const int ncg = (maxcols + 16 * TC - 1) / (16 * TC);
+        const int Wc = (maxcols + ncg - 1) / ncg; // columns per CTA, balanced
+        const size_t smem = WalkGeom<NL>::bytes(TC);
+        CUDA_TRY(c, cudaFuncSetAttribute(trsm_walk_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        c->kt_begin(label);
+        trsm_walk_kernel<NL><<<(unsigned)sizes.size() * ncg, 16 * TC, smem, c->cur>>>(d, ncg, Wc);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+        return 0;
+      }
     if(int rc = smem_opt_in(c, trsm_gemm_level<NL>))
       return rc;
     CUDA_TRY(c, cudaFuncSetAttribute(trsm_diag_level<NL>,
@@ -220,8 +255,9 @@ template <int NL> struct Launch
     cudaStream_t st = c->stream;
     c->cur = st;
     CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
-    CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
-    const bool sharded = c->world > 1;
+    if(J == 0)
+      CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
+    const bool sharded = c->sharded();
     limb_t *part = sharded ? c->part_global : c->part;
     const int Jsum = sharded ? c->J_global : J;
     if(J)
@@ -243,6 +279,8 @@ template <int NL> struct Launch
         schur_kernel<NL><<<grid, 128, 0, sg>>>(c->d_schur_g[g]);
         c->kt_end();
         CUDA_TRY(c, cudaGetLastError());
+        if(g == 0) // stage boundary "S assembled" (of the first group when the chain is cut into groups)
+          CUDA_TRY(c, cudaEventRecord(c->ev[3], sg));
         int rc = potrf(c, "potrf_S", c->d_potrfS_g[g], c->szS_g[g], c->d_status + 4 * J, J, false);
         if(rc)
           return rc;
@@ -316,6 +354,17 @@ template <int NL> struct Launch
     if(rc)
       return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[8], st));
+    if(sharded)
+      {
+        // a rank whose blocks failed (non-positive pivot, overflow, bad Q diagonal) has fed garbage
+        // into the exchanges: every rank must report the step as failed, not only that one
+        c->kt_begin("fail_flag_kernel");
+        fail_flag_kernel<<<1, 128, 0, st>>>(c->d_status, 5 * J + 1, c->d_flags, c->d_fail);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+        if(int rc2 = c->allreduce(c, c->d_fail, 1, 0, "nccl_allreduce_failure_flag"))
+          return rc2;
+      }
     return 0;
   }
   // one CTA per triangular system; unknowns in shared memory when the largest system fits
@@ -349,7 +398,7 @@ template <int NL> struct Launch
     const int J = c->J, N = c->N;
     cudaStream_t st = c->stream;
     c->cur = st;
-    const bool sharded = c->world > 1;
+    const bool sharded = c->sharded();
     limb_t *part = sharded ? c->part_global : c->part;
     const int Jsum = sharded ? c->J_global : J;
     // dx_j <- L_j^-1 dx_j

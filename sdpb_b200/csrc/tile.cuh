@@ -828,4 +828,157 @@ trsm_diag_level(const TrsmTileDesc *descs, int It)
       stg_reg<NL>(colp + (long)ii * G::ES, acc);
     }
 }
+
+// ---- the whole batched solve in ONE launch ---------------------------------
+// Columns of X = L^-1 B are independent, so a CTA that owns a group of columns of one matrix
+// can walk down ALL row tiles by itself: no level-synchronous launches (and none of their
+// tails), no kernel boundary between the update and the diagonal solve.  Per row tile:
+//   update  b_ic -= sum_{k < I0} l_ik x_kc   as (16 x TC) register tiles, TC = blockDim / 16,
+//           one pass per TC columns; a LAST tile with <= 8 rows switches to (8 x 2 TC) tiles, so
+//           a 40-row block (2.5 tiles) keeps every thread busy instead of half of them;
+//   solve   the 16 rows of the tile top to bottom, ONE THREAD PER COLUMN (every lane busy; the
+//           16-threads-per-row form spends most of its time with one row in sixteen active).
+// The block size is chosen by the host so that (columns per CTA) ~ blockDim: both phases then
+// use (nearly) all threads.  Same per-element operation order as the level kernels.
+template <int NL> struct WalkGeom
+{
+  typedef TileGeom<NL> G;
+  static constexpr int NTRI = TS * (TS + 1) / 2;
+  static constexpr size_t OFF_DIAG = 16;                                  // after the two mbarriers
+  static constexpr size_t OFF_RECIP = OFF_DIAG + (size_t)NTRI * G::SW * 4;
+  static constexpr size_t OFF_A = OFF_RECIP + (size_t)TS * G::RS * 4;
+  static constexpr size_t OFF_B = OFF_A + (size_t)2 * KC * TS * G::SW * 4;
+  static size_t bytes(int tc) { return OFF_B + (size_t)2 * KC * (2 * tc) * G::SW * 4; }
+};
+template <int NL>
+__global__ void __launch_bounds__(256, 2)
+trsm_walk_kernel(const TrsmTileDesc *descs, int ncg, int Wc)
+{
+  typedef TileGeom<NL> G;
+  typedef WalkGeom<NL> WG;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+  uint32_t *s_diag = reinterpret_cast<uint32_t *>(smem_raw + WG::OFF_DIAG);   // packed lower triangle
+  uint32_t *s_recip = reinterpret_cast<uint32_t *>(smem_raw + WG::OFF_RECIP);
+  uint32_t *s_a = reinterpret_cast<uint32_t *>(smem_raw + WG::OFF_A);
+  uint32_t *s_b = reinterpret_cast<uint32_t *>(smem_raw + WG::OFF_B);
+  const int nth = blockDim.x, TC = nth >> 4, BC = 2 * TC, t = threadIdx.x;
+  const TrsmTileDesc d = descs[blockIdx.x / ncg];
+  const int cg = blockIdx.x % ncg;
+  const int c_lo = cg * Wc, c_hi = min(d.ncols, c_lo + Wc);
+  if(c_lo >= c_hi || d.p == 0)
+    return;
+  if(t == 0)
+    {
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  __syncthreads();
+  uint32_t it = 0; // chunks staged so far: buffer and mbarrier phase
+  const int T = (d.p + TS - 1) / TS;
+  for(int It = 0; It < T; ++It)
+    {
+      const int I0 = It * TS, ni = min(TS, d.p - I0);
+      // ---- update: rows of this tile against everything solved above it
+      const bool wide = ni <= TS / 2;               // (8 x 2TC) tiles
+      const int rows = wide ? TS / 2 : TS, cols = wide ? BC : TC;
+      const int ti = wide ? (t & 7) : (t & 15), tj = wide ? (t >> 3) : (t >> 4);
+      for(int c0 = c_lo; c0 < c_hi && I0 > 0; c0 += cols)
+        {
+          // leading zeros of these columns (bases_blocks structure): rows above klo are exact zeros
+          const int klo = d.hb ? ((c0 / d.nb) * d.hb) & ~(KC - 1) : 0;
+          if(I0 <= klo)
+            continue;
+          const int nc = min(cols, c_hi - c0), K = I0 - klo;
+          const bool active = ti < ni && tj < nc;
+          Reg<NL> acc;
+          uint64_t *mine = d.B + ((long)(c0 + tj) * d.p + I0 + ti) * G::ES;
+          if(active)
+            ldg_reg<NL>(acc, mine);
+          else
+            mpfw::set_zero(acc);
+          const uint64_t *Abase = d.L + ((long)I0 + (long)klo * d.p) * G::ES; // (x, k) -> x + k p
+          const uint64_t *Bbase = d.B + ((long)c0 * d.p + klo) * G::ES;       // (x, k) -> x p + k
+          const int nchunks = (K + KC - 1) / KC;
+          auto issue = [&](int c) {
+            const uint32_t s = (it + c) & 1;
+            const int k0 = c * KC, kcnt = min(KC, K - k0);
+            if(t == 0)
+              mbar_expect_tx(&bar[s], (uint32_t)(G::EB * kcnt * (ni + nc)));
+            // copies of this chunk: kcnt x ni elements of L, kcnt x nc elements of X
+            for(int e = t; e < KC * (rows + cols); e += nth)
+              {
+                const bool isA = e < KC * rows;
+                const int q = isA ? e : e - KC * rows;
+                const int dk = isA ? q / rows : q / cols, dx = isA ? q % rows : q % cols;
+                if(dk >= kcnt || dx >= (isA ? ni : nc))
+                  continue;
+                if(isA)
+                  bulk_g2s(s_a + ((size_t)s * KC * TS + dk * TS + dx) * G::SW,
+                           Abase + ((long)dx + (long)(k0 + dk) * d.p) * G::ES, G::EB, &bar[s]);
+                else
+                  bulk_g2s(s_b + ((size_t)s * KC * BC + dk * BC + dx) * G::SW,
+                           Bbase + ((long)dx * d.p + (k0 + dk)) * G::ES, G::EB, &bar[s]);
+              }
+          };
+          issue(0);
+          for(int c = 0; c < nchunks; ++c)
+            {
+              if(c + 1 < nchunks)
+                issue(c + 1);
+              const uint32_t s = (it + c) & 1, parity = ((it + c) >> 1) & 1;
+              while(!mbar_try_wait(&bar[s], parity))
+                {
+                }
+              const int kcnt = min(KC, K - c * KC);
+              if(active)
+                {
+                  const uint32_t *pa = s_a + ((size_t)s * KC * TS + ti) * G::SW;
+                  const uint32_t *pb = s_b + ((size_t)s * KC * BC + tj) * G::SW;
+                  for(int kk = 0; kk < kcnt; ++kk)
+                    acc = mac_ss_nl<NL>(acc, pa + (size_t)kk * TS * G::SW, pb + (size_t)kk * BC * G::SW, true);
+                }
+              __syncthreads();
+            }
+          it += nchunks;
+          if(active)
+            stg_reg<NL>(mine, acc);
+        }
+      // ---- the factored diagonal tile (packed lower triangle) and its reciprocals
+      for(int e = t; e < TS * TS; e += nth)
+        {
+          const int x = e & (TS - 1), k = e >> 4;
+          if(x < ni && k <= x)
+            {
+              const uint4 *src = reinterpret_cast<const uint4 *>(d.L + ((long)(I0 + x) + (long)(I0 + k) * d.p) * G::ES);
+              uint4 *dst = reinterpret_cast<uint4 *>(s_diag + (size_t)tri_index(x, k) * G::SW);
+#pragma unroll
+              for(int w = 0; w < G::EB / 16; ++w)
+                dst[w] = src[w];
+            }
+        }
+      for(int w = t; w < ni * G::RS; w += nth)
+        s_recip[w] = d.recip[(long)I0 * G::RS + w];
+      __syncthreads(); // also: the updates stored above are visible to the column owners below
+      // ---- solve: one thread per column, rows top to bottom
+      for(int col = c_lo + t; col < c_hi; col += nth)
+        {
+          uint64_t *colp = d.B + ((long)col * d.p + I0) * G::ES;
+          for(int ii = 0; ii < ni; ++ii)
+            {
+              Reg<NL> acc;
+              ldg_reg<NL>(acc, colp + (long)ii * G::ES);
+              for(int kk = 0; kk < ii; ++kk)
+                acc = mac_nl<NL>(acc, s_diag + (size_t)tri_index(ii, kk) * G::SW,
+                                 reinterpret_cast<const uint32_t *>(colp + (long)kk * G::ES), true);
+              acc = div_nl<NL>(acc, s_diag + (size_t)tri_index(ii, ii) * G::SW, s_recip + ii * G::RS);
+              stg_reg<NL>(colp + (long)ii * G::ES, acc);
+            }
+        }
+      // the rows just solved are TMA sources of every later update of this CTA
+      fence_async_proxy();
+      __syncthreads();
+    }
+}
 } // namespace sdpb_b200

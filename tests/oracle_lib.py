@@ -78,6 +78,8 @@ def load_oracle():
     lib.oracle_scale_matrix.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_double, u64p, u64p]
     lib.oracle_stage_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.c_int]
     lib.oracle_num_threads.restype = ctypes.c_int
+    lib.oracle_set_num_threads.restype = None
+    lib.oracle_set_num_threads.argtypes = [ctypes.c_int]
     _lib = lib
     return lib
 

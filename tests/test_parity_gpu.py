@@ -338,3 +338,114 @@ def test_full_c3_properties():
     for k in ("X_chol", "Y_chol", "A_X_inv", "A_Y"):
         ol.assert_same(k, [got[k][2 * j + p] for j in pick for p in (0, 1)], want[k])
     ol.assert_same("L", [got["L"][j] for j in pick], want["L"])
+
+
+def test_cholesky_diagonals_are_the_factor_diagonals():
+    """sdpb_b200_cholesky_diagonals (what update_cond_numbers reads, step.cxx:187-189): the stacked
+    diagonals of X/Y factors, L_j and chol(Q) equal those of the factors the oracle computes."""
+    prec, shapes, N = 768, [(1, 7), (2, 5), (1, 9), (2, 3)], 9
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=4)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    want = sdp.run_step(ref)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    ctx.schur_step(sdp.X, sdp.Y)  # nothing but the status crosses PCIe
+    ew = ctx.ew
+    nxy = sum(s.psd_size(p) for s in ctx.shapes for p in (0, 1))
+    K = sum(s.schur_size for s in ctx.shapes)
+    Xd, Yd = np.zeros((nxy, ew), np.uint64), np.zeros((nxy, ew), np.uint64)
+    Sd, Qd = np.zeros((K, ew), np.uint64), np.zeros((N, ew), np.uint64)
+    ctx.cholesky_diagonals(Xd, Yd, Sd, Qd)
+
+    def diags(blocks):
+        return np.concatenate([np.stack([b[i, i] for i in range(b.shape[0])]) for b in blocks if b.shape[0]])
+
+    assert np.array_equal(Xd, diags(want["X_chol"]))
+    assert np.array_equal(Yd, diags(want["Y_chol"]))
+    assert np.array_equal(Sd, diags(want["L"]))
+    assert np.array_equal(Qd, diags([want["Q"]]))
+    ctx.close()
+
+
+def test_any_precision_kernels_are_built_on_demand():
+    """--precision is free in the reference (Environment.cxx:29-36).  320 bits (7 stored limbs) is
+    not linked into libsdpb_b200.so: the library builds libsdpb_b200_nl7.so with nvcc on first use
+    (a minute at this size), loads it, and the step is bit-exact like any other precision."""
+    prec, shapes, N = 320, [(1, 6), (2, 4), (1, 9)], 5
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=6)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    want = sdp.run_step(ref)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    got = sdp.run_step(ctx)
+    for k in KEYS:
+        ol.assert_same(k, got[k], want[k])
+    a, b = _adversarial_operands(prec, 1024, 5)
+    for op in (0, 1, 2, 3):
+        assert np.array_equal(ctx.scalar_op(op, a, b), ol.scalar_op(prec, op, a, b))
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,cut", [("c2", 12), ("c4-sample", None)])
+def test_named_config_shapes_bit_exact(name, cut):
+    """BASELINE configs C2 (448 bits, N = 60, P_j = 30) and C4 (960 bits, N = 1000) at their own
+    block shapes and full width; a dozen / two dozen blocks so that the oracle finishes in seconds
+    (C4's bands then have more than N rows, as Q must be positive definite)."""
+    from sdpb_b200.synthetic import WORKLOADS
+    prec, shapes, N = WORKLOADS[name]
+    shapes = shapes[:cut] if cut else shapes
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=2)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    want = sdp.run_step(ref)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    got = sdp.run_step(ctx)
+    for k in KEYS:
+        ol.assert_same(k, got[k], want[k])
+    want_dx, want_dy = sdp.solve_rhs()
+    ref.solve_schur_complement_equation(want_dx, want_dy)
+    dx, dy = sdp.solve_rhs()
+    ctx.solve_schur_complement_equation(dx, dy)
+    ol.assert_same("dy", dy, want_dy)
+    ol.assert_same("dx", dx, want_dx)
+    ctx.close()
+
+
+def test_schur_solve_takes_the_reduced_residue_of_the_references_layout():
+    """The reference stores r_y as one share per block (dy.blocks[j] = -B_j^T x_j, plus b on global
+    block 0; compute_primal_residues_and_error_p_b_Bx.cxx:24-34) and sums the shares inside
+    solve_schur_complement_equation.cxx:26-60.  The C-ABI takes the REDUCED vector (INTEGRATION.md's
+    shim adds the shares and all-reduces them): build the per-block shares, reduce them as the shim
+    does, and check the device solve against the oracle fed the same reduced r_y -- and that feeding
+    only the first block's share, the mistake an integrator could make, gives a different answer."""
+    prec, shapes, N = 768, [(1, 7), (2, 5), (1, 9)], 6
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=8)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    sdp.run_step(ref)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    sdp.run_step(ctx)
+    ew = ctx.ew
+    # per-block shares of r_y: random vectors standing in for -B_j^T x_j (+ b on block 0)
+    shares = [ol.random_matrix(prec, N, 1, 900 + j) for j in range(len(shapes))]
+    r_y = shares[0].reshape(N, ew).copy()
+    for sh in shares[1:]:
+        r_y = ol.scalar_op(prec, 1, r_y, sh.reshape(N, ew))   # mpf_add, block order
+    r_y = r_y.reshape(1, N, ew)
+    want_dx, _ = sdp.solve_rhs()
+    want_dy = r_y.copy()
+    ref.solve_schur_complement_equation(want_dx, want_dy)
+    dx, _ = sdp.solve_rhs()
+    dy = r_y.copy()
+    ctx.solve_schur_complement_equation(dx, dy)
+    ol.assert_same("dy", dy, want_dy)
+    ol.assert_same("dx", dx, want_dx)
+    dx1, _ = sdp.solve_rhs()
+    dy1 = shares[0].copy()
+    ctx.solve_schur_complement_equation(dx1, dy1)
+    assert not np.array_equal(dy1, dy)
+    ctx.close()
