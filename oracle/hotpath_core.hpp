@@ -288,13 +288,35 @@ inline void column_norm_partials(const std::vector<Matrix> &P_blocks, int N,
 }
 // ... partials added in (global) block order (the reference's AllReduce leaves
 // the cross-rank order open, Matrix_Normalizer.cxx:131), then sqrt (:136).
+// The canonical order of a sum over the (GLOBAL) blocks of per-block rows: the blocks are
+// taken in groups of BLOCK_SUM_GROUP consecutive global indices; every group is summed from an
+// exact zero in ascending block order, then the group sums are added, again from zero and
+// ascending.  (The reference's single-rank loop runs one accumulator through all blocks,
+// Matrix_Normalizer.cxx:82-88,126-129, and leaves the cross-rank order to MPI_Allreduce, :131;
+// a single chain is the one thing a GPU cannot shorten, and it grows with the number of GPUs --
+// 4800 dependent mpf_adds per column at 8 x 600 blocks.  Two levels keep the order fixed and
+// independent of the sharding, and cut the chain to 64 + J/64.)
+constexpr int BLOCK_SUM_GROUP = 64;
+inline void ordered_block_sum(const std::vector<std::vector<BigFloat>> &part, int N, std::vector<BigFloat> &total)
+{
+  total.assign(N, BigFloat());
+  std::vector<BigFloat> group(N);
+  for(size_t j0 = 0; j0 < part.size(); j0 += BLOCK_SUM_GROUP)
+    {
+      for(int c = 0; c < N; ++c)
+        group[c].zero();
+      for(size_t j = j0; j < part.size() && j < j0 + BLOCK_SUM_GROUP; ++j)
+        for(int c = 0; c < N; ++c)
+          group[c] += part[j][c];
+      for(int c = 0; c < N; ++c)
+        total[c] += group[c];
+    }
+}
 inline void norms_from_partials(const std::vector<std::vector<BigFloat>> &part, int N,
                                 std::vector<BigFloat> &norms)
 {
-  std::vector<BigFloat> total(N);
-  for(size_t j = 0; j < part.size(); ++j)
-    for(int c = 0; c < N; ++c)
-      total[c] += part[j][c];
+  std::vector<BigFloat> total;
+  ordered_block_sum(part, N, total);
   norms.assign(N, BigFloat());
   for(int c = 0; c < N; ++c)
     if(total[c].sgn() > 0)
@@ -331,15 +353,25 @@ inline void exact_syrk_upper_integer(const std::vector<Matrix> &Pn_blocks, int N
           }
       r0 += b.h;
     }
-#pragma omp parallel for schedule(dynamic, 1)
   for(int j = 0; j < N; ++j)
     for(int i = 0; i <= j; ++i)
-      {
-        __mpz_struct *acc = &Qz[(size_t)j * N + i];
-        mpz_set_ui(acc, 0);
-        for(size_t r = 0; r < rows; ++r)
-          mpz_addmul(acc, &z[r * N + i], &z[r * N + j]);
-      }
+      mpz_set_ui(&Qz[(size_t)j * N + i], 0);
+  // exact integer sums are order-free: rows are taken in chunks that stay in the caches while
+  // all N(N+1)/2 pairs of columns visit them (one pass over all rows per pair streams the whole
+  // matrix from DRAM N^2/2 times: 27 s instead of 13 s at K = 36 000, N = 300 on 16 cores)
+  const size_t chunk = 96;
+  for(size_t rb = 0; rb < rows; rb += chunk)
+    {
+      const size_t re = std::min(rows, rb + chunk);
+#pragma omp parallel for schedule(dynamic, 1)
+      for(int j = 0; j < N; ++j)
+        for(int i = 0; i <= j; ++i)
+          {
+            __mpz_struct *acc = &Qz[(size_t)j * N + i];
+            for(size_t r = rb; r < re; ++r)
+              mpz_addmul(acc, &z[r * N + i], &z[r * N + j]);
+          }
+    }
   for(auto &p : z)
     mpz_clear(&p);
 }
@@ -529,14 +561,18 @@ inline void schur_solve_forward(const SchurOutputs &f, std::vector<Matrix> &dx, 
         }
     }
 }
-// stage B, replicated: dy += part_j in GLOBAL block order; dy <- U^{-1} U^{-T} dy, Q = U^T U
+// stage B, replicated: dy += sum_j part_j (ordered_block_sum over the GLOBAL blocks);
+// dy <- U^{-1} U^{-T} dy, Q = U^T U
 inline void schur_solve_Q(const Matrix &U, const std::vector<std::vector<BigFloat>> &part_global,
                           Matrix &dy)
 {
   const int n = U.h;
-  for(size_t j = 0; j < part_global.size(); ++j)
+  {
+    std::vector<BigFloat> total;
+    ordered_block_sum(part_global, n, total); // two-level, in global block order (see there)
     for(int c = 0; c < n; ++c)
-      dy(c, 0) += part_global[j][c];
+      dy(c, 0) += total[c];
+  }
   BigFloat prod;
   for(int i = 0; i < n; ++i)
     {

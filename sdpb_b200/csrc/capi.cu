@@ -1783,7 +1783,7 @@ extern "C" int sdpb_b200_cholesky_diagonals(sdpb_b200_ctx *c, uint64_t *X_diag, 
     }
   CUDA_TRY(c, cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  const int count = 4 * c->J + 1;
+  const int count = 5 * c->J + 1; // 2J X, 2J Y, J S, Q
   diag_gather_kernel<<<std::min(count, 148 * 8), 128, 0, st>>>(c->d_diag, count, c->es, c->diag_buf);
   ++c->launches;
   CUDA_TRY(c, cudaGetLastError());

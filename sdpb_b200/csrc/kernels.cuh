@@ -128,8 +128,50 @@ template <int NL> __device__ __noinline__ Reg<NL> add_nl(Reg<NL> acc, Reg<NL> v)
   mpfw::add_signed<NL>(acc, v, v.sign);
   return acc;
 }
-// one warp per column: lane 0 adds the per-block partials in block order (the canonical,
-// sequential sum), then the warp takes sqrt and its reciprocal together (coop.cuh)
+// The canonical sum of per-block rows over the GLOBAL blocks (oracle: ordered_block_sum): groups
+// of BLOCK_SUM_GROUP consecutive blocks are summed from an exact zero in ascending order -- one
+// group per lane -- and lane 0 then adds the group sums in order.  The dependent chain is
+// 64 + J/64 mpf_adds instead of J (J grows with the number of GPUs).  Called by a whole warp;
+// the total is returned in lane 0.  scratch: 32 * TileGeom::SW words of shared memory.
+constexpr int BLOCK_SUM_GROUP = 64;
+template <int NL>
+__device__ __forceinline__ Reg<NL> ordered_block_sum(const limb_t *part, int J, int N, int c, uint32_t *scratch)
+{
+  typedef TileGeom<NL> G;
+  const int lane = threadIdx.x & 31;
+  const int ngroups = (J + BLOCK_SUM_GROUP - 1) / BLOCK_SUM_GROUP;
+  Reg<NL> total;
+  mpfw::set_zero(total);
+  for(int base = 0; base < ngroups; base += 32)
+    {
+      const int g = base + lane;
+      Reg<NL> acc, v;
+      mpfw::set_zero(acc);
+      if(g < ngroups)
+        {
+          const int j1 = min(J, (g + 1) * BLOCK_SUM_GROUP);
+          for(int j = g * BLOCK_SUM_GROUP; j < j1; ++j)
+            {
+              if(j + 4 < j1) // a sequential sum, but the loads need not wait for it
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(part + ((size_t)(j + 4) * N + c) * Fmt<NL>::ES));
+              ldg_reg<NL>(v, part + ((size_t)j * N + c) * Fmt<NL>::ES);
+              acc = add_nl<NL>(acc, v);
+            }
+        }
+      mpfw::store<NL>(scratch + lane * G::SW, acc);
+      __syncwarp();
+      if(lane == 0)
+        for(int q = 0; q < 32 && base + q < ngroups; ++q)
+          {
+            mpfw::load<NL>(v, scratch + q * G::SW);
+            total = add_nl<NL>(total, v);
+          }
+      __syncwarp();
+    }
+  return total;
+}
+// one warp per column: the canonical sum of the per-block partials, then the warp takes sqrt and
+// its reciprocal together (coop.cuh)
 template <int NL>
 __global__ void __launch_bounds__(32) norm_final_kernel(const limb_t *part, int J, int N,
                                                        limb_t *norms, uint32_t *recip)
@@ -138,21 +180,13 @@ __global__ void __launch_bounds__(32) norm_final_kernel(const limb_t *part, int 
   extern __shared__ __align__(16) unsigned char coop_raw[];
   coop::Work<NL> &ws = *reinterpret_cast<coop::Work<NL> *>(coop_raw);
   uint32_t *slot = reinterpret_cast<uint32_t *>(coop_raw + ((sizeof(coop::Work<NL>) + 15) & ~(size_t)15));
+  uint32_t *scratch = slot + G::SW;
   const int c = blockIdx.x;
   if(c >= N)
     return;
+  const Reg<NL> acc = ordered_block_sum<NL>(part, J, N, c, scratch);
   if(threadIdx.x == 0)
     {
-      // J grows with the number of GPUs (one row per GLOBAL block): register-form mpf_add
-      Reg<NL> acc, v;
-      mpfw::set_zero(acc);
-      for(int j = 0; j < J; ++j)
-        {
-          if(j + 8 < J) // sequential sum, but the loads need not wait for it
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(part + ((size_t)(j + 8) * N + c) * Fmt<NL>::ES));
-          ldg_reg<NL>(v, part + ((size_t)j * N + c) * Fmt<NL>::ES);
-          acc = add_nl<NL>(acc, v);
-        }
       mpfw::store<NL>(slot, acc);
       ws.flag = 0;
     }

@@ -308,7 +308,8 @@ template <int NL> struct Launch
     // not depend on how the blocks are sharded
     c->kt_begin("norm_final_kernel");
     {
-      const size_t sm = ((sizeof(coop::Work<NL>) + 15) & ~(size_t)15) + TileGeom<NL>::SW * 4;
+      const size_t sm = ((sizeof(coop::Work<NL>) + 15) & ~(size_t)15) + 33 * TileGeom<NL>::SW * 4;
+      CUDA_TRY(c, cudaFuncSetAttribute(norm_final_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       norm_final_kernel<NL><<<N, 32, sm, st>>>(part, Jsum, N, c->norms, c->recipN);
     }
     c->kt_end();
@@ -419,7 +420,7 @@ template <int NL> struct Launch
       if(int rc = c->allreduce(c, part, (size_t)Jsum * N * Fmt<NL>::ES, 1, "nccl_allreduce_dy_partials"))
         return rc;
     c->kt_begin("solve_dysum_kernel");
-    solve_dysum_kernel<NL><<<(N + 31) / 32, 32, 0, st>>>(part, Jsum, N, c->sol_y);
+    solve_dysum_kernel<NL><<<N, 32, 32 * TileGeom<NL>::SW * 4, st>>>(part, Jsum, N, c->sol_y);
     c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
     // dy <- U^-1 U^-T dy

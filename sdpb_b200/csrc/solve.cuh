@@ -19,8 +19,8 @@
 //                      available (forward: k ascending; backward: k descending)
 //   solve_gemvT_kernel part_j[c] = -(sum_r P_j(r,c) x_j(r)), one thread per
 //                      (block, column), rows ascending from an exact zero
-//   solve_dysum_kernel dy[c] += part_j[c] in GLOBAL block order (sequential:
-//                      the order is part of the result)
+//   solve_dysum_kernel dy[c] += sum_j part_j[c], the sum in the canonical two-level
+//                      order over the GLOBAL blocks (the order is part of the result)
 //   solve_gemv_kernel  x_j(r) += sum_c P_j(r,c) dy(c), one thread per stacked row
 //
 // Same canonical order as oracle/hotpath_core.hpp (schur_solve_forward / _Q /
@@ -124,25 +124,23 @@ solve_gemvT_kernel(const BandDesc *bands, int N, const limb_t *x, limb_t *part)
     }
 }
 
-// dy[c] += part[j*N + c], j = 0 .. J-1 in order
+// dy[c] += sum_j part[j*N + c], the sum in the canonical two-level order over the GLOBAL
+// blocks (ordered_block_sum, kernels.cuh); one warp per column
 template <int NL>
 __global__ void __launch_bounds__(32) solve_dysum_kernel(const limb_t *part, int J, int N, limb_t *dy)
 {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ __align__(16) uint32_t dysum_scratch[];
+  const int c = blockIdx.x;
   if(c >= N)
     return;
-  Reg<NL> acc, v;
-  ldg_reg<NL>(acc, dy + (size_t)c * Fmt<NL>::ES);
-  for(int j = 0; j < J; ++j)
+  const Reg<NL> total = ordered_block_sum<NL>(part, J, N, c, dysum_scratch);
+  if(threadIdx.x == 0)
     {
-      // the sum is sequential by definition (its order is part of the result); the loads are
-      // not: keep the next rows' lines on their way (J grows with the number of GPUs)
-      if(j + 8 < J)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(part + ((size_t)(j + 8) * N + c) * Fmt<NL>::ES));
-      ldg_reg<NL>(v, part + ((size_t)j * N + c) * Fmt<NL>::ES);
-      acc = add_nl<NL>(acc, v);
+      Reg<NL> acc;
+      ldg_reg<NL>(acc, dy + (size_t)c * Fmt<NL>::ES);
+      acc = add_nl<NL>(acc, total);
+      stg_reg<NL>(dy + (size_t)c * Fmt<NL>::ES, acc);
     }
-  stg_reg<NL>(dy + (size_t)c * Fmt<NL>::ES, acc);
 }
 
 // x(row0 + r) += sum_c P(r,c) dy(c), columns ascending from an exact zero
