@@ -226,6 +226,13 @@ def cpu_full(workload, steps, warmup, world=1, budget_s=None):
     # a short sample first: warms the library up and predicts the cost of the full step
     sname = workload + "-sample" if workload + "-sample" in WORKLOADS else None
     est = None
+    Ktot = sum(m * (m + 1) // 2 * n for m, n in shapes)
+    if sname is None and float(Ktot) * N * N > 2e10:
+        # no bounded sample with these shapes exists (N = 4096 needs >= 4096 stacked rows, and the
+        # exact syrk + Cholesky(Q) of that alone are CPU-hours): no CPU number rather than a guess
+        out.update(value=None, extrapolated=None, steps=0, warmup=0,
+                   sample="unavailable: the smallest well-posed sample of this workload is CPU-hours")
+        return out
     if sname:
         sprec, sshapes, sN = WORKLOADS[sname]
         sdp = SyntheticSDP(sprec, sshapes, sN, seed=1)
@@ -505,7 +512,8 @@ def main():
 
     # ---- the round-1 contract for comparison: EVERY output copied back (L_j, L_j^-1 B_j, chol(Q)) ----
     e2e_all_s, d2h_all = None, None
-    if not a.no_all_outputs:
+    all_bytes = sum((s.schur_size ** 2 + N * s.schur_size) * ctx.ew * 8 for s in ctx.shapes)
+    if not a.no_all_outputs and all_bytes < (8 << 30):  # pinned staging for L_j and L_j^-1 B_j
         Lh = pool.slab([(s.schur_size, s.schur_size, ctx.ew) for s in ctx.shapes])
         Ph = pool.slab([(N, s.schur_size, ctx.ew) for s in ctx.shapes])
         Qh = pool.empty((N, N, ctx.ew))

@@ -474,6 +474,62 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
     TRY_C(upload(&c->d_gemmSMA, gS));
   }
   {
+    // search direction (row N2): resident block-diagonal objects, vectors and descriptors
+    const size_t bytes = std::max<size_t>(16, c->wXY * 8);
+    for(limb_t **p : {&c->dirMXY, &c->dirR, &c->dirZ, &c->dirDX, &c->dirDY, &c->dirPR})
+      {
+        TRY_C(cudaMalloc(p, bytes));
+        TRY_C(cudaMemsetAsync(*p, 0, bytes, c->stream));
+      }
+    std::vector<BdmDesc> bd2;
+    std::vector<int> row_block((size_t)c->K);
+    int cols = 0;
+    for(int j = 0; j < num_blocks; ++j)
+      {
+        const BlockGeom &b = c->g[j];
+        for(long r = 0; r < b.P; ++r)
+          row_block[(size_t)(b.row0 + r)] = j;
+        for(int p = 0; p < 2; ++p)
+          {
+            const int q = 2 * j + p;
+            bd2.push_back(BdmDesc{(long)(c->oXY[q] / es), (long)(c->oV[q] / es), b.row0, b.s[p], b.h[p], b.m, b.n, cols});
+            cols += b.s[p];
+          }
+      }
+    c->bdm_cols = cols;
+    TRY_C(upload(&c->d_bdm, bd2));
+    TRY_C(upload(&c->d_row_block, row_block));
+    TRY_C(cudaMalloc(&c->dir_dual, std::max<size_t>(16, (size_t)c->K * es * 8)));
+    TRY_C(cudaMalloc(&c->dir_prp, (size_t)N * es * 8));
+    TRY_C(cudaMalloc(&c->dir_scal, 4 * es * 8));
+    TRY_C(cudaMalloc(&c->dir_part, std::max<size_t>(16, (size_t)2 * num_blocks * es * 8)));
+    TRY_C(cudaMalloc(&c->dir_colsum, std::max<size_t>(16, (size_t)cols * es * 8)));
+    const size_t pin = std::max<size_t>((size_t)c->K + N + 8, (size_t)2 * num_blocks + 8) * es * 8;
+    TRY_C(cudaMallocHost(&c->dir_pinned, pin));
+    {
+      // 0.5 as mpf_set_d(0.5) stores it (two limbs, the low one zero), top-aligned
+      std::vector<uint64_t> half(4 * es, 0);
+      half[es + 0] = (uint64_t)(uint32_t)0 | ((uint64_t)(uint32_t)1 << 32);
+      half[es + nl] = 0x8000000000000000ull;
+      TRY_C(cudaMemcpy(c->dir_scal, half.data(), half.size() * 8, cudaMemcpyHostToDevice));
+    }
+    auto products = [&](const limb_t *A, const limb_t *B, GemmTileDesc **out) -> cudaError_t {
+      std::vector<GemmTileDesc> gd;
+      for(int q = 0; q < 2 * num_blocks; ++q)
+        {
+          const int s = c->g[q / 2].s[q % 2];
+          gd.push_back(GemmTileDesc{A + c->oXY[q], B + c->oXY[q], c->smaT + c->oXY[q], 1, (long)s, 1, (long)s, s, s,
+                                    s, 0, 0, 0, 0, 0});
+        }
+      c->tiles_dir = sort_gemm(gd);
+      return upload(out, gd);
+    };
+    TRY_C(products(c->Xin, c->Yin, &c->d_gemmXY));
+    TRY_C(products(c->dirDX, c->dirDY, &c->d_gemmDXDY));
+    TRY_C(products(c->dirPR, c->Yin, &c->d_gemmPRY));
+    TRY_C(products(c->dirDX, c->Yin, &c->d_gemmDXY));
+  }
+  {
     // triangular systems of the Schur solves: every L_j (largest first), and Q = U^T U read as U^T
     std::vector<SolveTriDesc> sS, sQ{SolveTriDesc{c->Q, c->recipQ, (long)N, 1, N, 0}};
     for(const PotrfDesc &d : pS)
@@ -880,6 +936,17 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
   cudaFree(c->d_status);
   cudaFree(c->d_flags);
   cudaFree(c->d_fail);
+  for(limb_t *p : {c->dirMXY, c->dirR, c->dirZ, c->dirDX, c->dirDY, c->dirPR, c->dir_dual, c->dir_prp, c->dir_scal,
+                   c->dir_part, c->dir_colsum})
+    cudaFree(p);
+  cudaFree(c->d_bdm);
+  cudaFree(c->d_row_block);
+  cudaFree(c->d_gemmXY);
+  cudaFree(c->d_gemmDXDY);
+  cudaFree(c->d_gemmPRY);
+  cudaFree(c->d_gemmDXY);
+  if(c->dir_pinned)
+    cudaFreeHost(c->dir_pinned);
   cudaFree(c->d_diag);
   cudaFree(c->diag_buf);
   for(int g = 0; g < sdpb_b200_ctx::MAXG; ++g)
@@ -1186,6 +1253,9 @@ extern "C" int sdpb_b200_cholesky_decomposition(sdpb_b200_ctx *c, int which,
   int rc = copy_blocks_in(c, A, dst);
   if(rc)
     return rc;
+  // the pristine matrix stays resident too: -XY and the corrector's Frobenius product read it
+  if(c->wXY)
+    CUDA_TRY(c, cudaMemcpyAsync(which == 0 ? c->Xin : c->Yin, dst, c->wXY * 8, cudaMemcpyDeviceToDevice, c->stream));
   rc = dispatch_cholesky(c, which);
   if(rc)
     {
@@ -1238,6 +1308,8 @@ extern "C" int sdpb_b200_compute_bilinear_pairings(sdpb_b200_ctx *c,
   int rc = copy_blocks_in(c, Y, c->Y);
   if(rc)
     return rc;
+  if(c->wXY)
+    CUDA_TRY(c, cudaMemcpyAsync(c->Yin, c->Y, c->wXY * 8, cudaMemcpyDeviceToDevice, c->stream));
   CUDA_TRY(c, cudaEventRecord(c->ev[0], c->stream));
   rc = dispatch_pairings(c);
   if(rc)
@@ -1443,6 +1515,181 @@ extern "C" int sdpb_b200_scale_multiply_add(sdpb_b200_ctx *c, int alpha, const u
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
+
+// ------------------------------------------------------- search direction
+// Row N2: compute_search_direction.cxx:44-90 and the reductions of step.cxx:137-160
+// on objects that stay in HBM.  The factors (X_cholesky, L_j, L_j^-1 B_j, chol(Q)) and the
+// pristine X, Y are those of the preceding step / cholesky_decomposition + pairings calls.
+static int direction_ready(sdpb_b200_ctx *c, const char *what, bool need_minus_XY, bool need_direction)
+{
+  if(!c->have_factors || (need_minus_XY && !c->have_minus_XY) || (need_direction && !c->have_direction))
+    {
+      c->error = std::string(what) + " called out of order (needs a successful Schur-complement step"
+                 + (need_minus_XY ? ", direction_begin" : "") + (need_direction ? ", compute_search_direction" : "") + ")";
+      return SDPB_B200_ERR_STATE;
+    }
+  return 0;
+}
+// per block-parity scalars back to the host (2J packed elements)
+static int direction_scalars_out(sdpb_b200_ctx *c, uint64_t *out)
+{
+  const size_t bytes = (size_t)2 * c->J * c->es * 8;
+  if(bytes && out)
+    {
+      CUDA_TRY(c, cudaMemcpyAsync(c->dir_pinned, c->dir_part, bytes, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      memcpy(out, c->dir_pinned, bytes);
+    }
+  else
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int sdpb_b200_direction_begin(sdpb_b200_ctx *c, uint64_t *block_traces)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  if(int rc = direction_ready(c, "direction_begin", false, false))
+    return rc;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  c->kt_used = 0;
+  c->have_direction = false;
+  CUDA_TRY(c, cudaEventRecord(c->ev[9], c->stream));
+  if(int rc = table_for(c->nl)->direction(c, 0, 0))
+    {
+      cudaStreamSynchronize(c->stream);
+      return rc;
+    }
+  CUDA_TRY(c, cudaEventRecord(c->ev[10], c->stream));
+  if(int rc = direction_scalars_out(c, block_traces))
+    return rc;
+  cudaEventElapsedTime(&c->direction_ms, c->ev[9], c->ev[10]);
+  c->have_minus_XY = true;
+  return 0;
+}
+extern "C" int sdpb_b200_direction_R_errors(sdpb_b200_ctx *c, const uint64_t *mu, uint64_t *block_maxima)
+{
+  if(!c || !mu)
+    return SDPB_B200_ERR_ARG;
+  if(int rc = direction_ready(c, "direction_R_errors", true, false))
+    return rc;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  c->kt_used = 0;
+  memcpy(c->dir_pinned, mu, (size_t)c->es * 8);
+  CUDA_TRY(c, cudaMemcpyAsync(c->dir_scal + 2 * c->es, c->dir_pinned, (size_t)c->es * 8, cudaMemcpyHostToDevice,
+                              c->stream));
+  if(int rc = table_for(c->nl)->direction(c, 1, 0))
+    {
+      cudaStreamSynchronize(c->stream);
+      return rc;
+    }
+  return direction_scalars_out(c, block_maxima);
+}
+extern "C" int sdpb_b200_direction_set_residues(sdpb_b200_ctx *c, const uint64_t *const *primal_residues,
+                                                const uint64_t *const *dual_residues,
+                                                const uint64_t *primal_residue_p)
+{
+  if(!c || !primal_residue_p || (c->J && (!primal_residues || !dual_residues)))
+    return SDPB_B200_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const size_t es = (size_t)c->es;
+  for(int j = 0; j < c->J; ++j)
+    if(c->g[j].P && !dual_residues[j])
+      {
+        c->error = "direction_set_residues: dual_residues[" + std::to_string(j) + "] is null";
+        return SDPB_B200_ERR_ARG;
+      }
+  cudaStream_t main_stream = c->stream;
+  int rc = copy_blocks_in(c, primal_residues, c->dirPR);
+  if(rc)
+    return rc;
+  for(int j = 0; j < c->J; ++j)
+    memcpy(c->dir_pinned + (size_t)c->g[j].row0 * es, dual_residues[j], (size_t)c->g[j].P * es * 8);
+  memcpy(c->dir_pinned + (size_t)c->K * es, primal_residue_p, (size_t)c->N * es * 8);
+  if(c->K)
+    CUDA_TRY(c, cudaMemcpyAsync(c->dir_dual, c->dir_pinned, (size_t)c->K * es * 8, cudaMemcpyHostToDevice, main_stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->dir_prp, c->dir_pinned + (size_t)c->K * es, (size_t)c->N * es * 8,
+                              cudaMemcpyHostToDevice, main_stream));
+  CUDA_TRY(c, cudaStreamSynchronize(main_stream));
+  c->have_residues = true;
+  return 0;
+}
+extern "C" int sdpb_b200_compute_search_direction(sdpb_b200_ctx *c, const uint64_t *beta_mu, int is_corrector)
+{
+  if(!c || !beta_mu)
+    return SDPB_B200_ERR_ARG;
+  if(int rc = direction_ready(c, "compute_search_direction", true, is_corrector != 0))
+    return rc;
+  if(!c->have_residues)
+    {
+      c->error = "compute_search_direction called before direction_set_residues";
+      return SDPB_B200_ERR_STATE;
+    }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  c->kt_used = 0;
+  memcpy(c->dir_pinned, beta_mu, (size_t)c->es * 8);
+  CUDA_TRY(c, cudaMemcpyAsync(c->dir_scal, c->dir_pinned, (size_t)c->es * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaEventRecord(c->ev[9], c->stream));
+  if(int rc = table_for(c->nl)->direction(c, 2, is_corrector))
+    {
+      cudaStreamSynchronize(c->stream);
+      return rc;
+    }
+  CUDA_TRY(c, cudaEventRecord(c->ev[10], c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->direction_ms, c->ev[9], c->ev[10]);
+  c->have_direction = true;
+  return 0;
+}
+extern "C" int sdpb_b200_direction_frobenius(sdpb_b200_ctx *c, uint64_t *block_products)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  if(int rc = direction_ready(c, "direction_frobenius", true, true))
+    return rc;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  c->kt_used = 0;
+  if(int rc = table_for(c->nl)->direction(c, 3, 0))
+    {
+      cudaStreamSynchronize(c->stream);
+      return rc;
+    }
+  return direction_scalars_out(c, block_products);
+}
+extern "C" int sdpb_b200_direction_get(sdpb_b200_ctx *c, uint64_t *const *dx, uint64_t *const *dX, uint64_t *dy,
+                                       uint64_t *const *dY)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  if(int rc = direction_ready(c, "direction_get", true, true))
+    return rc;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const size_t es = (size_t)c->es;
+  std::vector<size_t> eXY(2 * c->J);
+  for(int q = 0; q < 2 * c->J; ++q)
+    eXY[q] = (size_t)c->g[q / 2].s[q % 2] * c->g[q / 2].s[q % 2];
+  int rc = copy_blocks_out(c, c->dirDX, c->oXY, dX, 2 * c->J, eXY);
+  if(!rc)
+    rc = copy_blocks_out(c, c->dirDY, c->oXY, dY, 2 * c->J, eXY);
+  if(rc)
+    {
+      cudaStreamSynchronize(c->stream);
+      return rc;
+    }
+  if(dx && c->K)
+    CUDA_TRY(c, cudaMemcpyAsync(c->dir_pinned, c->sol_x, (size_t)c->K * es * 8, cudaMemcpyDeviceToHost, c->stream));
+  if(dy)
+    CUDA_TRY(c, cudaMemcpyAsync(c->dir_pinned + (size_t)c->K * es, c->sol_y, (size_t)c->N * es * 8,
+                                cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(dx)
+    for(int j = 0; j < c->J; ++j)
+      if(dx[j])
+        memcpy(dx[j], c->dir_pinned + (size_t)c->g[j].row0 * es, (size_t)c->g[j].P * es * 8);
+  if(dy)
+    memcpy(dy, c->dir_pinned + (size_t)c->K * es, (size_t)c->N * es * 8);
+  return 0;
+}
+extern "C" float sdpb_b200_last_direction_ms(const sdpb_b200_ctx *c) { return c ? c->direction_ms : 0.f; }
 
 // ----------------------------------------------------- resident step
 // H2D of X and Y through one pinned staging buffer (two large copies instead

@@ -4,6 +4,7 @@
 #include "../../include/sdpb_b200.h"
 #include "kernels.cuh"
 #include "solve.cuh"
+#include "direction.cuh"
 
 #include <memory>
 #include <string>
@@ -146,6 +147,23 @@ struct sdpb_b200_ctx
   limb_t *smaA = nullptr, *smaB = nullptr, *smaT = nullptr, *smaC = nullptr; // wXY words each
   GemmTileDesc *d_gemmSMA = nullptr;
   int tiles_SMA = 0;
+  // search direction (row N2, direction.cuh): block-diagonal objects of the shape of X and the
+  // vectors of compute_search_direction, resident between the calls of one iteration
+  limb_t *dirMXY = nullptr, *dirR = nullptr, *dirZ = nullptr, *dirDX = nullptr, *dirDY = nullptr,
+         *dirPR = nullptr;          // -XY, R, Z, dX, dY, primal residues: wXY words each
+  limb_t *dir_dual = nullptr;       // dual residues, K elements (stacked like dx)
+  limb_t *dir_prp = nullptr;        // primal_residue_p, N elements
+  limb_t *dir_scal = nullptr;       // [0] beta mu  [1] 0.5 as mpf_set_d gives it  [2] mu
+  limb_t *dir_part = nullptr;       // per block-parity scalars (traces, maxima, Frobenius products)
+  limb_t *dir_colsum = nullptr;     // per column scratch of the Frobenius product
+  BdmDesc *d_bdm = nullptr;         // block-parity b = 2j + parity, in that order
+  int *d_row_block = nullptr;       // SDP block of every stacked row
+  int bdm_cols = 0;                 // sum of the block sizes s
+  GemmTileDesc *d_gemmXY = nullptr, *d_gemmDXDY = nullptr, *d_gemmPRY = nullptr, *d_gemmDXY = nullptr;
+  int tiles_dir = 0;
+  uint64_t *dir_pinned = nullptr;   // host staging: vectors up, per-block scalars down
+  bool have_XY = false, have_minus_XY = false, have_residues = false, have_direction = false;
+  float direction_ms = 0;
   long launches = 0; // kernels launched since creation
   cudaEvent_t ev[12] = {}; // 0,1 pairings; 2..8 Schur stages; 9,10,11 resident step
   float stage_ms[9] = {0};
@@ -192,6 +210,10 @@ struct LaunchTable
   int (*scale_multiply_add)(sdpb_b200_ctx *, int alpha, int beta); // smaC = alpha smaA smaB + beta smaC
   int (*scalar)(sdpb_b200_ctx *, int op, int k, long count, const limb_t *a,
                 const limb_t *b, limb_t *r);
+  // direction.cuh on the resident objects.  op 0: -XY and its per-block traces; 1: per-block
+  // max |-XY + mu I|; 2: compute_search_direction (arg: corrector phase); 3: per-block Frobenius
+  // products of (X + dX, Y + dY)
+  int (*direction)(sdpb_b200_ctx *, int op, int arg);
 };
 // weak: a development build may compile only some precisions (make NLS="14")
 #define F(n) extern "C" const LaunchTable sdpb_b200_launch_nl##n __attribute__((weak));

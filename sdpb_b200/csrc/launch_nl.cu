@@ -152,19 +152,35 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaGetLastError());
     return 0;
   }
-  // batched X <- L^{-1} B, level-synchronous; sizes sorted descending
+  // batched X <- L^{-1} B; sizes sorted descending.  Two schedules (same arithmetic):
+  //   levels  per 16-row tile one launch of trsm_gemm_level2 (register tiles, (8 x 32) on a ragged
+  //           last tile) and one of trsm_diag_level (one thread per column) -- the default;
+  //   walk    trsm_walk_kernel, the whole solve of a group of columns in one CTA and one launch.
+  //           Measured at c3 (profiles/r02_trsm_walk.md): slower.  A CTA that walks a 120-row block
+  //           alone is a chain of 7000 dependent multiply-accumulates (32 ms against 29 ms for the
+  //           whole batch), and even the 40-row blocks lose: 900 equal CTAs on 444 slots are 2.03
+  //           waves, and the diagonal phase waits for its operand loads with four warps per
+  //           scheduler.  SDPB_B200_TRSM=walk runs it everywhere, =hybrid on matrices of up to
+  //           WALK_MAX_TILES row tiles beside the level kernels for the taller ones, =levels1 the
+  //           round-1 update kernel (16 x 16 tiles only).
+  static constexpr int WALK_MAX_TILES = 3;
   static int trsm(sdpb_b200_ctx *c, const char *label, const TrsmTileDesc *d,
-                  const std::vector<int> &sizes, int maxcols)
+                  const std::vector<int> &sizes, int maxcols, cudaStream_t side, int ev0)
   {
     if(sizes.empty() || sizes[0] == 0 || maxcols == 0)
       return 0;
-    // default: the whole solve in one launch (trsm_walk_kernel); SDPB_B200_TRSM=levels keeps the
-    // level-synchronous pair of kernels for A/B measurements
-    static const bool levels = [] {
+    static const int mode = [] {
       const char *env = getenv("SDPB_B200_TRSM");
-      return env && std::string(env) == "levels";
+      const std::string m = env ? env : "levels";
+      return m == "walk" ? 2 : m == "hybrid" ? 0 : m == "levels1" ? 3 : 1;
     }();
-    if(!levels)
+    int nheavy = 0; // prefix of the (descending) batch that keeps the level kernels
+    while(nheavy < (int)sizes.size()
+          && (mode == 1 || mode == 3 || (mode == 0 && sizes[nheavy] > WALK_MAX_TILES * TS)))
+      ++nheavy;
+    const int nlight = (int)sizes.size() - nheavy;
+    cudaStream_t main_stream = c->cur;
+    if(nlight)
       {
         // block = 16 TC threads owning ~16 TC columns: the largest TC whose padding of the
         // column count stays within 3 % of the best one
@@ -182,26 +198,40 @@ template <int NL> struct Launch
         const size_t smem = WalkGeom<NL>::bytes(TC);
         CUDA_TRY(c, cudaFuncSetAttribute(trsm_walk_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-        c->kt_begin(label);
-        trsm_walk_kernel<NL><<<(unsigned)sizes.size() * ncg, 16 * TC, smem, c->cur>>>(d, ncg, Wc);
+        if(nheavy)
+          {
+            CUDA_TRY(c, c->after(main_stream, side, ev0));
+            c->cur = side;
+          }
+        c->kt_begin(sub(label, "walk"));
+        trsm_walk_kernel<NL><<<(unsigned)nlight * ncg, 16 * TC, smem, c->cur>>>(d + nheavy, ncg, Wc);
         c->kt_end();
+        c->cur = main_stream;
         CUDA_TRY(c, cudaGetLastError());
-        return 0;
       }
+    if(nheavy == 0)
+      return 0;
     if(int rc = smem_opt_in(c, trsm_gemm_level<NL>))
       return rc;
+    const size_t smem2 = WalkGeom<NL>::bytes(TS);
+    CUDA_TRY(c, cudaFuncSetAttribute(trsm_gemm_level2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem2));
     CUDA_TRY(c, cudaFuncSetAttribute(trsm_diag_level<NL>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-    const int T = (sizes[0] + TS - 1) / TS;
+    const std::vector<int> heavy(sizes.begin(), sizes.begin() + nheavy);
+    const int T = (heavy[0] + TS - 1) / TS;
     const char *l_gemm = sub(label, "gemm"), *l_diag = sub(label, "diag");
     for(int It = 0; It < T; ++It)
       {
-        const int n = alive(sizes, It);
+        const int n = alive(heavy, It);
         if(It > 0)
           {
             dim3 g(n, (maxcols + TS - 1) / TS);
             c->kt_begin(l_gemm);
-            trsm_gemm_level<NL><<<g, 256, TILE_SMEM, c->cur>>>(d, It);
+            if(mode == 3)
+              trsm_gemm_level<NL><<<g, 256, TILE_SMEM, c->cur>>>(d, It);
+            else
+              trsm_gemm_level2<NL><<<g, 256, smem2, c->cur>>>(d, It);
             c->kt_end();
           }
         dim3 g2(n, (maxcols + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
@@ -210,6 +240,8 @@ template <int NL> struct Launch
         c->kt_end();
       }
     CUDA_TRY(c, cudaGetLastError());
+    if(nlight)
+      CUDA_TRY(c, c->after(side, main_stream, ev0 + 1));
     return 0;
   }
   static int gemm(sdpb_b200_ctx *c, const char *label, const GemmTileDesc *d,
@@ -239,7 +271,7 @@ template <int NL> struct Launch
       {
         // T = V ; T <- L_X^{-1} T ; AX = T^T T
         CUDA_TRY(c, cudaMemcpyAsync(c->T, c->V, c->wV * 8, cudaMemcpyDeviceToDevice, c->cur));
-        int rc = trsm(c, "trsm_LXinv_V", c->d_trsmT, c->szT, c->max_mn);
+        int rc = trsm(c, "trsm_LXinv_V", c->d_trsmT, c->szT, c->max_mn, c->side(2), 14);
         if(rc)
           return rc;
         return gemm(c, "gemm_A_X_inv", c->d_gemmAX, c->n_gemm, c->tiles_AX);
@@ -284,7 +316,7 @@ template <int NL> struct Launch
         int rc = potrf(c, "potrf_S", c->d_potrfS_g[g], c->szS_g[g], c->d_status + 4 * J, J, false);
         if(rc)
           return rc;
-        rc = trsm(c, "trsm_Linv_B", c->d_trsmP_g[g], c->szP_g[g], N);
+        rc = trsm(c, "trsm_Linv_B", c->d_trsmP_g[g], c->szP_g[g], N, c->G == 1 ? c->side(1) : sg, 12);
         if(rc)
           return rc;
         dim3 g1(nb, (N + 63) / 64);
@@ -455,6 +487,151 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaGetLastError());
     return 0;
   }
+  // C = alpha A B + beta C on block-diagonal objects: gemm_tile_kernel into smaT, then the epilogue
+  static int bdm_product(sdpb_b200_ctx *c, const char *label, const GemmTileDesc *d, int alpha, int beta, limb_t *C)
+  {
+    if(int rc = gemm(c, label, d, c->n_gemm, c->tiles_dir))
+      return rc;
+    const long count = (long)(c->wXY / Fmt<NL>::ES);
+    if(count == 0)
+      return 0;
+    c->kt_begin("sma_epilogue_kernel");
+    sma_epilogue_kernel<NL><<<(unsigned)std::min<long>((count + 127) / 128, 148 * 16), 128, 0, c->cur>>>(
+      c->smaT, C, count, alpha, beta);
+    c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
+  static int bdm_elementwise(sdpb_b200_ctx *c, int op, const limb_t *A, limb_t *C)
+  {
+    const long count = (long)(c->wXY / Fmt<NL>::ES);
+    if(count == 0)
+      return 0;
+    c->kt_begin("bdm_elementwise_kernel");
+    bdm_elementwise_kernel<NL><<<(unsigned)std::min<long>((count + 127) / 128, 148 * 16), 128, 0, c->cur>>>(op, A, C, count);
+    c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
+  // cholesky_solve.cxx:4-13 with the resident factor of X, then symmetrize (and negate)
+  static int bdm_cholesky_solve_symmetrize(sdpb_b200_ctx *c, limb_t *Z, int negate)
+  {
+    const int nb = 2 * c->J;
+    if(c->bdm_cols == 0)
+      return 0;
+    const unsigned g = (unsigned)((c->bdm_cols + 63) / 64);
+    c->kt_begin("bdm_trsm_kernel");
+    bdm_trsm_kernel<NL, false><<<g, 64, 0, c->cur>>>(c->d_bdm, nb, c->bdm_cols, c->X, c->recipX, Z);
+    c->kt_end();
+    c->kt_begin("bdm_trsm_kernel");
+    bdm_trsm_kernel<NL, true><<<g, 64, 0, c->cur>>>(c->d_bdm, nb, c->bdm_cols, c->X, c->recipX, Z);
+    c->kt_end();
+    const int ms = c->max_s;
+    dim3 gs(nb, (unsigned)std::min<long>(((long)ms * (ms + 1) / 2 + 127) / 128, 65535));
+    c->kt_begin("bdm_symmetrize_kernel");
+    bdm_symmetrize_kernel<NL><<<gs, 128, 0, c->cur>>>(c->d_bdm, nb, Z, c->dir_scal + Fmt<NL>::ES, negate);
+    c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
+  static int direction(sdpb_b200_ctx *c, int op, int arg)
+  {
+    const int J = c->J, nb = 2 * J, N = c->N;
+    cudaStream_t st = c->stream;
+    c->cur = st;
+    constexpr int ES = Fmt<NL>::ES;
+    if(op == 0) // minus_XY = -X Y (step.cxx:137) and the trace of every block
+      {
+        if(int rc = bdm_product(c, "gemm_minus_XY", c->d_gemmXY, -1, 0, c->dirMXY))
+          return rc;
+        if(nb)
+          {
+            c->kt_begin("bdm_trace_kernel");
+            bdm_trace_kernel<NL><<<(nb + 63) / 64, 64, 0, st>>>(c->d_bdm, nb, c->dirMXY, c->dir_part);
+            c->kt_end();
+            CUDA_TRY(c, cudaGetLastError());
+          }
+        return 0;
+      }
+    if(op == 1) // compute_R_error.hxx, per block
+      {
+        if(nb)
+          {
+            c->kt_begin("bdm_max_abs_kernel");
+            bdm_max_abs_kernel<NL><<<nb, 32, 0, st>>>(c->d_bdm, nb, c->dirMXY, c->dir_scal + 2 * ES, c->dir_part);
+            c->kt_end();
+            CUDA_TRY(c, cudaGetLastError());
+          }
+        return 0;
+      }
+    if(op == 3) // frobenius_product_of_sums.cxx, per block
+      {
+        if(nb)
+          {
+            c->kt_begin("bdm_frobenius_kernel");
+            bdm_frobenius_kernel<NL><<<nb, 32, 0, st>>>(c->d_bdm, nb, c->Xin, c->dirDX, c->Yin, c->dirDY,
+                                                        c->dir_colsum, c->dir_part);
+            c->kt_end();
+            CUDA_TRY(c, cudaGetLastError());
+          }
+        return 0;
+      }
+    // ---- compute_search_direction.cxx:44-90 ----
+    const bool corrector = arg != 0;
+    const size_t bytes = c->wXY * 8;
+    // R = beta mu I - X Y (- dX dY in the corrector phase)
+    if(bytes)
+      CUDA_TRY(c, cudaMemcpyAsync(c->dirR, c->dirMXY, bytes, cudaMemcpyDeviceToDevice, st));
+    if(corrector)
+      if(int rc = bdm_product(c, "gemm_dX_dY", c->d_gemmDXDY, -1, 1, c->dirR))
+        return rc;
+    if(c->bdm_cols)
+      {
+        c->kt_begin("bdm_add_diagonal_kernel");
+        bdm_add_diagonal_kernel<NL><<<(c->bdm_cols + 127) / 128, 128, 0, st>>>(c->d_bdm, nb, c->bdm_cols, c->dirR,
+                                                                               c->dir_scal);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+      }
+    // Z = Symmetrize(X^-1 (PrimalResidues Y - R))
+    if(int rc = bdm_product(c, "gemm_PR_Y", c->d_gemmPRY, 1, 0, c->dirZ))
+      return rc;
+    if(int rc = bdm_elementwise(c, 0, c->dirR, c->dirZ))
+      return rc;
+    if(int rc = bdm_cholesky_solve_symmetrize(c, c->dirZ, 0))
+      return rc;
+    // dx = -dual_residues - Tr(A_p Z)
+    if(c->K)
+      {
+        c->kt_begin("schur_rhs_kernel");
+        schur_rhs_kernel<NL><<<(unsigned)((c->K + 63) / 64), 64, 0, st>>>(c->d_bdm, J, c->d_row_block, c->K, c->V,
+                                                                          c->dirZ, c->dir_dual, c->sol_x);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+      }
+    // dy = primal_residue_p; (dx, dy) <- solve_schur_complement_equation
+    CUDA_TRY(c, cudaMemcpyAsync(c->sol_y, c->dir_prp, (size_t)N * ES * 8, cudaMemcpyDeviceToDevice, st));
+    if(int rc = schur_solve(c))
+      return rc;
+    // dX = PrimalResidues + sum_p A_p dx_p
+    if(nb)
+      {
+        const int ms = c->max_s;
+        dim3 g(nb, (unsigned)std::min<long>(((long)ms * ms + 63) / 64, 65535));
+        c->kt_begin("weighted_sum_kernel");
+        weighted_sum_kernel<NL><<<g, 64, 0, st>>>(c->d_bdm, nb, c->V, c->sol_x, c->dir_scal + ES, c->dirDX);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+      }
+    if(int rc = bdm_elementwise(c, 1, c->dirPR, c->dirDX))
+      return rc;
+    // dY = -Symmetrize(X^-1 (dX Y - R))
+    if(int rc = bdm_product(c, "gemm_dX_Y", c->d_gemmDXY, 1, 0, c->dirDY))
+      return rc;
+    if(int rc = bdm_elementwise(c, 0, c->dirR, c->dirDY))
+      return rc;
+    return bdm_cholesky_solve_symmetrize(c, c->dirDY, 1);
+  }
   static int scalar(sdpb_b200_ctx *c, int op, int k, long count,
                     const limb_t *a, const limb_t *b, limb_t *r)
   {
@@ -483,4 +660,4 @@ template <int NL> struct Launch
 extern "C" __attribute__((visibility("default"))) const LaunchTable
   SDPB_CAT(sdpb_b200_launch_nl, SDPB_NL) = {&Launch<SDPB_NL>::cholesky, &Launch<SDPB_NL>::pairings,
      &Launch<SDPB_NL>::schur_and_Q, &Launch<SDPB_NL>::schur_solve, &Launch<SDPB_NL>::scale_multiply_add,
-     &Launch<SDPB_NL>::scalar};
+     &Launch<SDPB_NL>::scalar, &Launch<SDPB_NL>::direction};

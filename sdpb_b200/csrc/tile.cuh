@@ -721,10 +721,12 @@ potrf_trail_rl(const PotrfDesc *descs, int Jt, const int *status, int cyc_mod, i
     stg_reg<NL>(mine, acc);
 }
 
+// a factored diagonal tile as the packed lower triangle ([tri_index(x, k)] = L(J0+x, J0+k), x >= k:
+// 136 of the 256 slots, so that eight 64-column CTAs fit an SM) and the reciprocals of its pivots
 template <int NL> struct DiagSmem
 {
   typedef TileGeom<NL> G;
-  uint32_t diag[TS * TS * G::SW]; // [k][x] = L(J0+x, J0+k)
+  uint32_t diag[TS * (TS + 1) / 2 * G::SW];
   uint32_t recip[TS * G::RS];
 };
 // cooperative load of a factored diagonal tile and its reciprocals
@@ -741,7 +743,7 @@ __device__ __forceinline__ void load_diag(DiagSmem<NL> &sm, const uint64_t *A, l
         {
           const uint4 *src = reinterpret_cast<const uint4 *>(
             A + ((long)(J0 + x) * si + (long)(J0 + k) * sj) * G::ES);
-          uint4 *dst = reinterpret_cast<uint4 *>(sm.diag + (k * TS + x) * G::SW);
+          uint4 *dst = reinterpret_cast<uint4 *>(sm.diag + tri_index(x, k) * G::SW);
 #pragma unroll
           for(int w = 0; w < G::EB / 16; ++w)
             dst[w] = src[w];
@@ -752,7 +754,9 @@ __device__ __forceinline__ void load_diag(DiagSmem<NL> &sm, const uint64_t *A, l
   __syncthreads();
 }
 
-constexpr int ROWS_PER_CTA = 128;
+// columns per CTA of trsm_diag_level: 64 (two warps) keeps the padding of a 300-column band at
+// 6 % (3 x 128 would be 28 %) and lets eight CTAs share an SM
+constexpr int ROWS_PER_CTA = 64;
 
 // -------------------------------------------------------- triangular solve
 struct TrsmTileDesc // X <- L^{-1} B in place, L lower p x p (column-major)
@@ -801,7 +805,7 @@ __global__ void __launch_bounds__(256, 2) trsm_gemm_level(const TrsmTileDesc *de
     stg_reg<NL>(mine, acc);
 }
 template <int NL>
-__global__ void __launch_bounds__(ROWS_PER_CTA, 4)
+__global__ void __launch_bounds__(ROWS_PER_CTA, 8)
 trsm_diag_level(const TrsmTileDesc *descs, int It)
 {
   typedef TileGeom<NL> G;
@@ -822,9 +826,9 @@ trsm_diag_level(const TrsmTileDesc *descs, int It)
       Reg<NL> acc;
       ldg_reg<NL>(acc, colp + (long)ii * G::ES);
       for(int kk = 0; kk < ii; ++kk)
-        acc = mac_nl<NL>(acc, sm.diag + (kk * TS + ii) * G::SW,
+        acc = mac_nl<NL>(acc, sm.diag + tri_index(ii, kk) * G::SW,
                          reinterpret_cast<const uint32_t *>(colp + (long)kk * G::ES), true);
-      acc = div_nl<NL>(acc, sm.diag + (ii * TS + ii) * G::SW, sm.recip + ii * G::RS);
+      acc = div_nl<NL>(acc, sm.diag + tri_index(ii, ii) * G::SW, sm.recip + ii * G::RS);
       stg_reg<NL>(colp + (long)ii * G::ES, acc);
     }
 }
@@ -850,6 +854,111 @@ template <int NL> struct WalkGeom
   static constexpr size_t OFF_B = OFF_A + (size_t)2 * KC * TS * G::SW * 4;
   static size_t bytes(int tc) { return OFF_B + (size_t)2 * KC * (2 * tc) * G::SW * 4; }
 };
+// One update pass of the triangular solve: rows [I0, I0 + ni) of columns [c0, c1) receive
+// b_ic -= sum_{klo <= k < I0} l_ik x_kc.  Tile shape (16 x TC) or, `wide`, (8 x 2 TC) with
+// TC = blockDim / 16; operands staged by TMA in chunks of KC, double buffered (s_a: KC x 16
+// elements per buffer, s_b: KC x 2 TC).  `it` counts the chunks staged so far by this CTA.
+template <int NL>
+__device__ __forceinline__ void
+trsm_update_pass(const TrsmTileDesc &d, int I0, int ni, bool wide, int c0, int c1, int klo, uint64_t *bar,
+                 uint32_t *s_a, uint32_t *s_b, uint32_t &it)
+{
+  typedef TileGeom<NL> G;
+  const int nth = blockDim.x, TC = nth >> 4, BC = 2 * TC, t = threadIdx.x;
+  const int rows = wide ? TS / 2 : TS, cols = wide ? BC : TC;
+  const int ti = wide ? (t & 7) : (t & 15), tj = wide ? (t >> 3) : (t >> 4);
+  const int nc = min(cols, c1 - c0), K = I0 - klo;
+  const bool active = ti < ni && tj < nc;
+  Reg<NL> acc;
+  uint64_t *mine = d.B + ((long)(c0 + tj) * d.p + I0 + ti) * G::ES;
+  if(active)
+    ldg_reg<NL>(acc, mine);
+  else
+    mpfw::set_zero(acc);
+  const uint64_t *Abase = d.L + ((long)I0 + (long)klo * d.p) * G::ES; // (x, k) -> x + k p
+  const uint64_t *Bbase = d.B + ((long)c0 * d.p + klo) * G::ES;       // (x, k) -> x p + k
+  const int nchunks = (K + KC - 1) / KC;
+  auto issue = [&](int c) {
+    const uint32_t s = (it + c) & 1;
+    const int k0 = c * KC, kcnt = min(KC, K - k0);
+    if(t == 0)
+      mbar_expect_tx(&bar[s], (uint32_t)(G::EB * kcnt * (ni + nc)));
+    // copies of this chunk: kcnt x ni elements of L, kcnt x nc elements of X
+    for(int e = t; e < KC * (rows + cols); e += nth)
+      {
+        const bool isA = e < KC * rows;
+        const int q = isA ? e : e - KC * rows;
+        const int dk = isA ? q / rows : q / cols, dx = isA ? q % rows : q % cols;
+        if(dk >= kcnt || dx >= (isA ? ni : nc))
+          continue;
+        if(isA)
+          bulk_g2s(s_a + ((size_t)s * KC * TS + dk * TS + dx) * G::SW,
+                   Abase + ((long)dx + (long)(k0 + dk) * d.p) * G::ES, G::EB, &bar[s]);
+        else
+          bulk_g2s(s_b + ((size_t)s * KC * BC + dk * BC + dx) * G::SW,
+                   Bbase + ((long)dx * d.p + (k0 + dk)) * G::ES, G::EB, &bar[s]);
+      }
+  };
+  issue(0);
+  for(int c = 0; c < nchunks; ++c)
+    {
+      if(c + 1 < nchunks)
+        issue(c + 1);
+      const uint32_t s = (it + c) & 1, parity = ((it + c) >> 1) & 1;
+      while(!mbar_try_wait(&bar[s], parity))
+        {
+        }
+      const int kcnt = min(KC, K - c * KC);
+      if(active)
+        {
+          const uint32_t *pa = s_a + ((size_t)s * KC * TS + ti) * G::SW;
+          const uint32_t *pb = s_b + ((size_t)s * KC * BC + tj) * G::SW;
+          for(int kk = 0; kk < kcnt; ++kk)
+            acc = mac_ss_nl<NL>(acc, pa + (size_t)kk * TS * G::SW, pb + (size_t)kk * BC * G::SW, true);
+        }
+      __syncthreads();
+    }
+  it += nchunks;
+  if(active)
+    stg_reg<NL>(mine, acc);
+}
+
+// Level kernel with the two tile shapes of the walk kernel: CTAs whose row tile has more than 8
+// rows update a (16 x 16) tile, CTAs on a last tile of <= 8 rows an (8 x 32) one (half as many
+// CTAs, all 256 threads busy: a 40-row block is 2.5 tiles).  grid.y counts 16-column tiles.
+template <int NL>
+__global__ void __launch_bounds__(256, 2) trsm_gemm_level2(const TrsmTileDesc *descs, int It)
+{
+  typedef TileGeom<NL> G;
+  typedef WalkGeom<NL> WG;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+  uint32_t *s_a = reinterpret_cast<uint32_t *>(smem_raw + WG::OFF_A);
+  uint32_t *s_b = reinterpret_cast<uint32_t *>(smem_raw + WG::OFF_B);
+  const TrsmTileDesc d = descs[blockIdx.x];
+  const int I0 = It * TS;
+  if(I0 >= d.p)
+    return;
+  const int ni = min(TS, d.p - I0);
+  const bool wide = ni <= TS / 2;
+  const int cols = wide ? 2 * TS : TS;
+  const int c0 = blockIdx.y * cols;
+  if(c0 >= d.ncols)
+    return;
+  const int klo = d.hb ? ((c0 / d.nb) * d.hb) & ~(KC - 1) : 0;
+  if(I0 <= klo)
+    return; // nothing above this tile can be non-zero: no update
+  if(threadIdx.x == 0)
+    {
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  __syncthreads();
+  uint32_t it = 0;
+  trsm_update_pass<NL>(d, I0, ni, wide, c0, min(d.ncols, c0 + cols), klo, bar, s_a, s_b, it);
+}
+
 template <int NL>
 __global__ void __launch_bounds__(256, 2)
 trsm_walk_kernel(const TrsmTileDesc *descs, int ncg, int Wc)
@@ -882,68 +991,14 @@ trsm_walk_kernel(const TrsmTileDesc *descs, int ncg, int Wc)
       const int I0 = It * TS, ni = min(TS, d.p - I0);
       // ---- update: rows of this tile against everything solved above it
       const bool wide = ni <= TS / 2;               // (8 x 2TC) tiles
-      const int rows = wide ? TS / 2 : TS, cols = wide ? BC : TC;
-      const int ti = wide ? (t & 7) : (t & 15), tj = wide ? (t >> 3) : (t >> 4);
+      const int cols = wide ? BC : TC;
       for(int c0 = c_lo; c0 < c_hi && I0 > 0; c0 += cols)
         {
           // leading zeros of these columns (bases_blocks structure): rows above klo are exact zeros
           const int klo = d.hb ? ((c0 / d.nb) * d.hb) & ~(KC - 1) : 0;
           if(I0 <= klo)
             continue;
-          const int nc = min(cols, c_hi - c0), K = I0 - klo;
-          const bool active = ti < ni && tj < nc;
-          Reg<NL> acc;
-          uint64_t *mine = d.B + ((long)(c0 + tj) * d.p + I0 + ti) * G::ES;
-          if(active)
-            ldg_reg<NL>(acc, mine);
-          else
-            mpfw::set_zero(acc);
-          const uint64_t *Abase = d.L + ((long)I0 + (long)klo * d.p) * G::ES; // (x, k) -> x + k p
-          const uint64_t *Bbase = d.B + ((long)c0 * d.p + klo) * G::ES;       // (x, k) -> x p + k
-          const int nchunks = (K + KC - 1) / KC;
-          auto issue = [&](int c) {
-            const uint32_t s = (it + c) & 1;
-            const int k0 = c * KC, kcnt = min(KC, K - k0);
-            if(t == 0)
-              mbar_expect_tx(&bar[s], (uint32_t)(G::EB * kcnt * (ni + nc)));
-            // copies of this chunk: kcnt x ni elements of L, kcnt x nc elements of X
-            for(int e = t; e < KC * (rows + cols); e += nth)
-              {
-                const bool isA = e < KC * rows;
-                const int q = isA ? e : e - KC * rows;
-                const int dk = isA ? q / rows : q / cols, dx = isA ? q % rows : q % cols;
-                if(dk >= kcnt || dx >= (isA ? ni : nc))
-                  continue;
-                if(isA)
-                  bulk_g2s(s_a + ((size_t)s * KC * TS + dk * TS + dx) * G::SW,
-                           Abase + ((long)dx + (long)(k0 + dk) * d.p) * G::ES, G::EB, &bar[s]);
-                else
-                  bulk_g2s(s_b + ((size_t)s * KC * BC + dk * BC + dx) * G::SW,
-                           Bbase + ((long)dx * d.p + (k0 + dk)) * G::ES, G::EB, &bar[s]);
-              }
-          };
-          issue(0);
-          for(int c = 0; c < nchunks; ++c)
-            {
-              if(c + 1 < nchunks)
-                issue(c + 1);
-              const uint32_t s = (it + c) & 1, parity = ((it + c) >> 1) & 1;
-              while(!mbar_try_wait(&bar[s], parity))
-                {
-                }
-              const int kcnt = min(KC, K - c * KC);
-              if(active)
-                {
-                  const uint32_t *pa = s_a + ((size_t)s * KC * TS + ti) * G::SW;
-                  const uint32_t *pb = s_b + ((size_t)s * KC * BC + tj) * G::SW;
-                  for(int kk = 0; kk < kcnt; ++kk)
-                    acc = mac_ss_nl<NL>(acc, pa + (size_t)kk * TS * G::SW, pb + (size_t)kk * BC * G::SW, true);
-                }
-              __syncthreads();
-            }
-          it += nchunks;
-          if(active)
-            stg_reg<NL>(mine, acc);
+          trsm_update_pass<NL>(d, I0, ni, wide, c0, c_hi, klo, bar, s_a, s_b, it);
         }
       // ---- the factored diagonal tile (packed lower triangle) and its reciprocals
       for(int e = t; e < TS * TS; e += nth)

@@ -20,6 +20,27 @@ WORKLOADS = {
     "c4": (960, [(2, 40)] * 250 + [(1, 40)] * 750, 1000),
     "c4-sample": (960, [(2, 40)] * 6 + [(1, 40)] * 18, 1000),
     "tiny": (768, [(1, 6), (2, 4), (1, 9)], 5),
+    # C5, the synthetic sweep of BASELINE.json configs[4]: J in {256, 1024, 4096}, block dim P_j in
+    # {64, 256} (m = 1, n = P_j), N in {512, 4096}, prec in {256, 768, 1536}.  Named corners; every
+    # one needs sum P_j >= N (Q positive definite).  What does not fit 180 GB is listed in DESIGN.md.
+    "c5-j256-p64-n512": (768, [(1, 64)] * 256, 512),
+    "c5-j1024-p64-n512": (768, [(1, 64)] * 1024, 512),
+    "c5-j4096-p64-n512": (768, [(1, 64)] * 4096, 512),
+    "c5-j256-p256-n512": (768, [(1, 256)] * 256, 512),
+    "c5-j1024-p256-n512": (768, [(1, 256)] * 1024, 512),
+    "c5-j256-p64-n4096-256b": (256, [(1, 64)] * 256, 4096),
+    "c5-j256-p64-n4096": (768, [(1, 64)] * 256, 4096),
+    "c5-j256-p64-n4096-1536b": (1536, [(1, 64)] * 256, 4096),
+    "c5-j256-p256-n512-256b": (256, [(1, 256)] * 256, 512),
+    "c5-j256-p256-n512-1536b": (1536, [(1, 256)] * 256, 512),
+    # bounded samples for the CPU restatement (same block shapes and N; rows >= N)
+    "c5-j256-p64-n512-sample": (768, [(1, 64)] * 10, 512),
+    "c5-j1024-p64-n512-sample": (768, [(1, 64)] * 10, 512),
+    "c5-j4096-p64-n512-sample": (768, [(1, 64)] * 10, 512),
+    "c5-j256-p256-n512-sample": (768, [(1, 256)] * 3, 512),
+    "c5-j1024-p256-n512-sample": (768, [(1, 256)] * 3, 512),
+    "c5-j256-p256-n512-256b-sample": (256, [(1, 256)] * 3, 512),
+    "c5-j256-p256-n512-1536b-sample": (1536, [(1, 256)] * 3, 512),
 }
 
 
