@@ -261,7 +261,7 @@ def cpu_full(workload, steps, warmup, world=1, budget_s=None):
     walls = []
     t_start = time.perf_counter()
     n_warm = 0
-    if warmup > 0 and est is not None and 2 * est < budget_s:
+    if warmup > 0 and (est is None or 2 * est * world < budget_s):
         ref.schur_step(sdp.X, sdp.Y)
         n_warm = 1
     for it in range(max(1, steps)):
@@ -527,6 +527,47 @@ def main():
         barrier()
         e2e_all_s = (time.perf_counter() - e0) / a.steps
 
+    # ---- compute_search_direction on the resident objects ----
+    # (per Newton iteration: -XY + traces, R error, residues up, predictor, Frobenius products,
+    # corrector, direction down -- what step.cxx:131-176 does around the two Schur solves)
+    from sdpb_b200.synthetic import random_matrix as synth_matrix
+    rng = np.random.Generator(np.random.PCG64(0x5D9B2000 + rank))
+    pr = pool.slab([x.shape for x in sdp.X])
+    for dst in pr:
+        dst[...] = synth_matrix(rng, prec, dst.shape[1], dst.shape[0])
+    dr = pool.slab([x.shape for x in rx])
+    for dst in dr:
+        dst[...] = synth_matrix(rng, prec, dst.shape[1], 1)
+    prp = synth_matrix(rng, prec, N, 1)
+    p_pr, p_dr = ptr_array(pr), ptr_array(dr)
+    bm = np.zeros(ctx.ew, dtype=np.uint64)     # the packed element 0.125 (beta mu / mu stand-in)
+    bm[0] = 1 << 32                            # sign +1, exponent 0
+    bm[(prec + 63) // 64 + 2] = 1 << 61        # top limb
+    dir_dev, dir_wall, dir_k = {}, [], {}
+    for it in range(1 + a.steps):
+        barrier()
+        s0 = time.perf_counter()
+        ctx.direction_begin()
+        t_begin = ctx.last_direction_ms()
+        k_begin = ctx.kernel_timings()
+        ctx.direction_R_errors(bm)
+        ctx.direction_set_residues(p_pr, p_dr, prp)
+        ctx.compute_search_direction(bm, 0)
+        t_pred = ctx.last_direction_ms()
+        k_pred = ctx.kernel_timings()
+        ctx.direction_frobenius()
+        ctx.compute_search_direction(bm, 1)
+        t_corr = ctx.last_direction_ms()
+        wall_dir = time.perf_counter() - s0
+        if it >= 1:
+            dir_wall.append(wall_dir)
+            for k, v in (("minus_XY", t_begin), ("predictor", t_pred), ("corrector", t_corr)):
+                dir_dev.setdefault(k, []).append(v)
+            for name, ms in k_begin + k_pred:
+                dir_k.setdefault(name, []).append(ms)
+    barrier()
+    dir_api_s = float(np.mean(dir_wall))
+
     # ---- scale_multiply_add (-X Y and the other block GEMMs of step()) ----
     Ch = pool.slab([x.shape for x in sdp.X])
     sma_k = {}
@@ -638,6 +679,14 @@ def main():
                                    "kernels_ms": {k: round(float(np.mean(v)), 4) for k, v in sma_k.items()},
                                    "bytes_h2d": int(2 * sum(x.nbytes for x in Xh)),
                                    "bytes_d2h": int(sum(x.nbytes for x in Ch)), "cpu": sma_cpu},
+            "search_direction": {"what": "compute_search_direction.cxx:44-90 twice (predictor, corrector) plus "
+                                         "-XY, traces, R error and Frobenius products, on device-resident X, Y, "
+                                         "dX, dY, R, Z (SURVEY 8f rows N2); includes the two Schur solves; host "
+                                         "traffic: residues up, per-block scalars down",
+                                 "api_ms_host_buffers": dir_api_s * 1e3,
+                                 "device_ms": {k: round(float(np.mean(v)), 3) for k, v in dir_dev.items()},
+                                 "kernels_ms_predictor": {k: round(float(np.sum(v)) / a.steps, 4) for k, v in dir_k.items()},
+                                 "bytes_h2d": int(sum(x.nbytes for x in pr) + sum(x.nbytes for x in dr) + prp.nbytes)},
             "e2e_with_two_solves": {"what": "one Newton iteration's device work through the C-ABI with host "
                                             "buffers: the e2e step plus the predictor and corrector Schur solves",
                                     "value": e2e_s + 2 * solve_api_s, "unit": "s/iteration"},

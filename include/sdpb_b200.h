@@ -159,6 +159,44 @@ int sdpb_b200_scale_multiply_add(sdpb_b200_ctx *ctx, int alpha,
 int sdpb_b200_cholesky_diagonals(sdpb_b200_ctx *ctx, uint64_t *X_diag, uint64_t *Y_diag,
                                  uint64_t *S_diag, uint64_t *Q_diag);
 
+/* ---- The search direction on the device (compute_search_direction.cxx:44-90) ----------------
+ * step() forms R, Z, dx, dX, dy, dY from X, Y, their factors and the residues
+ * (run/step/step.cxx:131-176).  These calls keep all of that in HBM: the block products
+ * (scale_multiply_add.cxx:4-16), cholesky_solve (cholesky_solve.cxx:4-13), symmetrize
+ * (Block_Diagonal_Matrix.hxx:95-109), compute_schur_RHS (compute_schur_RHS.cxx:21-86), the Schur
+ * solves and constraint_matrix_weighted_sum (constraint_matrix_weighted_sum.cxx:14-66) run on the
+ * X, Y of the preceding step (sdpb_b200_schur_step, or cholesky_decomposition(X) +
+ * compute_bilinear_pairings(Y)) and its factors; only the residues go up and per-block scalars
+ * come down, until the caller asks for the direction itself.  Per iteration:
+ *
+ *   direction_begin            minus_XY = -X Y (step.cxx:137); block_traces[b], b = 2j + parity, is
+ *                              the trace of block b: mu = -(sum_b traces) / total_psd_rows (:138-146)
+ *   direction_R_errors         block_maxima[b] = max |(-XY + mu I)_b| (compute_R_error.hxx)
+ *   direction_set_residues     primal_residues (2J blocks, shape of X), dual_residues (J vectors of
+ *                              P_j elements), primal_residue_p (N elements, fully reduced -- see
+ *                              solve_schur_complement_equation above)
+ *   compute_search_direction   beta_mu = beta * mu (one packed element).  is_corrector = 0:
+ *                              R = beta mu I - XY; 1: R = beta mu I - XY - dX dY with the dX, dY of
+ *                              the preceding (predictor) call (compute_search_direction.cxx:50-56)
+ *   direction_frobenius        block_products[b] = sum_ij (X+dX)_ij (Y+dY)_ij of block b
+ *                              (corrector_centering_parameter.cxx, frobenius_product_of_sums.cxx)
+ *   direction_get              copies dx (J vectors), dX, dY (2J blocks), dy (N) back; any may be NULL
+ *
+ * Sums over blocks are left to the caller, in the canonical two-level order (groups of 64
+ * consecutive blocks) that csrc/host/direction.hpp::ordered_sum spells out; inside a block the
+ * order is fixed by the library.  Results are bit-identical to that host restatement. */
+int sdpb_b200_direction_begin(sdpb_b200_ctx *ctx, uint64_t *block_traces);
+int sdpb_b200_direction_R_errors(sdpb_b200_ctx *ctx, const uint64_t *mu, uint64_t *block_maxima);
+int sdpb_b200_direction_set_residues(sdpb_b200_ctx *ctx, const uint64_t *const *primal_residues,
+                                     const uint64_t *const *dual_residues,
+                                     const uint64_t *primal_residue_p);
+int sdpb_b200_compute_search_direction(sdpb_b200_ctx *ctx, const uint64_t *beta_mu, int is_corrector);
+int sdpb_b200_direction_frobenius(sdpb_b200_ctx *ctx, uint64_t *block_products);
+int sdpb_b200_direction_get(sdpb_b200_ctx *ctx, uint64_t *const *dx, uint64_t *const *dX, uint64_t *dy,
+                            uint64_t *const *dY);
+/* Device time of the last direction_begin / compute_search_direction, ms (CUDA events). */
+float sdpb_b200_last_direction_ms(const sdpb_b200_ctx *ctx);
+
 /* Device time of the last sdpb_b200_solve_schur_complement_equation, ms (CUDA events). */
 float sdpb_b200_last_solve_ms(const sdpb_b200_ctx *ctx);
 

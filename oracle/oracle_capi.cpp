@@ -3,6 +3,7 @@
 // libgmp, so tests drive both through identical inputs and compare bytes.
 // Build: make -C oracle   (-> oracle/liboracle.so)
 #include "hotpath_core.hpp"
+#include "../sdpb_b200/csrc/host/direction.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -29,6 +30,14 @@ struct oracle_ctx
   std::string error;
   double stage_ms[9];
   SchurOutputs shard; // state between the stages of the sharded model; after a step: L_j, P_j, chol(Q)
+  // search direction (row N2): what compute_search_direction.cxx:44-90 reads and writes
+  sdpb_host::Block_Info block_info;
+  std::vector<Matrix> bases;                  // 2J bilinear bases (h x n)
+  std::vector<Matrix> X, Y;                   // 2J, pristine inputs of the last step
+  std::vector<Matrix> minus_XY, primal_residues, dX, dY; // 2J
+  std::vector<Matrix> dual_residues, dx;      // J
+  Matrix primal_residue_p, dy;                // N x 1
+  bool have_minus_XY = false, have_residues = false, have_direction = false;
 };
 
 static void pack_out(const Matrix &m, uint64_t *out)
@@ -53,7 +62,14 @@ int oracle_create(oracle_ctx **out, int prec_bits, int num_blocks,
   c->N = N;
   c->J = num_blocks;
   for(int j = 0; j < num_blocks; ++j)
-    c->shapes.push_back(BlockShape{dims[j], num_points[j]});
+    {
+      c->shapes.push_back(BlockShape{dims[j], num_points[j]});
+      c->block_info.dimensions.push_back(dims[j]);
+      c->block_info.num_points.push_back(num_points[j]);
+    }
+  c->bases.resize(2 * num_blocks);
+  c->X.resize(2 * num_blocks);
+  c->Y.resize(2 * num_blocks);
   c->B.resize(num_blocks);
   c->V.resize(2 * num_blocks);
   c->X_cholesky.resize(2 * num_blocks);
@@ -78,6 +94,7 @@ int oracle_set_block(oracle_ctx *c, int j, const uint64_t *B,
       Matrix basis;
       const int h = sh.basis_height(p);
       unpack_matrix(basis, h, sh.n, p == 0 ? bases_even : bases_odd);
+      c->bases[2 * j + p] = basis;
       if(h > 0)
         make_bases_block(sh, p, basis, c->V[2 * j + p]);
       else
@@ -100,6 +117,7 @@ int oracle_cholesky_decomposition(oracle_ctx *c, int which,
       if(s == 0)
         continue;
       unpack_matrix(out[b], s, s, A[b]);
+      (which == 0 ? c->X : c->Y)[b] = out[b]; // the pristine matrix: -XY and the Frobenius product read it
       const int bad = cholesky_lower(out[b]);
       if(bad >= 0)
         {
@@ -463,6 +481,145 @@ int oracle_scale_multiply_add(oracle_ctx *c, int alpha, const uint64_t *const *A
       scale_multiply_add_block(al, Am, Bm, be, Cm);
       pack_out(Cm, C[b]);
     }
+  return 0;
+}
+
+// ---- the search direction (row N2): same call surface as sdpb_b200_direction_* ----
+// compute_search_direction.cxx:44-90 and the per-block reductions of step.cxx:137-160, by the
+// canonical host restatement of csrc/host/direction.hpp on this context's X, Y and factors.
+static void oracle_sma(oracle_ctx *c, int alpha, const std::vector<Matrix> &A, const std::vector<Matrix> &B, int beta,
+                       std::vector<Matrix> &C)
+{
+  const BigFloat al(alpha), be(beta);
+  C.resize(A.size());
+#pragma omp parallel for schedule(dynamic)
+  for(size_t b = 0; b < A.size(); ++b)
+    {
+      if(A[b].h == 0)
+        continue;
+      if(!beta)
+        C[b].resize(A[b].h, A[b].w);
+      scale_multiply_add_block(al, A[b], B[b], be, C[b]);
+    }
+}
+static void pack_scalars(const std::vector<BigFloat> &v, uint64_t *out)
+{
+  const size_t ew = (size_t)elem_words();
+  for(size_t i = 0; i < v.size(); ++i)
+    sdpb_host::pack(v[i], out + i * ew);
+}
+int oracle_direction_begin(oracle_ctx *c, uint64_t *block_traces)
+{
+  sdpb_host::set_precision(c->prec);
+  if((int)c->shard.schur_complement_cholesky.size() != c->J || c->shard.Q.h != c->N)
+    {
+      c->error = "direction_begin called out of order (needs a successful Schur-complement step)";
+      return 5;
+    }
+  oracle_sma(c, -1, c->X, c->Y, 0, c->minus_XY);
+  std::vector<BigFloat> traces;
+  sdpb_host::block_traces(c->minus_XY, traces);
+  if(block_traces)
+    pack_scalars(traces, block_traces);
+  c->have_minus_XY = true;
+  c->have_direction = false;
+  return 0;
+}
+int oracle_direction_R_errors(oracle_ctx *c, const uint64_t *mu, uint64_t *block_maxima)
+{
+  sdpb_host::set_precision(c->prec);
+  if(!c->have_minus_XY)
+    {
+      c->error = "direction_R_errors called out of order";
+      return 5;
+    }
+  BigFloat m;
+  sdpb_host::unpack(m, mu);
+  std::vector<BigFloat> maxima;
+  sdpb_host::block_R_errors(c->minus_XY, m, maxima);
+  pack_scalars(maxima, block_maxima);
+  return 0;
+}
+int oracle_direction_set_residues(oracle_ctx *c, const uint64_t *const *primal_residues,
+                                  const uint64_t *const *dual_residues, const uint64_t *primal_residue_p)
+{
+  sdpb_host::set_precision(c->prec);
+  c->primal_residues.resize(2 * c->J);
+  c->dual_residues.resize(c->J);
+  for(int b = 0; b < 2 * c->J; ++b)
+    {
+      const int s = c->shapes[b / 2].psd_size(b % 2);
+      if(s)
+        unpack_matrix(c->primal_residues[b], s, s, primal_residues[b]);
+      else
+        c->primal_residues[b].resize(0, 0);
+    }
+  for(int j = 0; j < c->J; ++j)
+    unpack_matrix(c->dual_residues[j], c->shapes[j].schur_size(), 1, dual_residues[j]);
+  unpack_matrix(c->primal_residue_p, c->N, 1, primal_residue_p);
+  c->have_residues = true;
+  return 0;
+}
+int oracle_compute_search_direction(oracle_ctx *c, const uint64_t *beta_mu, int is_corrector)
+{
+  sdpb_host::set_precision(c->prec);
+  if(!c->have_minus_XY || !c->have_residues || (is_corrector && !c->have_direction))
+    {
+      c->error = "compute_search_direction called out of order";
+      return 5;
+    }
+  BigFloat bm;
+  sdpb_host::unpack(bm, beta_mu);
+  if(!is_corrector)
+    {
+      c->dX = c->X;
+      c->dY = c->Y;
+      c->dx.resize(c->J);
+    }
+  sdpb_host::compute_search_direction(
+    c->block_info, c->bases, c->X, c->Y, c->X_cholesky, c->minus_XY, c->primal_residues, c->dual_residues,
+    c->primal_residue_p, bm, is_corrector != 0,
+    [&](int alpha, const std::vector<Matrix> &A, const std::vector<Matrix> &B, int beta, std::vector<Matrix> &C) {
+      oracle_sma(c, alpha, A, B, beta, C);
+    },
+    [&](std::vector<Matrix> &x, Matrix &y) { solve_schur_complement_equation(c->shard, x, y); }, c->dx, c->dX,
+    c->dy, c->dY);
+  c->have_direction = true;
+  return 0;
+}
+int oracle_direction_frobenius(oracle_ctx *c, uint64_t *block_products)
+{
+  sdpb_host::set_precision(c->prec);
+  if(!c->have_direction)
+    {
+      c->error = "direction_frobenius called out of order";
+      return 5;
+    }
+  std::vector<BigFloat> products;
+  sdpb_host::block_frobenius_products(c->X, c->dX, c->Y, c->dY, products);
+  pack_scalars(products, block_products);
+  return 0;
+}
+int oracle_direction_get(oracle_ctx *c, uint64_t *const *dx, uint64_t *const *dX, uint64_t *dy, uint64_t *const *dY)
+{
+  sdpb_host::set_precision(c->prec);
+  if(!c->have_direction)
+    {
+      c->error = "direction_get called out of order";
+      return 5;
+    }
+  for(int j = 0; j < c->J; ++j)
+    if(dx && dx[j])
+      pack_out(c->dx[j], dx[j]);
+  for(int b = 0; b < 2 * c->J; ++b)
+    {
+      if(dX && dX[b])
+        pack_out(c->dX[b], dX[b]);
+      if(dY && dY[b])
+        pack_out(c->dY[b], dY[b]);
+    }
+  if(dy)
+    pack_out(c->dy, dy);
   return 0;
 }
 

@@ -7,6 +7,7 @@
 #include "../sdpb_b200/csrc/host/cli.hpp"
 #include "../sdpb_b200/csrc/host/hot_path_c.hpp"
 
+#include <cstdlib>
 #include <cstring>
 
 struct oracle_ctx;
@@ -26,6 +27,13 @@ int oracle_initialize_schur_complement_solver(oracle_ctx *c, uint64_t *const *sc
 int oracle_solve_schur_complement_equation(oracle_ctx *c, uint64_t *const *dx, uint64_t *dy);
 int oracle_scale_multiply_add(oracle_ctx *c, int alpha, const uint64_t *const *A, const uint64_t *const *B, int beta,
                               uint64_t *const *C);
+int oracle_direction_begin(oracle_ctx *c, uint64_t *block_traces);
+int oracle_direction_R_errors(oracle_ctx *c, const uint64_t *mu, uint64_t *block_maxima);
+int oracle_direction_set_residues(oracle_ctx *c, const uint64_t *const *primal_residues,
+                                  const uint64_t *const *dual_residues, const uint64_t *primal_residue_p);
+int oracle_compute_search_direction(oracle_ctx *c, const uint64_t *beta_mu, int is_corrector);
+int oracle_direction_frobenius(oracle_ctx *c, uint64_t *block_products);
+int oracle_direction_get(oracle_ctx *c, uint64_t *const *dx, uint64_t *const *dX, uint64_t *dy, uint64_t *const *dY);
 }
 
 using namespace sdpb_host;
@@ -56,6 +64,26 @@ static Hot_Path_Table oracle_table(const Block_Info &bi, const SDP &sdp, int pre
   };
   t.scale_multiply_add = [](void *x, int al, const uint64_t *const *A, const uint64_t *const *B, int be,
                             uint64_t *const *C) { return oracle_scale_multiply_add((oracle_ctx *)x, al, A, B, be, C); };
+  // SDPB_ORACLE_HOST_DIRECTION=1: leave the direction to the solver's own host code path
+  // (direction.hpp called directly) instead of the oracle_direction_* entry points -- the two must
+  // give the same trajectory (tests/test_golden_trajectory.py)
+  if(!getenv("SDPB_ORACLE_HOST_DIRECTION"))
+    {
+      t.direction_begin = [](void *x, uint64_t *tr) { return oracle_direction_begin((oracle_ctx *)x, tr); };
+      t.direction_R_errors = [](void *x, const uint64_t *mu, uint64_t *mx) {
+        return oracle_direction_R_errors((oracle_ctx *)x, mu, mx);
+      };
+      t.direction_set_residues = [](void *x, const uint64_t *const *pr, const uint64_t *const *dr, const uint64_t *p) {
+        return oracle_direction_set_residues((oracle_ctx *)x, pr, dr, p);
+      };
+      t.compute_search_direction = [](void *x, const uint64_t *bm, int corr) {
+        return oracle_compute_search_direction((oracle_ctx *)x, bm, corr);
+      };
+      t.direction_frobenius = [](void *x, uint64_t *fp) { return oracle_direction_frobenius((oracle_ctx *)x, fp); };
+      t.direction_get = [](void *x, uint64_t *const *dx, uint64_t *const *dX, uint64_t *dy, uint64_t *const *dY) {
+        return oracle_direction_get((oracle_ctx *)x, dx, dX, dy, dY);
+      };
+    }
   t.last_error = [](const void *x) { return oracle_last_error((const oracle_ctx *)x); };
   t.destroy = [](void *x) { oracle_destroy((oracle_ctx *)x); };
   t.name = "cpu-oracle(libgmp)";

@@ -96,6 +96,20 @@ def load_library():
                                               ctypes.POINTER(ctypes.POINTER(ctypes.c_int))]
     lib.sdpb_b200_cholesky_diagonals.restype = ctypes.c_int
     lib.sdpb_b200_cholesky_diagonals.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, u64p]
+    lib.sdpb_b200_direction_begin.restype = ctypes.c_int
+    lib.sdpb_b200_direction_begin.argtypes = [ctypes.c_void_p, u64p]
+    lib.sdpb_b200_direction_R_errors.restype = ctypes.c_int
+    lib.sdpb_b200_direction_R_errors.argtypes = [ctypes.c_void_p, u64p, u64p]
+    lib.sdpb_b200_direction_set_residues.restype = ctypes.c_int
+    lib.sdpb_b200_direction_set_residues.argtypes = [ctypes.c_void_p, u64pp, u64pp, u64p]
+    lib.sdpb_b200_compute_search_direction.restype = ctypes.c_int
+    lib.sdpb_b200_compute_search_direction.argtypes = [ctypes.c_void_p, u64p, ctypes.c_int]
+    lib.sdpb_b200_direction_frobenius.restype = ctypes.c_int
+    lib.sdpb_b200_direction_frobenius.argtypes = [ctypes.c_void_p, u64p]
+    lib.sdpb_b200_direction_get.restype = ctypes.c_int
+    lib.sdpb_b200_direction_get.argtypes = [ctypes.c_void_p, u64pp, u64pp, u64p, u64pp]
+    lib.sdpb_b200_last_direction_ms.restype = ctypes.c_float
+    lib.sdpb_b200_last_direction_ms.argtypes = [ctypes.c_void_p]
     lib.sdpb_b200_scalar_op.restype = ctypes.c_int
     lib.sdpb_b200_scalar_op.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_long, u64p, u64p, u64p]
     _lib = lib
@@ -226,9 +240,45 @@ class StepContextBase:
         Q = self.empty(self.N, self.N)
         return L, P, Q
 
+    # ---- the search direction on the resident state (compute_search_direction.cxx:44-90) ----
+    def _dir(self, name):
+        return getattr(self.lib, self.PREFIX + name)
+
+    def direction_begin(self):
+        """minus_XY = -X Y on the X, Y of the last step; returns the per-block traces (2J, ew)."""
+        out = np.zeros((2 * self.J, self.ew), dtype=np.uint64)
+        self._check(self._dir("direction_begin")(self.handle, _ptr(out)))
+        return out
+
+    def direction_R_errors(self, mu):
+        out = np.zeros((2 * self.J, self.ew), dtype=np.uint64)
+        self._check(self._dir("direction_R_errors")(self.handle, _ptr(np.ascontiguousarray(mu)), _ptr(out)))
+        return out
+
+    def direction_set_residues(self, primal_residues, dual_residues, primal_residue_p):
+        self._check(self._dir("direction_set_residues")(self.handle, ptr_array(primal_residues),
+                                                         ptr_array(dual_residues), _ptr(primal_residue_p)))
+
+    def compute_search_direction(self, beta_mu, is_corrector):
+        self._check(self._dir("compute_search_direction")(self.handle, _ptr(np.ascontiguousarray(beta_mu)),
+                                                           int(bool(is_corrector))))
+
+    def direction_frobenius(self):
+        out = np.zeros((2 * self.J, self.ew), dtype=np.uint64)
+        self._check(self._dir("direction_frobenius")(self.handle, _ptr(out)))
+        return out
+
+    def direction_get(self):
+        """(dx [J vectors], dX [2J blocks], dy, dY [2J blocks]) of the last compute_search_direction."""
+        dx, dy = self.alloc_solve_vectors()
+        dX, dY = self.alloc_psd_blocks(), self.alloc_psd_blocks()
+        self._check(self._dir("direction_get")(self.handle, ptr_array(dx), ptr_array(dX), _ptr(dy), ptr_array(dY)))
+        return dx, dX, dy, dY
+
 
 class SchurContext(StepContextBase):
     """Device-resident state of the Schur-complement step on one B200."""
+    PREFIX = "sdpb_b200_"
 
     def __init__(self, prec_bits, shapes, N, device=0):
         super().__init__(prec_bits, shapes, N)
@@ -292,6 +342,9 @@ class SchurContext(StepContextBase):
 
     def last_solve_ms(self):
         return float(self.lib.sdpb_b200_last_solve_ms(self.handle))
+
+    def last_direction_ms(self):
+        return float(self.lib.sdpb_b200_last_direction_ms(self.handle))
 
     def schur_step(self, X, Y, X_chol=None, Y_chol=None, A_X_inv=None, A_Y=None, L=None, P=None, Q=None,
                    block_timings_ms=None):

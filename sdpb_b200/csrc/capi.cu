@@ -1091,6 +1091,11 @@ static const LaunchTable *module_table(int nl)
   const LaunchTable *t = static_cast<const LaunchTable *>(dlsym(h, sym.c_str()));
   if(!t)
     g_module_error = so + " lacks " + sym;
+  else if(t->ctx_bytes != sizeof(sdpb_b200_ctx) || t->table_bytes != sizeof(LaunchTable))
+    {
+      g_module_error = so + " was built from other sources than this library (delete it to have it rebuilt)";
+      t = nullptr;
+    }
   else
     g_modules[nl] = t;
   return t;

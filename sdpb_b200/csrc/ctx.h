@@ -203,6 +203,9 @@ struct sdpb_b200_ctx
 // per-precision kernel drivers, one table per stored-limb count NL
 struct LaunchTable
 {
+  // a precision module built from other sources than the library that loads it would read the
+  // context at wrong offsets: module_table (capi.cu) compares these two sizes before anything else
+  size_t ctx_bytes, table_bytes;
   int (*cholesky)(sdpb_b200_ctx *, int which);
   int (*pairings)(sdpb_b200_ctx *, int part); // 0: X chain (L_X^-1 V, A_X_inv); 1: Y chain (Y V, A_Y)
   int (*schur_and_Q)(sdpb_b200_ctx *);

@@ -41,6 +41,20 @@ static Hot_Path_Table b200_table(const Block_Info &bi, const SDP &sdp, int prec,
                             uint64_t *const *C) {
     return sdpb_b200_scale_multiply_add((sdpb_b200_ctx *)x, al, A, B, be, C);
   };
+  t.direction_begin = [](void *x, uint64_t *tr) { return sdpb_b200_direction_begin((sdpb_b200_ctx *)x, tr); };
+  t.direction_R_errors = [](void *x, const uint64_t *mu, uint64_t *mx) {
+    return sdpb_b200_direction_R_errors((sdpb_b200_ctx *)x, mu, mx);
+  };
+  t.direction_set_residues = [](void *x, const uint64_t *const *pr, const uint64_t *const *dr, const uint64_t *p) {
+    return sdpb_b200_direction_set_residues((sdpb_b200_ctx *)x, pr, dr, p);
+  };
+  t.compute_search_direction = [](void *x, const uint64_t *bm, int corr) {
+    return sdpb_b200_compute_search_direction((sdpb_b200_ctx *)x, bm, corr);
+  };
+  t.direction_frobenius = [](void *x, uint64_t *fp) { return sdpb_b200_direction_frobenius((sdpb_b200_ctx *)x, fp); };
+  t.direction_get = [](void *x, uint64_t *const *dx, uint64_t *const *dX, uint64_t *dy, uint64_t *const *dY) {
+    return sdpb_b200_direction_get((sdpb_b200_ctx *)x, dx, dX, dy, dY);
+  };
   t.last_error = [](const void *x) { return sdpb_b200_last_error((const sdpb_b200_ctx *)x); };
   t.destroy = [](void *x) { sdpb_b200_destroy((sdpb_b200_ctx *)x); };
   t.name = "sm_100a(libsdpb_b200.so)";

@@ -21,6 +21,13 @@ struct Hot_Path_Table
   int (*solve_schur_complement_equation)(void *, uint64_t *const *, uint64_t *) = nullptr;
   int (*scale_multiply_add)(void *, int, const uint64_t *const *, const uint64_t *const *, int, uint64_t *const *)
     = nullptr;
+  // rows N2 (sdpb_b200_direction_* / oracle_direction_*); all six or none
+  int (*direction_begin)(void *, uint64_t *) = nullptr;
+  int (*direction_R_errors)(void *, const uint64_t *, uint64_t *) = nullptr;
+  int (*direction_set_residues)(void *, const uint64_t *const *, const uint64_t *const *, const uint64_t *) = nullptr;
+  int (*compute_search_direction)(void *, const uint64_t *, int) = nullptr;
+  int (*direction_frobenius)(void *, uint64_t *) = nullptr;
+  int (*direction_get)(void *, uint64_t *const *, uint64_t *const *, uint64_t *, uint64_t *const *) = nullptr;
   const char *(*last_error)(const void *) = nullptr;
   void (*destroy)(void *) = nullptr;
   std::string name;
@@ -198,6 +205,98 @@ public:
         else
           C[b].resize(0, 0);
       }
+  }
+
+  // ---- rows N2: the search direction stays with the implementation ----
+  bool resident_direction() const override { return t.compute_search_direction != nullptr; }
+  void scalars_in(std::vector<BigFloat> &out, const Buf &buf) const
+  {
+    const size_t ew = (size_t)elem_words();
+    out.assign(2 * (size_t)bi.num_blocks(), BigFloat());
+    for(size_t b = 0; b < out.size(); ++b)
+      unpack(out[b], buf.data() + b * ew);
+  }
+  void direction_begin(std::vector<BigFloat> &block_traces) override
+  {
+    Buf buf(2 * (size_t)bi.num_blocks() * elem_words() + 1);
+    check(t.direction_begin(t.ctx, buf.data()));
+    scalars_in(block_traces, buf);
+  }
+  void direction_R_errors(const BigFloat &mu, std::vector<BigFloat> &maxima) override
+  {
+    Buf buf(2 * (size_t)bi.num_blocks() * elem_words() + 1), m((size_t)elem_words());
+    pack(mu, m.data());
+    check(t.direction_R_errors(t.ctx, m.data(), buf.data()));
+    scalars_in(maxima, buf);
+  }
+  void direction_set_residues(const std::vector<Matrix> &primal_residues, const std::vector<Matrix> &dual_residues,
+                              const Matrix &primal_residue_p) override
+  {
+    const size_t ew = (size_t)elem_words();
+    const int J = bi.num_blocks();
+    pack_psd(primal_residues);
+    for(int j = 0; j < J; ++j)
+      {
+        ioJ_dx[j].resize(dual_residues[j].a.size() * ew + 1);
+        if(!dual_residues[j].a.empty())
+          pack_matrix(dual_residues[j], ioJ_dx[j].data());
+      }
+    io_dy.resize((size_t)N * ew + 1);
+    pack_matrix(primal_residue_p, io_dy.data());
+    const auto pr = cptrs(in2J);
+    std::vector<const uint64_t *> pd(J);
+    for(int j = 0; j < J; ++j)
+      pd[j] = ioJ_dx[j].data();
+    check(t.direction_set_residues(t.ctx, pr.data(), pd.data(), io_dy.data()));
+  }
+  void compute_search_direction(const BigFloat &beta_mu, bool is_corrector) override
+  {
+    Buf bm((size_t)elem_words());
+    pack(beta_mu, bm.data());
+    check(t.compute_search_direction(t.ctx, bm.data(), is_corrector ? 1 : 0));
+  }
+  void direction_frobenius(std::vector<BigFloat> &products) override
+  {
+    Buf buf(2 * (size_t)bi.num_blocks() * elem_words() + 1);
+    check(t.direction_frobenius(t.ctx, buf.data()));
+    scalars_in(products, buf);
+  }
+  void direction_get(std::vector<Matrix> &dx, std::vector<Matrix> &dX, Matrix &dy, std::vector<Matrix> &dY) override
+  {
+    const size_t ew = (size_t)elem_words();
+    const int J = bi.num_blocks();
+    for(int j = 0; j < J; ++j)
+      ioJ_dx[j].resize((size_t)bi.schur_block_size(j) * ew + 1);
+    io_dy.resize((size_t)N * ew + 1);
+    for(int b = 0; b < 2 * J; ++b)
+      {
+        const size_t s = (size_t)bi.psd_matrix_block_size(b / 2, b % 2);
+        out2J[b].resize(s * s * ew);
+        inB2J[b].resize(s * s * ew);
+      }
+    const auto px = ptrs(ioJ_dx), pX = ptrs(out2J), pY = ptrs(inB2J);
+    check(t.direction_get(t.ctx, px.data(), pX.data(), io_dy.data(), pY.data()));
+    dx.resize(J);
+    dX.resize(2 * J);
+    dY.resize(2 * J);
+    for(int j = 0; j < J; ++j)
+      unpack_matrix(dx[j], bi.schur_block_size(j), 1, ioJ_dx[j].data());
+#pragma omp parallel for schedule(dynamic)
+    for(int b = 0; b < 2 * J; ++b)
+      {
+        const int s = bi.psd_matrix_block_size(b / 2, b % 2);
+        if(s)
+          {
+            unpack_matrix(dX[b], s, s, out2J[b].data());
+            unpack_matrix(dY[b], s, s, inB2J[b].data());
+          }
+        else
+          {
+            dX[b].resize(0, 0);
+            dY[b].resize(0, 0);
+          }
+      }
+    unpack_matrix(dy, N, 1, io_dy.data());
   }
 
   void solve_schur_complement_equation(std::vector<Matrix> &dx, Matrix &dy) override

@@ -9,6 +9,7 @@
 // search direction, step length, termination, iterations.json / out.txt) is
 // cheap O(sum s_p^3 + P N) host work and stays on the CPU as in the reference.
 #pragma once
+#include "direction.hpp"
 #include "eig.hpp"
 #include "sdp.hpp"
 
@@ -47,6 +48,23 @@ struct Hot_Path
   virtual void scale_multiply_add(int alpha, const std::vector<Matrix> &A, const std::vector<Matrix> &B, int beta,
                                   std::vector<Matrix> &C)
     = 0;
+  // ---- rows N2: the search direction on the implementation's own (device-resident) copies of
+  // X, Y, their factors and the step's temporaries (include/sdpb_b200.h, sdpb_b200_direction_*).
+  // An implementation without them leaves resident_direction() false and the solver runs the host
+  // restatement of direction.hpp -- the reference's own CPU code path.
+  virtual bool resident_direction() const { return false; }
+  virtual void direction_begin(std::vector<BigFloat> &) { throw std::logic_error("no resident direction"); }
+  virtual void direction_R_errors(const BigFloat &, std::vector<BigFloat> &) { throw std::logic_error("no resident direction"); }
+  virtual void direction_set_residues(const std::vector<Matrix> &, const std::vector<Matrix> &, const Matrix &)
+  {
+    throw std::logic_error("no resident direction");
+  }
+  virtual void compute_search_direction(const BigFloat &, bool) { throw std::logic_error("no resident direction"); }
+  virtual void direction_frobenius(std::vector<BigFloat> &) { throw std::logic_error("no resident direction"); }
+  virtual void direction_get(std::vector<Matrix> &, std::vector<Matrix> &, Matrix &, std::vector<Matrix> &)
+  {
+    throw std::logic_error("no resident direction");
+  }
   virtual std::string name() const = 0;
 };
 
@@ -197,38 +215,6 @@ inline void gemm_nn(const BigFloat &alpha, const Matrix &A, const Matrix &B, con
           }
       }
 }
-// B <- L^{-1} B (forward substitution)
-inline void trsm_lower_left(const Matrix &L, Matrix &B)
-{
-  BigFloat t;
-  for(int c = 0; c < B.w; ++c)
-    for(int i = 0; i < B.h; ++i)
-      {
-        for(int k = 0; k < i; ++k)
-          {
-            t = L(i, k);
-            t *= B(k, c);
-            B(i, c) -= t;
-          }
-        B(i, c) /= L(i, i);
-      }
-}
-// B <- L^{-T} B (back substitution)
-inline void trsm_lower_transpose_left(const Matrix &L, Matrix &B)
-{
-  BigFloat t;
-  for(int c = 0; c < B.w; ++c)
-    for(int i = B.h - 1; i >= 0; --i)
-      {
-        for(int k = i + 1; k < B.h; ++k)
-          {
-            t = L(k, i);
-            t *= B(k, c);
-            B(i, c) -= t;
-          }
-        B(i, c) /= L(i, i);
-      }
-}
 // B <- B L^{-T}
 inline void trsm_lower_transpose_right(const Matrix &L, Matrix &B)
 {
@@ -306,22 +292,6 @@ inline void axpy(const BigFloat &alpha, const Matrix &X, Matrix &Y)
       Y.a[i] += t;
     }
 }
-// Block_Diagonal_Matrix::symmetrize (Block_Diagonal_Matrix.hxx:95-109)
-inline void symmetrize(Matrix &A)
-{
-  const BigFloat half(0.5);
-  for(auto &x : A.a)
-    x *= half;
-  for(int j = 0; j < A.w; ++j)
-    for(int i = 0; i < j; ++i)
-      {
-        const BigFloat s = A(i, j) + A(j, i);
-        A(i, j) = s;
-        A(j, i) = s;
-      }
-  for(int i = 0; i < A.h; ++i)
-    A(i, i) += A(i, i);
-}
 // cholesky_condition_number (sdpb_util/cholesky_condition_number.hxx:8-36)
 inline BigFloat cholesky_condition_number(const Matrix &L)
 {
@@ -364,7 +334,7 @@ public:
   BigFloat primal_objective, dual_objective, duality_gap, primal_error_P, primal_error_p, dual_error,
     R_error;
   std::vector<Iteration_Record> iterations;
-  double hot_path_seconds = 0, host_seconds = 0;
+  double hot_path_seconds = 0, host_seconds = 0, direction_seconds = 0;
   std::function<void(const Iteration_Record &)> on_iteration;
 
   BigFloat primal_error() const { return Max(primal_error_P, primal_error_p); }
@@ -400,48 +370,10 @@ public:
     y.resize(s.N(), 1);
   }
 
-  // constraint_matrix_weighted_sum.cxx:14-66
+  // constraint_matrix_weighted_sum.cxx:14-66 (direction.hpp)
   void constraint_matrix_weighted_sum(const std::vector<Matrix> &a, std::vector<Matrix> &result) const
   {
-    const int J = block_info.num_blocks();
-#pragma omp parallel for schedule(dynamic)
-    for(int j = 0; j < J; ++j)
-      {
-        const int n = block_info.num_points[j], m = block_info.dimensions[j];
-        BigFloat acc, t;
-        const BigFloat half(0.5);
-        for(int parity = 0; parity < 2; ++parity)
-          {
-            Matrix &R = result[2 * j + parity];
-            const Matrix &bases = sdp.bilinear_bases[2 * j + parity];
-            const int h = bases.h;
-            R.zero();
-            for(int cb = 0; cb < m; ++cb)
-              for(int rb = 0; rb <= cb; ++rb)
-                {
-                  const int voff = (cb * (cb + 1) / 2 + rb) * n;
-                  for(int c = 0; c < h; ++c)
-                    for(int r = 0; r < h; ++r)
-                      {
-                        acc.zero();
-                        for(int k = 0; k < n; ++k)
-                          {
-                            t = bases(c, k);
-                            t *= a[j](voff + k, 0);
-                            t *= bases(r, k);
-                            acc += t;
-                          }
-                        if(cb != rb)
-                          acc *= half;
-                        R(rb * h + r, cb * h + c) = acc;
-                      }
-                }
-            if(m > 1)
-              for(int c = 0; c < R.w; ++c)
-                for(int r = c + 1; r < R.h; ++r)
-                  R(r, c) = R(c, r); // MakeSymmetric(UPPER)
-          }
-      }
+    sdpb_host::constraint_matrix_weighted_sum(block_info, sdp.bilinear_bases, a, result);
   }
 
   // compute_objectives.cxx
@@ -570,111 +502,11 @@ public:
       terminate_now = false;
   }
 
-  // cholesky_solve.cxx: Z <- L^{-T} L^{-1} Z per block
-  static void cholesky_solve(const std::vector<Matrix> &L, std::vector<Matrix> &Z)
-  {
-#pragma omp parallel for schedule(dynamic)
-    for(size_t b = 0; b < Z.size(); ++b)
-      {
-        trsm_lower_left(L[b], Z[b]);
-        trsm_lower_transpose_left(L[b], Z[b]);
-      }
-  }
   // C = alpha A B + beta C per block (scale_multiply_add.cxx): through the hot-path seam
   void scale_multiply_add(int alpha, const std::vector<Matrix> &A, const std::vector<Matrix> &B, int beta,
                           std::vector<Matrix> &C) const
   {
     hot.scale_multiply_add(alpha, A, B, beta, C);
-  }
-
-  // compute_schur_RHS.cxx:21-86: dx = -dual_residues - Tr(A_p Z)
-  void compute_schur_RHS(const std::vector<Matrix> &Z, std::vector<Matrix> &dx) const
-  {
-    const int J = block_info.num_blocks();
-#pragma omp parallel for schedule(dynamic)
-    for(int j = 0; j < J; ++j)
-      {
-        const int n = block_info.num_points[j], m = block_info.dimensions[j];
-        dx[j] = dual_residues[j];
-        for(auto &e : dx[j].a)
-          e = -e;
-        BigFloat acc, t, zq;
-        for(int parity = 0; parity < 2; ++parity)
-          {
-            const Matrix &bases = sdp.bilinear_bases[2 * j + parity];
-            const Matrix &Zb = Z[2 * j + parity];
-            const int h = bases.h;
-            for(int cb = 0; cb < m; ++cb)
-              for(int rb = 0; rb <= cb; ++rb)
-                {
-                  const int off = (cb * (cb + 1) / 2 + rb) * n;
-                  for(int k = 0; k < n; ++k)
-                    {
-                      // sum_a bases(a,k) * (Z_sub bases)(a,k), Z_sub = Z[rb h .., cb h ..]
-                      acc.zero();
-                      for(int a = 0; a < h; ++a)
-                        {
-                          zq.zero();
-                          for(int b = 0; b < h; ++b)
-                            {
-                              t = Zb(rb * h + a, cb * h + b);
-                              t *= bases(b, k);
-                              zq += t;
-                            }
-                          zq *= bases(a, k);
-                          acc += zq;
-                        }
-                      dx[j](off + k, 0) -= acc;
-                    }
-                }
-          }
-      }
-  }
-
-  // compute_search_direction.cxx:44-90
-  void compute_search_direction(const std::vector<Matrix> &minus_XY, const std::vector<Matrix> &L,
-                                const std::vector<Matrix> &P, const Matrix &Q,
-                                const std::vector<Matrix> &X_cholesky, const BigFloat &beta, const BigFloat &mu,
-                                const Matrix &primal_residue_p, bool is_corrector_phase,
-                                std::vector<Matrix> &dx, std::vector<Matrix> &dX, Matrix &dy,
-                                std::vector<Matrix> &dY) const
-  {
-    std::vector<Matrix> R(minus_XY);
-    if(is_corrector_phase)
-      scale_multiply_add(-1, dX, dY, 1, R);
-    const BigFloat bm = beta * mu;
-    for(auto &blk : R)
-      for(int i = 0; i < blk.h; ++i)
-        blk(i, i) += bm;
-    // Z = Symmetrize(X^{-1} (PrimalResidues Y - R))
-    std::vector<Matrix> Z(X);
-    scale_multiply_add(1, primal_residues, Y, 0, Z);
-    for(size_t b = 0; b < Z.size(); ++b)
-      for(size_t i = 0; i < Z[b].a.size(); ++i)
-        Z[b].a[i] -= R[b].a[i];
-    cholesky_solve(X_cholesky, Z);
-    for(auto &blk : Z)
-      symmetrize(blk);
-    compute_schur_RHS(Z, dx);
-    dy = primal_residue_p;
-    hot.solve_schur_complement_equation(dx, dy); // solve_schur_complement_equation.cxx:16-79
-    // dX = PrimalResidues + sum_p A_p dx[p]
-    constraint_matrix_weighted_sum(dx, dX);
-    for(size_t b = 0; b < dX.size(); ++b)
-      for(size_t i = 0; i < dX[b].a.size(); ++i)
-        dX[b].a[i] += primal_residues[b].a[i];
-    // dY = Symmetrize(X^{-1} (R - dX Y))
-    scale_multiply_add(1, dX, Y, 0, dY);
-    for(size_t b = 0; b < dY.size(); ++b)
-      for(size_t i = 0; i < dY[b].a.size(); ++i)
-        dY[b].a[i] -= R[b].a[i];
-    cholesky_solve(X_cholesky, dY);
-    for(auto &blk : dY)
-      {
-        symmetrize(blk);
-        for(auto &e : blk.a)
-          e = -e;
-      }
   }
 
   // step_length.cxx:27-46 (+ lower_triangular_inverse_congruence.cxx, min_eigenvalue.cxx)
@@ -735,50 +567,62 @@ public:
       hot.initialize_schur_complement_solver(schur_complement_cholesky, schur_off_diagonal, Q);
       hot_path_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
-      std::vector<Matrix> minus_XY(X);
-      scale_multiply_add(-1, X, Y, 0, minus_XY);
-      {
-        BigFloat tr;
-        for(const auto &blk : minus_XY)
-          for(int i = 0; i < blk.h; ++i)
-            tr += blk(i, i);
-        mu = -tr / BigFloat((long)total_psd_rows);
-      }
+      // With a resident direction (rows N2) X, Y, their factors, -XY, R, Z, dX, dY stay with the
+      // implementation (HBM); the host sees per-block scalars and, at the end, the direction.
+      // Otherwise the same sequence runs on the host (direction.hpp), as in the reference.
+      const bool resident = hot.resident_direction();
+      const auto td = std::chrono::steady_clock::now();
+      std::vector<Matrix> minus_XY;
+      std::vector<BigFloat> per_block;
+      if(resident)
+        hot.direction_begin(per_block);
+      else
+        {
+          minus_XY = X;
+          scale_multiply_add(-1, X, Y, 0, minus_XY);
+          block_traces(minus_XY, per_block);
+        }
+      mu = -ordered_sum(per_block) / BigFloat((long)total_psd_rows);
       if(mu > BigFloat(parameters.max_complementarity))
         {
           terminate_now = true;
           return;
         }
       // compute_R_error.hxx
+      if(resident)
+        hot.direction_R_errors(mu, per_block);
+      else
+        block_R_errors(minus_XY, mu, per_block);
       R_error.zero();
-      for(const auto &blk : minus_XY)
-        for(int j = 0; j < blk.w; ++j)
-          for(int i = 0; i < blk.h; ++i)
-            {
-              BigFloat v = blk(i, j);
-              if(i == j)
-                v += mu;
-              R_error = Max(R_error, Abs(v));
-            }
+      for(const auto &v : per_block)
+        R_error = Max(R_error, v);
+      if(resident)
+        hot.direction_set_residues(primal_residues, dual_residues, primal_residue_p);
+      auto search_direction = [&](const BigFloat &beta, bool is_corrector_phase) {
+        const BigFloat beta_mu = beta * mu;
+        if(resident)
+          hot.compute_search_direction(beta_mu, is_corrector_phase);
+        else
+          compute_search_direction(
+            block_info, sdp.bilinear_bases, X, Y, X_cholesky, minus_XY, primal_residues, dual_residues,
+            primal_residue_p, beta_mu, is_corrector_phase,
+            [&](int alpha, const std::vector<Matrix> &A, const std::vector<Matrix> &B, int beta_, std::vector<Matrix> &C) {
+              scale_multiply_add(alpha, A, B, beta_, C);
+            },
+            [&](std::vector<Matrix> &rx, Matrix &ry) { hot.solve_schur_complement_equation(rx, ry); }, dx, dX, dy,
+            dY);
+      };
       // predictor_centering_parameter.cxx
       const BigFloat beta_predictor
         = is_primal_and_dual_feasible ? BigFloat(0) : BigFloat(parameters.infeasible_centering_parameter);
-      compute_search_direction(minus_XY, schur_complement_cholesky, schur_off_diagonal, Q, X_cholesky,
-                               beta_predictor, mu, primal_residue_p, false, dx, dX, dy, dY);
+      search_direction(beta_predictor, false);
       // corrector_centering_parameter.cxx (+ frobenius_product_of_sums.cxx)
       {
-        BigFloat fp;
-        for(size_t b = 0; b < X.size(); ++b)
-          {
-            BigFloat t, u;
-            for(size_t i = 0; i < X[b].a.size(); ++i)
-              {
-                t = X[b].a[i] + dX[b].a[i];
-                u = Y[b].a[i] + dY[b].a[i];
-                t *= u;
-                fp += t;
-              }
-          }
+        if(resident)
+          hot.direction_frobenius(per_block);
+        else
+          block_frobenius_products(X, dX, Y, dY, per_block);
+        const BigFloat fp = ordered_sum(per_block);
         const BigFloat r = fp / (mu * BigFloat((long)total_psd_rows));
         const BigFloat beta = r < BigFloat(1) ? r * r : r;
         if(is_primal_and_dual_feasible)
@@ -786,8 +630,10 @@ public:
         else
           beta_corrector = Max(BigFloat(parameters.infeasible_centering_parameter), beta);
       }
-      compute_search_direction(minus_XY, schur_complement_cholesky, schur_off_diagonal, Q, X_cholesky,
-                               beta_corrector, mu, primal_residue_p, true, dx, dX, dy, dY);
+      search_direction(beta_corrector, true);
+      if(resident)
+        hot.direction_get(dx, dX, dy, dY);
+      direction_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - td).count();
       // update_cond_numbers.hxx
       Q_cond_number = cholesky_condition_number(Q);
       max_block_cond_number.zero();

@@ -17,11 +17,15 @@
 template <int NL> struct Launch
 {
   static constexpr size_t TILE_SMEM = sizeof(TileSmem<NL>);
+  // Dynamic shared memory: every kernel is opted in to the full 227 KB of an sm_100 CTA, not to the
+  // size of the launch at hand -- the attribute belongs to the (device, function) pair, and two
+  // contexts of one process (one host thread per GPU, or the in-process communicator) setting it
+  // to their own, different sizes race: "invalid argument" at the launch of the larger one.
+  static constexpr int SMEM_OPT_IN = 227 * 1024;
   // opt in to > 48 KB of dynamic shared memory, once per kernel and device
   template <typename K> static int smem_opt_in(sdpb_b200_ctx *c, K kernel)
   {
-    CUDA_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)TILE_SMEM));
+    CUDA_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
     return 0;
   }
   static constexpr size_t DIAG_SMEM = sizeof(DiagSmem<NL>);
@@ -51,8 +55,7 @@ template <int NL> struct Launch
     if(int rc = smem_opt_in(c, potrf_gemm_level<NL>))
       return rc;
     constexpr size_t WARP_SMEM = DIAG_WARPS * sizeof(WarpTileSmem<NL>);
-    CUDA_TRY(c, cudaFuncSetAttribute(potrf_diag_warp<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)WARP_SMEM));
+    CUDA_TRY(c, cudaFuncSetAttribute(potrf_diag_warp<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
     if(int rc = smem_opt_in(c, potrf_panel_rl<NL>))
       return rc;
     if(reset)
@@ -196,8 +199,7 @@ template <int NL> struct Launch
         const int ncg = (maxcols + 16 * TC - 1) / (16 * TC);
         const int Wc = (maxcols + ncg - 1) / ncg; // columns per CTA, balanced
         const size_t smem = WalkGeom<NL>::bytes(TC);
-        CUDA_TRY(c, cudaFuncSetAttribute(trsm_walk_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
+        CUDA_TRY(c, cudaFuncSetAttribute(trsm_walk_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
         if(nheavy)
           {
             CUDA_TRY(c, c->after(main_stream, side, ev0));
@@ -214,10 +216,9 @@ template <int NL> struct Launch
     if(int rc = smem_opt_in(c, trsm_gemm_level<NL>))
       return rc;
     const size_t smem2 = WalkGeom<NL>::bytes(TS);
-    CUDA_TRY(c, cudaFuncSetAttribute(trsm_gemm_level2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem2));
+    CUDA_TRY(c, cudaFuncSetAttribute(trsm_gemm_level2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
     CUDA_TRY(c, cudaFuncSetAttribute(trsm_diag_level<NL>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
     const std::vector<int> heavy(sizes.begin(), sizes.begin() + nheavy);
     const int T = (heavy[0] + TS - 1) / TS;
     const char *l_gemm = sub(label, "gemm"), *l_diag = sub(label, "diag");
@@ -341,7 +342,7 @@ template <int NL> struct Launch
     c->kt_begin("norm_final_kernel");
     {
       const size_t sm = ((sizeof(coop::Work<NL>) + 15) & ~(size_t)15) + 33 * TileGeom<NL>::SW * 4;
-      CUDA_TRY(c, cudaFuncSetAttribute(norm_final_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      CUDA_TRY(c, cudaFuncSetAttribute(norm_final_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
       norm_final_kernel<NL><<<N, 32, sm, st>>>(part, Jsum, N, c->norms, c->recipN);
     }
     c->kt_end();
@@ -353,7 +354,7 @@ template <int NL> struct Launch
         const size_t nsmem = ((size_t)c->crt.np * NormGeom<NL>::NDP + ((c->crt.np + 1) & ~1)) * 4
                              + (size_t)c->crt.np * 8;
         CUDA_TRY(c, cudaFuncSetAttribute(normalize_kernel<NL>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsmem));
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
         normalize_kernel<NL><<<g2, 128, nsmem, st>>>(c->d_bands, N, c->NS, c->K, c->norms,
                                                      c->recipN, c->prec, c->crt, c->R, c->d_flags);
         c->kt_end();
@@ -416,8 +417,7 @@ template <int NL> struct Launch
       smem_max = std::min<size_t>(smem_max, (size_t)atol(env));
     const int use_smem = need <= smem_max;
     const size_t smem = use_smem ? need : 0;
-    CUDA_TRY(c, cudaFuncSetAttribute(solve_tri_kernel<NL, BACK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)std::max<size_t>(smem, 1024)));
+    CUDA_TRY(c, cudaFuncSetAttribute(solve_tri_kernel<NL, BACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
     const int threads = std::min(SOLVE_MAX_THREADS, std::max(32, (maxp + 31) & ~31));
     c->kt_begin(label);
     solve_tri_kernel<NL, BACK><<<count, threads, smem, c->cur>>>(d, x, use_smem);
@@ -658,6 +658,6 @@ template <int NL> struct Launch
 #define SDPB_CAT2(a, b) a##b
 #define SDPB_CAT(a, b) SDPB_CAT2(a, b)
 extern "C" __attribute__((visibility("default"))) const LaunchTable
-  SDPB_CAT(sdpb_b200_launch_nl, SDPB_NL) = {&Launch<SDPB_NL>::cholesky, &Launch<SDPB_NL>::pairings,
+  SDPB_CAT(sdpb_b200_launch_nl, SDPB_NL) = {sizeof(sdpb_b200_ctx), sizeof(LaunchTable), &Launch<SDPB_NL>::cholesky, &Launch<SDPB_NL>::pairings,
      &Launch<SDPB_NL>::schur_and_Q, &Launch<SDPB_NL>::schur_solve, &Launch<SDPB_NL>::scale_multiply_add,
      &Launch<SDPB_NL>::scalar, &Launch<SDPB_NL>::direction};

@@ -78,6 +78,13 @@ def load_oracle():
     lib.oracle_scale_matrix.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_double, u64p, u64p]
     lib.oracle_stage_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.c_int]
     lib.oracle_num_threads.restype = ctypes.c_int
+    for name, args in (("direction_begin", [u64p]), ("direction_R_errors", [u64p, u64p]),
+                       ("direction_set_residues", [u64pp, u64pp, u64p]),
+                       ("compute_search_direction", [u64p, ctypes.c_int]), ("direction_frobenius", [u64p]),
+                       ("direction_get", [u64pp, u64pp, u64p, u64pp])):
+        f = getattr(lib, "oracle_" + name)
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_void_p] + args
     lib.oracle_set_num_threads.restype = None
     lib.oracle_set_num_threads.argtypes = [ctypes.c_int]
     _lib = lib
@@ -92,6 +99,8 @@ class OracleError(RuntimeError):
 
 
 class OracleContext(StepContextBase):
+    PREFIX = "oracle_"  # StepContextBase's direction_* methods call oracle_direction_* here
+
     def __init__(self, prec_bits, shapes, N):
         super().__init__(prec_bits, shapes, N)
         self.lib = load_oracle()

@@ -449,3 +449,90 @@ def test_schur_solve_takes_the_reduced_residue_of_the_references_layout():
     ctx.solve_schur_complement_equation(dx1, dy1)
     assert not np.array_equal(dy1, dy)
     ctx.close()
+
+
+def _random_residues(prec, ctx, N, seed):
+    pr = [ol.random_matrix(prec, s.psd_size(p), s.psd_size(p), seed + 17 * b + p)
+          for b, s in enumerate(ctx.shapes) for p in (0, 1)]
+    dr = [ol.random_matrix(prec, s.schur_size, 1, seed + 1000 + j) for j, s in enumerate(ctx.shapes)]
+    return pr, dr, ol.random_matrix(prec, N, 1, seed + 5000)
+
+
+DIRECTION_CASES = [
+    (768, [(1, 7), (2, 5), (1, 9), (2, 3)], 9),
+    (448, [(1, 6), (3, 3), (2, 4)], 5),
+    (1536, [(1, 9), (2, 4)], 6),
+    (664, [(1, 5), (1, 1)], 2),          # not a multiple of 64; a block whose odd parity is empty
+    (768, [(2, 40), (1, 40), (1, 33)], 37),
+]
+
+
+@pytest.mark.parametrize("prec,shapes,N", DIRECTION_CASES)
+def test_search_direction_bit_exact(prec, shapes, N):
+    """Rows N2: compute_search_direction.cxx:44-90 (R, Z, cholesky_solve, symmetrize, compute_schur_RHS,
+    the Schur solve, constraint_matrix_weighted_sum, dY) and the per-block reductions of step()
+    (traces of -XY, R error, Frobenius product) on the device-resident objects, against the host
+    restatement of csrc/host/direction.hpp: predictor, then corrector (which reads the predictor's
+    dX, dY), every output byte for byte."""
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=9)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    sdp.run_step(ref)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    ctx.schur_step(sdp.X, sdp.Y)
+    ol.assert_same("traces", ctx.direction_begin(), ref.direction_begin())
+    mu = ol.from_decimal(prec, "0.37251")
+    ol.assert_same("R errors", ctx.direction_R_errors(mu), ref.direction_R_errors(mu))
+    pr, dr, prp = _random_residues(prec, ctx, N, 77)
+    ctx.direction_set_residues(pr, dr, prp)
+    ref.direction_set_residues(pr, dr, prp)
+    for phase, beta_mu in ((0, "0.1117"), (1, "0.0433")):
+        bm = ol.from_decimal(prec, beta_mu)
+        ctx.compute_search_direction(bm, phase)
+        ref.compute_search_direction(bm, phase)
+        got, want = ctx.direction_get(), ref.direction_get()
+        for name, g, w in zip(("dx", "dX", "dy", "dY"), got, want):
+            ol.assert_same(f"{name} (phase {phase})", g, w)
+        ol.assert_same(f"Frobenius products (phase {phase})", ctx.direction_frobenius(), ref.direction_frobenius())
+    ctx.close()
+
+
+def test_search_direction_after_separate_calls_and_state_errors():
+    """The direction also runs on the X, Y of cholesky_decomposition(X) + compute_bilinear_pairings(Y)
+    + initialize_schur_complement_solver (the reference's call sequence), and out-of-order calls are
+    rejected with rc 5."""
+    from sdpb_b200.capi import SdpbB200Error
+    prec, shapes, N = 768, [(1, 7), (2, 5), (1, 9)], 8
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=12)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    sdp.run_step(ref)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    with pytest.raises(SdpbB200Error) as ei:
+        ctx.direction_begin()
+    assert ei.value.code == 5
+    ctx.cholesky_decomposition(0, sdp.X)
+    ctx.cholesky_decomposition(1, sdp.Y)
+    ctx.compute_bilinear_pairings(sdp.Y)
+    ctx.initialize_schur_complement_solver()
+    bm = ol.from_decimal(prec, "0.25")
+    with pytest.raises(SdpbB200Error) as ei:
+        ctx.compute_search_direction(bm, 0)      # before direction_begin
+    assert ei.value.code == 5
+    ol.assert_same("traces", ctx.direction_begin(), ref.direction_begin())
+    with pytest.raises(SdpbB200Error) as ei:
+        ctx.compute_search_direction(bm, 0)      # before the residues
+    assert ei.value.code == 5
+    pr, dr, prp = _random_residues(prec, ctx, N, 5)
+    ctx.direction_set_residues(pr, dr, prp)
+    ref.direction_set_residues(pr, dr, prp)
+    with pytest.raises(SdpbB200Error) as ei:
+        ctx.compute_search_direction(bm, 1)      # corrector before predictor
+    assert ei.value.code == 5
+    ctx.compute_search_direction(bm, 0)
+    ref.compute_search_direction(bm, 0)
+    for name, g, w in zip(("dx", "dX", "dy", "dY"), ctx.direction_get(), ref.direction_get()):
+        ol.assert_same(name, g, w)
+    ctx.close()

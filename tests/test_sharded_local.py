@@ -140,3 +140,73 @@ def test_failure_on_one_rank_fails_every_rank():
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_search_direction_sharded_matches_unsharded():
+    """Rows N2 under sharding: every rank computes the direction of its own blocks on its resident
+    objects; the Schur solve inside is the collective one (dy identical on all ranks).  Against the
+    unsharded host restatement, bit for bit."""
+    import sdpb_b200
+    from sdpb_b200.partition import partition_blocks
+    prec, N, world = 768, 9, 2
+    shapes = [(1, 6), (2, 4), (1, 9), (1, 5), (2, 3), (1, 8)]
+    owned = partition_blocks(shapes, N, world)
+
+    def residues(ids):
+        pr = [ol.random_matrix(prec, BlockShape(*shapes[j]).psd_size(p), BlockShape(*shapes[j]).psd_size(p),
+                               300 + 17 * j + p) for j in ids for p in (0, 1)]
+        dr = [ol.random_matrix(prec, BlockShape(*shapes[j]).schur_size, 1, 900 + j) for j in ids]
+        return pr, dr, ol.random_matrix(prec, N, 1, 4242)
+
+    from sdpb_b200.capi import BlockShape
+    full = ol.SyntheticSDP(prec, shapes, N, seed=5)
+    ref = ol.OracleContext(prec, shapes, N)
+    full.upload(ref)
+    full.run_step(ref)
+    want_tr = ref.direction_begin()
+    ref.direction_set_residues(*residues(range(len(shapes))))
+    bm = ol.from_decimal(prec, "0.2")
+    ref.compute_search_direction(bm, 0)
+    ref.compute_search_direction(bm, 1)
+    want = ref.direction_get()
+
+    ctxs, sdps = [], []
+    for r in range(world):
+        mine = owned[r]
+        sdp = ol.SyntheticSDP(prec, [shapes[j] for j in mine], N, seed=5, block_ids=mine)
+        ctx = sdpb_b200.SchurContext(prec, [shapes[j] for j in mine], N, device=0)
+        sdp.upload(ctx)
+        ctxs.append(ctx)
+        sdps.append(sdp)
+    sdpb_b200.SchurContext.comm_init_local(ctxs, len(shapes), owned)
+    results, errors = [None] * world, [None] * world
+
+    def rank_main(r):
+        try:
+            ctxs[r].schur_step(sdps[r].X, sdps[r].Y)
+            tr = ctxs[r].direction_begin()
+            ctxs[r].direction_set_residues(*residues(owned[r]))
+            ctxs[r].compute_search_direction(bm, 0)
+            ctxs[r].compute_search_direction(bm, 1)
+            results[r] = (tr, ctxs[r].direction_get())
+        except Exception as e:  # noqa: BLE001
+            errors[r] = e
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    try:
+        for r in range(world):
+            assert errors[r] is None, f"rank {r}: {errors[r]}"
+            tr, (dx, dX, dy, dY) = results[r]
+            mine = owned[r]
+            ol.assert_same(f"rank{r}.traces", tr, np.stack([want_tr[2 * j + p] for j in mine for p in (0, 1)]))
+            ol.assert_same(f"rank{r}.dx", dx, [want[0][j] for j in mine])
+            ol.assert_same(f"rank{r}.dX", dX, [want[1][2 * j + p] for j in mine for p in (0, 1)])
+            ol.assert_same(f"rank{r}.dy", dy, want[2])
+            ol.assert_same(f"rank{r}.dY", dY, [want[3][2 * j + p] for j in mine for p in (0, 1)])
+    finally:
+        for c in ctxs:
+            c.close()
