@@ -194,6 +194,21 @@ int sdpb_b200_compute_search_direction(sdpb_b200_ctx *ctx, const uint64_t *beta_
 int sdpb_b200_direction_frobenius(sdpb_b200_ctx *ctx, uint64_t *block_products);
 int sdpb_b200_direction_get(sdpb_b200_ctx *ctx, uint64_t *const *dx, uint64_t *const *dX, uint64_t *dy,
                             uint64_t *const *dY);
+/* step_length (run/step/step_length/step_length.cxx:27-46, with
+ * lower_triangular_inverse_congruence.cxx:5-18 and min_eigenvalue.cxx:8-33) on the resident
+ * Cholesky factors and the resident direction: block_min_eigenvalues[b], b = 2j + parity, is the
+ * smallest eigenvalue of L_b^-1 dM_b L_b^-T with (L, dM) = (chol X, dX) for which = 0 and
+ * (chol Y, dY) for which = 1 (2J packed elements; an empty block gives 0 and is skipped by the
+ * caller).  The caller finishes as the reference does: lambda = min over its blocks, MIN-reduced
+ * over its ranks (min_eigenvalue.cxx:31-32, exact), step = lambda > -gamma ? 1 : -gamma / lambda.
+ * El::HermitianEig is the un-vendored Elemental fork's; the operation order is the one
+ * csrc/host/step_length.hpp spells out (Householder tridiagonalisation, then Laguerre's iteration
+ * from the Gershgorin bound), and the result is bit-identical to that host restatement. */
+int sdpb_b200_step_length(sdpb_b200_ctx *ctx, int which, uint64_t *block_min_eigenvalues);
+/* Device time of the last sdpb_b200_step_length, ms (CUDA events). */
+float sdpb_b200_last_step_length_ms(const sdpb_b200_ctx *ctx);
+/* Laguerre steps per block-parity of the last sdpb_b200_step_length (2J ints); diagnostics. */
+int sdpb_b200_step_length_iterations(sdpb_b200_ctx *ctx, int *iterations);
 /* Device time of the last direction_begin / compute_search_direction, ms (CUDA events). */
 float sdpb_b200_last_direction_ms(const sdpb_b200_ctx *ctx);
 

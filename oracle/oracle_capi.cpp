@@ -4,6 +4,7 @@
 // Build: make -C oracle   (-> oracle/liboracle.so)
 #include "hotpath_core.hpp"
 #include "../sdpb_b200/csrc/host/direction.hpp"
+#include "../sdpb_b200/csrc/host/step_length.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -26,6 +27,7 @@ struct oracle_ctx
   std::vector<Matrix> B;               // J
   std::vector<Matrix> V;               // 2J bases_blocks
   std::vector<Matrix> X_cholesky;      // 2J
+  std::vector<Matrix> Y_cholesky;      // 2J (step_length reads it, row N3)
   std::vector<Matrix> AX, AY;          // 2J
   std::string error;
   double stage_ms[9];
@@ -73,6 +75,7 @@ int oracle_create(oracle_ctx **out, int prec_bits, int num_blocks,
   c->B.resize(num_blocks);
   c->V.resize(2 * num_blocks);
   c->X_cholesky.resize(2 * num_blocks);
+  c->Y_cholesky.resize(2 * num_blocks);
   c->AX.resize(2 * num_blocks);
   c->AY.resize(2 * num_blocks);
   for(double &x : c->stage_ms)
@@ -140,8 +143,7 @@ int oracle_cholesky_decomposition(oracle_ctx *c, int which,
     {
       if(L && L[b])
         pack_out(out[b], L[b]);
-      if(which == 0)
-        c->X_cholesky[b] = std::move(out[b]);
+      (which == 0 ? c->X_cholesky : c->Y_cholesky)[b] = std::move(out[b]);
     }
   c->stage_ms[0] += std::chrono::duration<double, std::milli>(
                       std::chrono::steady_clock::now() - t0)
@@ -620,6 +622,47 @@ int oracle_direction_get(oracle_ctx *c, uint64_t *const *dx, uint64_t *const *dX
     }
   if(dy)
     pack_out(c->dy, dy);
+  return 0;
+}
+
+// ---- step_length (row N3): same call surface as sdpb_b200_step_length ----
+// step_length.cxx:27-46 up to the reduction over the blocks: block_min_eigenvalues[b] = smallest
+// eigenvalue of L_b^-1 dM_b L_b^-T (csrc/host/step_length.hpp), M = X (which 0) or Y (which 1) of
+// the last step and dM = dX / dY of the last compute_search_direction; empty blocks give 0.
+int oracle_step_length(oracle_ctx *c, int which, uint64_t *block_min_eigenvalues)
+{
+  sdpb_host::set_precision(c->prec);
+  if(!c->have_direction)
+    {
+      c->error = "step_length called out of order (needs compute_search_direction)";
+      return 5;
+    }
+  const std::vector<Matrix> &L = which == 0 ? c->X_cholesky : c->Y_cholesky;
+  const std::vector<Matrix> &dM = which == 0 ? c->dX : c->dY;
+  std::vector<BigFloat> mins(2 * (size_t)c->J);
+#pragma omp parallel for schedule(dynamic)
+  for(int b = 0; b < 2 * c->J; ++b)
+    if(dM[b].h)
+      mins[b] = sdpb_host::block_min_eigenvalue(L[b], dM[b]);
+  pack_scalars(mins, block_min_eigenvalues);
+  return 0;
+}
+// unit test hooks: the smallest eigenvalue of L^-1 A L^-T for one s x s pair (L == NULL: of A
+// itself), and the number of Laguerre steps it took
+int oracle_min_eigenvalue(int prec, int s, const uint64_t *L, const uint64_t *A, uint64_t *out, int *iterations)
+{
+  sdpb_host::set_precision(prec);
+  Matrix Am, Lm;
+  unpack_matrix(Am, s, s, A);
+  if(L)
+    {
+      unpack_matrix(Lm, s, s, L);
+      sdpb_host::lower_triangular_inverse_congruence(Lm, Am);
+    }
+  std::vector<BigFloat> d, e;
+  sdpb_host::tridiagonalize(Am, d, e);
+  const BigFloat m = sdpb_host::tridiagonal_min_eigenvalue(d, e, iterations);
+  sdpb_host::pack(m, out);
   return 0;
 }
 

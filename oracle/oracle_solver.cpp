@@ -34,6 +34,7 @@ int oracle_direction_set_residues(oracle_ctx *c, const uint64_t *const *primal_r
 int oracle_compute_search_direction(oracle_ctx *c, const uint64_t *beta_mu, int is_corrector);
 int oracle_direction_frobenius(oracle_ctx *c, uint64_t *block_products);
 int oracle_direction_get(oracle_ctx *c, uint64_t *const *dx, uint64_t *const *dX, uint64_t *dy, uint64_t *const *dY);
+int oracle_step_length(oracle_ctx *c, int which, uint64_t *block_min_eigenvalues);
 }
 
 using namespace sdpb_host;
@@ -83,6 +84,7 @@ static Hot_Path_Table oracle_table(const Block_Info &bi, const SDP &sdp, int pre
       t.direction_get = [](void *x, uint64_t *const *dx, uint64_t *const *dX, uint64_t *dy, uint64_t *const *dY) {
         return oracle_direction_get((oracle_ctx *)x, dx, dX, dy, dY);
       };
+      t.step_length = [](void *x, int which, uint64_t *mins) { return oracle_step_length((oracle_ctx *)x, which, mins); };
     }
   t.last_error = [](const void *x) { return oracle_last_error((const oracle_ctx *)x); };
   t.destroy = [](void *x) { oracle_destroy((oracle_ctx *)x); };

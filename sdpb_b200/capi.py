@@ -108,6 +108,10 @@ def load_library():
     lib.sdpb_b200_direction_frobenius.argtypes = [ctypes.c_void_p, u64p]
     lib.sdpb_b200_direction_get.restype = ctypes.c_int
     lib.sdpb_b200_direction_get.argtypes = [ctypes.c_void_p, u64pp, u64pp, u64p, u64pp]
+    lib.sdpb_b200_step_length.restype = ctypes.c_int
+    lib.sdpb_b200_step_length.argtypes = [ctypes.c_void_p, ctypes.c_int, u64p]
+    lib.sdpb_b200_last_step_length_ms.restype = ctypes.c_float
+    lib.sdpb_b200_last_step_length_ms.argtypes = [ctypes.c_void_p]
     lib.sdpb_b200_last_direction_ms.restype = ctypes.c_float
     lib.sdpb_b200_last_direction_ms.argtypes = [ctypes.c_void_p]
     lib.sdpb_b200_scalar_op.restype = ctypes.c_int
@@ -274,6 +278,14 @@ class StepContextBase:
         dX, dY = self.alloc_psd_blocks(), self.alloc_psd_blocks()
         self._check(self._dir("direction_get")(self.handle, ptr_array(dx), ptr_array(dX), _ptr(dy), ptr_array(dY)))
         return dx, dX, dy, dY
+
+
+    def step_length(self, which):
+        """Per block-parity smallest eigenvalue of L^-1 dM L^-T (step_length.cxx:27-46), M = X / dX
+        (which 0) or Y / dY (which 1) of the last compute_search_direction; (2J, ew), empty blocks 0."""
+        out = np.zeros((2 * self.J, self.ew), dtype=np.uint64)
+        self._check(self._dir("step_length")(self.handle, int(which), _ptr(out)))
+        return out
 
 
 class SchurContext(StepContextBase):

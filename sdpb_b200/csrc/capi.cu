@@ -504,6 +504,9 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
     TRY_C(cudaMalloc(&c->dir_scal, 4 * es * 8));
     TRY_C(cudaMalloc(&c->dir_part, std::max<size_t>(16, (size_t)2 * num_blocks * es * 8)));
     TRY_C(cudaMalloc(&c->dir_colsum, std::max<size_t>(16, (size_t)cols * es * 8)));
+    for(limb_t **p : {&c->eig_d, &c->eig_e, &c->eig_e2})
+      TRY_C(cudaMalloc(p, std::max<size_t>(16, (size_t)cols * es * 8)));
+    TRY_C(cudaMalloc(&c->eig_iter, std::max<size_t>(16, (size_t)2 * num_blocks * sizeof(int))));
     const size_t pin = std::max<size_t>((size_t)c->K + N + 8, (size_t)2 * num_blocks + 8) * es * 8;
     TRY_C(cudaMallocHost(&c->dir_pinned, pin));
     {
@@ -511,6 +514,10 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
       std::vector<uint64_t> half(4 * es, 0);
       half[es + 0] = (uint64_t)(uint32_t)0 | ((uint64_t)(uint32_t)1 << 32);
       half[es + nl] = 0x8000000000000000ull;
+      // 2^-(prec - 16) = 2^r B^-q (one limb): where Laguerre's iteration stops (host/step_length.hpp)
+      const int kbits = prec_bits - 16, q = (kbits + 63) / 64, r = 64 * q - kbits;
+      half[3 * es + 0] = (uint64_t)(uint32_t)(1 - q) | ((uint64_t)(uint32_t)1 << 32);
+      half[3 * es + nl] = (uint64_t)1 << r;
       TRY_C(cudaMemcpy(c->dir_scal, half.data(), half.size() * 8, cudaMemcpyHostToDevice));
     }
     auto products = [&](const limb_t *A, const limb_t *B, GemmTileDesc **out) -> cudaError_t {
@@ -936,6 +943,9 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
   cudaFree(c->d_status);
   cudaFree(c->d_flags);
   cudaFree(c->d_fail);
+  for(limb_t *p : {c->eig_d, c->eig_e, c->eig_e2})
+    cudaFree(p);
+  cudaFree(c->eig_iter);
   for(limb_t *p : {c->dirMXY, c->dirR, c->dirZ, c->dirDX, c->dirDY, c->dirPR, c->dir_dual, c->dir_prp, c->dir_scal,
                    c->dir_part, c->dir_colsum})
     cudaFree(p);
@@ -1659,6 +1669,40 @@ extern "C" int sdpb_b200_direction_frobenius(sdpb_b200_ctx *c, uint64_t *block_p
       return rc;
     }
   return direction_scalars_out(c, block_products);
+}
+// Row N3: step_length.cxx:27-46 on the resident factors and direction.
+// block_min_eigenvalues[b], b = 2j + parity: smallest eigenvalue of L_b^-1 dM_b L_b^-T with
+// (L, dM) = (chol X, dX) for which = 0 and (chol Y, dY) for which = 1; empty blocks give 0.
+extern "C" int sdpb_b200_step_length(sdpb_b200_ctx *c, int which, uint64_t *block_min_eigenvalues)
+{
+  if(!c || (which != 0 && which != 1))
+    return SDPB_B200_ERR_ARG;
+  if(int rc = direction_ready(c, "step_length", true, true))
+    return rc;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  c->kt_used = 0;
+  CUDA_TRY(c, cudaEventRecord(c->ev[9], c->stream));
+  if(int rc = table_for(c->nl)->step_length(c, which))
+    {
+      cudaStreamSynchronize(c->stream);
+      return rc;
+    }
+  CUDA_TRY(c, cudaEventRecord(c->ev[10], c->stream));
+  if(int rc = direction_scalars_out(c, block_min_eigenvalues))
+    return rc;
+  cudaEventElapsedTime(&c->step_length_ms, c->ev[9], c->ev[10]);
+  return 0;
+}
+extern "C" float sdpb_b200_last_step_length_ms(const sdpb_b200_ctx *c) { return c ? c->step_length_ms : 0.f; }
+// Laguerre steps the last sdpb_b200_step_length took per block-parity (2J ints); diagnostics
+extern "C" int sdpb_b200_step_length_iterations(sdpb_b200_ctx *c, int *iterations)
+{
+  if(!c || !iterations)
+    return SDPB_B200_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if(c->J)
+    CUDA_TRY(c, cudaMemcpy(iterations, c->eig_iter, (size_t)2 * c->J * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
 }
 extern "C" int sdpb_b200_direction_get(sdpb_b200_ctx *c, uint64_t *const *dx, uint64_t *const *dX, uint64_t *dy,
                                        uint64_t *const *dY)

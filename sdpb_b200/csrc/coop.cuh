@@ -438,18 +438,14 @@ __device__ __forceinline__ bool recip_words(Work<NL> &ws, const uint32_t *dw, ui
   return ok;
 }
 
-// The pivot of one Cholesky column, by one whole warp: a > 0 is a packed element
-// in shared memory at `a` (header + 2NL words).  On return the same slot holds
-// l = mpf_sqrt(a) and Rs / Rg (shared / global, RW words; either may be null)
-// hold the reciprocal words of l that mpfw::div_recip takes.
-template <int NL>
-__device__ __forceinline__ void pivot(Work<NL> &ws, uint32_t *a, uint32_t *Rs, uint32_t *Rg)
+// a <- mpf_sqrt(a) in place, by one whole warp: a > 0 is a packed element in shared memory
+// (header + 2NL words)
+template <int NL> __device__ __forceinline__ void sqrt_elem(Work<NL> &ws, uint32_t *a)
 {
   typedef Work<NL> G;
   const int l = lane_id();
   const int32_t aexp = (int32_t)a[0];
   const int expodd = aexp & 1;
-  uint32_t *R = ws.E + G::MAXW;
   __syncwarp();
   const bool ok_sqrt = sqrt_words<NL>(ws, a + 2, expodd);
   if(ok_sqrt)
@@ -475,6 +471,16 @@ __device__ __forceinline__ void pivot(Work<NL> &ws, uint32_t *a, uint32_t *Rs, u
       mpfw::store<NL>(a, u);
     }
   __syncwarp();
+}
+// Rs / Rg (shared / global, RW words; either may be null) <- the reciprocal words of the packed
+// element a != 0 (shared memory) that mpfw::div_recip takes, by one whole warp
+template <int NL>
+__device__ __forceinline__ void recip_elem(Work<NL> &ws, const uint32_t *a, uint32_t *Rs, uint32_t *Rg)
+{
+  typedef Work<NL> G;
+  const int l = lane_id();
+  uint32_t *R = ws.E + G::MAXW;
+  __syncwarp();
   const bool ok_recip = recip_words<NL>(ws, a + 2, R);
   if(!ok_recip && l == 0)
     {
@@ -498,5 +504,16 @@ __device__ __forceinline__ void pivot(Work<NL> &ws, uint32_t *a, uint32_t *Rs, u
         Rg[i] = w;
     }
   __syncwarp();
+}
+
+// The pivot of one Cholesky column, by one whole warp: a > 0 is a packed element
+// in shared memory at `a` (header + 2NL words).  On return the same slot holds
+// l = mpf_sqrt(a) and Rs / Rg (shared / global, RW words; either may be null)
+// hold the reciprocal words of l that mpfw::div_recip takes.
+template <int NL>
+__device__ __forceinline__ void pivot(Work<NL> &ws, uint32_t *a, uint32_t *Rs, uint32_t *Rg)
+{
+  sqrt_elem<NL>(ws, a);
+  recip_elem<NL>(ws, a, Rs, Rg);
 }
 } // namespace coop

@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "solve.cuh"
 #include "direction.cuh"
+#include "eig.cuh"
 
 #include <memory>
 #include <string>
@@ -153,7 +154,7 @@ struct sdpb_b200_ctx
          *dirPR = nullptr;          // -XY, R, Z, dX, dY, primal residues: wXY words each
   limb_t *dir_dual = nullptr;       // dual residues, K elements (stacked like dx)
   limb_t *dir_prp = nullptr;        // primal_residue_p, N elements
-  limb_t *dir_scal = nullptr;       // [0] beta mu  [1] 0.5 as mpf_set_d gives it  [2] mu
+  limb_t *dir_scal = nullptr;       // [0] beta mu  [1] 0.5 as mpf_set_d gives it  [2] mu  [3] 2^-(prec-16)
   limb_t *dir_part = nullptr;       // per block-parity scalars (traces, maxima, Frobenius products)
   limb_t *dir_colsum = nullptr;     // per column scratch of the Frobenius product
   BdmDesc *d_bdm = nullptr;         // block-parity b = 2j + parity, in that order
@@ -164,6 +165,11 @@ struct sdpb_b200_ctx
   uint64_t *dir_pinned = nullptr;   // host staging: vectors up, per-block scalars down
   bool have_XY = false, have_minus_XY = false, have_residues = false, have_direction = false;
   float direction_ms = 0;
+  // step_length (row N3, eig.cuh): the congruence and the tridiagonalisation work in dirZ (dead
+  // after compute_search_direction); d, e, e^2 of the tridiagonal matrices stacked like the columns
+  limb_t *eig_d = nullptr, *eig_e = nullptr, *eig_e2 = nullptr;
+  int *eig_iter = nullptr; // Laguerre steps per block-parity of the last call
+  float step_length_ms = 0;
   long launches = 0; // kernels launched since creation
   cudaEvent_t ev[12] = {}; // 0,1 pairings; 2..8 Schur stages; 9,10,11 resident step
   float stage_ms[9] = {0};
@@ -217,6 +223,8 @@ struct LaunchTable
   // max |-XY + mu I|; 2: compute_search_direction (arg: corrector phase); 3: per-block Frobenius
   // products of (X + dX, Y + dY)
   int (*direction)(sdpb_b200_ctx *, int op, int arg);
+  // eig.cuh: per block-parity min eigenvalue of L^-1 dM L^-T into dir_part; which 0: X, dX; 1: Y, dY
+  int (*step_length)(sdpb_b200_ctx *, int which);
 };
 // weak: a development build may compile only some precisions (make NLS="14")
 #define F(n) extern "C" const LaunchTable sdpb_b200_launch_nl##n __attribute__((weak));

@@ -55,6 +55,7 @@ static Hot_Path_Table b200_table(const Block_Info &bi, const SDP &sdp, int prec,
   t.direction_get = [](void *x, uint64_t *const *dx, uint64_t *const *dX, uint64_t *dy, uint64_t *const *dY) {
     return sdpb_b200_direction_get((sdpb_b200_ctx *)x, dx, dX, dy, dY);
   };
+  t.step_length = [](void *x, int which, uint64_t *mins) { return sdpb_b200_step_length((sdpb_b200_ctx *)x, which, mins); };
   t.last_error = [](const void *x) { return sdpb_b200_last_error((const sdpb_b200_ctx *)x); };
   t.destroy = [](void *x) { sdpb_b200_destroy((sdpb_b200_ctx *)x); };
   t.name = "sm_100a(libsdpb_b200.so)";

@@ -28,6 +28,8 @@ struct Hot_Path_Table
   int (*compute_search_direction)(void *, const uint64_t *, int) = nullptr;
   int (*direction_frobenius)(void *, uint64_t *) = nullptr;
   int (*direction_get)(void *, uint64_t *const *, uint64_t *const *, uint64_t *, uint64_t *const *) = nullptr;
+  // row N3 (sdpb_b200_step_length / oracle_step_length); optional
+  int (*step_length)(void *, int, uint64_t *) = nullptr;
   const char *(*last_error)(const void *) = nullptr;
   void (*destroy)(void *) = nullptr;
   std::string name;
@@ -297,6 +299,16 @@ public:
           }
       }
     unpack_matrix(dy, N, 1, io_dy.data());
+  }
+
+  bool step_length_min_eigenvalues(int which, std::vector<BigFloat> &mins) override
+  {
+    if(!t.step_length)
+      return false;
+    Buf buf(2 * (size_t)bi.num_blocks() * elem_words() + 1);
+    check(t.step_length(t.ctx, which, buf.data()));
+    scalars_in(mins, buf);
+    return true;
   }
 
   void solve_schur_complement_equation(std::vector<Matrix> &dx, Matrix &dy) override

@@ -10,7 +10,7 @@
 // cheap O(sum s_p^3 + P N) host work and stays on the CPU as in the reference.
 #pragma once
 #include "direction.hpp"
-#include "eig.hpp"
+#include "step_length.hpp"
 #include "sdp.hpp"
 
 #include <chrono>
@@ -65,6 +65,10 @@ struct Hot_Path
   {
     throw std::logic_error("no resident direction");
   }
+  // row N3 (step_length.cxx:27-46): mins[b] = smallest eigenvalue of L_b^-1 dM_b L_b^-T for every
+  // non-empty block-parity b, with M = X, dM = dX (which = 0) or Y, dY (which = 1) of the resident
+  // direction; false: not available, the caller runs step_length.hpp on the host
+  virtual bool step_length_min_eigenvalues(int, std::vector<BigFloat> &) { return false; }
   virtual std::string name() const = 0;
 };
 
@@ -213,22 +217,6 @@ inline void gemm_nn(const BigFloat &alpha, const Matrix &A, const Matrix &B, con
             C(i, j) *= beta;
             C(i, j) += acc;
           }
-      }
-}
-// B <- B L^{-T}
-inline void trsm_lower_transpose_right(const Matrix &L, Matrix &B)
-{
-  BigFloat t;
-  for(int r = 0; r < B.h; ++r)
-    for(int j = 0; j < B.w; ++j)
-      {
-        for(int k = 0; k < j; ++k)
-          {
-            t = B(r, k);
-            t *= L(j, k);
-            B(r, j) -= t;
-          }
-        B(r, j) /= L(j, j);
       }
 }
 // cholesky::SolveAfter(UPPER) with Q = U^T U: x <- U^{-1} U^{-T} x
@@ -509,38 +497,25 @@ public:
     hot.scale_multiply_add(alpha, A, B, beta, C);
   }
 
-  // step_length.cxx:27-46 (+ lower_triangular_inverse_congruence.cxx, min_eigenvalue.cxx)
-  static BigFloat step_length(const std::vector<Matrix> &MCholesky, const std::vector<Matrix> &dM,
-                              const BigFloat &gamma)
+  // step_length.cxx:27-46 (+ lower_triangular_inverse_congruence.cxx, min_eigenvalue.cxx); the
+  // per-block eigenvalues come from the hot path when it keeps the direction resident (row N3)
+  BigFloat step_length(int which, const std::vector<Matrix> &MCholesky, const std::vector<Matrix> &dM,
+                       const BigFloat &gamma)
   {
-    std::vector<BigFloat> mins(dM.size());
-    std::vector<int> have(dM.size(), 0);
-    std::string error;
-#pragma omp parallel for schedule(dynamic)
-    for(size_t b = 0; b < dM.size(); ++b)
+    std::vector<BigFloat> mins;
+    if(!(hot.resident_direction() && hot.step_length_min_eigenvalues(which, mins)))
       {
-        if(dM[b].h == 0)
-          continue;
-        Matrix A(dM[b]);
-        trsm_lower_transpose_right(MCholesky[b], A); // A L^{-T}
-        trsm_lower_left(MCholesky[b], A);            // L^{-1} A
-        try
-          {
-            mins[b] = min_eigenvalue_symmetric(A);
-            have[b] = 1;
-          }
-        catch(std::exception &e)
-          {
-#pragma omp critical
-            error = e.what();
-          }
+        mins.assign(dM.size(), BigFloat());
+#pragma omp parallel for schedule(dynamic)
+        for(size_t b = 0; b < dM.size(); ++b)
+          if(dM[b].h)
+            mins[b] = block_min_eigenvalue(MCholesky[b], dM[b]);
       }
-    if(!error.empty())
-      throw std::runtime_error(error);
+    // El::Min over the blocks, AllReduce MIN over the ranks (min_eigenvalue.cxx:31-32): exact
     bool first = true;
     BigFloat lambda;
     for(size_t b = 0; b < dM.size(); ++b)
-      if(have[b] && (first || mins[b] < lambda))
+      if(dM[b].h && (first || mins[b] < lambda))
         {
           lambda = mins[b];
           first = false;
@@ -666,8 +641,8 @@ public:
         }
     }
     const BigFloat gamma(parameters.step_length_reduction);
-    primal_step_length = step_length(X_cholesky, dX, gamma);
-    dual_step_length = step_length(Y_cholesky, dY, gamma);
+    primal_step_length = step_length(0, X_cholesky, dX, gamma);
+    dual_step_length = step_length(1, Y_cholesky, dY, gamma);
     if(is_primal_and_dual_feasible)
       {
         primal_step_length = Min(primal_step_length, dual_step_length);

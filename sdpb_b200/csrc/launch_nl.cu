@@ -632,6 +632,51 @@ template <int NL> struct Launch
       return rc;
     return bdm_cholesky_solve_symmetrize(c, c->dirDY, 1);
   }
+  // step_length.cxx:27-46 up to the reduction over the blocks (row N3)
+  static int step_length(sdpb_b200_ctx *c, int which)
+  {
+    const int nb = 2 * c->J;
+    cudaStream_t st = c->stream;
+    c->cur = st;
+    constexpr int ES = Fmt<NL>::ES;
+    if(nb == 0 || c->bdm_cols == 0)
+      return 0;
+    const size_t smem = tridiag_smem_bytes<NL>(c->max_s);
+    if(smem > (size_t)SMEM_OPT_IN)
+      {
+        c->error = "step_length: a block of " + std::to_string(c->max_s) + " rows does not fit the tridiagonalisation kernel";
+        return SDPB_B200_ERR_ARG;
+      }
+    limb_t *A = c->dirZ;
+    const limb_t *L = which == 0 ? c->X : c->LY;
+    const uint32_t *recip = which == 0 ? c->recipX : c->recipY;
+    CUDA_TRY(c, cudaMemcpyAsync(A, which == 0 ? c->dirDX : c->dirDY, c->wXY * 8, cudaMemcpyDeviceToDevice, st));
+    // A := L^-1 A L^-T
+    const unsigned g = (unsigned)((c->bdm_cols + 63) / 64);
+    c->kt_begin("eig_trsm_rows_kernel");
+    eig_trsm_kernel<NL, true><<<g, 64, 0, st>>>(c->d_bdm, nb, c->bdm_cols, L, recip, A);
+    c->kt_end();
+    c->kt_begin("eig_trsm_cols_kernel");
+    eig_trsm_kernel<NL, false><<<g, 64, 0, st>>>(c->d_bdm, nb, c->bdm_cols, L, recip, A);
+    c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
+    // tridiagonal form, then the smallest eigenvalue
+    if(int rc = smem_opt_in(c, eig_tridiag_kernel<NL>))
+      return rc;
+    const int threads = std::min(1024, (c->max_s + 31) / 32 * 32);
+    c->kt_begin("eig_tridiag_kernel");
+    eig_tridiag_kernel<NL><<<nb, threads, smem, st>>>(c->d_bdm, A, c->eig_d, c->eig_e, c->dir_scal + ES);
+    c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
+    if(int rc = smem_opt_in(c, eig_laguerre_kernel<NL>))
+      return rc;
+    c->kt_begin("eig_laguerre_kernel");
+    eig_laguerre_kernel<NL><<<nb, 32, sizeof(LaguerreSmem<NL>), st>>>(c->d_bdm, c->eig_d, c->eig_e, c->eig_e2,
+                                                                      c->dir_scal + 3 * ES, c->dir_part, c->eig_iter);
+    c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
   static int scalar(sdpb_b200_ctx *c, int op, int k, long count,
                     const limb_t *a, const limb_t *b, limb_t *r)
   {
@@ -660,4 +705,4 @@ template <int NL> struct Launch
 extern "C" __attribute__((visibility("default"))) const LaunchTable
   SDPB_CAT(sdpb_b200_launch_nl, SDPB_NL) = {sizeof(sdpb_b200_ctx), sizeof(LaunchTable), &Launch<SDPB_NL>::cholesky, &Launch<SDPB_NL>::pairings,
      &Launch<SDPB_NL>::schur_and_Q, &Launch<SDPB_NL>::schur_solve, &Launch<SDPB_NL>::scale_multiply_add,
-     &Launch<SDPB_NL>::scalar, &Launch<SDPB_NL>::direction};
+     &Launch<SDPB_NL>::scalar, &Launch<SDPB_NL>::direction, &Launch<SDPB_NL>::step_length};

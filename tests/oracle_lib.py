@@ -81,10 +81,12 @@ def load_oracle():
     for name, args in (("direction_begin", [u64p]), ("direction_R_errors", [u64p, u64p]),
                        ("direction_set_residues", [u64pp, u64pp, u64p]),
                        ("compute_search_direction", [u64p, ctypes.c_int]), ("direction_frobenius", [u64p]),
-                       ("direction_get", [u64pp, u64pp, u64p, u64pp])):
+                       ("direction_get", [u64pp, u64pp, u64p, u64pp]), ("step_length", [ctypes.c_int, u64p])):
         f = getattr(lib, "oracle_" + name)
         f.restype = ctypes.c_int
         f.argtypes = [ctypes.c_void_p] + args
+    lib.oracle_min_eigenvalue.restype = ctypes.c_int
+    lib.oracle_min_eigenvalue.argtypes = [ctypes.c_int, ctypes.c_int, u64p, u64p, u64p, ctypes.POINTER(ctypes.c_int)]
     lib.oracle_set_num_threads.restype = None
     lib.oracle_set_num_threads.argtypes = [ctypes.c_int]
     _lib = lib

@@ -495,6 +495,11 @@ def test_search_direction_bit_exact(prec, shapes, N):
         for name, g, w in zip(("dx", "dX", "dy", "dY"), got, want):
             ol.assert_same(f"{name} (phase {phase})", g, w)
         ol.assert_same(f"Frobenius products (phase {phase})", ctx.direction_frobenius(), ref.direction_frobenius())
+        # row N3: step_length.cxx:27-46 on the resident factors and direction -- congruence with chol(X)
+        # / chol(Y), tridiagonalisation, Laguerre's iteration -- against csrc/host/step_length.hpp
+        for which in (0, 1):
+            ol.assert_same(f"min eigenvalues of L^-1 d{'XY'[which]} L^-T (phase {phase})",
+                           ctx.step_length(which), ref.step_length(which))
     ctx.close()
 
 
