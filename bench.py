@@ -544,6 +544,7 @@ def main():
     bm[0] = 1 << 32                            # sign +1, exponent 0
     bm[(prec + 63) // 64 + 2] = 1 << 61        # top limb
     dir_dev, dir_wall, dir_k = {}, [], {}
+    sl_dev, sl_wall, sl_k, sl_iters = {}, [], {}, []
     for it in range(1 + a.steps):
         barrier()
         s0 = time.perf_counter()
@@ -559,14 +560,28 @@ def main():
         ctx.compute_search_direction(bm, 1)
         t_corr = ctx.last_direction_ms()
         wall_dir = time.perf_counter() - s0
+        # row N3: step_length.cxx:27-46 for (X, dX) and (Y, dY) on the same resident objects
+        ctx.step_length(0)
+        t_slx = ctx.last_step_length_ms()
+        k_sl = ctx.kernel_timings()
+        ctx.step_length(1)
+        t_sly = ctx.last_step_length_ms()
+        wall_sl = time.perf_counter() - s0 - wall_dir
         if it >= 1:
             dir_wall.append(wall_dir)
+            sl_wall.append(wall_sl)
             for k, v in (("minus_XY", t_begin), ("predictor", t_pred), ("corrector", t_corr)):
                 dir_dev.setdefault(k, []).append(v)
+            for k, v in (("primal", t_slx), ("dual", t_sly)):
+                sl_dev.setdefault(k, []).append(v)
             for name, ms in k_begin + k_pred:
                 dir_k.setdefault(name, []).append(ms)
+            for name, ms in k_sl:
+                sl_k.setdefault(name, []).append(ms)
+            sl_iters = ctx.step_length_iterations()
     barrier()
     dir_api_s = float(np.mean(dir_wall))
+    sl_api_s = float(np.mean(sl_wall))
 
     # ---- scale_multiply_add (-X Y and the other block GEMMs of step()) ----
     Ch = pool.slab([x.shape for x in sdp.X])
@@ -687,6 +702,14 @@ def main():
                                  "device_ms": {k: round(float(np.mean(v)), 3) for k, v in dir_dev.items()},
                                  "kernels_ms_predictor": {k: round(float(np.sum(v)) / a.steps, 4) for k, v in dir_k.items()},
                                  "bytes_h2d": int(sum(x.nbytes for x in pr) + sum(x.nbytes for x in dr) + prp.nbytes)},
+            "step_length": {"what": "step_length.cxx:27-46 for (X, dX) and (Y, dY): congruence with the resident "
+                                    "Cholesky factors, Householder tridiagonalisation, Laguerre min eigenvalue "
+                                    "(SURVEY 8f row N3); 2J eigenvalues come down per call",
+                            "api_ms_both_calls": sl_api_s * 1e3,
+                            "device_ms": {k: round(float(np.mean(v)), 3) for k, v in sl_dev.items()},
+                            "kernels_ms_primal": {k: round(float(np.sum(v)) / a.steps, 4) for k, v in sl_k.items()},
+                            "laguerre_steps_max": int(max(sl_iters)) if sl_iters else 0,
+                            "laguerre_steps_mean": round(float(np.mean(sl_iters)), 2) if sl_iters else 0},
             "e2e_with_two_solves": {"what": "one Newton iteration's device work through the C-ABI with host "
                                             "buffers: the e2e step plus the predictor and corrector Schur solves",
                                     "value": e2e_s + 2 * solve_api_s, "unit": "s/iteration"},

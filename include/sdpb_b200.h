@@ -194,6 +194,10 @@ int sdpb_b200_compute_search_direction(sdpb_b200_ctx *ctx, const uint64_t *beta_
 int sdpb_b200_direction_frobenius(sdpb_b200_ctx *ctx, uint64_t *block_products);
 int sdpb_b200_direction_get(sdpb_b200_ctx *ctx, uint64_t *const *dx, uint64_t *const *dX, uint64_t *dy,
                             uint64_t *const *dY);
+/* dX, dY (2J blocks each, the shape of X) from the host into the resident direction -- for a
+ * caller that forms the direction itself and only wants step_length on the device.  Needs the
+ * factors of a step; either list may be NULL (that object keeps its contents). */
+int sdpb_b200_direction_put(sdpb_b200_ctx *ctx, const uint64_t *const *dX, const uint64_t *const *dY);
 /* step_length (run/step/step_length/step_length.cxx:27-46, with
  * lower_triangular_inverse_congruence.cxx:5-18 and min_eigenvalue.cxx:8-33) on the resident
  * Cholesky factors and the resident direction: block_min_eigenvalues[b], b = 2j + parity, is the

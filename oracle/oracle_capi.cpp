@@ -625,6 +625,28 @@ int oracle_direction_get(oracle_ctx *c, uint64_t *const *dx, uint64_t *const *dX
   return 0;
 }
 
+int oracle_direction_put(oracle_ctx *c, const uint64_t *const *dX, const uint64_t *const *dY)
+{
+  sdpb_host::set_precision(c->prec);
+  if((int)c->shard.schur_complement_cholesky.size() != c->J || c->shard.Q.h != c->N)
+    {
+      c->error = "direction_put called out of order (needs a successful Schur-complement step)";
+      return 5;
+    }
+  c->dX.resize(2 * c->J);
+  c->dY.resize(2 * c->J);
+  for(int b = 0; b < 2 * c->J; ++b)
+    {
+      const int s = c->shapes[b / 2].psd_size(b % 2);
+      if(dX)
+        unpack_matrix(c->dX[b], s, s, dX[b]);
+      if(dY)
+        unpack_matrix(c->dY[b], s, s, dY[b]);
+    }
+  if(dX && dY)
+    c->have_direction = true;
+  return 0;
+}
 // ---- step_length (row N3): same call surface as sdpb_b200_step_length ----
 // step_length.cxx:27-46 up to the reduction over the blocks: block_min_eigenvalues[b] = smallest
 // eigenvalue of L_b^-1 dM_b L_b^-T (csrc/host/step_length.hpp), M = X (which 0) or Y (which 1) of

@@ -108,6 +108,10 @@ def load_library():
     lib.sdpb_b200_direction_frobenius.argtypes = [ctypes.c_void_p, u64p]
     lib.sdpb_b200_direction_get.restype = ctypes.c_int
     lib.sdpb_b200_direction_get.argtypes = [ctypes.c_void_p, u64pp, u64pp, u64p, u64pp]
+    lib.sdpb_b200_direction_put.restype = ctypes.c_int
+    lib.sdpb_b200_direction_put.argtypes = [ctypes.c_void_p, u64pp, u64pp]
+    lib.sdpb_b200_step_length_iterations.restype = ctypes.c_int
+    lib.sdpb_b200_step_length_iterations.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
     lib.sdpb_b200_step_length.restype = ctypes.c_int
     lib.sdpb_b200_step_length.argtypes = [ctypes.c_void_p, ctypes.c_int, u64p]
     lib.sdpb_b200_last_step_length_ms.restype = ctypes.c_float
@@ -280,6 +284,10 @@ class StepContextBase:
         return dx, dX, dy, dY
 
 
+    def direction_put(self, dX, dY):
+        """Replace the resident dX, dY (2J blocks each) by the caller's."""
+        self._check(self._dir("direction_put")(self.handle, ptr_array(dX), ptr_array(dY)))
+
     def step_length(self, which):
         """Per block-parity smallest eigenvalue of L^-1 dM L^-T (step_length.cxx:27-46), M = X / dX
         (which 0) or Y / dY (which 1) of the last compute_search_direction; (2J, ew), empty blocks 0."""
@@ -354,6 +362,15 @@ class SchurContext(StepContextBase):
 
     def last_solve_ms(self):
         return float(self.lib.sdpb_b200_last_solve_ms(self.handle))
+
+    def last_step_length_ms(self):
+        return float(self.lib.sdpb_b200_last_step_length_ms(self.handle))
+
+    def step_length_iterations(self):
+        """Laguerre steps per block-parity of the last step_length call."""
+        out = (ctypes.c_int * max(1, 2 * self.J))()
+        self._check(self.lib.sdpb_b200_step_length_iterations(self.handle, out))
+        return list(out)[:2 * self.J]
 
     def last_direction_ms(self):
         return float(self.lib.sdpb_b200_last_direction_ms(self.handle))

@@ -1677,7 +1677,7 @@ extern "C" int sdpb_b200_step_length(sdpb_b200_ctx *c, int which, uint64_t *bloc
 {
   if(!c || (which != 0 && which != 1))
     return SDPB_B200_ERR_ARG;
-  if(int rc = direction_ready(c, "step_length", true, true))
+  if(int rc = direction_ready(c, "step_length", false, true))
     return rc;
   CUDA_TRY(c, cudaSetDevice(c->device));
   c->kt_used = 0;
@@ -1736,6 +1736,27 @@ extern "C" int sdpb_b200_direction_get(sdpb_b200_ctx *c, uint64_t *const *dx, ui
         memcpy(dx[j], c->dir_pinned + (size_t)c->g[j].row0 * es, (size_t)c->g[j].P * es * 8);
   if(dy)
     memcpy(dy, c->dir_pinned + (size_t)c->K * es, (size_t)c->N * es * 8);
+  return 0;
+}
+// dX, dY (2J blocks each, the shape of X) from the host into the resident direction: for a caller
+// that forms the direction itself and wants step_length on the device, and for tests.  Needs the
+// factors of a step; a block list may be NULL (that object is left as it is).
+extern "C" int sdpb_b200_direction_put(sdpb_b200_ctx *c, const uint64_t *const *dX, const uint64_t *const *dY)
+{
+  if(!c)
+    return SDPB_B200_ERR_ARG;
+  if(int rc = direction_ready(c, "direction_put", false, false))
+    return rc;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rc = dX ? copy_blocks_in(c, dX, c->dirDX) : 0;
+  if(!rc && dY)
+    rc = copy_blocks_in(c, dY, c->dirDY);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if(rc)
+    return rc;
+  CUDA_TRY(c, e);
+  if(dX && dY)
+    c->have_direction = true; // -XY and the residues are not touched
   return 0;
 }
 extern "C" float sdpb_b200_last_direction_ms(const sdpb_b200_ctx *c) { return c ? c->direction_ms : 0.f; }

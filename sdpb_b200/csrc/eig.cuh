@@ -98,8 +98,9 @@ template <int NL> __host__ __device__ constexpr size_t tridiag_smem_bytes(int s)
 }
 // A: the symmetric matrices, given by their lower triangles (destroyed); dd / ee: diagonal and sub-diagonal, stacked like the
 // columns of the block-diagonal object (cum_cols); half: 0.5 as mpf_set_d gives it
+constexpr int TRIDIAG_THREADS = 128; // rows beyond that wrap around; the rank-2 update uses all of them
 template <int NL>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(TRIDIAG_THREADS)
 eig_tridiag_kernel(const BdmDesc *d, limb_t *A, limb_t *dd, limb_t *ee, const limb_t *half)
 {
   typedef TileGeom<NL> G;
@@ -229,10 +230,12 @@ eig_tridiag_kernel(const BdmDesc *d, limb_t *A, limb_t *dd, limb_t *ee, const li
           sts_reg<NL>(w + (size_t)i * G::SW, acc);
         }
       __syncthreads();
-      // A(i,j) -= v_hi w_lo ; A(i,j) -= w_hi v_lo   (hi = max(i,j), lo = min(i,j))
-      for(int i = k + 1 + tid; i < s; i += T)
-        for(int j = k + 1; j < s; ++j)
+      // A(i,j) -= v_hi w_lo ; A(i,j) -= w_hi v_lo   (hi = max(i,j), lo = min(i,j)); the elements of
+      // the trailing matrix are dealt out to all threads, consecutive threads down a column
+      const int m = s - k - 1;
+      for(int q = tid; q < m * m; q += T)
           {
+            const int i = k + 1 + q % m, j = k + 1 + q / m;
             const int hi = i > j ? i : j, lo = i > j ? j : i;
             limb_t *e = Ab + ((long)j * s + i) * ES;
             Reg<NL> acc;

@@ -12,9 +12,11 @@
 #include "direction.hpp"
 #include "step_length.hpp"
 #include "sdp.hpp"
+#include "checkpoint.hpp"
 
 #include <chrono>
 #include <cmath>
+#include <csignal>
 #include <cstdio>
 #include <functional>
 #include <sys/stat.h>
@@ -87,6 +89,10 @@ struct Solver_Parameters
               infeasible_centering_parameter = "0.3", step_length_reduction = "0.7",
               max_complementarity = "1e100", min_primal_step = "0", min_dual_step = "0";
   std::string write_solution = "x,y"; // Write_Solution.cxx
+  // checkpoints (Solver_Parameters.cxx:140-156, sdpb/SDPB_Parameters.cxx:41-47,176-193)
+  std::string checkpoint_out, checkpoint_in;
+  bool checkpoint_out_set = false, checkpoint_in_set = false, no_final_checkpoint = false;
+  long checkpoint_interval = 3600;
   bool set(const std::string &key, const std::string &value)
   {
     auto flag = [&](bool &b) { b = value.empty() || value == "1" || value == "true"; };
@@ -109,8 +115,19 @@ struct Solver_Parameters
     else if(key == "minPrimalStep") min_primal_step = value;
     else if(key == "minDualStep") min_dual_step = value;
     else if(key == "writeSolution") write_solution = value;
-    else if(key == "checkpointInterval" || key == "verbosity" || key == "procGranularity"
-            || key == "maxSharedMemory" || key == "checkpointDir" || key == "noFinalCheckpoint")
+    else if(key == "checkpointDir" || key == "c")
+      {
+        checkpoint_out = value;
+        checkpoint_out_set = true;
+      }
+    else if(key == "initialCheckpointDir" || key == "i")
+      {
+        checkpoint_in = value;
+        checkpoint_in_set = true;
+      }
+    else if(key == "checkpointInterval") checkpoint_interval = std::stol(value);
+    else if(key == "noFinalCheckpoint") flag(no_final_checkpoint);
+    else if(key == "verbosity" || key == "procGranularity" || key == "maxSharedMemory")
       ; // accepted for command-line compatibility; no effect in this host
     else
       return false;
@@ -129,7 +146,8 @@ enum class Terminate_Reason
   MaxIterationsExceeded,
   MaxRuntimeExceeded,
   PrimalStepTooSmall,
-  DualStepTooSmall
+  DualStepTooSmall,
+  SIGTERM_Received
 };
 // SDP_Solver_Terminate_Reason.cxx:5-45
 inline const char *to_string(Terminate_Reason r)
@@ -146,6 +164,7 @@ inline const char *to_string(Terminate_Reason r)
     case Terminate_Reason::MaxComplementarityExceeded: return "maxComplementarity exceeded";
     case Terminate_Reason::PrimalStepTooSmall: return "primal step too small";
     case Terminate_Reason::DualStepTooSmall: return "dual step too small";
+    case Terminate_Reason::SIGTERM_Received: return "SIGTERM signal received";
     }
   return "?";
 }
@@ -322,6 +341,10 @@ public:
   BigFloat primal_objective, dual_objective, duality_gap, primal_error_P, primal_error_p, dual_error,
     R_error;
   std::vector<Iteration_Record> iterations;
+  // save_checkpoint.cxx / load_checkpoint.cxx (checkpoint.hpp): generations of the binary checkpoint
+  Checkpoint_State checkpoint;
+  bool loaded_checkpoint = false;
+  std::string options_json = "{}\n"; // the "options" object of checkpoint.json
   double hot_path_seconds = 0, host_seconds = 0, direction_seconds = 0;
   std::function<void(const Iteration_Record &)> on_iteration;
 
@@ -356,6 +379,17 @@ public:
           }
       }
     y.resize(s.N(), 1);
+    // SDP_Solver.cxx:20-38: the initial point above unless a checkpoint (binary, else text) loads
+    checkpoint.x = &x;
+    checkpoint.X = &X;
+    checkpoint.y = &y;
+    checkpoint.Y = &Y;
+    loaded_checkpoint = load_checkpoint(parameters.checkpoint_in, checkpoint,
+                                        parameters.checkpoint_in_set && !parameters.checkpoint_in.empty());
+  }
+  void save_checkpoint(const Solver_Parameters &parameters)
+  {
+    sdpb_host::save_checkpoint(parameters.checkpoint_out, checkpoint, options_json, "sdpb-b200");
   }
 
   // constraint_matrix_weighted_sum.cxx:14-66 (direction.hpp)
@@ -657,17 +691,51 @@ public:
       axpy(dual_step_length, dY[b], Y[b]);
   }
 
-  // SDP_Solver::run (run/run.cxx:184-470), without checkpoints and signals
+  // SIGTERM is latched by a handler installed for the duration of run() (Environment::sigterm_received
+  // in the reference, sdpb_util/Environment.hxx:26) and acted on at the top of the next iteration
+  static volatile std::sig_atomic_t &sigterm_flag()
+  {
+    static volatile std::sig_atomic_t flag = 0;
+    return flag;
+  }
+  static void on_sigterm(int) { sigterm_flag() = 1; }
+
+  // SDP_Solver::run (run/run.cxx:184-470)
   Terminate_Reason run(const Solver_Parameters &parameters)
   {
     Terminate_Reason reason = Terminate_Reason::MaxIterationsExceeded;
     const auto start = std::chrono::steady_clock::now();
+    auto last_checkpoint_time = start;
     BigFloat primal_step_length(0), dual_step_length(0);
     std::vector<Matrix> X_cholesky, Y_cholesky, A_Y;
     const size_t total_psd_rows = block_info.total_psd_rows();
+    sigterm_flag() = 0;
+    struct Handler_Guard
+    {
+      void (*old)(int);
+      Handler_Guard() : old(std::signal(SIGTERM, &SDP_Solver::on_sigterm)) {}
+      ~Handler_Guard()
+      {
+        if(old != SIG_ERR)
+          std::signal(SIGTERM, old);
+      }
+    } handler_guard;
     for(long iteration = 1;; ++iteration)
       {
         const auto iter_start = std::chrono::steady_clock::now();
+        // run.cxx:332-355: graceful exit on SIGTERM (the caller writes the checkpoint)
+        if(sigterm_flag())
+          {
+            reason = Terminate_Reason::SIGTERM_Received;
+            break;
+          }
+        // run.cxx:357-370: a checkpoint every checkpointInterval seconds
+        if(std::chrono::duration_cast<std::chrono::seconds>(iter_start - last_checkpoint_time).count()
+           >= parameters.checkpoint_interval)
+          {
+            save_checkpoint(parameters);
+            last_checkpoint_time = std::chrono::steady_clock::now();
+          }
         compute_objectives();
         {
           const auto t0 = std::chrono::steady_clock::now();
@@ -731,31 +799,66 @@ inline void write_vector_file(const std::string &path, const Matrix &v)
   if(!f.good())
     throw std::runtime_error("Error when writing to: " + path);
 }
-inline void write_iterations_json(const std::string &path, const std::vector<Iteration_Record> &its)
+// iterations.json, appended to as the iterations complete (run.cxx:304-316, print_iteration.cxx:77-108): a run
+// that dies at iteration k leaves the k-1 records it finished
+class Iterations_Json
 {
-  std::ofstream f(path);
-  f << "[";
-  for(size_t k = 0; k < its.size(); ++k)
-    {
-      const Iteration_Record &r = its[k];
-      char tm[96];
-      snprintf(tm, sizeof tm, ", \"total_time\": %.3f, \"iter_time\": %.3f", r.total_time, r.iter_time);
-      f << (k ? "," : "") << "\n{ \"iteration\":" << r.iteration << tm << ", \"mu\": \""
-        << format_bigfloat(r.mu) << "\", \"P-obj\": \"" << format_bigfloat(r.primal_objective)
-        << "\", \"D-obj\": \"" << format_bigfloat(r.dual_objective) << "\", \"gap\": \""
-        << format_bigfloat(r.duality_gap) << "\", \"P-err\": \"" << format_bigfloat(r.primal_error_P)
-        << "\", \"p-err\": \"" << format_bigfloat(r.primal_error_p) << "\", \"D-err\": \""
-        << format_bigfloat(r.dual_error) << "\", \"R-err\": \"" << format_bigfloat(r.R_error)
-        << "\", \"P-step\": \"" << format_bigfloat(r.primal_step_length) << "\", \"D-step\": \""
-        << format_bigfloat(r.dual_step_length) << "\", \"beta\": \"" << format_bigfloat(r.beta_corrector)
-        << "\", \"Q_cond_number\": \"" << format_bigfloat(r.Q_cond_number)
-        << "\", \"max_block_cond_number\": \"" << format_bigfloat(r.max_block_cond_number)
-        << "\", \"block_name\": \"" << r.block_name << "\" }";
-    }
-  f << "\n]";
-  if(!f.good())
-    throw std::runtime_error("Error when writing to: " + path);
-}
+  std::string path;
+  size_t written = 0;
+  bool open = false;
+
+public:
+  explicit Iterations_Json(const std::string &p) : path(p)
+  {
+    if(path.empty())
+      return;
+    std::ofstream f(path);
+    f << "[";
+    open = f.good();
+    if(!open)
+      fprintf(stderr, "Warning: cannot write to %s\n", path.c_str());
+  }
+  void append(const Iteration_Record &r)
+  {
+    if(!open)
+      return;
+    std::ofstream f(path, std::ios::app);
+    char tm[96];
+    snprintf(tm, sizeof tm, ", \"total_time\": %.3f, \"iter_time\": %.3f", r.total_time, r.iter_time);
+    f << (written ? "," : "") << "\n{ \"iteration\":" << r.iteration << tm << ", \"mu\": \""
+      << format_bigfloat(r.mu) << "\", \"P-obj\": \"" << format_bigfloat(r.primal_objective)
+      << "\", \"D-obj\": \"" << format_bigfloat(r.dual_objective) << "\", \"gap\": \""
+      << format_bigfloat(r.duality_gap) << "\", \"P-err\": \"" << format_bigfloat(r.primal_error_P)
+      << "\", \"p-err\": \"" << format_bigfloat(r.primal_error_p) << "\", \"D-err\": \""
+      << format_bigfloat(r.dual_error) << "\", \"R-err\": \"" << format_bigfloat(r.R_error)
+      << "\", \"P-step\": \"" << format_bigfloat(r.primal_step_length) << "\", \"D-step\": \""
+      << format_bigfloat(r.dual_step_length) << "\", \"beta\": \"" << format_bigfloat(r.beta_corrector)
+      << "\", \"Q_cond_number\": \"" << format_bigfloat(r.Q_cond_number)
+      << "\", \"max_block_cond_number\": \"" << format_bigfloat(r.max_block_cond_number)
+      << "\", \"block_name\": \"" << r.block_name << "\" }";
+    ++written;
+  }
+  // closes the array; idempotent
+  void close()
+  {
+    if(!open)
+      return;
+    std::ofstream f(path, std::ios::app);
+    f << "\n]";
+    open = false;
+    if(!f.good())
+      throw std::runtime_error("Error when writing to: " + path);
+  }
+  ~Iterations_Json()
+  {
+    try
+      {
+        close();
+      }
+    catch(...)
+      {}
+  }
+};
 inline void save_solution(const SDP_Solver &solver, Terminate_Reason reason, long runtime_seconds,
                           const std::string &out_dir, const std::string &write_solution)
 {
@@ -845,32 +948,59 @@ solve(const std::string &sdp_dir, const std::string &out_dir, const Solver_Param
   SDP sdp;
   read_sdp(sdp_dir, block_info, sdp);
   std::unique_ptr<Hot_Path> hot = make_hot_path(block_info, sdp);
-  SDP_Solver solver(parameters, block_info, sdp, *hot);
-  if(verbose)
-    solver.on_iteration = [](const Iteration_Record &r) {
-      printf("%4ld %8.2f  mu %.3e  P-obj %.10e  D-obj %.10e  gap %.2e  P-err %.2e  D-err %.2e  steps %.3g %.3g\n",
-             r.iteration, r.total_time, r.mu.to_double(), r.primal_objective.to_double(),
-             r.dual_objective.to_double(), r.duality_gap.to_double(),
-             Max(r.primal_error_P, r.primal_error_p).to_double(), r.dual_error.to_double(),
-             r.primal_step_length.to_double(), r.dual_step_length.to_double());
-      fflush(stdout);
-    };
-  const auto t0 = std::chrono::steady_clock::now();
-  const Terminate_Reason reason = solver.run(parameters);
-  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  if(!out_dir.empty())
+  // sdpb/SDPB_Parameters.cxx:176-193: checkpointDir defaults to <sdpDir>.ck, initialCheckpointDir to
+  // checkpointDir; an explicit initialCheckpointDir must hold a checkpoint
+  Solver_Parameters par = parameters;
+  if(!par.checkpoint_out_set)
     {
-      save_solution(solver, reason, (long)secs, out_dir, parameters.write_solution);
-      write_iterations_json(out_dir + "/iterations.json", solver.iterations);
+      std::string base = sdp_dir;
+      while(base.size() > 1 && base.back() == '/')
+        base.pop_back();
+      par.checkpoint_out = base + ".ck";
     }
+  if(!par.checkpoint_in_set)
+    par.checkpoint_in = par.checkpoint_out;
+  SDP_Solver solver(par, block_info, sdp, *hot);
+  {
+    std::ostringstream o; // the "options" object of checkpoint.json (Solver_Parameters.cxx:160-188)
+    o << "{\n    \"precision\": \"" << par.precision << "\",\n    \"maxIterations\": \"" << par.max_iterations
+      << "\",\n    \"checkpointInterval\": \"" << par.checkpoint_interval << "\",\n    \"sdpDir\": \"" << sdp_dir
+      << "\",\n    \"outDir\": \"" << out_dir << "\",\n    \"checkpointDir\": \"" << par.checkpoint_out
+      << "\",\n    \"initialCheckpointDir\": \"" << par.checkpoint_in << "\"\n}\n";
+    solver.options_json = o.str();
+  }
+  if(!out_dir.empty())
+    create_directories(out_dir);
+  Iterations_Json iterations_json(out_dir.empty() ? std::string() : out_dir + "/iterations.json");
+  solver.on_iteration = [&](const Iteration_Record &r) {
+    iterations_json.append(r);
+    if(verbose)
+      {
+        printf("%4ld %8.2f  mu %.3e  P-obj %.10e  D-obj %.10e  gap %.2e  P-err %.2e  D-err %.2e  steps %.3g %.3g\n",
+               r.iteration, r.total_time, r.mu.to_double(), r.primal_objective.to_double(),
+               r.dual_objective.to_double(), r.duality_gap.to_double(),
+               Max(r.primal_error_P, r.primal_error_p).to_double(), r.dual_error.to_double(),
+               r.primal_step_length.to_double(), r.dual_step_length.to_double());
+        fflush(stdout);
+      }
+  };
+  const auto t0 = std::chrono::steady_clock::now();
+  const Terminate_Reason reason = solver.run(par);
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  iterations_json.close();
+  // sdpb/solve.cxx:81-88: a final checkpoint unless --noFinalCheckpoint; always after SIGTERM
+  if(reason == Terminate_Reason::SIGTERM_Received || !par.no_final_checkpoint)
+    solver.save_checkpoint(par);
+  if(!out_dir.empty())
+    save_solution(solver, reason, (long)secs, out_dir, par.write_solution);
   if(summary)
     {
       char buf[512];
       snprintf(buf, sizeof buf,
                "{\"terminateReason\": \"%s\", \"iterations\": %zu, \"seconds\": %.3f, \"hot_path_seconds\": %.3f, "
-               "\"host_seconds\": %.3f, \"hot_path\": \"%s\"}",
+               "\"host_seconds\": %.3f, \"hot_path\": \"%s\", \"checkpoint_loaded\": %s, \"checkpoint_generation\": %ld}",
                to_string(reason), solver.iterations.size(), secs, solver.hot_path_seconds, solver.host_seconds,
-               hot->name().c_str());
+               hot->name().c_str(), solver.loaded_checkpoint ? "true" : "false", solver.checkpoint.current_generation);
       *summary = buf;
     }
   return reason;

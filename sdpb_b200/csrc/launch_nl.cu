@@ -663,9 +663,8 @@ template <int NL> struct Launch
     // tridiagonal form, then the smallest eigenvalue
     if(int rc = smem_opt_in(c, eig_tridiag_kernel<NL>))
       return rc;
-    const int threads = std::min(1024, (c->max_s + 31) / 32 * 32);
     c->kt_begin("eig_tridiag_kernel");
-    eig_tridiag_kernel<NL><<<nb, threads, smem, st>>>(c->d_bdm, A, c->eig_d, c->eig_e, c->dir_scal + ES);
+    eig_tridiag_kernel<NL><<<nb, TRIDIAG_THREADS, smem, st>>>(c->d_bdm, A, c->eig_d, c->eig_e, c->dir_scal + ES);
     c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
     if(int rc = smem_opt_in(c, eig_laguerre_kernel<NL>))

@@ -79,8 +79,9 @@ def diff_out_dirs(ours, golden, keys=("terminateReason", "primalObjective", "dua
                     if not close(p, q):
                         bad.append(f"c_minus_By[{j}][{i}]: {p[:40]} vs {q[:40]}")
                         break
-    bad += diff_iterations(os.path.join(ours, "iterations.json"), os.path.join(golden, iterations_name),
-                           max_iterations)
+    if iterations_name is not None:  # None: a run restarted from a checkpoint has its own iteration history
+        bad += diff_iterations(os.path.join(ours, "iterations.json"), os.path.join(golden, iterations_name),
+                               max_iterations)
     return bad
 
 

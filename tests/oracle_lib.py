@@ -81,7 +81,8 @@ def load_oracle():
     for name, args in (("direction_begin", [u64p]), ("direction_R_errors", [u64p, u64p]),
                        ("direction_set_residues", [u64pp, u64pp, u64p]),
                        ("compute_search_direction", [u64p, ctypes.c_int]), ("direction_frobenius", [u64p]),
-                       ("direction_get", [u64pp, u64pp, u64p, u64pp]), ("step_length", [ctypes.c_int, u64p])):
+                       ("direction_get", [u64pp, u64pp, u64p, u64pp]), ("step_length", [ctypes.c_int, u64p]),
+                       ("direction_put", [u64pp, u64pp])):
         f = getattr(lib, "oracle_" + name)
         f.restype = ctypes.c_int
         f.argtypes = [ctypes.c_void_p] + args

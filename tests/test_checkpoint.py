@@ -1,0 +1,121 @@
+"""Row N4: checkpoints of the solver state (csrc/host/checkpoint.hpp) behind the reference's options
+--checkpointDir / --initialCheckpointDir / --checkpointInterval / --noFinalCheckpoint, driven through
+the host solver on the CPU oracle.  The reference's own check is `run_sdpb_twice`
+(test/src/integration_tests/cases/end-to-end.test.cxx:114-122,313-315, issue #219): the second run
+loads the final checkpoint of the first and must reproduce the golden output."""
+import ctypes
+import filecmp
+import json
+import os
+
+import pytest
+
+import golden_check
+from test_golden_trajectory import CASES, _solve, _unpack
+
+
+def _args(root, out, ck, case, extra=()):
+    return (["--sdpDir", os.path.join(root, "sdp"), "--outDir", out, "--checkpointDir", ck,
+             "--precision", str(case["precision"])] + case["sdpb_args"] + list(extra))
+
+
+def test_second_run_loads_the_final_checkpoint_and_reproduces_the_golden(tmp_path, oracle):
+    lib = oracle.load_oracle()
+    name = "1d"
+    case = CASES[name]
+    root = _unpack(name, str(tmp_path))
+    out, ck = str(tmp_path / "out"), str(tmp_path / "ck")
+    first = _solve(lib, "oracle_solve", _args(root, out, ck, case))
+    assert not first["checkpoint_loaded"] and first["checkpoint_generation"] == 1
+    meta = json.load(open(os.path.join(ck, "checkpoint.json")))
+    assert meta["current"] == 1 and meta["backup"] == 0
+    assert os.path.exists(os.path.join(ck, "checkpoint_1_0"))
+    second = _solve(lib, "oracle_solve", _args(root, out, ck, case))
+    assert second["checkpoint_loaded"] and second["checkpoint_generation"] == 2
+    assert second["iterations"] <= 1          # already optimal: terminates before the first step
+    assert not os.path.exists(os.path.join(ck, "checkpoint_0_0"))   # the backup generation is removed
+    kw = {"iterations_name": None}
+    if case["out_txt_keys"]:
+        kw["keys"] = tuple(case["out_txt_keys"])
+    bad = golden_check.diff_out_dirs(out, os.path.join(root, "out"), **kw)
+    assert not bad, bad[:5]
+
+
+def test_interrupted_run_continues_bit_for_bit(tmp_path, oracle):
+    """maxIterations stops a run, the binary checkpoint holds x, X, y, Y exactly, and the restarted
+    run ends with the very files the uninterrupted run writes."""
+    lib = oracle.load_oracle()
+    name = "1d"
+    case = CASES[name]
+    root = _unpack(name, str(tmp_path))
+    ref_out = str(tmp_path / "ref_out")
+    whole = _solve(lib, "oracle_solve", _args(root, ref_out, str(tmp_path / "ref_ck"), case, ["--noFinalCheckpoint"]))
+    assert not os.path.exists(str(tmp_path / "ref_ck"))
+    out, ck = str(tmp_path / "out"), str(tmp_path / "ck")
+    cut = [a for a in case["sdpb_args"]]
+    part = _solve(lib, "oracle_solve", ["--sdpDir", os.path.join(root, "sdp"), "--outDir", out, "--checkpointDir", ck,
+                                        "--precision", str(case["precision"])] + cut + ["--maxIterations", "40"])
+    assert part["terminateReason"] == "maxIterations exceeded" and part["iterations"] == 40
+    rest = _solve(lib, "oracle_solve", _args(root, out, ck, case))
+    assert rest["checkpoint_loaded"]
+    assert rest["iterations"] + part["iterations"] == whole["iterations"]
+    for f in sorted(os.listdir(ref_out)):
+        if f.startswith(("x_", "y.txt", "z.txt")):
+            assert filecmp.cmp(os.path.join(ref_out, f), os.path.join(out, f), shallow=False), f
+
+
+def test_text_checkpoint_from_a_written_solution(tmp_path, oracle):
+    """load_text_checkpoint.cxx:6-46: x_*.txt, y.txt, X_matrix_*.txt, Y_matrix_*.txt of an out
+    directory are a valid initial checkpoint; the run started there is optimal at once."""
+    lib = oracle.load_oracle()
+    name = "1d"
+    case = CASES[name]
+    root = _unpack(name, str(tmp_path))
+    out1 = str(tmp_path / "out1")
+    args = [a for a in case["sdpb_args"]]
+    if "--writeSolution" in args:
+        k = args.index("--writeSolution")
+        del args[k:k + 2]
+    base = ["--sdpDir", os.path.join(root, "sdp"), "--precision", str(case["precision"])] + args
+    _solve(lib, "oracle_solve", base + ["--outDir", out1, "--checkpointDir", "", "--writeSolution", "x,y,X,Y"])
+    assert os.path.exists(os.path.join(out1, "X_matrix_0.txt"))
+    out2 = str(tmp_path / "out2")
+    second = _solve(lib, "oracle_solve", base + ["--outDir", out2, "--checkpointDir", "", "--initialCheckpointDir", out1,
+                                                 "--writeSolution", "x,y"])
+    assert second["checkpoint_loaded"] and second["iterations"] <= 2
+    bad = golden_check.diff_out_dirs(out2, os.path.join(root, "out"), iterations_name=None,
+                                     **({"keys": tuple(case["out_txt_keys"])} if case["out_txt_keys"] else {}))
+    assert not bad, bad[:5]
+
+
+def test_checkpoint_errors_carry_the_references_texts(tmp_path, oracle):
+    lib = oracle.load_oracle()
+    name = "1d"
+    case = CASES[name]
+    root = _unpack(name, str(tmp_path))
+    out, ck = str(tmp_path / "out"), str(tmp_path / "ck")
+    _solve(lib, "oracle_solve", _args(root, out, ck, case, ["--maxIterations", "3"]))
+
+    def fails(args):
+        argv = (ctypes.c_char_p * len(args))(*[a.encode() for a in args])
+        buf = ctypes.create_string_buffer(8192)
+        assert lib.oracle_solve(len(args), argv, buf, 8192) != 0
+        return buf.value.decode()
+
+    # an explicit --initialCheckpointDir must hold a checkpoint (SDPB_Parameters.cxx:186-193)
+    msg = fails(_args(root, out, ck, case, ["--initialCheckpointDir", str(tmp_path / "nowhere")]))
+    assert "Unable to load checkpoint from directory" in msg
+    # another precision: the element images have another length
+    other = dict(case, precision=case["precision"] + 128)
+    msg = fails(_args(root, out, ck, other))
+    assert "binary checkpoint file" in msg
+    # truncated file
+    path = os.path.join(ck, "checkpoint_1_0")
+    data = open(path, "rb").read()
+    open(path, "wb").write(data[:len(data) // 2])
+    msg = fails(_args(root, out, ck, case))
+    assert "Corrupted binary checkpoint file" in msg
+    # metadata pointing at a missing generation
+    os.remove(path)
+    msg = fails(_args(root, out, ck, case))
+    assert "Missing checkpoint file" in msg

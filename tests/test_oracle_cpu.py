@@ -154,3 +154,64 @@ def test_exact_syrk_direct_equals_the_references_crt_blas_route(prec, K, N):
     iu = np.triu_indices(N)
     assert np.array_equal(got[iu[1], iu[0]], want[iu[1], iu[0]])  # (col j, row i), i <= j
     assert want[iu[1], iu[0]].any()
+
+
+def _pack_doubles(prec, M):
+    s = M.shape[0]
+    out = np.zeros((s, s, elem_words(prec)), dtype=np.uint64)
+    for j in range(s):
+        for i in range(s):
+            out[j, i] = ol.from_decimal(prec, "%.40e" % M[i, j])
+    return out
+
+
+def _oracle_min_eigenvalue(prec, M, L=None):
+    import ctypes
+    s = M.shape[0]
+    out = np.zeros(elem_words(prec), dtype=np.uint64)
+    it = ctypes.c_int(0)
+    A = _pack_doubles(prec, M)
+    Lp = None if L is None else ol._ptr(_pack_doubles(prec, L))
+    ol.load_oracle().oracle_min_eigenvalue(prec, s, Lp, ol._ptr(A), ol._ptr(out), ctypes.byref(it))
+    return ol.to_double(prec, out), it.value
+
+
+def test_min_eigenvalue_restatement_against_lapack():
+    """Row N3's canonical algorithm (csrc/host/step_length.hpp: congruence, Householder
+    tridiagonalisation, Laguerre's iteration from the Gershgorin bound) against LAPACK in double:
+    generic matrices, the degenerate spectra that slow Laguerre down to linear convergence, exact
+    zeros, and the lower triangle being the one that is read (min_eigenvalue.cxx:28, LOWER)."""
+    prec = 768
+    rng = np.random.default_rng(5)
+
+    def check(M, L=None, max_iters=None):
+        got, iters = _oracle_min_eigenvalue(prec, M, L)
+        S = np.tril(M) + np.tril(M, -1).T
+        if L is not None:
+            Li = np.linalg.inv(L)
+            S = Li @ M @ Li.T
+            S = np.tril(S) + np.tril(S, -1).T
+        ev = np.linalg.eigvalsh(S)
+        scale = max(np.abs(ev).max(), 1e-300)
+        assert abs(got - ev[0]) <= 1e-12 * scale, (got, ev[0], iters)
+        if max_iters is not None:
+            assert iters <= max_iters, iters
+        return iters
+
+    for n in (1, 2, 3, 5, 20, 40):
+        A = rng.standard_normal((n, n))
+        check(A + A.T, max_iters=12)
+    check(np.diag(rng.standard_normal(10)), max_iters=2)
+    check(np.zeros((6, 6)), max_iters=0)
+    check(-3.0 * np.eye(7), max_iters=2)
+    Q, _ = np.linalg.qr(rng.standard_normal((12, 12)))
+    check(Q @ np.diag([1, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11.]) @ Q.T, max_iters=80)      # double root (to 1e-16)
+    check(Q @ np.diag([-1, -1, -1, 3, 4, 5, 6, 7, 8, 9, 10, 11.]) @ Q.T, max_iters=100)  # triple root
+    check(Q @ np.diag([1.0] * 11 + [2.0]) @ Q.T, max_iters=100)
+    W = np.diag(np.abs(np.arange(-10, 11)).astype(float)) + np.diag(np.ones(20), 1) + np.diag(np.ones(20), -1)
+    check(-W, max_iters=60)  # Wilkinson's matrix: the two largest eigenvalues agree to 1e-15
+    check(rng.standard_normal((9, 9)))  # not symmetric: only the lower triangle counts
+    n = 30
+    A = rng.standard_normal((n, n))
+    B = rng.standard_normal((n, n))
+    check(A + A.T, L=np.linalg.cholesky(B @ B.T + n * np.eye(n)), max_iters=12)

@@ -541,3 +541,54 @@ def test_search_direction_after_separate_calls_and_state_errors():
     for name, g, w in zip(("dx", "dX", "dy", "dY"), ctx.direction_get(), ref.direction_get()):
         ol.assert_same(name, g, w)
     ctx.close()
+
+
+def test_step_length_degenerate_spectra_bit_exact():
+    """Row N3 on directions put in by the caller (sdpb_b200_direction_put): an exact zero block, a
+    multiple of X (L^-1 dX L^-T = c I up to rounding: the spectrum Laguerre's iteration is slowest
+    on), a diagonal block, a tiny and a huge block, a block that is not symmetric (the lower
+    triangle is the one El::HermitianEig(LOWER) reads), 1 x 1 and 2 x 2 blocks and several warps of
+    rows -- every eigenvalue byte for byte against csrc/host/step_length.hpp."""
+    prec, shapes, N = 768, [(1, 2), (1, 3), (2, 40), (1, 40), (1, 33), (1, 7), (2, 5), (1, 9)], 11
+    ew = elem_words(prec)
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=21)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    sdp.run_step(ref)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    ctx.schur_step(sdp.X, sdp.Y)
+
+    def crafted(M, seed):
+        out = []
+        for b, blk in enumerate(M):
+            s = blk.shape[0]
+            kind = b % 6
+            if s == 0 or kind == 0:
+                d = np.zeros_like(blk)                                   # exact zero
+            elif kind == 1:
+                d = ol.scale_matrix(prec, blk, -2.5)                     # c * M
+            elif kind == 2:
+                d = np.zeros_like(blk)                                   # diagonal, distinct entries
+                for i in range(s):
+                    d[i, i] = ol.from_decimal(prec, str((-1) ** i * (i + 1) * 0.37))
+            elif kind == 3:
+                r = ol.random_matrix(prec, s, s, seed + b)               # not symmetric
+                d = ol.scale_matrix(prec, r, 1e-40)
+            elif kind == 4:
+                r = ol.random_matrix(prec, s, s, seed + b)
+                rt = np.ascontiguousarray(np.transpose(r, (1, 0, 2)))
+                d = ol.scale_matrix(prec, ol.scalar_op(prec, 1, r.reshape(-1, ew), rt.reshape(-1, ew)).reshape(s, s, ew), 1e30)
+            else:
+                d = ol.scale_matrix(prec, blk, 1.0)                      # + M itself: min eigenvalue 1
+            out.append(np.ascontiguousarray(d))
+        return out
+
+    for seed in (3, 4):
+        dX, dY = crafted(sdp.X, 100 * seed), crafted(sdp.Y, 100 * seed + 50)
+        ctx.direction_put(dX, dY)
+        ref.direction_put(dX, dY)
+        for which in (0, 1):
+            got, want = ctx.step_length(which), ref.step_length(which)
+            ol.assert_same(f"min eigenvalues, which={which}", got, want)
+    ctx.close()
