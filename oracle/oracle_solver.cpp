@@ -92,6 +92,26 @@ static Hot_Path_Table oracle_table(const Block_Info &bi, const SDP &sdp, int pre
   return t;
 }
 
+// test hook: rewrite a JSON sdp directory with binary block data (row N4)
+extern "C" int oracle_sdp_to_binary(const char *in_dir, const char *out_dir, int precision, char *err, size_t errlen)
+{
+  try
+    {
+      set_precision(precision);
+      convert_sdp_to_binary(in_dir, out_dir);
+      return 0;
+    }
+  catch(std::exception &e)
+    {
+      if(err && errlen)
+        {
+          strncpy(err, e.what(), errlen - 1);
+          err[errlen - 1] = 0;
+        }
+      return 1;
+    }
+}
+
 // argv: the reference's sdpb options (--sdpDir, --outDir, --precision, ...).
 // Returns 0 and writes a one-line JSON summary, or 1 with the error text.
 extern "C" int oracle_solve(int argc, const char *const *argv, char *summary, size_t summary_len)

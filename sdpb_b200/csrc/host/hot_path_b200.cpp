@@ -62,6 +62,26 @@ static Hot_Path_Table b200_table(const Block_Info &bi, const SDP &sdp, int prec,
   return t;
 }
 
+// an sdp directory with JSON block data rewritten with binary block data (block_data_bin.hpp)
+extern "C" int sdpb_b200_sdp_to_binary(const char *in_dir, const char *out_dir, int precision, char *err, size_t errlen)
+{
+  try
+    {
+      set_precision(precision);
+      convert_sdp_to_binary(in_dir, out_dir);
+      return 0;
+    }
+  catch(std::exception &e)
+    {
+      if(err && errlen)
+        {
+          strncpy(err, e.what(), errlen - 1);
+          err[errlen - 1] = 0;
+        }
+      return 1;
+    }
+}
+
 extern "C" int sdpb_b200_solve(int argc, const char *const *argv, char *summary, size_t summary_len)
 {
   auto put = [&](const std::string &s) {

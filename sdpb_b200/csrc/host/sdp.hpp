@@ -3,10 +3,12 @@
 // src/sdp_solve/SDP/read_objectives.cxx, read_block_data/Json_Block_Data_Parser.hxx:26-36,
 // src/sdp_solve/Block_Info/read_block_info.cxx:15-40).  Decimal strings are
 // parsed with mpf_set_str at the working precision, exactly what
-// El::BigFloat(string) does in the reference.  The binary (Boost
-// serialization) form and zip archives are out of scope.
+// El::BigFloat(string) does in the reference.  Block data may also come in the
+// binary (Boost serialization) form, block_data_<j>.bin (block_data_bin.hpp);
+// zip archives are not read.
 #pragma once
 #include "bigfloat.hpp"
+#include "block_data_bin.hpp"
 
 #include <cctype>
 #include <fstream>
@@ -312,19 +314,26 @@ inline void read_sdp(const std::string &sdp_dir, Block_Info &block_info, SDP &sd
   for(int j = 0; j < J; ++j)
     {
       const std::string suffix = "_" + std::to_string(j) + ".json";
-      if(!file_exists(sdp_dir + "/block_data" + suffix))
-        throw std::runtime_error("Only JSON block data is supported: missing " + sdp_dir
-                                 + "/block_data" + suffix
-                                 + " (write the SDP with pmp2sdp --outputFormat=json)");
+      const std::string bin = sdp_dir + "/block_data_" + std::to_string(j) + ".bin";
       const Json info = read_json(sdp_dir + "/block_info" + suffix);
       block_info.dimensions[j] = std::stoi(info.at("dim").text);
       block_info.num_points[j] = std::stoi(info.at("num_points").text);
-      const Json data = read_json(sdp_dir + "/block_data" + suffix);
       const int n = block_info.num_points[j];
-      json_matrix(data.at("bilinear_bases_even"), sdp.bilinear_bases[2 * j], n);
-      json_matrix(data.at("bilinear_bases_odd"), sdp.bilinear_bases[2 * j + 1], n);
-      json_vector(data.at("c"), sdp.primal_objective_c[j]);
-      json_matrix(data.at("B"), sdp.free_var_matrix[j], sdp.N());
+      // read_block_data.cxx: block_data_<j>.bin (what pmp2sdp writes by default) or .json
+      if(file_exists(bin))
+        read_block_data_bin(bin, block_info.schur_block_size(j), sdp.N(), n, block_info.bilinear_bases_height(j, 0),
+                            block_info.bilinear_bases_height(j, 1), sdp.free_var_matrix[j], sdp.primal_objective_c[j],
+                            sdp.bilinear_bases[2 * j], sdp.bilinear_bases[2 * j + 1]);
+      else if(file_exists(sdp_dir + "/block_data" + suffix))
+        {
+          const Json data = read_json(sdp_dir + "/block_data" + suffix);
+          json_matrix(data.at("bilinear_bases_even"), sdp.bilinear_bases[2 * j], n);
+          json_matrix(data.at("bilinear_bases_odd"), sdp.bilinear_bases[2 * j + 1], n);
+          json_vector(data.at("c"), sdp.primal_objective_c[j]);
+          json_matrix(data.at("B"), sdp.free_var_matrix[j], sdp.N());
+        }
+      else
+        throw std::runtime_error("Missing block data: neither " + bin + " nor " + sdp_dir + "/block_data" + suffix);
       // SDP::validate (SDP.hxx / SDP/SDP.cxx)
       for(int p = 0; p < 2; ++p)
         if(sdp.bilinear_bases[2 * j + p].h != block_info.bilinear_bases_height(j, p)
@@ -334,6 +343,31 @@ inline void read_sdp(const std::string &sdp_dir, Block_Info &block_info, SDP &sd
          || sdp.free_var_matrix[j].h != block_info.schur_block_size(j)
          || (sdp.free_var_matrix[j].h && sdp.free_var_matrix[j].w != sdp.N()))
         throw std::runtime_error("block " + std::to_string(j) + ": c / B have the wrong size");
+    }
+}
+// The same SDP with every block_data_<j>.json rewritten as block_data_<j>.bin (pmp2sdp
+// --outputFormat=bin, src/pmp2sdp/write_block_data.cxx); control / objectives / block_info /
+// normalization files are copied.
+inline void convert_sdp_to_binary(const std::string &in_dir, const std::string &out_dir)
+{
+  Block_Info block_info;
+  SDP sdp;
+  read_sdp(in_dir, block_info, sdp);
+  create_directories(out_dir);
+  auto copy = [&](const std::string &name) {
+    if(!file_exists(in_dir + "/" + name))
+      return;
+    std::ifstream src(in_dir + "/" + name, std::ios::binary);
+    std::ofstream dst(out_dir + "/" + name, std::ios::binary);
+    dst << src.rdbuf();
+  };
+  for(const char *name : {"control.json", "objectives.json", "normalization.json", "pmp_info.json"})
+    copy(name);
+  for(int j = 0; j < block_info.num_blocks(); ++j)
+    {
+      copy("block_info_" + std::to_string(j) + ".json");
+      write_block_data_bin(out_dir + "/block_data_" + std::to_string(j) + ".bin", sdp.free_var_matrix[j],
+                           sdp.primal_objective_c[j], sdp.bilinear_bases[2 * j], sdp.bilinear_bases[2 * j + 1]);
     }
 }
 } // namespace sdpb_host

@@ -119,3 +119,62 @@ def test_checkpoint_errors_carry_the_references_texts(tmp_path, oracle):
     os.remove(path)
     msg = fails(_args(root, out, ck, case))
     assert "Missing checkpoint file" in msg
+
+
+def _to_binary(lib, src, dst, prec):
+    buf = ctypes.create_string_buffer(4096)
+    lib.oracle_sdp_to_binary.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
+    rc = lib.oracle_sdp_to_binary(src.encode(), dst.encode(), prec, buf, 4096)
+    assert rc == 0, buf.value.decode()
+
+
+@pytest.mark.parametrize("name", ["1d", "dfibo"])
+def test_binary_block_data_replays_the_golden_trajectory(name, tmp_path, oracle):
+    """block_data_<j>.bin (SDP_Block_Data.cxx:32-48, boost_serialization.hxx:17-97; what stock pmp2sdp
+    writes by default): the fixture's JSON blocks are rewritten as Boost binary archives
+    (csrc/host/block_data_bin.hpp), the JSON is gone from the new directory, and the solver replays
+    the reference's golden trajectory from the .bin files -- dfibo has empty odd-parity bases
+    (0 x n matrices, whose padding row Elemental serialises too)."""
+    lib = oracle.load_oracle()
+    case = CASES[name]
+    root = _unpack(name, str(tmp_path))
+    bin_dir = str(tmp_path / "sdp_bin")
+    _to_binary(lib, os.path.join(root, "sdp"), bin_dir, case["precision"])
+    names = os.listdir(bin_dir)
+    assert any(f.endswith(".bin") for f in names) and not any(f.startswith("block_data") and f.endswith(".json") for f in names)
+    head = open(os.path.join(bin_dir, "block_data_0.bin"), "rb").read(48)
+    assert head[:8] == (22).to_bytes(8, "little") and head[8:30] == b"serialization::archive"
+    assert int.from_bytes(head[32:40], "little") == case["precision"]
+    out = str(tmp_path / "out")
+    summary = _solve(lib, "oracle_solve", ["--sdpDir", bin_dir, "--outDir", out, "--checkpointDir", "",
+                                           "--precision", str(case["precision"])] + case["sdpb_args"])
+    kw = {"iterations_name": case["iterations"]}
+    if case["out_txt_keys"]:
+        kw["keys"] = tuple(case["out_txt_keys"])
+    bad = golden_check.diff_out_dirs(out, os.path.join(root, "out"), **kw)
+    assert not bad, bad[:5]
+    assert summary["iterations"] == len(json.load(open(os.path.join(root, "out", case["iterations"]))))
+
+
+def test_binary_block_data_rejects_another_precision_and_truncation(tmp_path, oracle):
+    lib = oracle.load_oracle()
+    case = CASES["1d"]
+    root = _unpack("1d", str(tmp_path))
+    bin_dir = str(tmp_path / "sdp_bin")
+    _to_binary(lib, os.path.join(root, "sdp"), bin_dir, case["precision"])
+
+    def fails(args):
+        argv = (ctypes.c_char_p * len(args))(*[a.encode() for a in args])
+        buf = ctypes.create_string_buffer(8192)
+        assert lib.oracle_solve(len(args), argv, buf, 8192) != 0
+        return buf.value.decode()
+
+    base = ["--sdpDir", bin_dir, "--outDir", str(tmp_path / "out"), "--checkpointDir", ""]
+    msg = fails(base + ["--precision", str(case["precision"] + 64)])
+    assert "Read GMP precision: %d, expected: %d" % (case["precision"], case["precision"] + 64) in msg  # SDP_Block_Data.cxx:42-44
+    path = os.path.join(bin_dir, "block_data_0.bin")
+    data = open(path, "rb").read()
+    open(path, "wb").write(data[:len(data) - 100])
+    assert "Unexpected end of binary block data" in fails(base + ["--precision", str(case["precision"])])
+    open(path, "wb").write(b"\x00" * 64)
+    assert "Not a Boost binary archive" in fails(base + ["--precision", str(case["precision"])])
