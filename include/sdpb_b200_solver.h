@@ -34,7 +34,7 @@ extern "C" {
  *   (default checkpointDir; given explicitly it must hold a checkpoint), --checkpointInterval SECONDS,
  *   --noFinalCheckpoint: binary checkpoints checkpoint_<generation>_0 + checkpoint.json, or a text
  *   checkpoint (x_j.txt, y.txt, X_matrix_b.txt, Y_matrix_b.txt); SIGTERM ends the run gracefully
- *   with a checkpoint (src/sdp_solve/SDP_Solver/save_checkpoint.cxx, load_checkpoint/*.cxx,
+ *   with a checkpoint (src/sdp_solve/SDP_Solver/save_checkpoint.cxx, load_checkpoint/,
  *   run/run.cxx:332-370, src/sdpb/solve.cxx:81-88)
  *   --device N (CUDA ordinal, default 0), --verbose
  * Returns 0 and writes a one-line JSON summary (terminateReason, iterations,
