@@ -320,8 +320,11 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
       return bail(rc);
   }
   c->NS = (N + 15) & ~15; // residue row stride: whole 16-column tiles, pad columns stay zero
-  TRY_C(cudaMalloc(&c->R, std::max<size_t>(4, (size_t)c->crt.np * c->K * c->NS * 4)));
-  TRY_C(cudaMemset(c->R, 0, std::max<size_t>(4, (size_t)c->crt.np * c->K * c->NS * 4)));
+  c->KR = (c->K + SI_KS - 1) / SI_KS * SI_KS; // whole pipeline stages of the tensor-path syrk; pad rows stay zero
+  if(const char *e = getenv("SDPB_B200_SYRK"))
+    c->syrk_imma = std::string(e) != "imad";
+  TRY_C(cudaMalloc(&c->R, std::max<size_t>(4, (size_t)c->crt.np * c->KR * c->NS * 4)));
+  TRY_C(cudaMemset(c->R, 0, std::max<size_t>(4, (size_t)c->crt.np * c->KR * c->NS * 4)));
   TRY_C(cudaMalloc(&c->Qres, (size_t)c->crt.np * N * N * 4));
   TRY_C(cudaMemset(c->Qres, 0, (size_t)c->crt.np * N * N * 4));
   // descriptors

@@ -65,6 +65,8 @@ struct sdpb_b200_ctx
            *d_M = nullptr, *d_Mhalf = nullptr, *d_pow28p = nullptr;
   uint64_t *d_inv64 = nullptr;
   int NS = 0; // row stride of the residue planes R (N rounded up to 16)
+  long KR = 0; // rows of a residue plane: K rounded up to the 64-row stages of syrk_imma_kernel, pad rows zero
+  int syrk_imma = 1; // exact syrk on the integer tensor path (syrk_imma.cuh); 0: IMAD.WIDE (syrk_mod_kernel)
   CrtTables crt{};
 
   // tile-kernel descriptors (tile.cuh); matrices sorted by cost, largest first

@@ -11,6 +11,7 @@
 #pragma once
 #include "mpfx.h"
 #include "tile.cuh"
+#include "syrk_imma.cuh"
 
 #include <climits>
 #include <cuda_runtime.h>

@@ -355,20 +355,40 @@ template <int NL> struct Launch
                              + (size_t)c->crt.np * 8;
         CUDA_TRY(c, cudaFuncSetAttribute(normalize_kernel<NL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
-        normalize_kernel<NL><<<g2, 128, nsmem, st>>>(c->d_bands, N, c->NS, c->K, c->norms,
+        normalize_kernel<NL><<<g2, 128, nsmem, st>>>(c->d_bands, N, c->NS, c->KR, c->norms,
                                                      c->recipN, c->prec, c->crt, c->R, c->d_flags);
         c->kt_end();
     CUDA_TRY(c, cudaGetLastError());
       }
     CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
-    {
-      const int nt = (N + 15) / 16;
-      dim3 g3(nt * (nt + 1) / 2, c->crt.np);
-      c->kt_begin("syrk_mod_kernel");
-      syrk_mod_kernel<4><<<g3, 256, 0, st>>>(c->R, c->K, N, c->NS, c->d_primes, c->Qres);
-      c->kt_end();
-    CUDA_TRY(c, cudaGetLastError());
-    }
+    if(c->syrk_imma && c->KR)
+      {
+        // byte-slice products on the integer tensor path (syrk_imma.cuh): re-pack the planes in
+        // place, then one CTA per 64 x 64 tile pair and prime
+        const long groups = (long)c->crt.np * c->KR / 4;
+        c->kt_begin("syrk_pack_kernel");
+        syrk_pack_kernel<4><<<(unsigned)std::min<long>((groups * c->NS + 255) / 256, 148L * 32), 256, 0, st>>>(
+          c->R, groups, c->K, c->KR, c->NS);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+        CUDA_TRY(c, cudaFuncSetAttribute(syrk_imma_kernel<SI_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SMEM_OPT_IN));
+        const int nt = (N + SI_TILE - 1) / SI_TILE;
+        dim3 g3(nt * (nt + 1) / 2, c->crt.np);
+        c->kt_begin("syrk_imma_kernel");
+        syrk_imma_kernel<SI_STAGES><<<g3, 256, SI_SMEM, st>>>(c->R, c->KR, N, c->NS, c->d_primes, c->d_inv64, c->Qres);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+      }
+    else
+      {
+        const int nt = (N + 15) / 16;
+        dim3 g3(nt * (nt + 1) / 2, c->crt.np);
+        c->kt_begin("syrk_mod_kernel");
+        syrk_mod_kernel<4><<<g3, 256, 0, st>>>(c->R, c->KR, N, c->NS, c->d_primes, c->Qres);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+      }
     // exact integers: the cross-GPU sum is order-free.  Residues are < 2^28, so a
     // plain u32 sum over <= 16 ranks cannot overflow; the CRT kernel reduces mod p.
     if(sharded)

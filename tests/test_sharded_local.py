@@ -169,6 +169,7 @@ def test_search_direction_sharded_matches_unsharded():
     ref.compute_search_direction(bm, 0)
     ref.compute_search_direction(bm, 1)
     want = ref.direction_get()
+    want_min = [ref.step_length(0), ref.step_length(1)]  # row N3: per block-parity, local to the owner
 
     ctxs, sdps = [], []
     for r in range(world):
@@ -188,7 +189,7 @@ def test_search_direction_sharded_matches_unsharded():
             ctxs[r].direction_set_residues(*residues(owned[r]))
             ctxs[r].compute_search_direction(bm, 0)
             ctxs[r].compute_search_direction(bm, 1)
-            results[r] = (tr, ctxs[r].direction_get())
+            results[r] = (tr, ctxs[r].direction_get(), [ctxs[r].step_length(0), ctxs[r].step_length(1)])
         except Exception as e:  # noqa: BLE001
             errors[r] = e
 
@@ -200,8 +201,11 @@ def test_search_direction_sharded_matches_unsharded():
     try:
         for r in range(world):
             assert errors[r] is None, f"rank {r}: {errors[r]}"
-            tr, (dx, dX, dy, dY) = results[r]
+            tr, (dx, dX, dy, dY), mins = results[r]
             mine = owned[r]
+            for which in (0, 1):
+                ol.assert_same(f"rank{r}.min eigenvalues {which}", mins[which],
+                               np.stack([want_min[which][2 * j + p] for j in mine for p in (0, 1)]))
             ol.assert_same(f"rank{r}.traces", tr, np.stack([want_tr[2 * j + p] for j in mine for p in (0, 1)]))
             ol.assert_same(f"rank{r}.dx", dx, [want[0][j] for j in mine])
             ol.assert_same(f"rank{r}.dX", dX, [want[1][2 * j + p] for j in mine for p in (0, 1)])
