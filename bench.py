@@ -117,7 +117,7 @@ def algorithmic_bytes(kernel, prec, shapes, N):
             tot += P * N * E
         elif kernel == "normalize_kernel":  # reads P, writes the restored P (+ residues, not counted)
             tot += 2 * P * N * E
-    if kernel == "syrk_mod_kernel":  # exact integer syrk
+    if kernel in ("syrk_mod_kernel", "syrk_imma_kernel"):  # exact integer syrk (SURVEY 8d row "syrk Q'")
         tot = K * N * 8 * L + N * (N + 1) // 2 * 8 * (2 * L + 1)
     elif kernel == "crt_restore_kernel":
         tot = N * (N + 1) // 2 * (8 * (2 * L + 1) + E)

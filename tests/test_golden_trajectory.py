@@ -84,7 +84,7 @@ def test_host_solver_library_exports_declared_symbols_and_has_no_cpu_hot_path():
     text = open(os.path.join(ROOT, "include", "sdpb_b200_solver.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     names = sorted(set(re.findall(r"\b(sdpb_b200_[a-z_0-9]+)\s*\(", text)))
-    assert names == ["sdpb_b200_solve"]
+    assert names == ["sdpb_b200_sdp_to_binary", "sdpb_b200_solve"]
     path = os.path.join(ROOT, "sdpb_b200", "libsdpb_b200_host.so")
     lib = ctypes.CDLL(path)
     for n in names:
