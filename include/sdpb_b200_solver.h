@@ -22,7 +22,8 @@ extern "C" {
  * as "--key=value", "--key value" or bare flags:
  *   --sdpDir DIR (required; a directory as pmp2sdp writes it: control.json, objectives.json,
  *                 block_info_<j>.json and block_data_<j>.bin (Boost binary, the default of
- *                 pmp2sdp) or block_data_<j>.json; src/sdp_solve/SDP/read_block_data/SDP_Block_Data.cxx:32-48)
+ *                 pmp2sdp) or block_data_<j>.json; src/sdp_solve/SDP/read_block_data/SDP_Block_Data.cxx:32-48),
+ *                 or the stored zip archive `pmp2sdp --zip` packs that directory into)
  *   --outDir DIR (out.txt, iterations.json, x_j.txt, y.txt, z.txt, c_minus_By/c_minus_By.json;
  *                 src/sdpb/save_solution.cxx:21-165, SDP_Solver/run/print_iteration.cxx:77-108)
  *   --precision BITS, --maxIterations, --dualityGapThreshold, --primalErrorThreshold,

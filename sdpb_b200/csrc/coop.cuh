@@ -356,8 +356,12 @@ __device__ __forceinline__ bool sqrt_words(Work<NL> &ws, const uint32_t *uw, int
 }
 
 // R (N2+4 words, into Rout, shared or global) = floor(beta^(4 NL + 1) / D), D = dw[0..N2)
+// seeded: ws.V holds the rsqrt iterate of the square root D was just taken of (sqrt_words): with
+// d = Dn / beta^N2 = sqrt(t) up to the root's floor, beta^W / (2 d) IS beta^W / (2 sqrt(t)), so the
+// top words of V seed the LAST rung directly and the lower rungs (a single lane's register code up
+// to 9 words, then the 17-word rung) are skipped.  The exact final correction decides as before.
 template <int NL>
-__device__ __forceinline__ bool recip_words(Work<NL> &ws, const uint32_t *dw, uint32_t *Rout)
+__device__ __forceinline__ bool recip_words(Work<NL> &ws, const uint32_t *dw, uint32_t *Rout, bool seeded = false)
 {
   typedef Work<NL> G;
   const int l = lane_id();
@@ -368,7 +372,15 @@ __device__ __forceinline__ bool recip_words(Work<NL> &ws, const uint32_t *dw, ui
   int lv[12];
   const int nlv = ladder(WF, lv);
   constexpr int WS = LadderEntry<WF, SOLO_MAX>::value;
-  if(l == 0)
+  const int WSEED = lv[1]; // the last rung's WP
+  if(seeded)
+    {
+      // V (WFS words) -> its top WSEED words, less a few units (the rung wants an iterate from below)
+      wcopy(ws.Vp, ws.V + (G::WFS - WSEED), WSEED);
+      wcopy(ws.V, ws.Vp, WSEED);
+      wsub_small(ws.V, WSEED, 8u, ws.scratch, ws.scratch2);
+    }
+  else if(l == 0)
     {
       uint32_t top[WS], v[WS];
 #pragma unroll
@@ -380,9 +392,9 @@ __device__ __forceinline__ bool recip_words(Work<NL> &ws, const uint32_t *dw, ui
         ws.V[i] = v[i];
     }
   __syncwarp();
-  for(int q = nlv - 2; q >= 0; --q)
+  for(int q = seeded ? 0 : nlv - 2; q >= 0; --q)
     {
-      if(lv[q] <= WS)
+      if(lv[q] <= WS && !seeded)
         continue;
       const int W = lv[q], WP = lv[q + 1];
       wcopy(ws.Vp, ws.V, WP);
@@ -440,7 +452,8 @@ __device__ __forceinline__ bool recip_words(Work<NL> &ws, const uint32_t *dw, ui
 
 // a <- mpf_sqrt(a) in place, by one whole warp: a > 0 is a packed element in shared memory
 // (header + 2NL words)
-template <int NL> __device__ __forceinline__ void sqrt_elem(Work<NL> &ws, uint32_t *a)
+// returns true (uniformly) if the fast path closed, i.e. ws.V holds the rsqrt iterate of a
+template <int NL> __device__ __forceinline__ bool sqrt_elem(Work<NL> &ws, uint32_t *a)
 {
   typedef Work<NL> G;
   const int l = lane_id();
@@ -471,17 +484,26 @@ template <int NL> __device__ __forceinline__ void sqrt_elem(Work<NL> &ws, uint32
       mpfw::store<NL>(a, u);
     }
   __syncwarp();
+  return ok_sqrt;
 }
 // Rs / Rg (shared / global, RW words; either may be null) <- the reciprocal words of the packed
 // element a != 0 (shared memory) that mpfw::div_recip takes, by one whole warp
 template <int NL>
-__device__ __forceinline__ void recip_elem(Work<NL> &ws, const uint32_t *a, uint32_t *Rs, uint32_t *Rg)
+__device__ __forceinline__ void recip_elem(Work<NL> &ws, const uint32_t *a, uint32_t *Rs, uint32_t *Rg,
+                                           bool seeded = false)
 {
   typedef Work<NL> G;
   const int l = lane_id();
   uint32_t *R = ws.E + G::MAXW;
   __syncwarp();
-  const bool ok_recip = recip_words<NL>(ws, a + 2, R);
+  bool ok_recip = recip_words<NL>(ws, a + 2, R, seeded);
+  if(!ok_recip && seeded) // uniform; the seed was off (it never is for d = sqrt(t)): the full ladder
+    {
+      if(l == 0)
+        ws.flag += 1; // the tests count this like any other fallback
+      __syncwarp();
+      ok_recip = recip_words<NL>(ws, a + 2, R, false);
+    }
   if(!ok_recip && l == 0)
     {
       ws.flag += 1;
@@ -513,7 +535,7 @@ __device__ __forceinline__ void recip_elem(Work<NL> &ws, const uint32_t *a, uint
 template <int NL>
 __device__ __forceinline__ void pivot(Work<NL> &ws, uint32_t *a, uint32_t *Rs, uint32_t *Rg)
 {
-  sqrt_elem<NL>(ws, a);
-  recip_elem<NL>(ws, a, Rs, Rg);
+  const bool seed = sqrt_elem<NL>(ws, a);
+  recip_elem<NL>(ws, a, Rs, Rg, seed);
 }
 } // namespace coop

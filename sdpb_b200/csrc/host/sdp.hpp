@@ -5,10 +5,11 @@
 // parsed with mpf_set_str at the working precision, exactly what
 // El::BigFloat(string) does in the reference.  Block data may also come in the
 // binary (Boost serialization) form, block_data_<j>.bin (block_data_bin.hpp);
-// zip archives are not read.
+// an SDP packed by `pmp2sdp --zip` (a stored zip, zip_store.hpp) is unpacked first.
 #pragma once
 #include "bigfloat.hpp"
 #include "block_data_bin.hpp"
+#include "zip_store.hpp"
 
 #include <cctype>
 #include <fstream>
@@ -289,9 +290,13 @@ inline void json_matrix(const Json &v, Matrix &out, int width_if_empty)
     }
 }
 
-// Read `sdp_dir` (plain directory, JSON block files).
-inline void read_sdp(const std::string &sdp_dir, Block_Info &block_info, SDP &sdp)
+// Read `sdp_dir`: a plain directory, or the zip archive `pmp2sdp --zip` packs it into.
+inline void read_sdp(const std::string &sdp_path, Block_Info &block_info, SDP &sdp)
 {
+  std::unique_ptr<Extracted_Zip> unpacked;
+  if(is_regular_file(sdp_path))
+    unpacked.reset(new Extracted_Zip(sdp_path));
+  const std::string sdp_dir = unpacked ? unpacked->dir : sdp_path;
   const Json control = read_json(sdp_dir + "/control.json");
   const int J = std::stoi(control.at("num_blocks").text);
   {

@@ -70,6 +70,10 @@ def main():
                       "sdpb_args": args.split(), "iterations": iters, "out_txt_keys": keys}
         print(name, os.path.getsize(path) // 1024, "KiB")
     json.dump(meta, open(os.path.join(HERE, "cases.json"), "w"), indent=1)
+    # the reference's own zipped SDP (written by its pvm2sdp at precision 1024, stored entries with
+    # data descriptors as libarchive streams them): byte copy, the fixture of the zip reader
+    import shutil
+    shutil.copyfile("/root/reference/test/data/sdp.zip", os.path.join(HERE, "sdp.zip"))
 
 
 if __name__ == "__main__":

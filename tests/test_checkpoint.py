@@ -178,3 +178,35 @@ def test_binary_block_data_rejects_another_precision_and_truncation(tmp_path, or
     assert "Unexpected end of binary block data" in fails(base + ["--precision", str(case["precision"])])
     open(path, "wb").write(b"\x00" * 64)
     assert "Not a Boost binary archive" in fails(base + ["--precision", str(case["precision"])])
+
+
+def test_zipped_sdp_of_the_reference_reads_like_its_unpacked_directory(tmp_path, oracle):
+    """`pmp2sdp --zip` stores, never deflates (src/pmp2sdp/Archive_Writer.cxx:10-14); sdpb reads the
+    archive in place.  tests/golden/sdp.zip is the reference's own test/data/sdp.zip (libarchive:
+    local headers with data descriptors).  Solving from the archive and from the directory Python's
+    zipfile unpacks it into must write identical files."""
+    import zipfile
+    from test_golden_trajectory import GOLDEN
+    lib = oracle.load_oracle()
+    archive = os.path.join(GOLDEN, "sdp.zip")
+    unpacked = str(tmp_path / "sdp")
+    with zipfile.ZipFile(archive) as z:
+        assert all(i.compress_type == zipfile.ZIP_STORED for i in z.infolist())
+        z.extractall(unpacked)
+    base = ["--precision", "1024", "--checkpointDir", "", "--maxIterations", "60", "--writeSolution", "x,y",
+            "--dualityGapThreshold", "1e-30", "--primalErrorThreshold", "1e-30", "--dualErrorThreshold", "1e-30"]
+    a = _solve(lib, "oracle_solve", ["--sdpDir", archive, "--outDir", str(tmp_path / "out_zip")] + base)
+    b = _solve(lib, "oracle_solve", ["--sdpDir", unpacked, "--outDir", str(tmp_path / "out_dir")] + base)
+    assert a["iterations"] == b["iterations"] and a["terminateReason"] == b["terminateReason"]
+    for f in ("x_0.txt", "y.txt"):
+        assert filecmp.cmp(str(tmp_path / "out_zip" / f), str(tmp_path / "out_dir" / f), shallow=False), f
+    assert not [d for d in os.listdir(os.environ.get("TMPDIR", "/tmp")) if d.startswith("sdpb_b200_sdp_")]
+    # a deflated archive is refused with a pointer to the reference's writer
+    deflated = str(tmp_path / "deflated.zip")
+    with zipfile.ZipFile(deflated, "w", zipfile.ZIP_DEFLATED) as z:
+        for f in os.listdir(unpacked):
+            z.write(os.path.join(unpacked, f), f)
+    argv = ["--sdpDir", deflated, "--outDir", str(tmp_path / "o")] + base
+    cargv = (ctypes.c_char_p * len(argv))(*[x.encode() for x in argv])
+    buf = ctypes.create_string_buffer(8192)
+    assert lib.oracle_solve(len(argv), cargv, buf, 8192) != 0 and "is compressed" in buf.value.decode()
