@@ -177,6 +177,125 @@ extern "C" int sdpb_b200_stored_limbs(int prec_bits)
   return mpfx::stored_limbs(prec_bits);
 }
 
+// batched GEMM descriptors, largest k first; returns the number of 16 x 16 output tiles
+static int sort_gemm(std::vector<GemmTileDesc> &v)
+{
+  std::stable_sort(v.begin(), v.end(), [](const GemmTileDesc &a, const GemmTileDesc &b) { return a.K > b.K; });
+  int tiles = 0;
+  for(auto &d : v)
+    {
+      d.tile0 = tiles;
+      tiles += ((d.M + TS - 1) / TS) * ((d.N + TS - 1) / TS);
+    }
+  return tiles;
+}
+// The large operand / result regions of scale_multiply_add and of the resident search direction are
+// allocated on first use: a caller that only runs the Schur-complement step (and the largest C5
+// corner, J = 1024 blocks of 256 rows at N = 512) does not pay 10 x the size of X for them.
+static int ensure_sma_temp(sdpb_b200_ctx *c)
+{
+  if(c->smaT)
+    return 0;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaMalloc(&c->smaT, std::max<size_t>(16, c->wXY * 8)));
+  return 0;
+}
+static int ensure_sma(sdpb_b200_ctx *c)
+{
+  if(c->d_gemmSMA)
+    return 0;
+  if(int rc = ensure_sma_temp(c))
+    return rc;
+  {
+    // scale_multiply_add: C_b = A_b B_b on s x s blocks, column-major
+    const size_t bytes = std::max<size_t>(16, c->wXY * 8);
+    CUDA_TRY(c, cudaMalloc(&c->smaA, bytes));
+    CUDA_TRY(c, cudaMalloc(&c->smaB, bytes));
+    CUDA_TRY(c, cudaMalloc(&c->smaC, bytes));
+    std::vector<GemmTileDesc> gS;
+    for(int q = 0; q < 2 * c->J; ++q)
+      {
+        const int s = c->g[q / 2].s[q % 2];
+        gS.push_back(GemmTileDesc{c->smaA + c->oXY[q], c->smaB + c->oXY[q], c->smaT + c->oXY[q], 1, (long)s,
+                                  1, (long)s, s, s, s, 0, 0, 0, 0, 0});
+      }
+    c->tiles_SMA = sort_gemm(gS);
+    CUDA_TRY(c, upload(&c->d_gemmSMA, gS));
+  }
+  return 0;
+}
+static int ensure_direction(sdpb_b200_ctx *c)
+{
+  if(c->d_gemmXY)
+    return 0;
+  if(int rc = ensure_sma_temp(c))
+    return rc;
+  const int es = c->es, nl = c->nl, N = c->N;
+  {
+    // search direction (row N2): resident block-diagonal objects, vectors and descriptors
+    const size_t bytes = std::max<size_t>(16, c->wXY * 8);
+    for(limb_t **p : {&c->dirMXY, &c->dirR, &c->dirZ, &c->dirDX, &c->dirDY, &c->dirPR})
+      {
+        CUDA_TRY(c, cudaMalloc(p, bytes));
+        CUDA_TRY(c, cudaMemsetAsync(*p, 0, bytes, c->stream));
+      }
+    std::vector<BdmDesc> bd2;
+    std::vector<int> row_block((size_t)c->K);
+    int cols = 0;
+    for(int j = 0; j < c->J; ++j)
+      {
+        const BlockGeom &b = c->g[j];
+        for(long r = 0; r < b.P; ++r)
+          row_block[(size_t)(b.row0 + r)] = j;
+        for(int p = 0; p < 2; ++p)
+          {
+            const int q = 2 * j + p;
+            bd2.push_back(BdmDesc{(long)(c->oXY[q] / es), (long)(c->oV[q] / es), b.row0, b.s[p], b.h[p], b.m, b.n, cols});
+            cols += b.s[p];
+          }
+      }
+    c->bdm_cols = cols;
+    CUDA_TRY(c, upload(&c->d_bdm, bd2));
+    CUDA_TRY(c, upload(&c->d_row_block, row_block));
+    CUDA_TRY(c, cudaMalloc(&c->dir_dual, std::max<size_t>(16, (size_t)c->K * es * 8)));
+    CUDA_TRY(c, cudaMalloc(&c->dir_prp, (size_t)N * es * 8));
+    CUDA_TRY(c, cudaMalloc(&c->dir_scal, 4 * es * 8));
+    CUDA_TRY(c, cudaMalloc(&c->dir_part, std::max<size_t>(16, (size_t)2 * c->J * es * 8)));
+    CUDA_TRY(c, cudaMalloc(&c->dir_colsum, std::max<size_t>(16, (size_t)cols * es * 8)));
+    for(limb_t **p : {&c->eig_d, &c->eig_e, &c->eig_e2})
+      CUDA_TRY(c, cudaMalloc(p, std::max<size_t>(16, (size_t)cols * es * 8)));
+    CUDA_TRY(c, cudaMalloc(&c->eig_iter, std::max<size_t>(16, (size_t)2 * c->J * sizeof(int))));
+    const size_t pin = std::max<size_t>((size_t)c->K + N + 8, (size_t)2 * c->J + 8) * es * 8;
+    CUDA_TRY(c, cudaMallocHost(&c->dir_pinned, pin));
+    {
+      // 0.5 as mpf_set_d(0.5) stores it (two limbs, the low one zero), top-aligned
+      std::vector<uint64_t> half(4 * es, 0);
+      half[es + 0] = (uint64_t)(uint32_t)0 | ((uint64_t)(uint32_t)1 << 32);
+      half[es + nl] = 0x8000000000000000ull;
+      // 2^-(prec - 16) = 2^r B^-q (one limb): where Laguerre's iteration stops (host/step_length.hpp)
+      const int kbits = c->prec - 16, q = (kbits + 63) / 64, r = 64 * q - kbits;
+      half[3 * es + 0] = (uint64_t)(uint32_t)(1 - q) | ((uint64_t)(uint32_t)1 << 32);
+      half[3 * es + nl] = (uint64_t)1 << r;
+      CUDA_TRY(c, cudaMemcpy(c->dir_scal, half.data(), half.size() * 8, cudaMemcpyHostToDevice));
+    }
+    auto products = [&](const limb_t *A, const limb_t *B, GemmTileDesc **out) -> cudaError_t {
+      std::vector<GemmTileDesc> gd;
+      for(int q = 0; q < 2 * c->J; ++q)
+        {
+          const int s = c->g[q / 2].s[q % 2];
+          gd.push_back(GemmTileDesc{A + c->oXY[q], B + c->oXY[q], c->smaT + c->oXY[q], 1, (long)s, 1, (long)s, s, s,
+                                    s, 0, 0, 0, 0, 0});
+        }
+      c->tiles_dir = sort_gemm(gd);
+      return upload(out, gd);
+    };
+    CUDA_TRY(c, products(c->Xin, c->Yin, &c->d_gemmXY));
+    CUDA_TRY(c, products(c->dirDX, c->dirDY, &c->d_gemmDXDY));
+    CUDA_TRY(c, products(c->dirPR, c->Yin, &c->d_gemmPRY));
+    CUDA_TRY(c, products(c->dirDX, c->Yin, &c->d_gemmDXY));
+  }
+  return 0;
+}
 extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
                                 int num_blocks, const int *dims,
                                 const int *num_points, int N, char *err,
@@ -395,17 +514,6 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
     for(auto &d : v)
       sizes.push_back(d.p);
   };
-  auto sort_gemm = [](std::vector<GemmTileDesc> &v) {
-    std::stable_sort(v.begin(), v.end(),
-                     [](const GemmTileDesc &a, const GemmTileDesc &b) { return a.K > b.K; });
-    int tiles = 0;
-    for(auto &d : v)
-      {
-        d.tile0 = tiles;
-        tiles += ((d.M + TS - 1) / TS) * ((d.N + TS - 1) / TS);
-      }
-    return tiles;
-  };
   sort_trsm(tT, c->szT);
   sort_trsm(tP, c->szP);
   for(auto &d : pX)
@@ -458,86 +566,6 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
         TRY_C(upload(&c->d_schur_g[g], gs));
         TRY_C(upload(&c->d_bands_g[g], gb));
       }
-  }
-  {
-    // scale_multiply_add: C_b = A_b B_b on s x s blocks, column-major
-    const size_t bytes = std::max<size_t>(16, c->wXY * 8);
-    TRY_C(cudaMalloc(&c->smaA, bytes));
-    TRY_C(cudaMalloc(&c->smaB, bytes));
-    TRY_C(cudaMalloc(&c->smaT, bytes));
-    TRY_C(cudaMalloc(&c->smaC, bytes));
-    std::vector<GemmTileDesc> gS;
-    for(int q = 0; q < 2 * num_blocks; ++q)
-      {
-        const int s = c->g[q / 2].s[q % 2];
-        gS.push_back(GemmTileDesc{c->smaA + c->oXY[q], c->smaB + c->oXY[q], c->smaT + c->oXY[q], 1, (long)s,
-                                  1, (long)s, s, s, s, 0, 0, 0, 0, 0});
-      }
-    c->tiles_SMA = sort_gemm(gS);
-    TRY_C(upload(&c->d_gemmSMA, gS));
-  }
-  {
-    // search direction (row N2): resident block-diagonal objects, vectors and descriptors
-    const size_t bytes = std::max<size_t>(16, c->wXY * 8);
-    for(limb_t **p : {&c->dirMXY, &c->dirR, &c->dirZ, &c->dirDX, &c->dirDY, &c->dirPR})
-      {
-        TRY_C(cudaMalloc(p, bytes));
-        TRY_C(cudaMemsetAsync(*p, 0, bytes, c->stream));
-      }
-    std::vector<BdmDesc> bd2;
-    std::vector<int> row_block((size_t)c->K);
-    int cols = 0;
-    for(int j = 0; j < num_blocks; ++j)
-      {
-        const BlockGeom &b = c->g[j];
-        for(long r = 0; r < b.P; ++r)
-          row_block[(size_t)(b.row0 + r)] = j;
-        for(int p = 0; p < 2; ++p)
-          {
-            const int q = 2 * j + p;
-            bd2.push_back(BdmDesc{(long)(c->oXY[q] / es), (long)(c->oV[q] / es), b.row0, b.s[p], b.h[p], b.m, b.n, cols});
-            cols += b.s[p];
-          }
-      }
-    c->bdm_cols = cols;
-    TRY_C(upload(&c->d_bdm, bd2));
-    TRY_C(upload(&c->d_row_block, row_block));
-    TRY_C(cudaMalloc(&c->dir_dual, std::max<size_t>(16, (size_t)c->K * es * 8)));
-    TRY_C(cudaMalloc(&c->dir_prp, (size_t)N * es * 8));
-    TRY_C(cudaMalloc(&c->dir_scal, 4 * es * 8));
-    TRY_C(cudaMalloc(&c->dir_part, std::max<size_t>(16, (size_t)2 * num_blocks * es * 8)));
-    TRY_C(cudaMalloc(&c->dir_colsum, std::max<size_t>(16, (size_t)cols * es * 8)));
-    for(limb_t **p : {&c->eig_d, &c->eig_e, &c->eig_e2})
-      TRY_C(cudaMalloc(p, std::max<size_t>(16, (size_t)cols * es * 8)));
-    TRY_C(cudaMalloc(&c->eig_iter, std::max<size_t>(16, (size_t)2 * num_blocks * sizeof(int))));
-    const size_t pin = std::max<size_t>((size_t)c->K + N + 8, (size_t)2 * num_blocks + 8) * es * 8;
-    TRY_C(cudaMallocHost(&c->dir_pinned, pin));
-    {
-      // 0.5 as mpf_set_d(0.5) stores it (two limbs, the low one zero), top-aligned
-      std::vector<uint64_t> half(4 * es, 0);
-      half[es + 0] = (uint64_t)(uint32_t)0 | ((uint64_t)(uint32_t)1 << 32);
-      half[es + nl] = 0x8000000000000000ull;
-      // 2^-(prec - 16) = 2^r B^-q (one limb): where Laguerre's iteration stops (host/step_length.hpp)
-      const int kbits = prec_bits - 16, q = (kbits + 63) / 64, r = 64 * q - kbits;
-      half[3 * es + 0] = (uint64_t)(uint32_t)(1 - q) | ((uint64_t)(uint32_t)1 << 32);
-      half[3 * es + nl] = (uint64_t)1 << r;
-      TRY_C(cudaMemcpy(c->dir_scal, half.data(), half.size() * 8, cudaMemcpyHostToDevice));
-    }
-    auto products = [&](const limb_t *A, const limb_t *B, GemmTileDesc **out) -> cudaError_t {
-      std::vector<GemmTileDesc> gd;
-      for(int q = 0; q < 2 * num_blocks; ++q)
-        {
-          const int s = c->g[q / 2].s[q % 2];
-          gd.push_back(GemmTileDesc{A + c->oXY[q], B + c->oXY[q], c->smaT + c->oXY[q], 1, (long)s, 1, (long)s, s, s,
-                                    s, 0, 0, 0, 0, 0});
-        }
-      c->tiles_dir = sort_gemm(gd);
-      return upload(out, gd);
-    };
-    TRY_C(products(c->Xin, c->Yin, &c->d_gemmXY));
-    TRY_C(products(c->dirDX, c->dirDY, &c->d_gemmDXDY));
-    TRY_C(products(c->dirPR, c->Yin, &c->d_gemmPRY));
-    TRY_C(products(c->dirDX, c->Yin, &c->d_gemmDXY));
   }
   {
     // triangular systems of the Schur solves: every L_j (largest first), and Q = U^T U read as U^T
@@ -1511,6 +1539,8 @@ extern "C" int sdpb_b200_scale_multiply_add(sdpb_b200_ctx *c, int alpha, const u
       return SDPB_B200_ERR_ARG;
     }
   CUDA_TRY(c, cudaSetDevice(c->device));
+  if(int rc0 = ensure_sma(c))
+    return rc0;
   int rc = copy_blocks_in(c, A, c->smaA);
   if(!rc)
     rc = copy_blocks_in(c, B, c->smaB);
@@ -1568,6 +1598,8 @@ extern "C" int sdpb_b200_direction_begin(sdpb_b200_ctx *c, uint64_t *block_trace
     return SDPB_B200_ERR_ARG;
   if(int rc = direction_ready(c, "direction_begin", false, false))
     return rc;
+  if(int rc = ensure_direction(c))
+    return rc;
   CUDA_TRY(c, cudaSetDevice(c->device));
   c->kt_used = 0;
   c->have_direction = false;
@@ -1609,6 +1641,8 @@ extern "C" int sdpb_b200_direction_set_residues(sdpb_b200_ctx *c, const uint64_t
   if(!c || !primal_residue_p || (c->J && (!primal_residues || !dual_residues)))
     return SDPB_B200_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->device));
+  if(int rc0 = ensure_direction(c))
+    return rc0;
   const size_t es = (size_t)c->es;
   for(int j = 0; j < c->J; ++j)
     if(c->g[j].P && !dual_residues[j])
@@ -1749,6 +1783,8 @@ extern "C" int sdpb_b200_direction_put(sdpb_b200_ctx *c, const uint64_t *const *
   if(!c)
     return SDPB_B200_ERR_ARG;
   if(int rc = direction_ready(c, "direction_put", false, false))
+    return rc;
+  if(int rc = ensure_direction(c))
     return rc;
   CUDA_TRY(c, cudaSetDevice(c->device));
   int rc = dX ? copy_blocks_in(c, dX, c->dirDX) : 0;

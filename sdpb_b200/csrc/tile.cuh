@@ -36,6 +36,16 @@ constexpr int KC = 4;  // k-chunk
 __device__ __forceinline__ int tile_ti() { return (threadIdx.x & 7) + ((threadIdx.x >> 2) & 8); }
 __device__ __forceinline__ int tile_tj() { return ((threadIdx.x >> 3) & 3) + ((threadIdx.x >> 4) & 12); }
 
+// Resident CTAs per SM the 256-thread tile kernels are compiled for.  Two (128 registers per
+// thread) up to ~1100 bits; beyond that an element no longer fits next to the accumulator and the
+// product in 128 registers (NL = 26: 3 KB of spill stack per thread), so one CTA with 255.
+#ifndef SDPB_TILE_OCC_ONE_FROM
+#define SDPB_TILE_OCC_ONE_FROM 20
+#endif
+template <int NL> struct TileOcc
+{
+  static constexpr int value = NL >= SDPB_TILE_OCC_ONE_FROM ? 1 : 2;
+};
 template <int NL> struct TileGeom
 {
   static constexpr int ES = (NL + 2) & ~1;                  // 64-bit words / element
@@ -248,7 +258,7 @@ __device__ __forceinline__ void band_range(const GemmTileDesc &d, int i0, int i1
 // grid.x = total number of 16x16 tiles over all matrices (host prefix sums in
 // `tile0`); the matrix of a tile is found by binary search.
 template <int NL>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, TileOcc<NL>::value)
 gemm_tile_kernel(const GemmTileDesc *descs, int count)
 {
   typedef TileGeom<NL> G;
@@ -442,7 +452,7 @@ __device__ __forceinline__ void potrf_tile_update(Reg<NL> &acc, const PotrfDesc 
 // `descs` is sorted by size (largest first); grid.x covers the prefix of
 // matrices that still have a block column Jt.
 template <int NL>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, TileOcc<NL>::value)
 potrf_gemm_level(const PotrfDesc *descs, int Jt, const int *status)
 {
   typedef TileGeom<NL> G;
@@ -590,7 +600,7 @@ potrf_diag_warp(const PotrfDesc *descs, int count, int Jt, int *status)
 //   potrf_panel_rl  one CTA per tile below it: X = A_tile L_JJ^{-T}
 //   potrf_trail_rl  one CTA per tile (It >= Kt > Jt): a_ij -= sum_{k in column Jt} l_ik l_jk
 template <int NL>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, TileOcc<NL>::value)
 potrf_diag_rl(const PotrfDesc *descs, int Jt, int *status)
 {
   typedef TileGeom<NL> G;
@@ -614,7 +624,7 @@ potrf_diag_rl(const PotrfDesc *descs, int Jt, int *status)
     }
 }
 template <int NL>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, TileOcc<NL>::value)
 potrf_panel_rl(const PotrfDesc *descs, int Jt, const int *status)
 {
   typedef TileGeom<NL> G;
@@ -685,7 +695,7 @@ __global__ void panel_pack(const PotrfDesc *descs, int Jt, uint64_t *buf, int *s
 
 // cyc_mod > 1: only the tile columns Kt with Kt % cyc_mod == cyc_rem (this rank's share)
 template <int NL>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, TileOcc<NL>::value)
 potrf_trail_rl(const PotrfDesc *descs, int Jt, const int *status, int cyc_mod, int cyc_rem)
 {
   typedef TileGeom<NL> G;
@@ -774,7 +784,7 @@ struct TrsmTileDesc // X <- L^{-1} B in place, L lower p x p (column-major)
 //   trsm_gemm_level  16x16 tiles: b_ic -= sum_{k<I0} l_ik x_kc
 //   trsm_diag_level  one THREAD per column: the 16 rows of the tile top to bottom
 template <int NL>
-__global__ void __launch_bounds__(256, 2) trsm_gemm_level(const TrsmTileDesc *descs, int It)
+__global__ void __launch_bounds__(256, TileOcc<NL>::value) trsm_gemm_level(const TrsmTileDesc *descs, int It)
 {
   typedef TileGeom<NL> G;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -927,7 +937,7 @@ trsm_update_pass(const TrsmTileDesc &d, int I0, int ni, bool wide, int c0, int c
 // rows update a (16 x 16) tile, CTAs on a last tile of <= 8 rows an (8 x 32) one (half as many
 // CTAs, all 256 threads busy: a 40-row block is 2.5 tiles).  grid.y counts 16-column tiles.
 template <int NL>
-__global__ void __launch_bounds__(256, 2) trsm_gemm_level2(const TrsmTileDesc *descs, int It)
+__global__ void __launch_bounds__(256, TileOcc<NL>::value) trsm_gemm_level2(const TrsmTileDesc *descs, int It)
 {
   typedef TileGeom<NL> G;
   typedef WalkGeom<NL> WG;
@@ -960,7 +970,7 @@ __global__ void __launch_bounds__(256, 2) trsm_gemm_level2(const TrsmTileDesc *d
 }
 
 template <int NL>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, TileOcc<NL>::value)
 trsm_walk_kernel(const TrsmTileDesc *descs, int ncg, int Wc)
 {
   typedef TileGeom<NL> G;

@@ -31,6 +31,7 @@ WORKLOADS = {
     "c5-j256-p64-n4096-256b": (256, [(1, 64)] * 256, 4096),
     "c5-j256-p64-n4096": (768, [(1, 64)] * 256, 4096),
     "c5-j256-p64-n4096-1536b": (1536, [(1, 64)] * 256, 4096),
+    "c5-j256-p64-n512-1536b": (1536, [(1, 64)] * 256, 512),
     "c5-j256-p256-n512-256b": (256, [(1, 256)] * 256, 512),
     "c5-j256-p256-n512-1536b": (1536, [(1, 256)] * 256, 512),
     # bounded samples for the CPU restatement (same block shapes and N; rows >= N)
