@@ -178,6 +178,63 @@ bdm_trsm_kernel(const BdmDesc *d, int count, int total_cols, const limb_t *L, co
         stg_reg<NL>(x + (long)i * Fmt<NL>::ES, acc);
       }
 }
+// The same three substitutions, right-looking, one CTA per block-parity: step k divides the k-th
+// unknown of every line by the pivot (one thread per line), then ALL threads of the CTA subtract its
+// multiple from the unknowns still open -- element by element, so every element still receives its
+// updates in the canonical order (k ascending; MODE 1: k descending) and the result is bit-identical
+// to the one-thread-per-line kernels above, but the dependent chain is s (division + a few
+// multiply-accumulates) long instead of s^2 / 2.
+//   MODE 0: B <- L^-1 B   (lines = columns of B, unknowns down the column)
+//   MODE 1: B <- L^-T B   (lines = columns, unknowns up the column)
+//   MODE 2: B <- B L^-T   (lines = rows of B, unknowns along the row)
+constexpr int BDM_RL_THREADS = 128;
+template <int NL, int MODE>
+__global__ void __launch_bounds__(BDM_RL_THREADS)
+bdm_trsm_rl_kernel(const BdmDesc *d, const limb_t *L, const uint32_t *recip, limb_t *B)
+{
+  typedef TileGeom<NL> G;
+  constexpr int ES = Fmt<NL>::ES;
+  extern __shared__ __align__(16) uint32_t bdm_xk[]; // the unknowns solved in this step, one per line
+  const BdmDesc b = d[blockIdx.x];
+  const int s = b.s, tid = threadIdx.x, T = blockDim.x;
+  if(s == 0)
+    return;
+  limb_t *Bb = B + b.off * ES;
+  const limb_t *Lb = L + b.off * ES;
+  const uint32_t *rc = recip + (long)b.cum_cols * G::RS;
+  // element (unknown u, line l) of B, in elements
+  auto at = [&](int u, int l) -> long { return MODE == 2 ? (long)u * s + l : (long)l * s + u; };
+  for(int step = 0; step < s; ++step)
+    {
+      const int k = MODE == 1 ? s - 1 - step : step;
+      for(int l = tid; l < s; l += T)
+        {
+          Reg<NL> x;
+          limb_t *e = Bb + at(k, l) * ES;
+          ldg_reg<NL>(x, e);
+          x = div_nl<NL>(x, elem32<NL>(Lb, (long)k * s + k), rc + (long)k * G::RS);
+          stg_reg<NL>(e, x);
+          mpfw::store<NL>(bdm_xk + (size_t)l * G::SW, x);
+        }
+      __syncthreads();
+      const int m = MODE == 1 ? k : s - 1 - k; // unknowns still open
+      for(int q = tid; q < m * s; q += T)
+        {
+          // consecutive threads on consecutive memory: MODE 2 runs down the lines (rows), the others
+          // down the open unknowns of one line
+          const int u = MODE == 2 ? k + 1 + q / s : (MODE == 1 ? q % m : k + 1 + q % m);
+          const int l = MODE == 2 ? q % s : q / m;
+          // forward: L(u, k); transposed: L(k, u)
+          const long le = MODE == 1 ? (long)u * s + k : (long)k * s + u;
+          limb_t *e = Bb + at(u, l) * ES;
+          Reg<NL> acc;
+          ldg_reg<NL>(acc, e);
+          acc = mac_nl<NL>(acc, elem32<NL>(Lb, le), bdm_xk + (size_t)l * G::SW, true);
+          stg_reg<NL>(e, acc);
+        }
+      __syncthreads();
+    }
+}
 // compute_schur_RHS: dx(off + k) = -dual_residues(off + k) - sum_parity sum_a bases(a,k) (sum_b Z(rb h + a, cb h + b) bases(b,k)),
 // off = (cb (cb+1)/2 + rb) n.  One thread per stacked row; d: the EVEN-parity descriptor of every
 // SDP block followed by its odd one (index 2j, 2j+1).

@@ -533,19 +533,59 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaGetLastError());
     return 0;
   }
+  // B <- L^-1 B (mode 0), L^-T B (1), B L^-T (2) on every block-parity: right-looking, one CTA per
+  // block (direction.cuh); blocks too large for the shared-memory line buffer take the
+  // one-thread-per-line kernels
+  static int bdm_trsm_rl(sdpb_b200_ctx *c, int mode, const limb_t *L, const uint32_t *recip, limb_t *B)
+  {
+    const int nb = 2 * c->J;
+    if(c->bdm_cols == 0)
+      return 0;
+    const size_t smem = (size_t)c->max_s * TileGeom<NL>::SW * 4;
+    if(smem > (size_t)SMEM_OPT_IN)
+      {
+        const unsigned g = (unsigned)((c->bdm_cols + 63) / 64);
+        c->kt_begin("bdm_trsm_kernel");
+        if(mode == 0)
+          bdm_trsm_kernel<NL, false><<<g, 64, 0, c->cur>>>(c->d_bdm, nb, c->bdm_cols, L, recip, B);
+        else if(mode == 1)
+          bdm_trsm_kernel<NL, true><<<g, 64, 0, c->cur>>>(c->d_bdm, nb, c->bdm_cols, L, recip, B);
+        else
+          eig_trsm_kernel<NL, true><<<g, 64, 0, c->cur>>>(c->d_bdm, nb, c->bdm_cols, L, recip, B);
+        c->kt_end();
+        CUDA_TRY(c, cudaGetLastError());
+        return 0;
+      }
+    c->kt_begin("bdm_trsm_rl_kernel");
+    if(mode == 0)
+      {
+        CUDA_TRY(c, cudaFuncSetAttribute(bdm_trsm_rl_kernel<NL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
+        bdm_trsm_rl_kernel<NL, 0><<<nb, BDM_RL_THREADS, smem, c->cur>>>(c->d_bdm, L, recip, B);
+      }
+    else if(mode == 1)
+      {
+        CUDA_TRY(c, cudaFuncSetAttribute(bdm_trsm_rl_kernel<NL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
+        bdm_trsm_rl_kernel<NL, 1><<<nb, BDM_RL_THREADS, smem, c->cur>>>(c->d_bdm, L, recip, B);
+      }
+    else
+      {
+        CUDA_TRY(c, cudaFuncSetAttribute(bdm_trsm_rl_kernel<NL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
+        bdm_trsm_rl_kernel<NL, 2><<<nb, BDM_RL_THREADS, smem, c->cur>>>(c->d_bdm, L, recip, B);
+      }
+    c->kt_end();
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+  }
   // cholesky_solve.cxx:4-13 with the resident factor of X, then symmetrize (and negate)
   static int bdm_cholesky_solve_symmetrize(sdpb_b200_ctx *c, limb_t *Z, int negate)
   {
     const int nb = 2 * c->J;
     if(c->bdm_cols == 0)
       return 0;
-    const unsigned g = (unsigned)((c->bdm_cols + 63) / 64);
-    c->kt_begin("bdm_trsm_kernel");
-    bdm_trsm_kernel<NL, false><<<g, 64, 0, c->cur>>>(c->d_bdm, nb, c->bdm_cols, c->X, c->recipX, Z);
-    c->kt_end();
-    c->kt_begin("bdm_trsm_kernel");
-    bdm_trsm_kernel<NL, true><<<g, 64, 0, c->cur>>>(c->d_bdm, nb, c->bdm_cols, c->X, c->recipX, Z);
-    c->kt_end();
+    if(int rc = bdm_trsm_rl(c, 0, c->X, c->recipX, Z)) // L^-1 Z
+      return rc;
+    if(int rc = bdm_trsm_rl(c, 1, c->X, c->recipX, Z)) // L^-T (.)
+      return rc;
     const int ms = c->max_s;
     dim3 gs(nb, (unsigned)std::min<long>(((long)ms * (ms + 1) / 2 + 127) / 128, 65535));
     c->kt_begin("bdm_symmetrize_kernel");
@@ -672,14 +712,10 @@ template <int NL> struct Launch
     const uint32_t *recip = which == 0 ? c->recipX : c->recipY;
     CUDA_TRY(c, cudaMemcpyAsync(A, which == 0 ? c->dirDX : c->dirDY, c->wXY * 8, cudaMemcpyDeviceToDevice, st));
     // A := L^-1 A L^-T
-    const unsigned g = (unsigned)((c->bdm_cols + 63) / 64);
-    c->kt_begin("eig_trsm_rows_kernel");
-    eig_trsm_kernel<NL, true><<<g, 64, 0, st>>>(c->d_bdm, nb, c->bdm_cols, L, recip, A);
-    c->kt_end();
-    c->kt_begin("eig_trsm_cols_kernel");
-    eig_trsm_kernel<NL, false><<<g, 64, 0, st>>>(c->d_bdm, nb, c->bdm_cols, L, recip, A);
-    c->kt_end();
-    CUDA_TRY(c, cudaGetLastError());
+    if(int rc = bdm_trsm_rl(c, 2, L, recip, A)) // A L^-T
+      return rc;
+    if(int rc = bdm_trsm_rl(c, 0, L, recip, A)) // L^-1 (.)
+      return rc;
     // tridiagonal form, then the smallest eigenvalue
     if(int rc = smem_opt_in(c, eig_tridiag_kernel<NL>))
       return rc;

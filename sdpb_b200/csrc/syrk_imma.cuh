@@ -196,22 +196,30 @@ syrk_imma_kernel(const uint32_t *__restrict__ P, long KR, int N, int NS, const u
               a[s][2] = r1[0];
               a[s][3] = r1[8];
             }
+          // two column tiles at a time; the 16 slice pairs in an order that keeps the updates of
+          // one accumulator (same weight sa + sb, same tile) at least six instructions apart -- a
+          // warp issues in order, and two warps per scheduler do not hide an IMMA's latency
 #pragma unroll
-          for(int n = 0; n < 4; ++n)
+          for(int n2 = 0; n2 < 4; n2 += 2)
             {
-              uint32_t b[4][2];
+              uint32_t b[2][4][2];
 #pragma unroll
-              for(int s = 0; s < 4; ++s)
-                {
-                  const uint32_t *r0 = Bj + (s * 16 + kk * 8 + t) * SI_CS + n * 8;
-                  b[s][0] = r0[0];
-                  b[s][1] = r0[4 * SI_CS];
-                }
+              for(int q = 0; q < 2; ++q)
 #pragma unroll
-              for(int sa = 0; sa < 4; ++sa)
+                for(int s = 0; s < 4; ++s)
+                  {
+                    const uint32_t *r0 = Bj + (s * 16 + kk * 8 + t) * SI_CS + (n2 + q) * 8;
+                    b[q][s][0] = r0[0];
+                    b[q][s][1] = r0[4 * SI_CS];
+                  }
+              constexpr int ORDER[16][2] = {{0, 0}, {0, 1}, {0, 2}, {0, 3}, {1, 3}, {2, 3}, {3, 3}, {1, 0},
+                                            {1, 1}, {1, 2}, {2, 2}, {3, 2}, {2, 0}, {2, 1}, {3, 1}, {3, 0}};
 #pragma unroll
-                for(int sb = 0; sb < 4; ++sb)
-                  si_mma(acc[sa + sb][n], a[sa], b[sb][0], b[sb][1]);
+              for(int o = 0; o < 16; ++o)
+#pragma unroll
+                for(int q = 0; q < 2; ++q)
+                  si_mma(acc[ORDER[o][0] + ORDER[o][1]][n2 + q], a[ORDER[o][0]], b[q][ORDER[o][1]][0],
+                         b[q][ORDER[o][1]][1]);
             }
         }
       if(++since == SI_FOLD)

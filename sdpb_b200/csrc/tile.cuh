@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(256, TileOcc<NL>::value) trsm_gemm_level(const
     stg_reg<NL>(mine, acc);
 }
 template <int NL>
-__global__ void __launch_bounds__(ROWS_PER_CTA, 8)
+__global__ void __launch_bounds__(ROWS_PER_CTA, 4 * TileOcc<NL>::value)
 trsm_diag_level(const TrsmTileDesc *descs, int It)
 {
   typedef TileGeom<NL> G;
