@@ -131,7 +131,15 @@ struct Extracted_Zip
     if(!mkdtemp(buf.data()))
       throw std::runtime_error("Unable to create a temporary directory for " + zip_path);
     dir = buf.data();
-    extract_stored_zip(zip_path, dir);
+    try
+      {
+        extract_stored_zip(zip_path, dir);
+      }
+    catch(...)
+      {
+        remove_tree(dir); // a throwing constructor runs no destructor
+        throw;
+      }
   }
   static void remove_tree(const std::string &p)
   {

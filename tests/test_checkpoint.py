@@ -188,6 +188,8 @@ def test_zipped_sdp_of_the_reference_reads_like_its_unpacked_directory(tmp_path,
     import zipfile
     from test_golden_trajectory import GOLDEN
     lib = oracle.load_oracle()
+    tmp_root = os.environ.get("TMPDIR", "/tmp")
+    before = set(d for d in os.listdir(tmp_root) if d.startswith("sdpb_b200_sdp_"))
     archive = os.path.join(GOLDEN, "sdp.zip")
     unpacked = str(tmp_path / "sdp")
     with zipfile.ZipFile(archive) as z:
@@ -200,7 +202,6 @@ def test_zipped_sdp_of_the_reference_reads_like_its_unpacked_directory(tmp_path,
     assert a["iterations"] == b["iterations"] and a["terminateReason"] == b["terminateReason"]
     for f in ("x_0.txt", "y.txt"):
         assert filecmp.cmp(str(tmp_path / "out_zip" / f), str(tmp_path / "out_dir" / f), shallow=False), f
-    assert not [d for d in os.listdir(os.environ.get("TMPDIR", "/tmp")) if d.startswith("sdpb_b200_sdp_")]
     # a deflated archive is refused with a pointer to the reference's writer
     deflated = str(tmp_path / "deflated.zip")
     with zipfile.ZipFile(deflated, "w", zipfile.ZIP_DEFLATED) as z:
@@ -210,3 +211,5 @@ def test_zipped_sdp_of_the_reference_reads_like_its_unpacked_directory(tmp_path,
     cargv = (ctypes.c_char_p * len(argv))(*[x.encode() for x in argv])
     buf = ctypes.create_string_buffer(8192)
     assert lib.oracle_solve(len(argv), cargv, buf, 8192) != 0 and "is compressed" in buf.value.decode()
+    # the unpacked copies are gone again, also after the failure
+    assert set(d for d in os.listdir(tmp_root) if d.startswith("sdpb_b200_sdp_")) == before
