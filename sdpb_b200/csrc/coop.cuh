@@ -535,7 +535,10 @@ __device__ __forceinline__ void recip_elem(Work<NL> &ws, const uint32_t *a, uint
 template <int NL>
 __device__ __forceinline__ void pivot(Work<NL> &ws, uint32_t *a, uint32_t *Rs, uint32_t *Rg)
 {
-  const bool seed = sqrt_elem<NL>(ws, a);
+  // The seed is as good as d = sqrt(t) holds: to the NR = 2 NL - 2 words of the root.  The last rung
+  // wants NL + 3 words, so the short precisions (NL < 7, below 320 bits) climb the whole ladder.
+  constexpr bool SEED_OK = 2 * NL - 2 >= NL + 3 + 2;
+  const bool seed = sqrt_elem<NL>(ws, a) && SEED_OK;
   recip_elem<NL>(ws, a, Rs, Rg, seed);
 }
 } // namespace coop
