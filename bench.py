@@ -724,6 +724,11 @@ def main():
             "e2e_with_two_solves": {"what": "one Newton iteration's device work through the C-ABI with host "
                                             "buffers: the e2e step plus the predictor and corrector Schur solves",
                                     "value": e2e_s + 2 * solve_api_s, "unit": "s/iteration"},
+            "e2e_newton_iteration": {"what": "everything of one Newton iteration that runs on the device, through the "
+                                             "C-ABI with host buffers: the e2e step, the search direction (predictor "
+                                             "and corrector, both Schur solves inside) and both step lengths "
+                                             "(SURVEY 8 rows a + N1 + N2 + N3)",
+                                     "value": None if dir_error else e2e_s + dir_api_s + sl_api_s, "unit": "s/iteration"},
             "e2e_all_outputs": {"what": "round-1 contract: sdpb_b200_schur_step with EVERY output copied back "
                                         "(X/Y factors, L_j, L_j^-1 B_j, chol(Q))",
                                 "value": e2e_all_s, "unit": "s/step", "d2h_bytes_per_step": d2h_all},
