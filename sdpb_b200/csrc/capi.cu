@@ -531,22 +531,63 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
     // CTA slots, so splitting the batch only multiplies the level count (G = 1: 145 ms,
     // 2: 156, 4: 153); the mechanism stays for shapes with few, large blocks
     int G = 1;
+    // default: ONE group.  Measured at c3 on the round-2 tree: one group 104.7 ms, interleaved groups
+    // 113.6 (2) / 111.5 (3), split by size class 106.0 (c4: 642 / 646) -- see the note below
+    bool by_size = false, forced = false;
     if(const char *env = getenv("SDPB_B200_GROUPS"))
-      G = atoi(env);
-    c->G = std::max(1, std::min(std::min(G, (int)sdpb_b200_ctx::MAXG), std::max(1, num_blocks)));
+      {
+        by_size = forced = std::string(env) == "size"; // "size": split whatever the block count
+        G = by_size ? 1 : atoi(env);
+      }
     std::vector<int> order(num_blocks);
     for(int j = 0; j < num_blocks; ++j)
       order[j] = j;
     std::stable_sort(order.begin(), order.end(),
                      [&](int a, int b) { return c->g[a].P > c->g[b].P; });
+    // Split by size: the batched Cholesky of the S_j is level-synchronous over 16-row tiles, and
+    // once the small blocks have dropped out its late levels are short chains of pivots on a few
+    // large blocks that leave most of the machine idle.  With the blocks in two size classes
+    // (c3: 150 of 120 rows, 450 of 40) the small class gets its own stream: its factorisation is
+    // over after a few levels and its triangular solves fill the SMs under the large blocks'
+    // pivot chains.  The split is where the tile count drops the most; none if it never halves.
+    // (Measured: it does not pay -- the two chains' kernels mostly queue behind one another instead
+    // of sharing the SMs -- so it is an option, SDPB_B200_GROUPS=size, not the default.)
+    std::vector<int> group_of(num_blocks, 0);
+    if(by_size && (forced ? num_blocks >= 2 : num_blocks >= 2 * 148))
+      {
+        auto tiles = [&](int k) { return (c->g[order[k]].P + TS - 1) / TS; };
+        int cut = 0, best = 0;
+        for(int k = 1; k < num_blocks; ++k)
+          if(tiles(k - 1) - tiles(k) > best)
+            {
+              best = tiles(k - 1) - tiles(k);
+              cut = k;
+            }
+        if(best > 0 && (forced || (cut >= 148 / 2 && num_blocks - cut >= 148 && 2 * tiles(cut) <= tiles(0))))
+          {
+            G = 2;
+            for(int k = cut; k < num_blocks; ++k)
+              group_of[k] = 1;
+          }
+        else
+          by_size = false;
+      }
+    else
+      by_size = false;
+    c->G = std::max(1, std::min(std::min(G, (int)sdpb_b200_ctx::MAXG), std::max(1, num_blocks)));
+    if(!by_size)
+      for(int k = 0; k < num_blocks; ++k)
+        group_of[k] = k % c->G; // interleaved: the largest blocks dealt round-robin
     for(int g = 0; g < c->G; ++g)
       {
         std::vector<PotrfDesc> gp;
         std::vector<TrsmTileDesc> gt;
         std::vector<SchurDesc> gs;
         std::vector<BandDesc> gb;
-        for(int k = g; k < num_blocks; k += c->G)
+        for(int k = 0; k < num_blocks; ++k)
           {
+            if(group_of[k] != g)
+              continue;
             const int j = order[k];
             const BlockGeom &b = c->g[j];
             gp.push_back(PotrfDesc{c->S + c->oS[j], c->recipS + (size_t)b.row0 * rs, b.P, 1,

@@ -220,20 +220,33 @@ def test_scale_multiply_add_bit_exact(prec, shapes, N):
     ctx.close()
 
 
-def test_block_groups_on_side_streams_bit_exact(monkeypatch):
-    """The S chain cut into interleaved groups of blocks on separate streams
-    (SDPB_B200_GROUPS) must not change a bit."""
-    prec, shapes, N = 768, [(1, 9), (2, 5), (1, 17), (1, 4), (2, 9), (1, 12), (1, 3)], 9
+@pytest.mark.parametrize("groups", ["3", "size"])
+def test_block_groups_on_side_streams_bit_exact(monkeypatch, groups):
+    """The S chain cut into groups of blocks on separate streams (SDPB_B200_GROUPS) must not change
+    a bit: interleaved groups ("3"), and the split by size class that is the default for batches
+    with two classes of blocks ("size" forces it at this small block count: the 33- and 27-row
+    blocks against the rest), also on a second step and on a single stream."""
+    prec, shapes, N = 768, [(1, 9), (2, 5), (1, 17), (1, 4), (2, 11), (1, 12), (1, 3), (2, 9)], 9
     sdp = ol.SyntheticSDP(prec, shapes, N, seed=8)
     ref = ol.OracleContext(prec, shapes, N)
     sdp.upload(ref)
     want = sdp.run_step(ref)
-    monkeypatch.setenv("SDPB_B200_GROUPS", "3")
+    monkeypatch.setenv("SDPB_B200_GROUPS", groups)
     ctx = sdpb_b200.SchurContext(prec, shapes, N)
     sdp.upload(ctx)
     got = sdp.run_step(ctx)
     for k in KEYS:
         ol.assert_same(k, got[k], want[k])
+    ctx.set_concurrency(0)
+    again = sdp.run_step(ctx)
+    for k in KEYS:
+        ol.assert_same(k + " (2nd step, single stream)", again[k], want[k])
+    want_dx, want_dy = sdp.solve_rhs()
+    ref.solve_schur_complement_equation(want_dx, want_dy)
+    dx, dy = sdp.solve_rhs()
+    ctx.solve_schur_complement_equation(dx, dy)
+    ol.assert_same("dy", dy, want_dy)
+    ol.assert_same("dx", dx, want_dx)
     ctx.close()
 
 
