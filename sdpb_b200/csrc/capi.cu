@@ -1889,23 +1889,34 @@ extern "C" int sdpb_b200_upload_XY(sdpb_b200_ctx *c, const uint64_t *const *X,
 
 // The whole hot path from device-resident X, Y (sdpb_b200_upload_XY): every
 // kernel is enqueued back to back, one host synchronisation at the end.
-static int enqueue_step(sdpb_b200_ctx *c)
+// y_uploaded: Yin is still arriving on another stream (sdpb_b200_schur_step uploads Y on the copy
+// stream while the X chain already runs); the event marks its arrival.  null: Yin is in place.
+static int enqueue_step(sdpb_b200_ctx *c, cudaEvent_t y_uploaded = nullptr)
 {
   cudaStream_t st = c->stream;
   c->kt_used = 0;
   c->have_factors = false;
   CUDA_TRY(c, cudaEventRecord(c->ev[9], st));
+  // chol(Y) on a side stream, the A_Y chain on another, chol(X) -> A_X_inv here.  Y and LY are set
+  // up on chol(Y)'s stream: nothing of the X chain reads them, so the X chain does not wait for Y.
+  cudaStream_t sl = c->side(3);
+  if(c->wXY)
+    CUDA_TRY(c, cudaMemcpyAsync(c->X, c->Xin, c->wXY * 8, cudaMemcpyDeviceToDevice, st));
+  if(sl != st)
+    {
+      // (evf[1] is recorded again by dispatch_pairings later: a wait refers to the record that
+      // precedes it, so sharing the event is safe)
+      CUDA_TRY(c, cudaEventRecord(c->evf[1], st)); // everything enqueued before this step (uploads of X)
+      CUDA_TRY(c, cudaStreamWaitEvent(sl, c->evf[1], 0));
+    }
+  if(y_uploaded)
+    CUDA_TRY(c, cudaStreamWaitEvent(sl, y_uploaded, 0));
   if(c->wXY)
     {
-      CUDA_TRY(c, cudaMemcpyAsync(c->X, c->Xin, c->wXY * 8, cudaMemcpyDeviceToDevice, st));
-      CUDA_TRY(c, cudaMemcpyAsync(c->Y, c->Yin, c->wXY * 8, cudaMemcpyDeviceToDevice, st));
-      CUDA_TRY(c, cudaMemcpyAsync(c->LY, c->Yin, c->wXY * 8, cudaMemcpyDeviceToDevice, st));
+      CUDA_TRY(c, cudaMemcpyAsync(c->Y, c->Yin, c->wXY * 8, cudaMemcpyDeviceToDevice, sl));
+      CUDA_TRY(c, cudaMemcpyAsync(c->LY, c->Yin, c->wXY * 8, cudaMemcpyDeviceToDevice, sl));
     }
-  // chol(Y) on a side stream, the A_Y chain on another, chol(X) -> A_X_inv here
-  CUDA_TRY(c, cudaEventRecord(c->evf[2], st)); // X, Y, LY in place
-  cudaStream_t sl = c->side(3);
-  if(sl != st)
-    CUDA_TRY(c, cudaStreamWaitEvent(sl, c->evf[2], 0));
+  CUDA_TRY(c, cudaEventRecord(c->evf[2], sl)); // Y, LY in place (what the A_Y chain waits for)
   c->cur = sl;
   int rc = dispatch_cholesky(c, 1);
   c->cur = st;
@@ -2072,6 +2083,7 @@ extern "C" int sdpb_b200_schur_step(
           c->error = "null input block " + std::to_string(q);
           return SDPB_B200_ERR_ARG;
         }
+  // (both streams are idle here: every call of this library ends with their synchronisation)
   for(int which = 0; which < 2; ++which)
     {
       const uint64_t *const *A = which == 0 ? X : Y;
@@ -2094,13 +2106,18 @@ extern "C" int sdpb_b200_schur_step(
               words += sr * sr * c->es;
               ++r;
             }
-          CUDA_TRY(c, cudaMemcpyAsync(dst + c->oXY[q], A[q], words * 8, cudaMemcpyHostToDevice, c->stream));
+          // X on the main stream, Y on the copy stream: the X chain (chol X, L_X^-1 V, A_X_inv) starts
+          // as soon as X is up and runs under Y's upload
+          CUDA_TRY(c, cudaMemcpyAsync(dst + c->oXY[q], A[q], words * 8, cudaMemcpyHostToDevice,
+                                      which == 0 ? c->stream : c->copy));
           q = r;
         }
     }
-  int rc = enqueue_step(c);
+  CUDA_TRY(c, cudaEventRecord(c->evd[1], c->copy)); // Y uploaded
+  int rc = enqueue_step(c, c->evd[1]);
   if(rc)
     {
+      cudaStreamSynchronize(c->copy);
       cudaStreamSynchronize(c->stream); // the uploads still read the caller's buffers
       return rc;
     }
