@@ -539,6 +539,9 @@ def test_search_direction_after_separate_calls_and_state_errors():
     with pytest.raises(SdpbB200Error) as ei:
         ctx.compute_search_direction(bm, 0)      # before direction_begin
     assert ei.value.code == 5
+    with pytest.raises(SdpbB200Error) as ei:
+        ctx.step_length(0)                       # row N3 needs a direction (computed or put)
+    assert ei.value.code == 5
     ol.assert_same("traces", ctx.direction_begin(), ref.direction_begin())
     with pytest.raises(SdpbB200Error) as ei:
         ctx.compute_search_direction(bm, 0)      # before the residues
