@@ -41,7 +41,7 @@ namespace mpfw
 #endif
 
 #ifdef MPFW_COUNT_RARE
-static long rare_mul_count = 0, rare_sub_count = 0, recip_fallbacks = 0, sqrt_fallbacks = 0; // host fuzz: rare paths exercised?
+static long rare_mul_count = 0, rare_sub_count = 0, recip_fallbacks = 0, sqrt_fallbacks = 0, div_exact_count = 0, div_fast_count = 0; // host fuzz: rare paths exercised?
 #endif
 // ------------------------------------------------------------------ carries
 // (t2:t1:t0) += a * b
@@ -1339,6 +1339,7 @@ MPFW_D void div_recip(Reg<NL> &x, int32_t dsign, int32_t dexp, const uint32_t *d
   constexpr int n2 = 2 * NL, RW = 2 * NL + 4;
   // ---- q~ = words [2n+3, 4n+3) of U*R, columns >= 2n+1 only ----
   uint32_t q[n2];
+  uint32_t guard = 0; // word n2+2 of the column sum: the first fraction word below q~
   {
     uint32_t t0 = 0, t1 = 0, t2 = 0;
     constexpr int C0 = n2 + 1;
@@ -1352,6 +1353,8 @@ MPFW_D void div_recip(Reg<NL> &x, int32_t dsign, int32_t dexp, const uint32_t *d
             if(j >= 0 && j < RW)
               mac3(t0, t1, t2, x.w[i], R[j]);
           }
+        if(c == n2 + 2)
+          guard = t0;
         if(c >= n2 + 3 && c - (n2 + 3) < n2)
           q[c - (n2 + 3)] = t0;
         t0 = t1;
@@ -1360,6 +1363,18 @@ MPFW_D void div_recip(Reg<NL> &x, int32_t dsign, int32_t dexp, const uint32_t *d
       }
     // column n2+RW-1 = 4n+3 is word 2n of q~: always zero (q < beta^(2n))
   }
+  // With W = the columns >= 2n+1 that were formed, Q = U beta^(2n-2) / D (real) and R = floor(
+  // beta^(4n+1) / D):  W / beta^(2n+3) <= Q < W / beta^(2n+3) + 2n / beta + beta^-3  (the dropped
+  // columns hold fewer than 2n beta^(2n+2); R's own floor costs less than beta^-3), and
+  // W / beta^(2n+3) < q~ + (guard + 1) / beta.  So guard + 2n + 2 <= beta already proves
+  // floor(Q) = q~: the exact remainder (a second half product) is formed only on the 2^-26 of
+  // the inputs whose fraction sits within 64 units of a whole number (exact quotients among them).
+  static_assert(2 * NL + 2 <= 64, "the guard-word test of div_recip assumes 2n + 2 <= 64");
+#ifdef MPFW_COUNT_RARE
+  ++(guard > 0xFFFFFFFFu - 64u ? div_exact_count : div_fast_count);
+#endif
+  if(guard > 0xFFFFFFFFu - 64u)
+  {
   // ---- rem = (U beta^(2n-2) - q~ D) mod beta^(2n+1) ----
   uint32_t rem[n2 + 1];
   {
@@ -1414,6 +1429,7 @@ MPFW_D void div_recip(Reg<NL> &x, int32_t dsign, int32_t dexp, const uint32_t *d
           q[c] = s;
         }
     }
+  }
   // ---- assemble (mpfx::div): strip one leading zero limb ----
   const bool adj = (q[n2 - 1] | q[n2 - 2]) == 0;
 #pragma unroll

@@ -203,6 +203,73 @@ template <int NL> static long run(long iters)
           ++dbad;
         }
     }
+  // quotients whose fraction sits m / 2^32 below a whole number, m = 0 .. 160: the band in which
+  // div_recip's guard word switches between "decided" and "form the exact remainder"
+  for(int m = 0; m <= 160; ++m)
+    for(int rep = 0; rep < 8; ++rep)
+      {
+        constexpr int n2 = 2 * NL;
+        uint32_t K[n2], D[n2], prod[2 * n2];
+        for(int i = 0; i < n2; ++i)
+          {
+            K[i] = (uint32_t)rnd();
+            D[i] = (uint32_t)rnd();
+          }
+        K[n2 - 1] = 0; // K = q beta + (beta - m), q of n2 - 2 words
+        if(K[n2 - 2] == 0)
+          K[n2 - 2] = 1;
+        K[0] = (uint32_t)(0u - (uint32_t)m);
+        if(D[n2 - 1] == 0)
+          D[n2 - 1] = 1 + (uint32_t)(rnd() % 5);
+        if(rep & 1)
+          D[n2 - 1] = 1 + (uint32_t)(rnd() % 3); // small top word: coarse quotient grid
+        for(int i = 0; i < 2 * n2; ++i)
+          prod[i] = 0;
+        for(int i = 0; i < n2; ++i)
+          {
+            uint64_t carry = 0;
+            for(int j = 0; j < n2; ++j)
+              {
+                const uint64_t t = (uint64_t)K[i] * D[j] + prod[i + j] + carry;
+                prod[i + j] = (uint32_t)t;
+                carry = t >> 32;
+              }
+            prod[i + n2] = (uint32_t)carry;
+          }
+        // U = floor(K D / beta^(n2-1)), needs to fit n2 words with a non-zero top limb
+        if(prod[2 * n2 - 1] != 0)
+          continue;
+        mpfx::Num<NL> u, d, want, got;
+        for(int i = 0; i < NL; ++i)
+          {
+            u.d[i] = (uint64_t)prod[n2 - 1 + 2 * i] | ((uint64_t)prod[n2 + 2 * i] << 32);
+            d.d[i] = (uint64_t)D[2 * i] | ((uint64_t)D[2 * i + 1] << 32);
+          }
+        if(u.d[NL - 1] == 0 || d.d[NL - 1] == 0)
+          continue;
+        u.sign = (rnd() & 1) ? 1 : -1;
+        d.sign = (rnd() & 1) ? 1 : -1;
+        u.exp = (int32_t)(rnd() % 7) - 3;
+        d.exp = (int32_t)(rnd() % 7) - 3;
+        mpfx::div(want, u, d);
+        uint32_t R[2 * NL + 4];
+        mpfw::reciprocal<NL>(R, d);
+        mpfw::Reg<NL> ru, rd;
+        mpfw::from_num(ru, u);
+        mpfw::from_num(rd, d);
+        mpfw::div_recip<NL>(ru, rd.sign, rd.exp, rd.w, R);
+        mpfw::to_num(got, ru);
+        if(!same(got, want))
+          {
+            if(dbad < 5)
+              {
+                printf("DIV MISMATCH (guard band, m = %d) NL=%d\n", m, NL);
+                dump("u", u);
+                dump("d", d);
+              }
+            ++dbad;
+          }
+      }
   // fast reciprocal / sqrt against the reference routines
   long rbad = 0, sbad = 0;
   for(long it = 0; it < iters / 4; ++it)
@@ -267,7 +334,8 @@ int main(int argc, char **argv)
          mpfw::recip_fallbacks, mpfw::sqrt_fallbacks);
   if(mpfw::recip_fallbacks || mpfw::sqrt_fallbacks)
     return 3;
-  if(mpfw::rare_mul_count == 0 || mpfw::rare_sub_count == 0)
+  printf("division: guard word decided %ld, exact remainder formed %ld\n", mpfw::div_fast_count, mpfw::div_exact_count);
+  if(mpfw::rare_mul_count == 0 || mpfw::rare_sub_count == 0 || mpfw::div_exact_count == 0 || mpfw::div_fast_count == 0)
     {
       printf("rare paths not covered\n");
       return 2;
