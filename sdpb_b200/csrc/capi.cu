@@ -408,6 +408,14 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
   for(auto &e : c->evf)
     TRY_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   TRY_C(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+  {
+    int least = 0, greatest = 0;
+    TRY_C(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    const char *env = getenv("SDPB_B200_PRIORITY");
+    if(!env || atoi(env) != 0)
+      for(auto &p : c->prio)
+        TRY_C(cudaStreamCreateWithPriority(&p, cudaStreamNonBlocking, greatest));
+  }
   for(auto &e : c->evd)
     TRY_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if(const char *env = getenv("SDPB_B200_CONCURRENCY"))
@@ -575,6 +583,7 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
     else
       by_size = false;
     c->G = std::max(1, std::min(std::min(G, (int)sdpb_b200_ctx::MAXG), std::max(1, num_blocks)));
+    c->split_by_size = by_size && c->G == 2;
     if(!by_size)
       for(int k = 0; k < num_blocks; ++k)
         group_of[k] = k % c->G; // interleaved: the largest blocks dealt round-robin
@@ -1048,6 +1057,9 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
       cudaEventDestroy(e);
   if(c->copy)
     cudaStreamDestroy(c->copy);
+  for(auto &p : c->prio)
+    if(p)
+      cudaStreamDestroy(p);
   if(c->pinned)
     cudaFreeHost(c->pinned);
   for(auto &k : c->kt)
@@ -1899,7 +1911,7 @@ static int enqueue_step(sdpb_b200_ctx *c, cudaEvent_t y_uploaded = nullptr)
   CUDA_TRY(c, cudaEventRecord(c->ev[9], st));
   // chol(Y) on a side stream, the A_Y chain on another, chol(X) -> A_X_inv here.  Y and LY are set
   // up on chol(Y)'s stream: nothing of the X chain reads them, so the X chain does not wait for Y.
-  cudaStream_t sl = c->side(3);
+  cudaStream_t sl = c->prio[1] ? c->urgent(1) : c->side(3), sx = c->urgent(0);
   if(c->wXY)
     CUDA_TRY(c, cudaMemcpyAsync(c->X, c->Xin, c->wXY * 8, cudaMemcpyDeviceToDevice, st));
   if(sl != st)
@@ -1923,9 +1935,19 @@ static int enqueue_step(sdpb_b200_ctx *c, cudaEvent_t y_uploaded = nullptr)
   if(rc)
     return rc;
   CUDA_TRY(c, cudaEventRecord(c->evd[0], sl));
+  // chol(X) on its own urgent stream: evf[1] (recorded above on st) covers the copy of X
+  if(sx != st)
+    {
+      if(sl == st) // (not reached: urgent streams exist together) evf[1] not recorded yet
+        CUDA_TRY(c, cudaEventRecord(c->evf[1], st));
+      CUDA_TRY(c, cudaStreamWaitEvent(sx, c->evf[1], 0));
+    }
+  c->cur = sx;
   rc = dispatch_cholesky(c, 0);
+  c->cur = st;
   if(rc)
     return rc;
+  CUDA_TRY(c, c->after(sx, st, 16));
   CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
   rc = dispatch_pairings(c, 2);
   if(rc)

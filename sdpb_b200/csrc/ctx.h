@@ -121,7 +121,7 @@ struct sdpb_b200_ctx
   cudaStream_t copy = nullptr; // D2H of finished outputs while the step is still running (schur_step)
   cudaEvent_t evd[2] = {};     // [0] chol(Y) done
   cudaStream_t aux[MAXG] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t evf[16] = {};
+  cudaEvent_t evf[20] = {};
   int concurrency = 1, G = 1;
   PotrfDesc *d_potrfS_g[MAXG] = {};
   TrsmTileDesc *d_trsmP_g[MAXG] = {};
@@ -130,6 +130,12 @@ struct sdpb_b200_ctx
   std::vector<int> szS_g[MAXG], szP_g[MAXG], blocks_g[MAXG]; // blocks_g: local block indices of a group
   int nblk_g[MAXG] = {}, maxP_g[MAXG] = {};
   cudaStream_t side(int k) const { return concurrency ? aux[k] : stream; }
+  // two streams of the greatest priority for the latency-bound chains (the pivot chains of chol(X)
+  // and chol(Y) are a few warps per SM for milliseconds): their CTAs are placed ahead of the pending
+  // CTAs of the throughput kernels running beside them, instead of queueing behind them
+  cudaStream_t prio[2] = {nullptr, nullptr};
+  bool split_by_size = false; // the S chain runs as two size classes (group 0 = the large blocks)
+  cudaStream_t urgent(int k) const { return concurrency && prio[k] ? prio[k] : stream; }
   // `to` waits for everything enqueued on `from` so far
   cudaError_t after(cudaStream_t from, cudaStream_t to, int e)
   {

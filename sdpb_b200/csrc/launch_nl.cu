@@ -219,6 +219,12 @@ template <int NL> struct Launch
     CUDA_TRY(c, cudaFuncSetAttribute(trsm_gemm_level2<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
     CUDA_TRY(c, cudaFuncSetAttribute(trsm_diag_level<NL>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
+    CUDA_TRY(c, cudaFuncSetAttribute(trsm_diag_tile<NL>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN));
+    // diagonal solves of a level: one thread per column from this many columns (all matrices of the
+    // level together) on, the 16 x 16 form (trsm_diag_tile) below it
+    const char *tile_env = getenv("SDPB_B200_TRSM_TILE_BELOW"); // (read per call: the tests switch it)
+    const long tile_below = tile_env ? atol(tile_env) : 32768L;
     const std::vector<int> heavy(sizes.begin(), sizes.begin() + nheavy);
     const int T = (heavy[0] + TS - 1) / TS;
     const char *l_gemm = sub(label, "gemm"), *l_diag = sub(label, "diag");
@@ -235,9 +241,18 @@ template <int NL> struct Launch
               trsm_gemm_level2<NL><<<g, 256, smem2, c->cur>>>(d, It);
             c->kt_end();
           }
-        dim3 g2(n, (maxcols + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
         c->kt_begin(l_diag);
-        trsm_diag_level<NL><<<g2, ROWS_PER_CTA, DIAG_SMEM, c->cur>>>(d, It);
+        if((long)n * maxcols <= tile_below)
+          {
+            // too few columns to fill the SMs with one thread each: 16 x 16 threads per tile
+            dim3 g2(n, (maxcols + TS - 1) / TS);
+            trsm_diag_tile<NL><<<g2, 256, sizeof(DiagTileSmem<NL>), c->cur>>>(d, It);
+          }
+        else
+          {
+            dim3 g2(n, (maxcols + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
+            trsm_diag_level<NL><<<g2, ROWS_PER_CTA, DIAG_SMEM, c->cur>>>(d, It);
+          }
         c->kt_end();
       }
     CUDA_TRY(c, cudaGetLastError());
@@ -303,7 +318,9 @@ template <int NL> struct Launch
     // per group of blocks: S_j -> Cholesky(S_j) -> P_j = L_j^{-1} B_j -> column-norm partials
     for(int g = 0; g < c->G && J; ++g)
       {
-        cudaStream_t sg = g == 0 ? st : c->side(g);
+        // two size classes: the large blocks' chain (long pivot chains on few matrices) goes on a
+        // stream of the greatest priority, the small blocks' kernels fill the SMs under it
+        cudaStream_t sg = g == 0 ? (c->split_by_size ? c->urgent(0) : st) : c->side(g);
         CUDA_TRY(c, c->after(st, sg, 4 + g));
         c->cur = sg;
         const int nb = c->nblk_g[g], mp = c->maxP_g[g];
@@ -327,6 +344,8 @@ template <int NL> struct Launch
         CUDA_TRY(c, cudaGetLastError());
       }
     c->cur = st;
+    if(c->split_by_size && J)
+      CUDA_TRY(c, c->after(c->urgent(0), st, 8));
     for(int g = 1; g < c->G && J; ++g)
       CUDA_TRY(c, c->after(c->side(g), st, 8 + g));
     CUDA_TRY(c, cudaEventRecord(c->ev[4], st));

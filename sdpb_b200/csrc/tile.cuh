@@ -599,8 +599,10 @@ potrf_diag_warp(const PotrfDesc *descs, int count, int Jt, int *status)
 //   potrf_diag_rl   one CTA per matrix: factor the (already updated) diagonal tile
 //   potrf_panel_rl  one CTA per tile below it: X = A_tile L_JJ^{-T}
 //   potrf_trail_rl  one CTA per tile (It >= Kt > Jt): a_ij -= sum_{k in column Jt} l_ik l_jk
+// (one CTA per matrix and a serial chain of pivots: compiled for one CTA per SM, so that the
+// pivot code keeps its operands in registers instead of the spill stack)
 template <int NL>
-__global__ void __launch_bounds__(256, TileOcc<NL>::value)
+__global__ void __launch_bounds__(256, 1)
 potrf_diag_rl(const PotrfDesc *descs, int Jt, int *status)
 {
   typedef TileGeom<NL> G;
@@ -841,6 +843,56 @@ trsm_diag_level(const TrsmTileDesc *descs, int It)
       acc = div_nl<NL>(acc, sm.diag + tri_index(ii, ii) * G::SW, sm.recip + ii * G::RS);
       stg_reg<NL>(colp + (long)ii * G::ES, acc);
     }
+}
+
+// The same diagonal solve with the 16 steps of a tile shared by 16 x 16 threads (element (i, c) of
+// the tile per thread, as potrf_row_tile_solve does for the panel of a factorisation): step k is
+// one division of row k and one update of the rows below it, so the chain of a tile is
+// 16 (div + mac) instead of the 136 operations one thread per column runs through.  It costs
+// ~2.5x the pipe time (most lanes of a step idle), so the host takes it only where the batch is too
+// small to fill the SMs with one thread per column (BASELINE configs 0 and 1: N = 20 / 60).
+// Same per-element order: updates in ascending k, then the division.
+template <int NL> struct DiagTileSmem
+{
+  typedef TileGeom<NL> G;
+  DiagSmem<NL> d;
+  uint32_t x[2][TS * G::SW]; // the solved row k, one element per column of the tile
+};
+template <int NL>
+__global__ void __launch_bounds__(256, TileOcc<NL>::value)
+trsm_diag_tile(const TrsmTileDesc *descs, int It)
+{
+  typedef TileGeom<NL> G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  DiagTileSmem<NL> &sm = *reinterpret_cast<DiagTileSmem<NL> *>(smem_raw);
+  const TrsmTileDesc d = descs[blockIdx.x];
+  const int I0 = It * TS, c0 = blockIdx.y * TS;
+  if(I0 >= d.p || c0 >= d.ncols)
+    return;
+  load_diag<NL>(sm.d, d.L, 1, d.p, d.recip, d.p, It);
+  const int ti = tile_ti(), tj = tile_tj();
+  const int ni = min(TS, d.p - I0), nc = min(TS, d.ncols - c0);
+  const bool active = ti < ni && tj < nc;
+  uint64_t *mine = d.B + ((long)(c0 + tj) * d.p + I0 + ti) * G::ES;
+  Reg<NL> acc;
+  if(active)
+    ldg_reg<NL>(acc, mine);
+  else
+    mpfw::set_zero(acc);
+  for(int kk = 0; kk < ni; ++kk)
+    {
+      uint32_t *xs = sm.x[kk & 1];
+      if(active && ti == kk)
+        {
+          acc = div_nl<NL>(acc, sm.d.diag + tri_index(kk, kk) * G::SW, sm.d.recip + kk * G::RS);
+          mpfw::store<NL>(xs + tj * G::SW, acc);
+        }
+      __syncthreads();
+      if(active && ti > kk)
+        acc = mac_ss_nl<NL>(acc, sm.d.diag + tri_index(ti, kk) * G::SW, xs + tj * G::SW, true);
+    }
+  if(active)
+    stg_reg<NL>(mine, acc);
 }
 
 // ---- the whole batched solve in ONE launch ---------------------------------

@@ -250,6 +250,27 @@ def test_block_groups_on_side_streams_bit_exact(monkeypatch, groups):
     ctx.close()
 
 
+@pytest.mark.parametrize("below", ["0", "1000000000"])
+def test_trsm_diagonal_solve_forms_bit_exact(monkeypatch, below):
+    """The diagonal solves of L^-1 B and L_X^-1 V have two schedules -- one thread per column
+    (trsm_diag_level, full-size batches) and 16 x 16 threads per tile (trsm_diag_tile, batches too
+    small to fill the SMs) -- chosen by the column count of a level; SDPB_B200_TRSM_TILE_BELOW
+    forces either.  Both must reproduce the oracle bit for bit (ragged last tiles, m = 2 blocks,
+    a column count that is not a multiple of 16)."""
+    prec, shapes, N = 768, [(1, 40), (2, 17), (1, 9), (2, 6), (1, 33)], 21
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=12)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    want = sdp.run_step(ref)
+    monkeypatch.setenv("SDPB_B200_TRSM_TILE_BELOW", below)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    got = sdp.run_step(ctx)
+    for k in KEYS:
+        ol.assert_same(k, got[k], want[k])
+    ctx.close()
+
+
 def test_separate_calls_match_fused_step():
     prec, shapes, N = 256, [(1, 6), (2, 3)], 4
     sdp = ol.SyntheticSDP(prec, shapes, N, seed=5)

@@ -20,7 +20,7 @@ d = json.load(open('gpurun_out/bench_r02_${V}_$w.json'))
 print('$w', 'ms/step', round(d['ms_per_step'], 2), 'e2e', round(d['e2e']['value'] * 1e3, 2), d['stages_ms'])
 PY
 done
-SDPB_B200_CONCURRENCY=0 timeout 600 ncu --set full --import-source on --sampling-interval 0 --clock-control none -k regex:potrf_diag_rl -s 25 -c 1 -o /tmp/diag_rl python bench.py --steps 1 --warmup 3 --no-cpu --no-all-outputs > /dev/null 2>&1
+SDPB_B200_CONCURRENCY=0 timeout 600 ncu --set full --import-source on --warp-sampling-interval 1 --clock-control none -k regex:potrf_diag_rl -s 25 -c 1 -o /tmp/diag_rl python bench.py --steps 1 --warmup 3 --no-cpu --no-all-outputs > /dev/null 2>&1
 ncu -i /tmp/diag_rl.ncu-rep --page source --print-source sass --csv > gpurun_out/prof_r02_${V}_potrf_diag_rl_source.csv
 ncu -i /tmp/diag_rl.ncu-rep --page source --print-source cuda --csv > gpurun_out/prof_r02_${V}_potrf_diag_rl_cuda.csv 2>&1
 ncu -i /tmp/diag_rl.ncu-rep --page raw --csv > gpurun_out/prof_r02_${V}_potrf_diag_rl_raw.csv
