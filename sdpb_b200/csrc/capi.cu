@@ -539,9 +539,11 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
     // CTA slots, so splitting the batch only multiplies the level count (G = 1: 145 ms,
     // 2: 156, 4: 153); the mechanism stays for shapes with few, large blocks
     int G = 1;
-    // default: ONE group.  Measured at c3 on the round-2 tree: one group 104.7 ms, interleaved groups
-    // 113.6 (2) / 111.5 (3), split by size class 106.0 (c4: 642 / 646) -- see the note below
-    bool by_size = false, forced = false;
+    // default: the split by size class where the batch has two classes (note below), else ONE
+    // group.  Measured at c3: one group 98.2 ms, split by size with the large blocks' chain on a
+    // stream of the greatest priority 94.3 ms (without the priority 99.3: the round-2 v5 finding),
+    // interleaved groups 113.6 (2) / 111.5 (3)
+    bool by_size = c->prio[0] != nullptr, forced = false;
     if(const char *env = getenv("SDPB_B200_GROUPS"))
       {
         by_size = forced = std::string(env) == "size"; // "size": split whatever the block count
@@ -558,8 +560,10 @@ extern "C" int sdpb_b200_create(sdpb_b200_ctx **out, int prec_bits, int device,
     // (c3: 150 of 120 rows, 450 of 40) the small class gets its own stream: its factorisation is
     // over after a few levels and its triangular solves fill the SMs under the large blocks'
     // pivot chains.  The split is where the tile count drops the most; none if it never halves.
-    // (Measured: it does not pay -- the two chains' kernels mostly queue behind one another instead
-    // of sharing the SMs -- so it is an option, SDPB_B200_GROUPS=size, not the default.)
+    // (On streams of equal priority it does not pay -- the two chains' kernels mostly queue behind
+    // one another instead of sharing the SMs; with the large blocks' chain on a stream of the
+    // greatest priority its short kernels are placed at once and the small blocks' CTAs fill the
+    // rest: 98.2 -> 94.3 ms at c3.  SDPB_B200_GROUPS=1 keeps one group.)
     std::vector<int> group_of(num_blocks, 0);
     if(by_size && (forced ? num_blocks >= 2 : num_blocks >= 2 * 148))
       {
@@ -1031,6 +1035,8 @@ extern "C" void sdpb_b200_destroy(sdpb_b200_ctx *c)
                    c->dir_part, c->dir_colsum})
     cudaFree(p);
   cudaFree(c->d_bdm);
+  for(auto &kv : c->bdm_trsm_descs)
+    cudaFree(kv.second);
   cudaFree(c->d_row_block);
   cudaFree(c->d_gemmXY);
   cudaFree(c->d_gemmDXDY);

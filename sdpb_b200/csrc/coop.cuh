@@ -155,6 +155,9 @@ __device__ __forceinline__ int wclz(const uint32_t *a, int n)
 // (columns below C0 are not formed, the carry out of column TO-1 is dropped):
 // the one primitive behind mpfw's mul_low / mul_mid / mul_high.
 // t: scratch, 3 * (TO - C0) words.  out must not alias a or b.
+// (inlined at its dozen call sites on purpose: out of line -- measured, profiles/r02_summary.md --
+// the kernel shrinks from 32 000 to 16 000 instructions and instruction-fetch stalls halve, but the
+// call sites lose their compile-time column ranges and the pivot gets 10 % slower)
 __device__ __forceinline__ void wmul(uint32_t *out, const uint32_t *a, int KA, const uint32_t *b,
                                      int KB, int C0, int FROM, int TO, uint32_t *t)
 {
@@ -165,13 +168,22 @@ __device__ __forceinline__ void wmul(uint32_t *out, const uint32_t *a, int KA, c
     {
       const int k = base + l, c = C0 + k;
       uint32_t s0 = 0, s1 = 0, s2 = 0;
-      if(k < ncols)
-        {
-          const int ilo = c - (KB - 1) > 0 ? c - (KB - 1) : 0;
-          const int ihi = c < KA - 1 ? c : KA - 1;
+      // One trip count for the whole warp -- the rows i that ANY column of this round needs -- so
+      // that a[i] is a broadcast load at a uniform address and the loop carries no per-lane
+      // bounds; a lane whose column does not reach row i adds a zero product.
+      const int cmin = C0 + base, cmax = C0 + (base + 32 < ncols ? base + 32 : ncols) - 1;
+      const int ulo = cmin - (KB - 1) > 0 ? cmin - (KB - 1) : 0;
+      const int uhi = cmax < KA - 1 ? cmax : KA - 1;
+      const bool on = k < ncols;
 #pragma unroll 4
-          for(int i = ilo; i <= ihi; ++i)
-            mpfw::mac3(s0, s1, s2, a[i], b[c - i]);
+      for(int i = ulo; i <= uhi; ++i)
+        {
+          const int j = c - i;
+          const uint32_t bv = (on && j >= 0 && j < KB) ? b[j] : 0u;
+          mpfw::mac3(s0, s1, s2, a[i], bv);
+        }
+      if(on)
+        {
           t0[k] = s0;
           t1[k] = s1;
           t2[k] = s2;

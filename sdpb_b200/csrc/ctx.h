@@ -7,7 +7,9 @@
 #include "direction.cuh"
 #include "eig.cuh"
 
+#include <map>
 #include <memory>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -134,6 +136,10 @@ struct sdpb_b200_ctx
   // and chol(Y) are a few warps per SM for milliseconds): their CTAs are placed ahead of the pending
   // CTAs of the throughput kernels running beside them, instead of queueing behind them
   cudaStream_t prio[2] = {nullptr, nullptr};
+  // block-diagonal solves on the tile kernels (launch_nl.cu bdm_trsm_tiles): block-parities sorted
+  // by size, their sizes, cumulative columns, and the descriptor arrays per (L, B, mode)
+  std::vector<int> bdm_sorted, bdm_sizes, bdm_cum;
+  std::map<std::tuple<const void *, const void *, int>, TrsmTileDesc *> bdm_trsm_descs;
   bool split_by_size = false; // the S chain runs as two size classes (group 0 = the large blocks)
   cudaStream_t urgent(int k) const { return concurrency && prio[k] ? prio[k] : stream; }
   // `to` waits for everything enqueued on `from` so far

@@ -168,15 +168,18 @@ template <int NL> struct Launch
   //           round-1 update kernel (16 x 16 tiles only).
   static constexpr int WALK_MAX_TILES = 3;
   static int trsm(sdpb_b200_ctx *c, const char *label, const TrsmTileDesc *d,
-                  const std::vector<int> &sizes, int maxcols, cudaStream_t side, int ev0)
+                  const std::vector<int> &sizes, int maxcols, cudaStream_t side, int ev0,
+                  bool levels_only = false)
   {
     if(sizes.empty() || sizes[0] == 0 || maxcols == 0)
       return 0;
-    static const int mode = [] {
+    static const int env_mode = [] {
       const char *env = getenv("SDPB_B200_TRSM");
       const std::string m = env ? env : "levels";
       return m == "walk" ? 2 : m == "hybrid" ? 0 : m == "levels1" ? 3 : 1;
     }();
+    // (descriptors with general strides -- bdm_trsm_tiles -- are for the level kernels only)
+    const int mode = levels_only && env_mode != 3 ? 1 : env_mode;
     int nheavy = 0; // prefix of the (descending) batch that keeps the level kernels
     while(nheavy < (int)sizes.size()
           && (mode == 1 || mode == 3 || (mode == 0 && sizes[nheavy] > WALK_MAX_TILES * TS)))
@@ -555,11 +558,94 @@ template <int NL> struct Launch
   // B <- L^-1 B (mode 0), L^-T B (1), B L^-T (2) on every block-parity: right-looking, one CTA per
   // block (direction.cuh); blocks too large for the shared-memory line buffer take the
   // one-thread-per-line kernels
+  // The same three solves on the tile kernels of the Schur-complement step (trsm_gemm_level2 +
+  // trsm_diag_level / trsm_diag_tile) through descriptors with general strides:
+  //   mode 0  B <- L^-1 B   the standard view
+  //   mode 1  B <- L^-T B   both index ranges reversed, i' = s-1-i: M(i', k') = L(k, i) is lower
+  //                         triangular, the substitution runs forward in i', i.e. k descending
+  //   mode 2  B <- B L^-T   B read by rows: unknown u of line l at B(l, u)
+  // Every element receives the same operations in the same order as in bdm_trsm_rl_kernel (updates
+  // in the canonical order of the unknowns, then the division), so the bits are the same; the work
+  // runs as 16 x 16 register tiles with TMA-staged operands instead of one element per thread and
+  // step through global memory.  Descriptor arrays are built on first use per (L, B, mode).
+  static int bdm_trsm_tiles(sdpb_b200_ctx *c, int mode, const limb_t *L, const uint32_t *recip, limb_t *B)
+  {
+    typedef TileGeom<NL> G;
+    constexpr int ES = Fmt<NL>::ES;
+    const int nb = 2 * c->J;
+    if(c->bdm_cols == 0)
+      return 0;
+    if(c->bdm_sorted.empty())
+      {
+        std::vector<int> cum(nb + 1, 0);
+        for(int q = 0; q < nb; ++q)
+          cum[q + 1] = cum[q] + c->g[q / 2].s[q % 2];
+        c->bdm_sorted.resize(nb);
+        for(int q = 0; q < nb; ++q)
+          c->bdm_sorted[q] = q;
+        std::stable_sort(c->bdm_sorted.begin(), c->bdm_sorted.end(),
+                         [&](int a, int b) { return c->g[a / 2].s[a % 2] > c->g[b / 2].s[b % 2]; });
+        c->bdm_sizes.clear();
+        for(int q : c->bdm_sorted)
+          if(c->g[q / 2].s[q % 2] > 0)
+            c->bdm_sizes.push_back(c->g[q / 2].s[q % 2]);
+        c->bdm_cum = cum;
+      }
+    if(c->bdm_sizes.empty())
+      return 0;
+    const auto key = std::make_tuple((const void *)L, (const void *)B, mode);
+    auto it = c->bdm_trsm_descs.find(key);
+    if(it == c->bdm_trsm_descs.end())
+      {
+        std::vector<TrsmTileDesc> v;
+        for(int q : c->bdm_sorted)
+          {
+            const long s = c->g[q / 2].s[q % 2];
+            if(s == 0)
+              continue;
+            const uint64_t *Lb = L + c->oXY[q];
+            uint64_t *Bb = B + c->oXY[q];
+            const uint32_t *rc = recip + (long)c->bdm_cum[q] * G::RS;
+            TrsmTileDesc d{Lb, rc, Bb, (int)s, (int)s, 0, 0};
+            if(mode == 1)
+              {
+                d.L = Lb + ((s - 1) * s + (s - 1)) * ES;
+                d.lsi = -s;
+                d.lsk = -1;
+                d.B = Bb + (s - 1) * ES;
+                d.bsi = -1;
+                d.bsc = s;
+                d.recip = rc + (s - 1) * G::RS;
+                d.rstep = -1;
+              }
+            else if(mode == 2)
+              {
+                d.bsi = s;
+                d.bsc = 1;
+              }
+            v.push_back(d);
+          }
+        TrsmTileDesc *dev = nullptr;
+        CUDA_TRY(c, cudaMalloc(&dev, v.size() * sizeof(TrsmTileDesc)));
+        CUDA_TRY(c, cudaMemcpy(dev, v.data(), v.size() * sizeof(TrsmTileDesc), cudaMemcpyHostToDevice));
+        it = c->bdm_trsm_descs.emplace(key, dev).first;
+      }
+    static const char *labels[3] = {"bdm_trsm_Linv", "bdm_trsm_LinvT", "bdm_trsm_right_LinvT"};
+    return trsm(c, labels[mode], it->second, c->bdm_sizes, c->max_s, c->cur, 0, true);
+  }
   static int bdm_trsm_rl(sdpb_b200_ctx *c, int mode, const limb_t *L, const uint32_t *recip, limb_t *B)
   {
     const int nb = 2 * c->J;
     if(c->bdm_cols == 0)
       return 0;
+    {
+      // "tiles": the level kernels of the step through strided descriptors (bdm_trsm_tiles).  Bit
+      // for bit the same, but measured slower at c3 (2.9 against 2.1 ms per solve: blocks of 20 and
+      // 40 rows pad to 32 and 48 in 16 x 16 tiles and fill 20 of 32 lanes in the diagonal solves)
+      const char *env = getenv("SDPB_B200_BDM_TRSM");
+      if(env && std::string(env) == "tiles")
+        return bdm_trsm_tiles(c, mode, L, recip, B);
+    }
     const size_t smem = (size_t)c->max_s * TileGeom<NL>::SW * 4;
     if(smem > (size_t)SMEM_OPT_IN)
       {

@@ -744,7 +744,7 @@ template <int NL> struct DiagSmem
 // cooperative load of a factored diagonal tile and its reciprocals
 template <int NL>
 __device__ __forceinline__ void load_diag(DiagSmem<NL> &sm, const uint64_t *A, long si, long sj,
-                                          const uint32_t *recip, int s, int Jt)
+                                          const uint32_t *recip, int s, int Jt, long rstep = 1)
 {
   typedef TileGeom<NL> G;
   const int J0 = Jt * TS, nd = min(TS, s - J0);
@@ -762,7 +762,7 @@ __device__ __forceinline__ void load_diag(DiagSmem<NL> &sm, const uint64_t *A, l
         }
     }
   for(int w = threadIdx.x; w < nd * G::RS; w += blockDim.x)
-    sm.recip[w] = recip[(long)J0 * G::RS + w];
+    sm.recip[w] = recip[(long)(J0 + w / G::RS) * rstep * G::RS + w % G::RS];
   __syncthreads();
 }
 
@@ -780,6 +780,21 @@ struct TrsmTileDesc // X <- L^{-1} B in place, L lower p x p (column-major)
   // right-hand sides that are bases_blocks (see GemmTileDesc): column c is zero above row
   // (c / nb) hb, and so is the solution; hb == 0: dense
   int hb, nb;
+  // General views, in elements (0 = the standard column-major one): L(i, k) at L + i lsi + k lsk,
+  // B(i, c) at B + i bsi + c bsc, the reciprocal of pivot i at recip + i rstep RS.  The level
+  // kernels then also run L^-T B (both index ranges reversed: a forward substitution again, the
+  // unknowns in descending order) and B L^-T (B read by rows) of the block-diagonal solves.
+  long lsi = 0, lsk = 0, bsi = 0, bsc = 0;
+  int rstep = 0;
+};
+struct TrsmView
+{
+  long lsi, lsk, bsi, bsc, rstep;
+  __device__ __forceinline__ explicit TrsmView(const TrsmTileDesc &d)
+    : lsi(d.lsi ? d.lsi : 1), lsk(d.lsk ? d.lsk : d.p), bsi(d.bsi ? d.bsi : 1), bsc(d.bsc ? d.bsc : d.p),
+      rstep(d.rstep ? d.rstep : 1)
+  {
+  }
 };
 
 // Row tile It of every solve of the batch (sorted by p, largest first):
@@ -804,14 +819,15 @@ __global__ void __launch_bounds__(256, TileOcc<NL>::value) trsm_gemm_level(const
   const int nc = min(TS, d.ncols - c0), ni = min(TS, d.p - I0);
   const bool active = ti < ni && tj < nc;
   Reg<NL> acc;
-  uint64_t *mine = d.B + ((long)(c0 + tj) * d.p + I0 + ti) * G::ES;
+  const TrsmView v(d);
+  uint64_t *mine = d.B + ((long)(c0 + tj) * v.bsc + (long)(I0 + ti) * v.bsi) * G::ES;
   if(active)
     ldg_reg<NL>(acc, mine);
   else
     mpfw::set_zero(acc);
   uint32_t it = 0;
-  Operand A{d.L + ((long)I0 + (long)klo * d.p) * G::ES, 1, d.p, ni};
-  Operand B{d.B + ((long)c0 * d.p + klo) * G::ES, d.p, 1, nc};
+  Operand A{d.L + ((long)I0 * v.lsi + (long)klo * v.lsk) * G::ES, v.lsi, v.lsk, ni};
+  Operand B{d.B + ((long)c0 * v.bsc + (long)klo * v.bsi) * G::ES, v.bsc, v.bsi, nc};
   tile_k_loop<NL>(acc, true, A, B, I0 - klo, sm, it, active);
   if(active)
     stg_reg<NL>(mine, acc);
@@ -827,21 +843,23 @@ trsm_diag_level(const TrsmTileDesc *descs, int It)
   const int I0 = It * TS, col0 = blockIdx.y * ROWS_PER_CTA;
   if(I0 >= d.p || col0 >= d.ncols)
     return;
-  load_diag<NL>(sm, d.L, 1, d.p, d.recip, d.p, It);
+  const TrsmView v(d);
+  load_diag<NL>(sm, d.L, v.lsi, v.lsk, d.recip, d.p, It, v.rstep);
   const int col = col0 + threadIdx.x;
   if(col >= d.ncols)
     return;
   const int ni = min(TS, d.p - I0);
-  uint64_t *colp = d.B + ((long)col * d.p + I0) * G::ES;
+  uint64_t *colp = d.B + ((long)col * v.bsc + (long)I0 * v.bsi) * G::ES;
+  const long rs = v.bsi * G::ES; // words between consecutive rows of the column
   for(int ii = 0; ii < ni; ++ii)
     {
       Reg<NL> acc;
-      ldg_reg<NL>(acc, colp + (long)ii * G::ES);
+      ldg_reg<NL>(acc, colp + ii * rs);
       for(int kk = 0; kk < ii; ++kk)
         acc = mac_nl<NL>(acc, sm.diag + tri_index(ii, kk) * G::SW,
-                         reinterpret_cast<const uint32_t *>(colp + (long)kk * G::ES), true);
+                         reinterpret_cast<const uint32_t *>(colp + kk * rs), true);
       acc = div_nl<NL>(acc, sm.diag + tri_index(ii, ii) * G::SW, sm.recip + ii * G::RS);
-      stg_reg<NL>(colp + (long)ii * G::ES, acc);
+      stg_reg<NL>(colp + ii * rs, acc);
     }
 }
 
@@ -869,11 +887,12 @@ trsm_diag_tile(const TrsmTileDesc *descs, int It)
   const int I0 = It * TS, c0 = blockIdx.y * TS;
   if(I0 >= d.p || c0 >= d.ncols)
     return;
-  load_diag<NL>(sm.d, d.L, 1, d.p, d.recip, d.p, It);
+  const TrsmView v(d);
+  load_diag<NL>(sm.d, d.L, v.lsi, v.lsk, d.recip, d.p, It, v.rstep);
   const int ti = tile_ti(), tj = tile_tj();
   const int ni = min(TS, d.p - I0), nc = min(TS, d.ncols - c0);
   const bool active = ti < ni && tj < nc;
-  uint64_t *mine = d.B + ((long)(c0 + tj) * d.p + I0 + ti) * G::ES;
+  uint64_t *mine = d.B + ((long)(c0 + tj) * v.bsc + (long)(I0 + ti) * v.bsi) * G::ES;
   Reg<NL> acc;
   if(active)
     ldg_reg<NL>(acc, mine);
@@ -932,13 +951,14 @@ trsm_update_pass(const TrsmTileDesc &d, int I0, int ni, bool wide, int c0, int c
   const int nc = min(cols, c1 - c0), K = I0 - klo;
   const bool active = ti < ni && tj < nc;
   Reg<NL> acc;
-  uint64_t *mine = d.B + ((long)(c0 + tj) * d.p + I0 + ti) * G::ES;
+  const TrsmView v(d);
+  uint64_t *mine = d.B + ((long)(c0 + tj) * v.bsc + (long)(I0 + ti) * v.bsi) * G::ES;
   if(active)
     ldg_reg<NL>(acc, mine);
   else
     mpfw::set_zero(acc);
-  const uint64_t *Abase = d.L + ((long)I0 + (long)klo * d.p) * G::ES; // (x, k) -> x + k p
-  const uint64_t *Bbase = d.B + ((long)c0 * d.p + klo) * G::ES;       // (x, k) -> x p + k
+  const uint64_t *Abase = d.L + ((long)I0 * v.lsi + (long)klo * v.lsk) * G::ES; // (x, k) -> x lsi + k lsk
+  const uint64_t *Bbase = d.B + ((long)c0 * v.bsc + (long)klo * v.bsi) * G::ES; // (x, k) -> x bsc + k bsi
   const int nchunks = (K + KC - 1) / KC;
   auto issue = [&](int c) {
     const uint32_t s = (it + c) & 1;
@@ -955,10 +975,10 @@ trsm_update_pass(const TrsmTileDesc &d, int I0, int ni, bool wide, int c0, int c
           continue;
         if(isA)
           bulk_g2s(s_a + ((size_t)s * KC * TS + dk * TS + dx) * G::SW,
-                   Abase + ((long)dx + (long)(k0 + dk) * d.p) * G::ES, G::EB, &bar[s]);
+                   Abase + ((long)dx * v.lsi + (long)(k0 + dk) * v.lsk) * G::ES, G::EB, &bar[s]);
         else
           bulk_g2s(s_b + ((size_t)s * KC * BC + dk * BC + dx) * G::SW,
-                   Bbase + ((long)dx * d.p + (k0 + dk)) * G::ES, G::EB, &bar[s]);
+                   Bbase + ((long)dx * v.bsc + (long)(k0 + dk) * v.bsi) * G::ES, G::EB, &bar[s]);
       }
   };
   issue(0);
