@@ -173,7 +173,9 @@ def recorded_traffic(workload, kernel):
     step, from the committed `ncu --set full` capture (profiles/traffic_*.json), or None."""
     import glob
     best = None
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json"))):
+    import re
+    natural = lambda p: [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", os.path.basename(p))]
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")), key=natural):  # the newest capture wins
         try:
             with open(path) as f:
                 d = json.load(f)

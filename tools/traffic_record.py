@@ -34,8 +34,10 @@ def emit(label, picked, note):
     print(label, len(picked), "launches", round(tot / 1e9, 3), "GB", round(sum(l["ms"] for l in launches), 3), "ms")
 
 
-# one step's L_j^-1 B_j: the 15 consecutive trsm launches whose grids count 600 or 150 blocks
-is_B = lambda b: b["kernel"].startswith("trsm_") and b["grid"].split(",")[0].strip("( ") in ("600", "150")
+# one step's L_j^-1 B_j: the consecutive trsm launches whose grids count 600 or 150 blocks (one group:
+# 7 update + 8 diagonal levels = 15), or 150 and then 450 blocks (split by size class: 15 + 5 = 20)
+is_B = lambda b: b["kernel"].startswith("trsm_") and b["grid"].split(",")[0].strip("( ") in ("600", "150", "450")
+want = 20 if any(is_B(b) and b["grid"].split(",")[0].strip("( ") == "450" for b in recs) else 15
 start = next(i for i, b in enumerate(recs) if is_B(b))
 step = []
 for b in recs[start:]:
@@ -43,10 +45,10 @@ for b in recs[start:]:
         step.append(b)
     elif step and b["kernel"].startswith("trsm_"):
         break
-    if len(step) == 15:
+    if len(step) == want:
         break
-assert len(step) == 15, len(step)
-emit("trsm_Linv_B", step, "the 15 launches of one step")
+assert len(step) == want, len(step)
+emit("trsm_Linv_B", step, "the %d launches of one step" % want)
 syrk = [b for b in recs if b["kernel"] == "syrk_imma_kernel"][:1]
 pack = [b for b in recs if b["kernel"] == "syrk_pack_kernel"][:1]
 if syrk:
