@@ -108,12 +108,37 @@ template <int NL> struct Launch
     const bool dist = c->world > 1 && sizes.size() == 1 && sizes[0] >= c->qdist_min_N && c->bcast;
     const int mod = dist ? c->world : 1, me = dist ? c->rank : 0;
     const char *l_diag = sub(label, "diag"), *l_panel = sub(label, "panel"), *l_trail = sub(label, "trail");
+    const char *l_fused = sub(label, "diag+panel");
+    // one matrix on one rank: the pipelined diagonal + panel kernel, as long as its grid is
+    // co-resident (the panel CTAs wait for CTA 0's columns).  c->d_flags[3] is its progress word,
+    // zero since the start of the step (init_flags).  SDPB_B200_POTRF_FUSED=0: the two kernels.
+    bool fused = !dist && sizes.size() == 1 && c->d_flags;
+    if(const char *env = getenv("SDPB_B200_POTRF_FUSED"))
+      fused = fused && atoi(env) != 0;
+    int resident = 0;
+    if(fused)
+      {
+        if(int rc = smem_opt_in(c, potrf_diag_panel_rl<NL>))
+          return rc;
+        int per_sm = 0, sms = 0;
+        CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, potrf_diag_panel_rl<NL>, 256, TILE_SMEM));
+        CUDA_TRY(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        resident = per_sm * sms;
+        CUDA_TRY(c, cudaMemsetAsync(c->d_flags + 3, 0, sizeof(int), c->cur));
+      }
     for(int Jt = 0; Jt < T; ++Jt)
       {
         const int n = alive(sizes, Jt), nbelow = alive(sizes, Jt + 1);
         const int tb = (sizes[0] - (Jt + 1) * TS + TS - 1) / TS; // tiles below / right of Jt
         const bool mine = Jt % mod == me;
-        if(mine)
+        if(mine && fused && nbelow && 1 + tb <= resident)
+          {
+            // diagonal tile and panel in one launch, the panel one column behind (tile.cuh)
+            c->kt_begin(l_fused);
+            potrf_diag_panel_rl<NL><<<1 + tb, 256, TILE_SMEM, c->cur>>>(d, Jt, status, c->d_flags + 3);
+            c->kt_end();
+          }
+        else if(mine)
           {
             c->kt_begin(l_diag);
             potrf_diag_rl<NL><<<n, 256, TILE_SMEM, c->cur>>>(d, Jt, status);

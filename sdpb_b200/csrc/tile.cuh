@@ -645,6 +645,155 @@ potrf_panel_rl(const PotrfDesc *descs, int Jt, const int *status)
     mpfw::set_zero(acc);
   potrf_row_tile_solve<NL>(acc, d, It, Jt, sm);
 }
+// ---- diagonal tile and panel in ONE launch, pipelined column by column ------------------------
+// The panel tiles below a diagonal tile need column k of its factor (and pivot k's reciprocal)
+// only at THEIR step k, so they do not have to wait for the whole tile: CTA 0 factors the diagonal
+// tile and publishes every column as it is finished (the factor entries go straight to the matrix,
+// a progress word counts the columns); CTA b >= 1 owns panel tile Jt + b and runs one column behind.
+// A level of a single large matrix then costs the 16 pivots of the diagonal tile plus one panel
+// step instead of the pivots plus a whole panel solve (94 of 490 us per level of Cholesky(Q) at
+// c3).  Same arithmetic, same order per element as potrf_diag_rl + potrf_panel_rl.
+// Forward progress: CTA 0 never waits; the grid (1 + tiles below <= 2 x 148) is co-resident.
+constexpr int POTRF_FUSED_FAIL = 0x7fffffff;
+__device__ __forceinline__ int ld_acquire_gpu(const int *p)
+{
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v)
+{
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <int NL>
+__global__ void __launch_bounds__(256, TileOcc<NL>::value)
+potrf_diag_panel_rl(const PotrfDesc *descs, int Jt, int *status, int *progress)
+{
+  typedef TileGeom<NL> G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileSmem<NL> &sm = *reinterpret_cast<TileSmem<NL> *>(smem_raw);
+  const PotrfDesc d = descs[0];
+  const int J0 = Jt * TS;
+  if(J0 >= d.s || status[d.id] >= 0)
+    return;
+  tile_smem_init(sm);
+  const int ti = tile_ti(), tj = tile_tj(), t = threadIdx.x;
+  const int nd = min(TS, d.s - J0);
+  Reg<NL> acc;
+  if(blockIdx.x == 0)
+    {
+      // ---- the diagonal tile (potrf_diag_tile), every column published as soon as it is final
+      if(ti < nd && tj < nd && ti >= tj)
+        ldg_reg<NL>(acc, d.A + ((long)(J0 + ti) * d.si + (long)(J0 + tj) * d.sj) * G::ES);
+      else
+        mpfw::set_zero(acc);
+      for(int kk = 0; kk < nd; ++kk)
+        {
+          uint32_t *pslot = sm.diag + (kk * TS + kk) * G::SW;
+          if(ti == kk && tj == kk)
+            {
+              if(acc.sign <= 0)
+                sm.bad = J0 + kk;
+              else
+                mpfw::store<NL>(pslot, acc);
+            }
+          __syncthreads();
+          if(sm.bad >= 0)
+            {
+              if(t == 0)
+                {
+                  status[d.id] = sm.bad;
+                  __threadfence();
+                  st_release_gpu(progress, POTRF_FUSED_FAIL); // wake the panel CTAs: they leave
+                }
+              return;
+            }
+          if(t < 32)
+            {
+              coop::pivot<NL>(sm.work, pslot, sm.recip + kk * G::RS, d.recip + (long)(J0 + kk) * G::RS);
+              __threadfence(); // the reciprocal words (global) before the progress word
+            }
+          __syncthreads();
+          if(ti == kk && tj == kk)
+            {
+              mpfw::load<NL>(acc, pslot);
+              stg_reg<NL>(d.A + ((long)(J0 + ti) * d.si + (long)(J0 + tj) * d.sj) * G::ES, acc);
+              __threadfence();
+            }
+          if(tj == kk && ti > kk && ti < nd)
+            {
+              const uint32_t *piv = sm.diag + (kk * TS + kk) * G::SW;
+              acc = div_nl<NL>(acc, piv, sm.recip + kk * G::RS);
+              mpfw::store<NL>(sm.diag + (kk * TS + ti) * G::SW, acc);
+              stg_reg<NL>(d.A + ((long)(J0 + ti) * d.si + (long)(J0 + tj) * d.sj) * G::ES, acc);
+              __threadfence();
+            }
+          __syncthreads();
+          if(t == 0)
+            st_release_gpu(progress, J0 + kk + 1); // columns J0 .. J0+kk of the factor are in place
+          if(ti > kk && tj > kk && ti >= tj && ti < nd)
+            acc = mac_nl<NL>(acc, sm.diag + (kk * TS + ti) * G::SW, sm.diag + (kk * TS + tj) * G::SW, true);
+        }
+      // exact zeros above the diagonal (the factor itself went out column by column)
+      if(ti < nd && tj < nd && ti < tj)
+        {
+          Reg<NL> z;
+          mpfw::set_zero(z);
+          stg_reg<NL>(d.A + ((long)(J0 + ti) * d.si + (long)(J0 + tj) * d.sj) * G::ES, z);
+        }
+      return;
+    }
+  // ---- panel tile It = Jt + blockIdx.x (potrf_row_tile_solve), one column behind the diagonal tile
+  const int It = Jt + (int)blockIdx.x, I0 = It * TS;
+  if(I0 >= d.s)
+    return;
+  const int ni = min(TS, d.s - I0);
+  if(ti < ni && tj < nd)
+    ldg_reg<NL>(acc, d.A + ((long)(I0 + ti) * d.si + (long)(J0 + tj) * d.sj) * G::ES);
+  else
+    mpfw::set_zero(acc);
+  for(int kk = 0; kk < nd; ++kk)
+    {
+      if(t == 0)
+        {
+          int seen;
+          while((seen = ld_acquire_gpu(progress)) < J0 + kk + 1)
+            __nanosleep(200);
+          sm.bad = seen == POTRF_FUSED_FAIL ? 1 : -1;
+        }
+      __syncthreads();
+      if(sm.bad >= 0)
+        return;
+      // column kk of the factored diagonal tile (rows kk .. nd-1) and pivot kk's reciprocal, past L1
+      for(int e = t; e < (nd - kk) * (G::EB / 16); e += 256)
+        {
+          const int x = kk + e / (G::EB / 16), w = e % (G::EB / 16);
+          const uint4 *src = reinterpret_cast<const uint4 *>(
+            d.A + ((long)(J0 + x) * d.si + (long)(J0 + kk) * d.sj) * G::ES);
+          reinterpret_cast<uint4 *>(sm.diag + (kk * TS + x) * G::SW)[w] = __ldcg(src + w);
+        }
+      for(int w = t; w < G::RS; w += 256)
+        sm.recip[kk * G::RS + w] = __ldcg(d.recip + (long)(J0 + kk) * G::RS + w);
+      __syncthreads();
+      uint32_t *xs = sm.vec[kk & 1];
+      if(tj == kk && ti < ni)
+        {
+          const uint32_t *piv = sm.diag + (kk * TS + kk) * G::SW;
+          acc = div_nl<NL>(acc, piv, sm.recip + kk * G::RS);
+          mpfw::store<NL>(xs + ti * G::SW, acc);
+        }
+      __syncthreads();
+      if(tj > kk && tj < nd && ti < ni)
+        acc = mac_nl<NL>(acc, xs + ti * G::SW, sm.diag + (kk * TS + tj) * G::SW, true);
+    }
+  if(ti < ni && tj < nd)
+    {
+      stg_reg<NL>(d.A + ((long)(I0 + ti) * d.si + (long)(J0 + tj) * d.sj) * G::ES, acc);
+      Reg<NL> z;
+      mpfw::set_zero(z);
+      stg_reg<NL>(d.A + ((long)(J0 + tj) * d.si + (long)(I0 + ti) * d.sj) * G::ES, z);
+    }
+}
 // block column Jt (rows J0.., its 16 columns) <-> a contiguous buffer, for the broadcast of the
 // panel-distributed Cholesky; the last word carries the matrix's status (a failed pivot on the
 // owner must stop every rank)

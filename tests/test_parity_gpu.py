@@ -271,6 +271,55 @@ def test_trsm_diagonal_solve_forms_bit_exact(monkeypatch, below):
     ctx.close()
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_cholesky_Q_pipelined_and_two_kernel_forms_bit_exact(monkeypatch, fused):
+    """Cholesky(Q) runs its diagonal tile and the panel below it in one launch, the panel one column
+    behind (potrf_diag_panel_rl); SDPB_B200_POTRF_FUSED=0 keeps the two kernels.  N = 53 gives four
+    levels with a ragged last tile; both forms must reproduce the oracle, on a second step too."""
+    prec, shapes, N = 768, [(1, 30), (2, 9), (1, 17)], 53
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=21)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    want = sdp.run_step(ref)
+    monkeypatch.setenv("SDPB_B200_POTRF_FUSED", fused)
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    for rep in range(2):
+        got = sdp.run_step(ctx)
+        for k in KEYS:
+            ol.assert_same(k + f" (step {rep})", got[k], want[k])
+    ctx.close()
+
+
+def test_rank_deficient_Q_ends_like_the_oracle():
+    """Fewer stacked rows than columns (K = 11 < N = 20): Q = P^T P is singular, the pivots from
+    column 12 on are rounding noise, and whether -- and where -- Cholesky(Q) meets a non-positive
+    one is decided by the arithmetic.  The CUDA path must end exactly like the oracle: the same
+    error (a failing pivot inside the first diagonal tile also wakes the waiting panel CTA of the
+    pipelined kernel) or the same bits."""
+    prec, shapes, N = 768, [(1, 5), (1, 6)], 20
+    sdp = ol.SyntheticSDP(prec, shapes, N, seed=4)
+    ref = ol.OracleContext(prec, shapes, N)
+    sdp.upload(ref)
+    want, want_err = None, None
+    try:
+        want = sdp.run_step(ref)
+    except ol.OracleError as e:
+        want_err = e
+    ctx = sdpb_b200.SchurContext(prec, shapes, N)
+    sdp.upload(ctx)
+    if want_err is None:
+        got = sdp.run_step(ctx)
+        for k in KEYS:
+            ol.assert_same(k, got[k], want[k])
+    else:
+        with pytest.raises(sdpb_b200.SdpbB200Error) as ei:
+            sdp.run_step(ctx)
+        assert ei.value.code == want_err.code
+        assert ei.value.message == want_err.message
+    ctx.close()
+
+
 def test_separate_calls_match_fused_step():
     prec, shapes, N = 256, [(1, 6), (2, 3)], 4
     sdp = ol.SyntheticSDP(prec, shapes, N, seed=5)
