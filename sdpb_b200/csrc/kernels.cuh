@@ -509,16 +509,18 @@ crt_restore_kernel(const uint32_t *__restrict__ Qres, int N, int prec,
   for(int a = 0; a < np; ++a)
     {
       const uint32_t pa = T.primes[a];
+      const uint64_t inva = T.inv64[a]; // Barrett: the 64-bit `%` by a run-time prime is a ~70-instruction
+                                        // routine, and this recurrence is 2 np^2 / 2 of them in a row
       // a sum of per-rank residues when the blocks are sharded over GPUs
-      uint64_t t = Qres[((size_t)a * N + i) * N + j] % pa;
+      uint32_t t = barrett_mod(Qres[((size_t)a * N + i) * N + j], pa, inva);
       for(int b = 0; b < a; ++b)
         {
           // t = (t - v_b) * p_b^{-1} mod p_a
-          const uint64_t vb = v[b] % pa;
-          const uint64_t diff = t >= vb ? t - vb : t + pa - vb;
-          t = (diff * T.ginv[(size_t)a * np + b]) % pa;
+          const uint32_t vb = barrett_mod(v[b], pa, inva);
+          const uint32_t diff = t >= vb ? t - vb : t + pa - vb;
+          t = barrett_mod((uint64_t)diff * T.ginv[(size_t)a * np + b], pa, inva);
         }
-      v[a] = (uint32_t)t;
+      v[a] = t;
     }
   // x = v0 + p0 (v1 + p1 (v2 + ...)) in 32-bit words
   uint32_t x[MAXMW];
